@@ -1,0 +1,159 @@
+/* nisqa_b200.h - C ABI of the B200-native NISQA predict engine (libnisqa_b200.so).
+ *
+ * Drop-in boundary: the reference has no FFI; its seam for this path is the
+ * Python function boundary
+ *     NL.predict_dim(model, ds, bs, dev, num_workers)   reference nisqa/NISQA_lib.py:1441-1467
+ *     NL.predict_mos(model, ds, bs, dev, num_workers)   reference nisqa/NISQA_lib.py:1420-1439
+ * called from nisqaModel.predict() (reference nisqa/NISQA_model.py:54-81).  Everything below
+ * that seam - get_librosa_melspec (lib:2284-2331) minus the file decode, segment_specs
+ * (lib:2239-2282), Framewise/AdaptCNN/StandardCNN (lib:428-836), SelfAttention/LSTM
+ * (lib:897-1040), PoolAttFF/PoolLastStepBi (lib:1099-1183) and the NISQA / NISQA_DIM
+ * containers (lib:29-268) - runs inside this library as hand-written sm_100a CUDA.
+ *
+ * Plain C types only: pointers and sizes, no torch types.  All functions return 0 on
+ * success and a negative nisqa_status on failure; nisqa_last_error() gives the message.
+ * No exceptions cross the ABI.  One engine handle per GPU / rank; a handle is not
+ * thread-safe.  There is NO CPU fallback: every entry point fails loudly without a device.
+ */
+#ifndef NISQA_B200_H
+#define NISQA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NISQA_B200_ABI_VERSION 1
+
+typedef struct nisqa_engine nisqa_engine;
+
+/* architectures of the shipped checkpoints */
+enum nisqa_arch {
+  NISQA_ARCH_ADAPT_SA_ATTFF  = 0, /* nisqa.tar, nisqa_mos_only.tar: AdaptCNN + SelfAttention + PoolAttFF */
+  NISQA_ARCH_STD_LSTM_LASTBI = 1  /* nisqa_tts.tar: StandardCNN + BiLSTM + PoolLastStepBi            */
+};
+
+enum nisqa_sample_fmt { NISQA_FMT_S16 = 0, NISQA_FMT_F32 = 1 };
+
+/* per-clip status written to status_out; the Python wrapper maps them onto the reference's
+ * ValueError messages (lib:2259-2263 "Sample too short", lib:2276-2277 "n_wins > max_length") */
+enum nisqa_clip_status { NISQA_CLIP_OK = 0, NISQA_CLIP_TOO_SHORT = 1, NISQA_CLIP_TOO_LONG = 2 };
+
+enum nisqa_status {
+  NISQA_SUCCESS = 0,
+  NISQA_ERR_INVALID = -1,      /* bad argument / unsupported configuration        */
+  NISQA_ERR_CUDA = -2,         /* CUDA runtime error (no device, OOM, launch)     */
+  NISQA_ERR_WEIGHTS = -3,      /* missing / mis-shaped tensor in load_weights     */
+  NISQA_ERR_STATE = -4,        /* call order (e.g. predict before load_weights)   */
+  NISQA_ERR_NCCL = -5
+};
+
+/* stages readable through nisqa_stage_dump after a predict call (parity tests) */
+enum nisqa_stage {
+  NISQA_STAGE_MEL_DB   = 0, /* per clip [n_mels, n_frames] row-major, clamped (lib:2330), clips concatenated */
+  NISQA_STAGE_POOL1    = 1, /* [n_seg, 16, 24, W1] NCHW like the reference tensors           */
+  NISQA_STAGE_POOL2    = 2, /* [n_seg, 32, 12, W2]                                           */
+  NISQA_STAGE_CONV3    = 3, /* [n_seg, 64, 12, W2]                                           */
+  NISQA_STAGE_POOL3    = 4, /* [n_seg, 64, 6, W3]                                            */
+  NISQA_STAGE_CONV5    = 5, /* [n_seg, 64, 6, W3]                                            */
+  NISQA_STAGE_CNN_FEAT = 6, /* [n_seg, 384] (adapt, index c*6+h) or [n_seg, 20] (standard)   */
+  NISQA_STAGE_TD_IN    = 7, /* adapt only: LayerNorm(Linear 384->64) [n_seg, 64]             */
+  NISQA_STAGE_TD_OUT   = 8  /* [n_seg, 64] (self-attention) or [n_seg, 256] (BiLSTM fwd||bwd) */
+};
+
+/* Mirrors the checkpoint 'args' the hot path consumes. */
+typedef struct nisqa_config {
+  int32_t abi_version;   /* NISQA_B200_ABI_VERSION */
+  int32_t arch;          /* enum nisqa_arch */
+  int32_t n_out;         /* 1 (NISQA) or 5 (NISQA_DIM: mos,noi,dis,col,loud - lib:1461-1465) */
+  int32_t n_fft;         /* ms_n_fft = 4096 */
+  int32_t n_mels;        /* ms_n_mels = 48  */
+  int32_t seg_len;       /* ms_seg_length = 15 */
+  int32_t seg_hop;       /* ms_seg_hop_length (4 | 1) */
+  int32_t max_segments;  /* ms_max_segments (1300 | 6000) */
+  double  hop_s;         /* ms_hop_length seconds: hop = (int)(sr*hop_s), lib:2308 */
+  double  win_s;         /* ms_win_length seconds: win = (int)(sr*win_s), lib:2309 */
+  double  fmax;          /* ms_fmax Hz */
+  int32_t sa_layers;     /* td_sa_num_layers (adapt arch), else 0 */
+  int32_t max_chunk_segments; /* 0 = default; upper bound on segments processed per internal pass */
+} nisqa_config;
+
+/* One state_dict entry, passed straight through: name as in the checkpoint
+ * ("cnn.model.conv1.weight", ...), fp32 host data, up to 4 dims. */
+typedef struct nisqa_tensor {
+  const char*  name;
+  const float* data;
+  int32_t      ndim;
+  int64_t      dims[4];
+} nisqa_tensor;
+
+int  nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg);
+void nisqa_destroy(nisqa_engine* e);
+const char* nisqa_last_error(const nisqa_engine* e);
+
+/* replaces model.load_state_dict(checkpoint['model_state_dict'], strict=True), model:1023:
+ * folds eval-mode BatchNorm into the convolutions, repacks to the kernel layouts, uploads. */
+int  nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n);
+
+/* replaces the body of predict_dim / predict_mos for n_clips clips given as mono PCM in HOST
+ * memory (already channel-selected / mono-mixed by the caller, lib:2298-2304).
+ *   pcm[i]         : n_samples[i] samples of sample_fmt
+ *   sample_rate[i] : native rate of clip i (ms_sr=None path, lib:2304)
+ *   scores_out     : [n_clips, n_out] fp32 (NaN rows for clips whose status != OK)
+ *   n_segments_out : [n_clips] int32 - n_wins as returned by segment_specs (lib:2282)
+ *   status_out     : [n_clips] int32 - enum nisqa_clip_status
+ * Synchronous: results are valid in host memory on return. */
+int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
+                       const void* const* pcm, const int64_t* n_samples,
+                       const int32_t* sample_rate, int sample_fmt,
+                       float* scores_out, int32_t* n_segments_out, int32_t* status_out);
+
+/* Same computation with the packed PCM already resident in device memory (clips laid back
+ * to back, clip i starting at element offset pcm_offsets[i]); scores stay on the device
+ * (scores_dev [n_clips, n_out]).  Asynchronous on the engine stream unless sync != 0.
+ * Used by bench.py for the "inputs resident in HBM" throughput figure. */
+int  nisqa_predict_pcm_device(nisqa_engine* e, int n_clips,
+                              const void* pcm_dev, const int64_t* pcm_offsets,
+                              const int64_t* n_samples, const int32_t* sample_rate,
+                              int sample_fmt, float* scores_dev,
+                              int32_t* n_segments_out, int32_t* status_out, int sync);
+
+/* Copy an intermediate of the LAST predict call to host memory (parity tests).  Only valid
+ * when that call fitted in one internal pass.  Returns the number of floats written (>=0)
+ * or a negative status; with out == NULL returns the required count. */
+int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap);
+
+/* Pure host arithmetic (no device work): frames / segments / status for a clip length,
+ * exactly as lib:2308 + librosa's frame count + lib:2257-2277. */
+int  nisqa_segment_counts(const nisqa_config* cfg, int64_t n_samples, int32_t sample_rate,
+                          int32_t* n_frames, int32_t* n_segments, int32_t* status);
+
+/* Host copy of the engine's mel filterbank for a sample rate: dense [n_mels, n_fft/2+1]. */
+int  nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64_t cap);
+
+/* Single exchange step of the multi-GPU path: gather the per-rank score rows
+ * onto every rank with one ncclAllGather on the engine stream.
+ *   nccl_comm : ncclComm_t of the caller (one rank per GPU)
+ *   local_dev : [max_rows, n_out] fp32 device rows of this rank (padded to max_rows)
+ *   global_dev: [world, max_rows, n_out] fp32 device buffer */
+int  nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm /* NULL: the engine's own */,
+                       const float* local_dev, int max_rows, float* global_dev);
+/* Engine-owned communicator: rank 0 calls nisqa_nccl_unique_id (128 bytes), the caller ships
+ * the id to every rank (torch.distributed broadcast), every rank calls nisqa_nccl_init. */
+int  nisqa_nccl_unique_id(nisqa_engine* e, void* id128);
+int  nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void* id128);
+
+/* bookkeeping for bench.py */
+int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
+void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t the engine launches on */
+/* average device time (ms) of the named kernel group during the last predict call, measured
+ * with CUDA events on the engine stream when profiling was enabled; <0 if unknown.
+ * groups: "frontend", "cnn", "td", "pool" */
+int    nisqa_set_profiling(nisqa_engine* e, int on);
+double nisqa_group_ms(const nisqa_engine* e, const char* group);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NISQA_B200_H */

@@ -1,0 +1,955 @@
+// engine.cu - C-ABI of libnisqa_b200.so (include/nisqa_b200.h) and the host runtime around the
+// kernels: checkpoint tensor repacking (BatchNorm folding, k-major linears), per-sample-rate
+// front-end tables (periodic Hann, Slaney mel filterbank as band-major CSR - restating
+// librosa.filters.mel in double precision), pass planning (exact frame / segment counts,
+// reference nisqa/NISQA_lib.py:2308-2309, 2257-2277), device workspaces and launches.
+//
+// There is no CPU fallback: without a usable CUDA device nisqa_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nisqa_b200.h"
+#include "common.cuh"
+
+namespace nisqa {
+// frontend.cu
+void launch_frontend(cudaStream_t, const void*, int, const ClipDesc*, int, const int*, int,
+                     const FbTables*, const float2*, float*, unsigned*, int);
+void launch_seg_table(cudaStream_t, const ClipDesc*, int, const int*, const unsigned*, int, int,
+                      int*, float*, int*);
+void launch_mel_dump(cudaStream_t, const float*, const ClipDesc*, int, const unsigned*, float*);
+// cnn.cu
+void launch_conv1(cudaStream_t, int, const float*, const int*, const float*, const float*,
+                  const float*, float*, int);
+void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
+void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
+// td.cu
+struct SaLayerParams {
+  const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
+  const float* b2; const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+};
+struct PoolHeadParams { const float* W1T; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3; };
+struct LstmParams { const float* w_ih; const float* w_hh; const float* b; const float* w_pool; };
+void launch_lin_ln(cudaStream_t, const float*, const float*, const float*, const float*, const float*, float*, int);
+void launch_fc20(cudaStream_t, const float*, const float*, const float*, float*, int);
+void launch_qkv(cudaStream_t, const float*, const float*, const float*, float*, int);
+void launch_sa_layer(cudaStream_t, const float*, const float*, const ClipDesc*, int, const int*, int,
+                     const SaLayerParams&, float*);
+void launch_pool_att(cudaStream_t, const float*, const ClipDesc*, int, int, const PoolHeadParams&, int, float*, float*);
+void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmParams&, float*, float*, float, float*);
+}  // namespace nisqa
+
+using namespace nisqa;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct FbEntry {
+  int sr = 0, hop = 0, win = 0;
+  std::vector<float> dense;      // [n_mels][n_bins] host copy (nisqa_mel_filterbank)
+  DevBuf window, band_start, band_k0, weights;
+};
+
+struct ClipPlan {
+  int hop, win, n_frames, n_seg, status, fb_id;
+};
+
+struct TimerSlot {
+  std::string name;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  double ms = 0.0;
+  int launches = 0;
+};
+
+}  // namespace
+
+struct nisqa_engine {
+  nisqa_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool weights_loaded = false;
+  bool profiling = false;
+  std::vector<TimerSlot> timers;
+
+  // weights arena (device) + offsets
+  DevBuf warena;
+  std::map<std::string, size_t> woff;   // float offsets into warena
+  float pool_bias_std = 0.f;
+
+  // front-end tables
+  std::vector<FbEntry*> fbs;
+  DevBuf fb_table;       // FbTables[]
+  DevBuf tw4096;         // float2[4096]
+
+  // per-pass workspaces
+  DevBuf pcm, clips, prefixes, clipmax, mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
+      qkv, logits, feats20, tdout, partial, scores, dump;
+  HostBuf h_tables, h_scores;
+
+  // description of the last pass (stage dumps)
+  std::vector<ClipDesc> last_clips;
+  int last_n_seg = 0, last_n_frames = 0, last_passes = 0;
+  const float* last_td_in = nullptr;
+  const float* last_td_out = nullptr;
+
+  // engine-owned NCCL communicator (multi-GPU gather)
+  void* nccl_comm = nullptr;
+  int nccl_world = 1, nccl_rank = 0;
+
+  ~nisqa_engine() {
+    for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); delete f; }
+    DevBuf* all[] = {&warena, &fb_table, &tw4096, &pcm, &clips, &prefixes, &clipmax, &mel, &segtab, &act1,
+                     &act2, &act3, &act4, &act5, &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout,
+                     &partial, &scores, &dump};
+    for (auto* b : all) b->release();
+    h_tables.release(); h_scores.release();
+    for (auto& t : timers) for (auto& e : t.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int fail(nisqa_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  return code;
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(e, NISQA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---------------------------------------------------------------- timing of kernel groups
+struct Scope {
+  nisqa_engine* e; TimerSlot* slot = nullptr; cudaEvent_t stop = nullptr;
+  Scope(nisqa_engine* e_, const char* name, int n_launch = 1) : e(e_) {
+    e->launches += n_launch;
+    if (!e->profiling) return;
+    for (auto& t : e->timers) if (t.name == name) slot = &t;
+    if (!slot) { e->timers.push_back(TimerSlot()); slot = &e->timers.back(); slot->name = name; }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, e->stream);
+    slot->ev.push_back({a, b});
+    slot->launches += n_launch;
+    stop = b;
+  }
+  ~Scope() { if (stop) cudaEventRecord(stop, e->stream); }
+};
+
+void collect_timers(nisqa_engine* e) {
+  for (auto& t : e->timers) {
+    for (auto& ev : t.ev) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) t.ms += ms;
+      cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    t.ev.clear();
+  }
+}
+
+// ---------------------------------------------------------------- host arithmetic (a2, a6)
+void plan_clip(const nisqa_config& c, int64_t n_samples, int sr, ClipPlan* p) {
+  // reference lib:2308-2309: int(sr * seconds) in double precision, truncation
+  p->hop = (int)((double)sr * c.hop_s);
+  p->win = (int)((double)sr * c.win_s);
+  p->n_frames = 0; p->n_seg = 0; p->status = NISQA_CLIP_TOO_SHORT; p->fb_id = -1;
+  if (p->hop < 1 || p->win < 1 || p->win > c.n_fft || n_samples < 1) return;
+  // librosa.stft(center=True): frames = 1 + (n + 2*(n_fft/2) - n_fft) / hop = 1 + n / hop
+  const int64_t frames = 1 + n_samples / p->hop;
+  const int64_t n_wins = frames - (c.seg_len - 1);          // lib:2257
+  p->n_frames = (int)std::min<int64_t>(frames, INT32_MAX);
+  if (n_wins < 1) return;                                    // lib:2258-2263
+  const int64_t n_seg = (c.seg_hop > 1) ? (n_wins + c.seg_hop - 1) / c.seg_hop : n_wins;  // lib:2271-2273
+  p->n_seg = (int)std::min<int64_t>(n_seg, INT32_MAX);
+  if (c.max_segments > 0 && n_seg > c.max_segments) { p->status = NISQA_CLIP_TOO_LONG; return; }  // lib:2276-2277
+  p->status = NISQA_CLIP_OK;
+}
+
+// ---------------------------------------------------------------- librosa.filters.mel in double
+double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = (min_log_hz - 0.0) / f_sp;
+  const double logstep = log(6.4) / 27.0;
+  if (f >= min_log_hz) return min_log_mel + log(f / min_log_hz) / logstep;
+  return (f - 0.0) / f_sp;
+}
+double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = (min_log_hz - 0.0) / f_sp;
+  const double logstep = log(6.4) / 27.0;
+  if (m >= min_log_mel) return min_log_hz * exp(logstep * (m - min_log_mel));
+  return 0.0 + f_sp * m;
+}
+void np_linspace(double start, double stop, int num, std::vector<double>& y) {
+  y.resize(num);
+  const double step = (stop - start) / (double)(num - 1);
+  for (int i = 0; i < num; ++i) { volatile double t = (double)i * step; y[i] = t + start; }
+  y[num - 1] = stop;
+}
+
+int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
+  for (size_t i = 0; i < e->fbs.size(); ++i)
+    if (e->fbs[i]->sr == sr) { *id_out = (int)i; return 0; }
+  const nisqa_config& c = e->cfg;
+  const int n_bins = c.n_fft / 2 + 1, n_mels = c.n_mels;
+  FbEntry* fb = new FbEntry();
+  fb->sr = sr; fb->hop = hop; fb->win = win;
+  std::vector<double> fftfreqs, mels, mel_f(n_mels + 2);
+  np_linspace(0.0, (double)sr / 2, n_bins, fftfreqs);
+  np_linspace(hz_to_mel(0.0), hz_to_mel(c.fmax), n_mels + 2, mels);
+  for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(mels[i]);
+  fb->dense.assign((size_t)n_mels * n_bins, 0.f);
+  std::vector<int> band_start(n_mels + 1, 0), band_k0(n_mels, 0);
+  std::vector<float> wts;
+  for (int i = 0; i < n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    int k0 = -1, k1 = -1;
+    for (int k = 0; k < n_bins; ++k) {
+      const double lower = -(mel_f[i] - fftfreqs[k]) / fd0;
+      const double upper = (mel_f[i + 2] - fftfreqs[k]) / fd1;
+      const float tri = (float)std::max(0.0, std::min(lower, upper));   // float32 triangle ...
+      const float w = (float)((double)tri * enorm);                      // ... then `weights *= enorm`
+      fb->dense[(size_t)i * n_bins + k] = w;
+      if (w != 0.f) { if (k0 < 0) k0 = k; k1 = k; }
+    }
+    band_start[i] = (int)wts.size();
+    band_k0[i] = k0 < 0 ? 0 : k0;
+    if (k0 >= 0) for (int k = k0; k <= k1; ++k) wts.push_back(fb->dense[(size_t)i * n_bins + k]);
+  }
+  band_start[n_mels] = (int)wts.size();
+  if (wts.empty()) wts.push_back(0.f);
+  // scipy.signal.get_window('hann', win, fftbins=True): periodic Hann in float64 -> float32
+  std::vector<float> window(win);
+  for (int n = 0; n < win; ++n) window[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)win));
+  if (win == 1) window[0] = 1.f;
+  CK(fb->window.reserve(window.size() * 4));
+  CK(fb->band_start.reserve(band_start.size() * 4));
+  CK(fb->band_k0.reserve(band_k0.size() * 4));
+  CK(fb->weights.reserve(wts.size() * 4));
+  CK(cudaMemcpy(fb->window.p, window.data(), window.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fb->band_start.p, band_start.data(), band_start.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fb->band_k0.p, band_k0.data(), band_k0.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fb->weights.p, wts.data(), wts.size() * 4, cudaMemcpyHostToDevice));
+  e->fbs.push_back(fb);
+  // refresh the device table of FbTables
+  std::vector<FbTables> tab(e->fbs.size());
+  for (size_t i = 0; i < e->fbs.size(); ++i) {
+    tab[i].window = e->fbs[i]->window.as<float>();
+    tab[i].band_start = e->fbs[i]->band_start.as<int>();
+    tab[i].band_k0 = e->fbs[i]->band_k0.as<int>();
+    tab[i].weights = e->fbs[i]->weights.as<float>();
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(e->fb_table.reserve(tab.size() * sizeof(FbTables) + 64 * sizeof(FbTables)));
+  CK(cudaMemcpy(e->fb_table.p, tab.data(), tab.size() * sizeof(FbTables), cudaMemcpyHostToDevice));
+  *id_out = (int)e->fbs.size() - 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- weight repacking
+struct TensorView { const float* d; int nd; int64_t dims[4]; int64_t numel; };
+
+struct Packer {
+  nisqa_engine* e;
+  std::map<std::string, TensorView> t;
+  std::vector<float> arena;
+  std::string missing;
+  const TensorView* get(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = t.find(name);
+    if (it == t.end()) { if (missing.empty()) missing = "missing tensor " + name; return nullptr; }
+    const TensorView& v = it->second;
+    bool ok = v.nd == (int)shape.size();
+    int i = 0;
+    for (int64_t s : shape) { if (ok && v.dims[i] != s) ok = false; ++i; }
+    if (!ok) { if (missing.empty()) missing = "bad shape for tensor " + name; return nullptr; }
+    return &v;
+  }
+  size_t alloc(const std::string& key, size_t n) {
+    size_t off = (arena.size() + 63) / 64 * 64;     // 256-byte aligned blocks
+    arena.resize(off + n, 0.f);
+    e->woff[key] = off;
+    return off;
+  }
+};
+
+bool pack_conv(Packer& P, int idx, int cin, int cout) {
+  char nm[96];
+  auto name = [&](const char* fmt) { snprintf(nm, sizeof nm, fmt, idx); return std::string(nm); };
+  const TensorView* w = P.get(name("cnn.model.conv%d.weight"), {cout, cin, 3, 3});
+  const TensorView* b = P.get(name("cnn.model.conv%d.bias"), {cout});
+  const TensorView* g = P.get(name("cnn.model.bn%d.weight"), {cout});
+  const TensorView* be = P.get(name("cnn.model.bn%d.bias"), {cout});
+  const TensorView* mu = P.get(name("cnn.model.bn%d.running_mean"), {cout});
+  const TensorView* var = P.get(name("cnn.model.bn%d.running_var"), {cout});
+  if (!w || !b || !g || !be || !mu || !var) return false;
+  const size_t wo = P.alloc(name("conv%d.w"), (size_t)cin * 9 * cout);
+  const size_t bo = P.alloc(name("conv%d.b"), cout);
+  for (int co = 0; co < cout; ++co) {
+    // eval-mode BatchNorm2d (eps 1e-5) folded into the convolution
+    const double s = (double)g->d[co] / sqrt((double)var->d[co] + 1e-5);
+    P.arena[bo + co] = (float)(((double)b->d[co] - (double)mu->d[co]) * s + (double)be->d[co]);
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < 9; ++tap)
+        P.arena[wo + ((size_t)ci * 9 + tap) * cout + co] =
+            (float)((double)w->d[((size_t)co * cin + ci) * 9 + tap] * s);
+  }
+  return true;
+}
+
+// dst[k][j] = src[j][perm(k)] for a [n_out][n_in] PyTorch Linear weight
+void pack_linear_T(Packer& P, size_t off, const TensorView* w, int n_out, int n_in, float scale = 1.f) {
+  for (int k = 0; k < n_in; ++k)
+    for (int j = 0; j < n_out; ++j) P.arena[off + (size_t)k * n_out + j] = w->d[(size_t)j * n_in + k] * scale;
+}
+
+int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
+  Packer P; P.e = e;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].name || !tensors[i].data) continue;
+    TensorView v; v.d = tensors[i].data; v.nd = tensors[i].ndim; v.numel = 1;
+    for (int d = 0; d < 4; ++d) { v.dims[d] = d < v.nd ? tensors[i].dims[d] : 1; v.numel *= v.dims[d]; }
+    P.t[tensors[i].name] = v;
+  }
+  e->woff.clear();
+  const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
+  for (int i = 1; i <= 6; ++i)
+    if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+
+  if (e->cfg.arch == NISQA_ARCH_ADAPT_SA_ATTFF) {
+    const std::string td = "time_dependency.model.";
+    const TensorView* lw = P.get(td + "linear.weight", {64, 384});
+    const TensorView* lb = P.get(td + "linear.bias", {64});
+    const TensorView* ng = P.get(td + "norm1.weight", {64});
+    const TensorView* nb = P.get(td + "norm1.bias", {64});
+    if (!lw || !lb || !ng || !nb) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    size_t o = P.alloc("lin.wT", 384 * 64);
+    // engine feature order k' = h*64 + c  <->  reference view(-1, 64*6) order c*6 + h (lib:706)
+    for (int h = 0; h < 6; ++h)
+      for (int c = 0; c < 64; ++c)
+        for (int j = 0; j < 64; ++j) P.arena[o + ((size_t)h * 64 + c) * 64 + j] = lw->d[(size_t)j * 384 + c * 6 + h];
+    o = P.alloc("lin.b", 64); memcpy(&P.arena[o], lb->d, 256);
+    o = P.alloc("ln0.g", 64); memcpy(&P.arena[o], ng->d, 256);
+    o = P.alloc("ln0.b", 64); memcpy(&P.arena[o], nb->d, 256);
+    for (int l = 0; l < e->cfg.sa_layers; ++l) {
+      char pf[96]; snprintf(pf, sizeof pf, "time_dependency.model.layers.%d.", l);
+      char key[64];
+      const std::string p(pf);
+      const TensorView* iw = P.get(p + "self_attn.in_proj_weight", {192, 64});
+      const TensorView* ib = P.get(p + "self_attn.in_proj_bias", {192});
+      const TensorView* ow = P.get(p + "self_attn.out_proj.weight", {64, 64});
+      const TensorView* ob = P.get(p + "self_attn.out_proj.bias", {64});
+      const TensorView* w1 = P.get(p + "linear1.weight", {64, 64});
+      const TensorView* b1 = P.get(p + "linear1.bias", {64});
+      const TensorView* w2 = P.get(p + "linear2.weight", {64, 64});
+      const TensorView* b2 = P.get(p + "linear2.bias", {64});
+      const TensorView* g1 = P.get(p + "norm1.weight", {64});
+      const TensorView* e1 = P.get(p + "norm1.bias", {64});
+      const TensorView* g2 = P.get(p + "norm2.weight", {64});
+      const TensorView* e2 = P.get(p + "norm2.bias", {64});
+      if (!iw || !ib || !ow || !ob || !w1 || !b1 || !w2 || !b2 || !g1 || !e1 || !g2 || !e2)
+        return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+      auto K = [&](const char* s) { snprintf(key, sizeof key, "sa%d.%s", l, s); return std::string(key); };
+      o = P.alloc(K("qkvT"), 3 * 4096);
+      for (int part = 0; part < 3; ++part) {
+        const float sc = part == 0 ? 0.125f : 1.f;      // q * 1/sqrt(64): exact power of two
+        for (int k = 0; k < 64; ++k)
+          for (int j = 0; j < 64; ++j)
+            P.arena[o + part * 4096 + k * 64 + j] = iw->d[(size_t)(part * 64 + j) * 64 + k] * sc;
+      }
+      o = P.alloc(K("qkvb"), 192);
+      for (int j = 0; j < 192; ++j) P.arena[o + j] = ib->d[j] * (j < 64 ? 0.125f : 1.f);
+      o = P.alloc(K("woT"), 4096); pack_linear_T(P, o, ow, 64, 64);
+      o = P.alloc(K("bo"), 64); memcpy(&P.arena[o], ob->d, 256);
+      o = P.alloc(K("w1T"), 4096); pack_linear_T(P, o, w1, 64, 64);
+      o = P.alloc(K("b1"), 64); memcpy(&P.arena[o], b1->d, 256);
+      o = P.alloc(K("w2T"), 4096); pack_linear_T(P, o, w2, 64, 64);
+      o = P.alloc(K("b2"), 64); memcpy(&P.arena[o], b2->d, 256);
+      o = P.alloc(K("ln1g"), 64); memcpy(&P.arena[o], g1->d, 256);
+      o = P.alloc(K("ln1b"), 64); memcpy(&P.arena[o], e1->d, 256);
+      o = P.alloc(K("ln2g"), 64); memcpy(&P.arena[o], g2->d, 256);
+      o = P.alloc(K("ln2b"), 64); memcpy(&P.arena[o], e2->d, 256);
+    }
+    const int nh = e->cfg.n_out;
+    const size_t oW1 = P.alloc("pool.w1T", (size_t)nh * 64 * 128), ob1 = P.alloc("pool.b1", nh * 128),
+                 ow2 = P.alloc("pool.w2", nh * 128), ob2 = P.alloc("pool.b2", nh),
+                 ow3 = P.alloc("pool.w3", nh * 64), ob3 = P.alloc("pool.b3", nh);
+    for (int h = 0; h < nh; ++h) {
+      char pf[64];
+      if (nh == 1) snprintf(pf, sizeof pf, "pool.model.");
+      else snprintf(pf, sizeof pf, "pool_layers.%d.model.", h);   // head order mos,noi,dis,col,loud (lib:1461-1465)
+      const std::string p(pf);
+      const TensorView* w1 = P.get(p + "linear1.weight", {128, 64});
+      const TensorView* b1 = P.get(p + "linear1.bias", {128});
+      const TensorView* w2 = P.get(p + "linear2.weight", {1, 128});
+      const TensorView* b2 = P.get(p + "linear2.bias", {1});
+      const TensorView* w3 = P.get(p + "linear3.weight", {1, 64});
+      const TensorView* b3 = P.get(p + "linear3.bias", {1});
+      if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+      pack_linear_T(P, oW1 + (size_t)h * 64 * 128, w1, 128, 64);
+      memcpy(&P.arena[ob1 + h * 128], b1->d, 512);
+      memcpy(&P.arena[ow2 + h * 128], w2->d, 512);
+      P.arena[ob2 + h] = b2->d[0];
+      memcpy(&P.arena[ow3 + h * 64], w3->d, 256);
+      P.arena[ob3 + h] = b3->d[0];
+    }
+  } else {
+    const TensorView* fw = P.get("cnn.model.fc_out.weight", {20, 768});
+    const TensorView* fb = P.get("cnn.model.fc_out.bias", {20});
+    if (!fw || !fb) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    size_t o = P.alloc("fc.wT", 768 * 20);
+    // engine order k' = (h*2 + w)*64 + c  <->  reference view order c*12 + h*2 + w (lib:830)
+    for (int hw = 0; hw < 12; ++hw)
+      for (int c = 0; c < 64; ++c)
+        for (int j = 0; j < 20; ++j) P.arena[o + ((size_t)hw * 64 + c) * 20 + j] = fw->d[(size_t)j * 768 + c * 12 + hw];
+    o = P.alloc("fc.b", 32); memcpy(&P.arena[o], fb->d, 80);
+    const std::string p = "time_dependency.model.lstm.";
+    const size_t owi = P.alloc("lstm.wih", 2 * 512 * 20), owh = P.alloc("lstm.whh", 2 * 512 * 128),
+                 obb = P.alloc("lstm.b", 2 * 512);
+    for (int d = 0; d < 2; ++d) {
+      const std::string sfx = d ? "_reverse" : "";
+      const TensorView* wi = P.get(p + "weight_ih_l0" + sfx, {512, 20});
+      const TensorView* wh = P.get(p + "weight_hh_l0" + sfx, {512, 128});
+      const TensorView* bi = P.get(p + "bias_ih_l0" + sfx, {512});
+      const TensorView* bh = P.get(p + "bias_hh_l0" + sfx, {512});
+      if (!wi || !wh || !bi || !bh) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+      memcpy(&P.arena[owi + (size_t)d * 512 * 20], wi->d, 512 * 20 * 4);
+      memcpy(&P.arena[owh + (size_t)d * 512 * 128], wh->d, 512 * 128 * 4);
+      for (int g = 0; g < 512; ++g) P.arena[obb + d * 512 + g] = bi->d[g] + bh->d[g];
+    }
+    const TensorView* pw = P.get("pool.model.linear.weight", {1, 256});
+    const TensorView* pb = P.get("pool.model.linear.bias", {1});
+    if (!pw || !pb) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    o = P.alloc("lastbi.w", 256); memcpy(&P.arena[o], pw->d, 1024);
+    e->pool_bias_std = pb->d[0];
+  }
+  // conv1 is stored as [tap][16]: same as the generic [ci=1][tap][cout] packing.
+  CK(e->warena.reserve(P.arena.size() * 4));
+  CK(cudaMemcpy(e->warena.p, P.arena.data(), P.arena.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+const float* W(nisqa_engine* e, const std::string& key) {
+  return e->warena.as<float>() + e->woff.at(key);
+}
+
+// ---------------------------------------------------------------- one pass over a run of clips
+struct PassInput {
+  int n_clips;
+  const ClipPlan* plan;               // [n_clips]
+  const int64_t* n_samples;           // [n_clips]
+  // exactly one of the two sources:
+  const void* const* host_pcm;        // per-clip host pointers, or
+  const void* dev_pcm; const int64_t* dev_off;   // packed device buffer + element offsets
+  int fmt;
+  float* scores_dev_out;              // optional device destination [n_clips][n_out]
+  float* scores_host_out;             // optional host destination
+};
+
+int run_pass(nisqa_engine* e, const PassInput& in) {
+  const nisqa_config& c = e->cfg;
+  const int n = in.n_clips;
+  const int std_mode = c.arch == NISQA_ARCH_STD_LSTM_LASTBI;
+  const size_t esz = in.fmt == NISQA_FMT_F32 ? 4 : 2;
+  // ---- tables
+  std::vector<ClipDesc>& cl = e->last_clips;
+  cl.assign(n, ClipDesc());
+  std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0);
+  long long pcm_elems = 0;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1;
+  for (int i = 0; i < n; ++i) {
+    const ClipPlan& p = in.plan[i];
+    ClipDesc& d = cl[i];
+    const bool ok = p.status == NISQA_CLIP_OK;
+    d.n_samples = (int)in.n_samples[i];
+    d.fb_id = ok ? p.fb_id : 0;
+    d.hop = p.hop; d.win = p.win;
+    d.s0 = (c.n_fft - p.win) / 2 - c.n_fft / 2;      // pad_center lpad minus the reflect pad
+    d.n_frames = ok ? p.n_frames : 0;
+    d.n_seg = ok ? p.n_seg : 0;
+    d.frame_off = n_frames; d.seg_off = n_seg; d.pair_off = n_pairs;
+    if (in.host_pcm) { d.pcm_off = pcm_elems; pcm_elems += ((long long)in.n_samples[i] + 15) / 16 * 16; }
+    else d.pcm_off = in.dev_off[i];
+    pair_prefix[i] = n_pairs; seg_prefix[i] = n_seg; qt_prefix[i] = n_qt;
+    n_frames += d.n_frames; n_seg += d.n_seg;
+    n_pairs += (d.n_frames + 1) / 2;
+    n_qt += (d.n_seg + 127) / 128;
+    if (ok) Q = std::max(Q, (p.win + 1023) / 1024);
+  }
+  pair_prefix[n] = n_pairs; seg_prefix[n] = n_seg; qt_prefix[n] = n_qt;
+  e->last_n_seg = n_seg; e->last_n_frames = n_frames;
+  const int n_out = c.n_out;
+
+  CK(e->scores.reserve((size_t)n * n_out * 4));
+  float* scores = in.scores_dev_out ? in.scores_dev_out : e->scores.as<float>();
+
+  // ---- upload tables (one pinned block: ClipDesc[n] | 3 prefix arrays)
+  const size_t tb_clips = (size_t)n * sizeof(ClipDesc);
+  const size_t tb_pref = (size_t)(n + 1) * 4;
+  CK(e->h_tables.reserve(tb_clips + 3 * tb_pref));
+  CK(cudaStreamSynchronize(e->stream));        // pinned block may still be in flight from the last pass
+  char* ht = e->h_tables.as<char>();
+  memcpy(ht, cl.data(), tb_clips);
+  memcpy(ht + tb_clips, pair_prefix.data(), tb_pref);
+  memcpy(ht + tb_clips + tb_pref, seg_prefix.data(), tb_pref);
+  memcpy(ht + tb_clips + 2 * tb_pref, qt_prefix.data(), tb_pref);
+  CK(e->clips.reserve(tb_clips));
+  CK(e->prefixes.reserve(3 * tb_pref));
+  CK(e->clipmax.reserve((size_t)n * 4));
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(e->clips.p, ht, tb_clips, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->clipmax.p, 0, (size_t)n * 4, st));
+  const ClipDesc* d_clips = e->clips.as<ClipDesc>();
+  const int* d_pair = e->prefixes.as<int>();
+  const int* d_seg = d_pair + (n + 1);
+  const int* d_qt = d_pair + 2 * (n + 1);
+
+  if (n_seg == 0) {   // nothing valid in this pass: NaN scores
+    CK(cudaMemsetAsync(scores, 0xFF, (size_t)n * n_out * 4, st));
+  } else {
+    // ---- PCM
+    const void* d_pcm = in.dev_pcm;
+    if (in.host_pcm) {
+      CK(e->pcm.reserve((size_t)pcm_elems * esz));
+      for (int i = 0; i < n; ++i)
+        if (cl[i].n_frames > 0)
+          CK(cudaMemcpyAsync(e->pcm.as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
+                             (size_t)in.n_samples[i] * esz, cudaMemcpyHostToDevice, st));
+      d_pcm = e->pcm.p;
+    }
+    // ---- workspaces
+    const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
+    const int FEAT = std_mode ? 768 : 384;
+    CK(e->mel.reserve((size_t)n_frames * kMels * 4));
+    CK(e->segtab.reserve((size_t)n_seg * 12));
+    CK(e->act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
+    CK(e->act2.reserve((size_t)n_seg * 12 * W2 * 32 * 4));
+    CK(e->act3.reserve((size_t)n_seg * 12 * W2 * 64 * 4));
+    CK(e->act4.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    CK(e->act5.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    CK(e->feats.reserve((size_t)n_seg * FEAT * 4));
+    int* seg_frame0 = e->segtab.as<int>();
+    float* seg_thr = reinterpret_cast<float*>(seg_frame0 + n_seg);
+    int* seg_clip = seg_frame0 + 2 * (size_t)n_seg;
+
+    { Scope s(e, "frontend");
+      launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, d_pair, n_pairs,
+                      e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), e->mel.as<float>(),
+                      e->clipmax.as<unsigned>(), Q); }
+    { Scope s(e, "seg_table");
+      launch_seg_table(st, d_clips, n, d_seg, e->clipmax.as<unsigned>(), c.seg_hop, n_seg,
+                       seg_frame0, seg_thr, seg_clip); }
+    { Scope s(e, "conv1");
+      launch_conv1(st, std_mode, e->mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
+                   W(e, "conv1.b"), e->act1.as<float>(), n_seg); }
+    { Scope s(e, "conv2");
+      launch_conv_layer(st, std_mode, 2, e->act1.as<float>(), W(e, "conv2.w"), W(e, "conv2.b"), e->act2.as<float>(), n_seg); }
+    { Scope s(e, "conv3");
+      launch_conv_layer(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.w"), W(e, "conv3.b"), e->act3.as<float>(), n_seg); }
+    { Scope s(e, "conv4");
+      launch_conv_layer(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.w"), W(e, "conv4.b"), e->act4.as<float>(), n_seg); }
+    { Scope s(e, "conv5");
+      launch_conv_layer(st, std_mode, 5, e->act4.as<float>(), W(e, "conv5.w"), W(e, "conv5.b"), e->act5.as<float>(), n_seg); }
+    { Scope s(e, "conv6");
+      launch_conv_layer(st, std_mode, 6, e->act5.as<float>(), W(e, "conv6.w"), W(e, "conv6.b"), e->feats.as<float>(), n_seg); }
+
+    if (!std_mode) {
+      CK(e->xa.reserve((size_t)n_seg * 64 * 4));
+      CK(e->xb.reserve((size_t)n_seg * 64 * 4));
+      CK(e->qkv.reserve((size_t)n_seg * 192 * 4));
+      CK(e->logits.reserve((size_t)n_seg * n_out * 4));
+      CK(e->tdout.reserve((size_t)n_seg * 64 * 4));
+      { Scope s(e, "lin_ln");
+        launch_lin_ln(st, e->feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), e->tdout.as<float>(), n_seg); }
+      e->last_td_in = e->tdout.as<float>();
+      const float* cur = e->tdout.as<float>();
+      float* pp[2] = {e->xa.as<float>(), e->xb.as<float>()};
+      for (int l = 0; l < c.sa_layers; ++l) {
+        char k[32];
+        auto K = [&](const char* s2) { snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
+        { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, K("qkvT")), W(e, K("qkvb")), e->qkv.as<float>(), n_seg); }
+        SaLayerParams P;
+        P.WoT = W(e, K("woT")); P.bo = W(e, K("bo")); P.W1T = W(e, K("w1T")); P.b1 = W(e, K("b1"));
+        P.W2T = W(e, K("w2T")); P.b2 = W(e, K("b2")); P.ln1_g = W(e, K("ln1g")); P.ln1_b = W(e, K("ln1b"));
+        P.ln2_g = W(e, K("ln2g")); P.ln2_b = W(e, K("ln2b"));
+        { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, e->qkv.as<float>(), d_clips, n, d_qt, n_qt, P, pp[l & 1]); }
+        cur = pp[l & 1];
+      }
+      e->last_td_out = cur;
+      PoolHeadParams H;
+      H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
+      H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
+      { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, e->logits.as<float>(), scores); }
+    } else {
+      CK(e->feats20.reserve((size_t)n_seg * 20 * 4));
+      CK(e->tdout.reserve((size_t)n_seg * 256 * 4));
+      CK(e->partial.reserve((size_t)n * 2 * 4));
+      { Scope s(e, "fc_out"); launch_fc20(st, e->feats.as<float>(), W(e, "fc.wT"), W(e, "fc.b"), e->feats20.as<float>(), n_seg); }
+      LstmParams L;
+      L.w_ih = W(e, "lstm.wih"); L.w_hh = W(e, "lstm.whh"); L.b = W(e, "lstm.b"); L.w_pool = W(e, "lastbi.w");
+      { Scope s(e, "lstm", 2);
+        launch_lstm(st, e->feats20.as<float>(), d_clips, n, L, e->tdout.as<float>(), e->partial.as<float>(), e->pool_bias_std, scores); }
+      e->last_td_in = nullptr;
+      e->last_td_out = e->tdout.as<float>();
+    }
+  }
+  CK(cudaGetLastError());
+  if (in.scores_host_out) {
+    CK(e->h_scores.reserve((size_t)n * n_out * 4));
+    CK(cudaMemcpyAsync(e->h_scores.p, scores, (size_t)n * n_out * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(in.scores_host_out, e->h_scores.p, (size_t)n * n_out * 4);
+  }
+  return 0;
+}
+
+int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, const void* dev_pcm,
+                   const int64_t* dev_off, const int64_t* n_samples, const int32_t* sample_rate,
+                   int fmt, float* scores_host, float* scores_dev, int32_t* n_seg_out,
+                   int32_t* status_out, int sync) {
+  if (!e) return NISQA_ERR_INVALID;
+  if (!e->weights_loaded) return fail(e, NISQA_ERR_STATE, "nisqa_load_weights has not been called");
+  if (n_clips < 0 || (n_clips > 0 && (!n_samples || !sample_rate)))
+    return fail(e, NISQA_ERR_INVALID, "null argument");
+  if (fmt != NISQA_FMT_S16 && fmt != NISQA_FMT_F32) return fail(e, NISQA_ERR_INVALID, "sample_fmt");
+  CK(cudaSetDevice(e->device));
+  for (auto& t : e->timers) { t.ms = 0.0; t.launches = 0; }
+  std::vector<ClipPlan> plan(n_clips);
+  for (int i = 0; i < n_clips; ++i) {
+    if (n_samples[i] > (int64_t)INT32_MAX) return fail(e, NISQA_ERR_INVALID, "clip longer than 2^31 samples");
+    plan_clip(e->cfg, n_samples[i], sample_rate[i], &plan[i]);
+    if (plan[i].status == NISQA_CLIP_OK) {
+      int rc = build_fb(e, sample_rate[i], plan[i].hop, plan[i].win, &plan[i].fb_id);
+      if (rc) return rc;
+    }
+    if (n_seg_out) n_seg_out[i] = plan[i].n_seg;
+    if (status_out) status_out[i] = plan[i].status;
+  }
+  const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
+  int i0 = 0;
+  e->last_passes = 0;
+  while (i0 < n_clips) {
+    int i1 = i0; long long segs = 0;
+    while (i1 < n_clips) {
+      const long long s = plan[i1].status == NISQA_CLIP_OK ? plan[i1].n_seg : 0;
+      if (i1 > i0 && segs + s > max_seg) break;
+      segs += s; ++i1;
+    }
+    PassInput in;
+    in.n_clips = i1 - i0; in.plan = plan.data() + i0; in.n_samples = n_samples + i0;
+    in.host_pcm = host_pcm ? host_pcm + i0 : nullptr;
+    in.dev_pcm = dev_pcm; in.dev_off = dev_off ? dev_off + i0 : nullptr;
+    in.fmt = fmt;
+    in.scores_dev_out = scores_dev ? scores_dev + (size_t)i0 * e->cfg.n_out : nullptr;
+    in.scores_host_out = scores_host ? scores_host + (size_t)i0 * e->cfg.n_out : nullptr;
+    int rc = run_pass(e, in);
+    if (rc) return rc;
+    ++e->last_passes;
+    i0 = i1;
+  }
+  if (sync || scores_host || e->profiling) CK(cudaStreamSynchronize(e->stream));
+  if (e->profiling) collect_timers(e);
+  return 0;
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
+  if (!out || !cfg) return NISQA_ERR_INVALID;
+  *out = nullptr;
+  nisqa_engine* e = new nisqa_engine();
+  e->cfg = *cfg; e->device = device;
+  *out = e;     // returned even on failure so that nisqa_last_error() can be read
+  if (cfg->abi_version != NISQA_B200_ABI_VERSION) return fail(e, NISQA_ERR_INVALID, "abi_version mismatch");
+  if (cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF && cfg->arch != NISQA_ARCH_STD_LSTM_LASTBI)
+    return fail(e, NISQA_ERR_INVALID, "unsupported architecture");
+  if (cfg->n_fft != kNfft || cfg->n_mels != kMels || cfg->seg_len != kSegLen)
+    return fail(e, NISQA_ERR_INVALID, "engine is built for n_fft=4096, n_mels=48, seg_length=15");
+  if (cfg->n_out != 1 && cfg->n_out != 5) return fail(e, NISQA_ERR_INVALID, "n_out must be 1 or 5");
+  if (cfg->arch == NISQA_ARCH_STD_LSTM_LASTBI && cfg->n_out != 1) return fail(e, NISQA_ERR_INVALID, "n_out");
+  if (cfg->seg_hop < 1 || cfg->hop_s <= 0 || cfg->win_s <= 0 || cfg->fmax <= 0)
+    return fail(e, NISQA_ERR_INVALID, "bad front-end parameters");
+  if (cfg->arch == NISQA_ARCH_ADAPT_SA_ATTFF && (cfg->sa_layers < 1 || cfg->sa_layers > 8))
+    return fail(e, NISQA_ERR_INVALID, "sa_layers");
+  int count = 0;
+  CK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(e, NISQA_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(e, NISQA_ERR_CUDA, "libnisqa_b200 is compiled for sm_100a only");
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  std::vector<float2> tw(4096);
+  for (int j = 0; j < 4096; ++j) {
+    const double a = -2.0 * M_PI * (double)j / 4096.0;
+    tw[j] = make_float2((float)cos(a), (float)sin(a));
+  }
+  CK(e->tw4096.reserve(tw.size() * sizeof(float2)));
+  CK(cudaMemcpy(e->tw4096.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void nisqa_destroy(nisqa_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  delete e;
+}
+
+const char* nisqa_last_error(const nisqa_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
+  if (!e || !tensors || n <= 0) return NISQA_ERR_INVALID;
+  if (!e->stream) return fail(e, NISQA_ERR_STATE, "engine was not created successfully");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  int rc = pack_weights(e, tensors, n);
+  if (rc) return rc;
+  e->weights_loaded = true;
+  return 0;
+}
+
+int nisqa_predict_pcm(nisqa_engine* e, int n_clips, const void* const* pcm, const int64_t* n_samples,
+                      const int32_t* sample_rate, int sample_fmt, float* scores_out,
+                      int32_t* n_segments_out, int32_t* status_out) {
+  if (!e) return NISQA_ERR_INVALID;
+  if (n_clips > 0 && (!pcm || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
+  return predict_common(e, n_clips, pcm, nullptr, nullptr, n_samples, sample_rate, sample_fmt,
+                        scores_out, nullptr, n_segments_out, status_out, 1);
+}
+
+int nisqa_predict_pcm_device(nisqa_engine* e, int n_clips, const void* pcm_dev, const int64_t* pcm_offsets,
+                             const int64_t* n_samples, const int32_t* sample_rate, int sample_fmt,
+                             float* scores_dev, int32_t* n_segments_out, int32_t* status_out, int sync) {
+  if (!e) return NISQA_ERR_INVALID;
+  if (n_clips > 0 && (!pcm_dev || !pcm_offsets || !scores_dev)) return fail(e, NISQA_ERR_INVALID, "null argument");
+  return predict_common(e, n_clips, nullptr, pcm_dev, pcm_offsets, n_samples, sample_rate, sample_fmt,
+                        nullptr, scores_dev, n_segments_out, status_out, sync);
+}
+
+int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
+  if (!e) return NISQA_ERR_INVALID;
+  if (e->last_passes != 1) return fail(e, NISQA_ERR_STATE, "stage dump needs a predict call that ran in one pass");
+  cudaSetDevice(e->device);
+  const int std_mode = e->cfg.arch == NISQA_ARCH_STD_LSTM_LASTBI;
+  const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
+  const int64_t ns = e->last_n_seg;
+  int64_t count = 0;
+  const float* src = nullptr;
+  int hw = 0, ch = 0;    // NHWC -> NCHW conversion when ch > 0
+  switch (stage) {
+    case NISQA_STAGE_MEL_DB: count = (int64_t)e->last_n_frames * kMels; break;
+    case NISQA_STAGE_POOL1: src = e->act1.as<float>(); hw = 24 * W1; ch = 16; break;
+    case NISQA_STAGE_POOL2: src = e->act2.as<float>(); hw = 12 * W2; ch = 32; break;
+    case NISQA_STAGE_CONV3: src = e->act3.as<float>(); hw = 12 * W2; ch = 64; break;
+    case NISQA_STAGE_POOL3: src = e->act4.as<float>(); hw = 6 * W3; ch = 64; break;
+    case NISQA_STAGE_CONV5: src = e->act5.as<float>(); hw = 6 * W3; ch = 64; break;
+    case NISQA_STAGE_CNN_FEAT:
+      if (std_mode) { src = e->feats20.as<float>(); count = ns * 20; }
+      else { src = e->feats.as<float>(); hw = 6; ch = 64; }     // [h][c] -> c*6+h
+      break;
+    case NISQA_STAGE_TD_IN:
+      if (std_mode || !e->last_td_in) return fail(e, NISQA_ERR_INVALID, "stage not available for this architecture");
+      src = e->last_td_in; count = ns * 64; break;
+    case NISQA_STAGE_TD_OUT: src = e->last_td_out; count = ns * (std_mode ? 256 : 64); break;
+    default: return fail(e, NISQA_ERR_INVALID, "unknown stage");
+  }
+  if (ch > 0) count = ns * hw * ch;
+  if (!out) return count;
+  if (cap < count) return fail(e, NISQA_ERR_INVALID, "stage dump buffer too small");
+  if (count == 0) return 0;
+  cudaStream_t st = e->stream;
+  if (stage == NISQA_STAGE_MEL_DB) {
+    CK(e->dump.reserve((size_t)count * 4));
+    launch_mel_dump(st, e->mel.as<float>(), e->clips.as<ClipDesc>(), (int)e->last_clips.size(),
+                    e->clipmax.as<unsigned>(), e->dump.as<float>());
+    src = e->dump.as<float>();
+  } else if (ch > 0) {
+    CK(e->dump.reserve((size_t)count * 4));
+    launch_nhwc_to_nchw(st, src, e->dump.as<float>(), ns, hw, ch);
+    src = e->dump.as<float>();
+  }
+  if (!src) return fail(e, NISQA_ERR_STATE, "stage was not produced");
+  CK(cudaMemcpyAsync(out, src, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return count;
+}
+
+int nisqa_segment_counts(const nisqa_config* cfg, int64_t n_samples, int32_t sample_rate,
+                         int32_t* n_frames, int32_t* n_segments, int32_t* status) {
+  if (!cfg) return NISQA_ERR_INVALID;
+  ClipPlan p;
+  plan_clip(*cfg, n_samples, sample_rate, &p);
+  if (n_frames) *n_frames = p.n_frames;
+  if (n_segments) *n_segments = p.n_seg;
+  if (status) *status = p.status;
+  return 0;
+}
+
+int nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64_t cap) {
+  if (!e || !out) return NISQA_ERR_INVALID;
+  if (!e->stream) return fail(e, NISQA_ERR_STATE, "engine was not created successfully");
+  CK(cudaSetDevice(e->device));
+  const int hop = (int)((double)sample_rate * e->cfg.hop_s), win = (int)((double)sample_rate * e->cfg.win_s);
+  if (hop < 1 || win < 1 || win > e->cfg.n_fft) return fail(e, NISQA_ERR_INVALID, "unsupported sample rate");
+  int id = -1;
+  int rc = build_fb(e, sample_rate, hop, win, &id);
+  if (rc) return rc;
+  const std::vector<float>& d = e->fbs[id]->dense;
+  if (cap < (int64_t)d.size()) return fail(e, NISQA_ERR_INVALID, "buffer too small");
+  memcpy(out, d.data(), d.size() * 4);
+  return 0;
+}
+
+int64_t nisqa_kernel_launches(const nisqa_engine* e) { return e ? e->launches : 0; }
+void* nisqa_stream(const nisqa_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int nisqa_set_profiling(nisqa_engine* e, int on) {
+  if (!e) return NISQA_ERR_INVALID;
+  e->profiling = on != 0;
+  return 0;
+}
+
+double nisqa_group_ms(const nisqa_engine* e, const char* group) {
+  if (!e || !group) return -1.0;
+  const std::string g(group);
+  double total = 0.0; bool found = false;
+  for (const auto& t : e->timers) {
+    const bool cnn = t.name.compare(0, 4, "conv") == 0;
+    const bool td = t.name == "lin_ln" || t.name == "qkv" || t.name == "sa_layer" || t.name == "fc_out" || t.name == "lstm";
+    const bool match = t.name == g || (g == "cnn" && cnn) || (g == "td" && td) ||
+                       (g == "frontend" && t.name == "seg_table");
+    if (match) { total += t.ms; found = true; }
+  }
+  return found ? total : -1.0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ NCCL (resolved at run time)
+// The single exchange step of the multi-GPU path.  libnccl is bound with dlopen/dlsym so that
+// the library has no link-time NCCL dependency (the torch-bundled libnccl.so.2 that is already
+// in the process is reused when present).
+struct NcclId { char internal[128]; };   // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api(std::string* why) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (api.lib) break; }
+    if (!api.lib) for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (api.lib) {
+      api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+      api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllGather) {
+    if (why) *why = "libnccl.so.2 could not be loaded (dlopen/dlsym)";
+    return nullptr;
+  }
+  return &api;
+}
+}  // namespace
+
+extern "C" {
+
+int nisqa_nccl_unique_id(nisqa_engine* e, void* id128) {
+  if (!e || !id128) return NISQA_ERR_INVALID;
+  std::string why;
+  NcclApi* a = nccl_api(&why);
+  if (!a) return fail(e, NISQA_ERR_NCCL, why);
+  int rc = a->GetUniqueId(id128);
+  if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclGetUniqueId: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));
+  return 0;
+}
+
+int nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void* id128) {
+  if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return NISQA_ERR_INVALID;
+  std::string why;
+  NcclApi* a = nccl_api(&why);
+  if (!a) return fail(e, NISQA_ERR_NCCL, why);
+  CK(cudaSetDevice(e->device));
+  NcclId id; memcpy(&id, id128, sizeof id);
+  void* comm = nullptr;
+  int rc = a->CommInitRank(&comm, world, id, rank);
+  if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclCommInitRank: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));
+  e->nccl_comm = comm; e->nccl_world = world; e->nccl_rank = rank;
+  return 0;
+}
+
+int nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm, const float* local_dev, int max_rows, float* global_dev) {
+  if (!e || !local_dev || !global_dev || max_rows < 0) return NISQA_ERR_INVALID;
+  std::string why;
+  NcclApi* a = nccl_api(&why);
+  if (!a) return fail(e, NISQA_ERR_NCCL, why);
+  void* comm = nccl_comm ? nccl_comm : e->nccl_comm;
+  if (!comm) return fail(e, NISQA_ERR_STATE, "no NCCL communicator: call nisqa_nccl_init or pass one");
+  CK(cudaSetDevice(e->device));
+  const size_t count = (size_t)max_rows * e->cfg.n_out;
+  int rc = a->AllGather(local_dev, global_dev, count, /*ncclFloat32*/ 7, comm, e->stream);
+  if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclAllGather: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));
+  e->launches += 1;
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // extern "C"

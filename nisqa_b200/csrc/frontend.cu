@@ -1,0 +1,258 @@
+// frontend.cu - PCM -> mel dB  (reference nisqa/NISQA_lib.py:2308-2330 via librosa 0.8.1
+// stft / filters.mel / amplitude_to_db; restated in oracle/librosa_compat.py).
+//
+// One CTA (4 warps) per PAIR of STFT frames of one clip.  The two real frames are packed as
+// z = a + i*b into one complex transform.  Only win <= 1024*Q of the 4096 inputs are non-zero
+// (Hann window zero-padded to n_fft), and a circular shift does not change |X|, so the
+// 4096-point DFT is computed as a radix-4 decimation-in-frequency step whose butterflies
+// collapse to a twiddle multiply, followed by four independent 1024-point FFTs (one per warp,
+// residue r = k mod 4).  Each 1024-point FFT is two in-register radix-32 passes with one
+// shared-memory transpose.  Then: unpack the two real spectra, |.|, sparse mel (band-major
+// CSR), 10*log10(max(1e-8, M^2)), and a per-clip atomic max for the top_db clamp, which is
+// applied by the consumers (conv1 / stage dump) as max(dB, clipmax - 80).
+#include "common.cuh"
+
+namespace nisqa {
+
+// e^{-2 pi i k / 32}, k = 0..15
+__device__ __forceinline__ float2 w32(int k) {
+  switch (k) {
+    case 0:  return make_float2(1.0f, 0.0f);
+    case 1:  return make_float2(0.98078528040323043f, -0.19509032201612825f);
+    case 2:  return make_float2(0.92387953251128674f, -0.38268343236508978f);
+    case 3:  return make_float2(0.83146961230254524f, -0.55557023301960218f);
+    case 4:  return make_float2(0.70710678118654757f, -0.70710678118654757f);
+    case 5:  return make_float2(0.55557023301960229f, -0.83146961230254524f);
+    case 6:  return make_float2(0.38268343236508984f, -0.92387953251128674f);
+    case 7:  return make_float2(0.19509032201612833f, -0.98078528040323043f);
+    case 8:  return make_float2(0.0f, -1.0f);
+    case 9:  return make_float2(-0.19509032201612819f, -0.98078528040323043f);
+    case 10: return make_float2(-0.38268343236508973f, -0.92387953251128674f);
+    case 11: return make_float2(-0.55557023301960196f, -0.83146961230254535f);
+    case 12: return make_float2(-0.70710678118654746f, -0.70710678118654757f);
+    case 13: return make_float2(-0.83146961230254535f, -0.55557023301960218f);
+    case 14: return make_float2(-0.92387953251128674f, -0.38268343236508989f);
+    default: return make_float2(-0.98078528040323043f, -0.19509032201612861f);
+  }
+}
+
+__host__ __device__ constexpr int rev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// In-register 32-point forward DFT, decimation in frequency: X[rev5(i)] ends up in x[i].
+__device__ __forceinline__ void fft32(float2 (&x)[32]) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const int k = j * (16 / half);
+        const float2 a = x[base + j], b = x[base + j + half];
+        x[base + j] = make_float2(a.x + b.x, a.y + b.y);
+        const float2 d = make_float2(a.x - b.x, a.y - b.y);
+        if (k == 0) x[base + j + half] = d;
+        else if (k == 8) x[base + j + half] = make_float2(d.y, -d.x);
+        else x[base + j + half] = cmul(d, w32(k));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // numpy.pad(mode='reflect') index map, valid for any i (repeated reflection when the pad
+  // is longer than the signal)
+  if (n <= 1) return 0;
+  const int period = 2 * n - 2;
+  int m = i % period;
+  if (m < 0) m += period;
+  return (m < n) ? m : period - m;
+}
+
+template <typename T> __device__ __forceinline__ float sample_to_float(T v);
+template <> __device__ __forceinline__ float sample_to_float<short>(short v) {
+  return (float)v * (1.0f / 32768.0f);   // libsndfile PCM16 -> float
+}
+template <> __device__ __forceinline__ float sample_to_float<float>(float v) { return v; }
+
+constexpr int kFeThreads = 128;
+constexpr int kScratchPerWarp = 32 * 33;          // float2 elements, padded transpose tile
+constexpr int kMagStride = 2052;
+
+__host__ __device__ constexpr int fe_region0_bytes(int Q) {
+  return (1024 * Q * 8 > 2 * kMagStride * 4) ? 1024 * Q * 8 : 2 * kMagStride * 4;
+}
+int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWarp * 8; }
+
+template <typename T>
+__global__ void __launch_bounds__(kFeThreads)
+frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
+                const int* __restrict__ pair_prefix, const FbTables* __restrict__ fbs,
+                const float2* __restrict__ tw4096, float* __restrict__ mel,
+                unsigned* __restrict__ clipmax, int Q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* zin = reinterpret_cast<float2*>(smem_raw);                     // [1024*Q] packed input
+  float* mags = reinterpret_cast<float*>(smem_raw);                      // aliases zin later
+  float2* scratch = reinterpret_cast<float2*>(smem_raw + fe_region0_bytes(Q));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = blockIdx.x;
+  const int c = upper_slot(pair_prefix, n_clips, P);
+  const ClipDesc cd = clips[c];
+  const FbTables fb = fbs[cd.fb_id];
+  const int tA = 2 * (P - cd.pair_off);
+  const int tB = tA + 1;
+  const bool validB = tB < cd.n_frames;
+  const T* y = pcm + cd.pcm_off;
+
+  // ---- a. windowed, reflect-padded frame pair -> zin
+  for (int n = tid; n < 1024 * Q; n += kFeThreads) {
+    float a = 0.f, b = 0.f;
+    if (n < cd.win) {
+      const float wv = __ldg(fb.window + n);
+      const int ia = cd.s0 + tA * cd.hop + n;
+      a = wv * sample_to_float<T>(y[reflect_index(ia, cd.n_samples)]);
+      if (validB) b = wv * sample_to_float<T>(y[reflect_index(ia + cd.hop, cd.n_samples)]);
+    }
+    zin[n] = make_float2(a, b);
+  }
+  __syncthreads();
+
+  // ---- b. warp r: 1024-point FFT of the residue-r subsequence
+  {
+    const int r = warp;
+    float2 x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = lane + 32 * j;
+      float2 v = zin[n];
+      for (int q = 1; q < Q; ++q) {               // general radix-4 DIF butterfly (Q==1: none)
+        const float2 u = zin[n + 1024 * q];
+        switch ((r * q) & 3) {                    // u * (-i)^(r q)
+          case 0: v.x += u.x; v.y += u.y; break;
+          case 1: v.x += u.y; v.y -= u.x; break;
+          case 2: v.x -= u.x; v.y -= u.y; break;
+          default: v.x -= u.y; v.y += u.x; break;
+        }
+      }
+      if (r != 0) v = cmul(v, __ldg(tw4096 + ((r * n) & 4095)));
+      x[j] = v;
+    }
+    fft32(x);                                      // A_l[q] at x[rev5(q)]
+    float2* tile = scratch + r * kScratchPerWarp;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      float2 v = x[rev5(q)];
+      if (q != 0) v = cmul(v, __ldg(tw4096 + ((4 * lane * q) & 4095)));   // W_1024^(l q)
+      tile[lane * 33 + q] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 32; ++l) x[l] = tile[l * 33 + lane];
+    __syncwarp();
+    fft32(x);                                      // Z_r[lane + 32 p] at x[rev5(p)]
+#pragma unroll
+    for (int p = 0; p < 32; ++p) tile[lane + 32 * p] = x[rev5(p)];
+  }
+  __syncthreads();
+
+  // ---- c. unpack the two real spectra, magnitudes (bins 0..2048)
+  for (int k = tid; k < kBins; k += kFeThreads) {
+    const int kk = (kNfft - k) & (kNfft - 1);
+    const float2 zk = scratch[(k & 3) * kScratchPerWarp + (k >> 2)];
+    const float2 zn = scratch[(kk & 3) * kScratchPerWarp + (kk >> 2)];
+    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+    const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+    mags[k] = sqrtf(ar * ar + ai * ai);
+    mags[kMagStride + k] = sqrtf(br * br + bi * bi);
+  }
+  __syncthreads();
+
+  // ---- d. sparse mel + dB + clip max
+  float wmax = -INFINITY;
+  for (int item = warp; item < 2 * kMels; item += kFeThreads / 32) {
+    const int f = item / kMels, b = item - f * kMels;
+    if (f == 1 && !validB) continue;
+    const int beg = __ldg(fb.band_start + b), len = __ldg(fb.band_start + b + 1) - beg;
+    const int k0 = __ldg(fb.band_k0 + b);
+    const float* mg = mags + f * kMagStride + k0;
+    float s = 0.f;
+    for (int i = lane; i < len; i += 32) s = fmaf(__ldg(fb.weights + beg + i), mg[i], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float p = s * s;
+      const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
+      mel[(size_t)(cd.frame_off + tA + f) * kMels + b] = db;
+      wmax = fmaxf(wmax, db);
+    }
+  }
+  if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
+}
+
+// Per-segment lookup rows, built once per pass after the front-end:
+//   seg_frame0[s] = first mel row of segment s,  seg_thr[s] = clipmax(clip) - 80  (top_db)
+__global__ void seg_table_kernel(const ClipDesc* __restrict__ clips, int n_clips,
+                                 const int* __restrict__ seg_prefix,
+                                 const unsigned* __restrict__ clipmax, int seg_hop, int n_seg,
+                                 int* __restrict__ seg_frame0, float* __restrict__ seg_thr,
+                                 int* __restrict__ seg_clip) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const int c = upper_slot(seg_prefix, n_clips, s);
+  const ClipDesc cd = clips[c];
+  seg_frame0[s] = cd.frame_off + (s - cd.seg_off) * seg_hop;
+  seg_thr[s] = key2f(clipmax[c]) - 80.0f;
+  seg_clip[s] = c;
+}
+
+// stage dump helper: mel[frame][48] -> per clip [48][n_frames] with the top_db clamp applied
+__global__ void mel_dump_kernel(const float* __restrict__ mel, const ClipDesc* __restrict__ clips,
+                                int n_clips, const unsigned* __restrict__ clipmax,
+                                float* __restrict__ out) {
+  const int c = blockIdx.y;
+  const ClipDesc cd = clips[c];
+  const float thr = key2f(clipmax[c]) - 80.0f;
+  const int n = cd.n_frames * kMels;
+  float* o = out + (size_t)cd.frame_off * kMels;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / cd.n_frames, t = i - b * cd.n_frames;
+    o[i] = fmaxf(mel[(size_t)(cd.frame_off + t) * kMels + b], thr);
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDesc* clips,
+                     int n_clips, const int* pair_prefix, int n_pairs, const FbTables* fbs,
+                     const float2* tw4096, float* mel, unsigned* clipmax, int Q) {
+  const int smem = frontend_smem_bytes(Q);
+  if (fmt_f32) {
+    cudaFuncSetAttribute(frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    frontend_kernel<float><<<n_pairs, kFeThreads, smem, st>>>(
+        (const float*)pcm, clips, n_clips, pair_prefix, fbs, tw4096, mel, clipmax, Q);
+  } else {
+    cudaFuncSetAttribute(frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    frontend_kernel<short><<<n_pairs, kFeThreads, smem, st>>>(
+        (const short*)pcm, clips, n_clips, pair_prefix, fbs, tw4096, mel, clipmax, Q);
+  }
+}
+
+void launch_seg_table(cudaStream_t st, const ClipDesc* clips, int n_clips, const int* seg_prefix,
+                      const unsigned* clipmax, int seg_hop, int n_seg, int* seg_frame0,
+                      float* seg_thr, int* seg_clip) {
+  seg_table_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(clips, n_clips, seg_prefix, clipmax,
+                                                        seg_hop, n_seg, seg_frame0, seg_thr,
+                                                        seg_clip);
+}
+
+void launch_mel_dump(cudaStream_t st, const float* mel, const ClipDesc* clips, int n_clips,
+                     const unsigned* clipmax, float* out) {
+  dim3 grid(8, n_clips);
+  mel_dump_kernel<<<grid, 256, 0, st>>>(mel, clips, n_clips, clipmax, out);
+}
+
+}  // namespace nisqa

@@ -1,0 +1,106 @@
+"""Host-side WAV ingest for the engine.
+
+Mirrors what ``lb.load(path, sr=None[, mono=False])`` + the channel pick does at reference
+``nisqa/NISQA_lib.py:2298-2306`` (libsndfile float conversion; mono = float32 mean over
+channels; ``ms_channel`` picks one channel of a multi-channel file), but keeps mono PCM16
+files as int16 so the host->device copy is half the size and the ``/32768`` happens on the
+device (bit-identical: division by a power of two).
+
+Returns ``(samples, sample_rate)`` where samples is a contiguous 1-D ``int16`` or ``float32``
+array.  Any parse problem raises ``ValueError('Could not load file ...')`` exactly like the
+reference's bare ``except`` (lib:2305-2306).
+"""
+import struct
+
+import numpy as np
+
+_INV = {8: np.float32(1.0 / 128.0), 24: np.float32(1.0 / 8388608.0)}
+
+
+def _parse(buf):
+    if len(buf) < 12 or buf[0:4] != b"RIFF" or buf[8:12] != b"WAVE":
+        raise ValueError("not RIFF/WAVE")
+    pos, fmt, payload = 12, None, None
+    n = len(buf)
+    while pos + 8 <= n:
+        cid = bytes(buf[pos:pos + 4])
+        (csz,) = struct.unpack_from("<I", buf, pos + 4)
+        start = pos + 8
+        end = min(start + csz, n)
+        if cid == b"fmt ":
+            tag, ch, sr, _, _, bits = struct.unpack_from("<HHIIHH", buf, start)
+            if tag == 0xFFFE and end - start >= 26:
+                (tag,) = struct.unpack_from("<H", buf, start + 24)
+            fmt = (tag, ch, sr, bits)
+        elif cid == b"data":
+            payload = (start, end)
+        pos = start + csz + (csz & 1)
+    if fmt is None or payload is None or fmt[1] < 1:
+        raise ValueError("missing fmt/data")
+    return fmt, payload
+
+
+def read_wav(path, ms_channel=None):
+    """-> (1-D int16 | float32 contiguous array, sample_rate:int)."""
+    try:
+        with open(path, "rb") as f:
+            buf = f.read()
+        (tag, ch, sr, bits), (s, e) = _parse(memoryview(buf))
+        width = bits // 8
+        n_frames = (e - s) // (width * ch)
+        raw = np.frombuffer(buf, dtype=np.uint8, count=n_frames * ch * width, offset=s)
+        if tag == 1 and bits == 16:
+            x = raw.view("<i2").reshape(n_frames, ch)
+            if ch == 1:
+                return np.ascontiguousarray(x[:, 0]), int(sr)
+            if ms_channel is not None:
+                return np.ascontiguousarray(x[:, ms_channel]), int(sr)
+            y = x.astype(np.float32) / np.float32(32768.0)
+        elif tag == 1 and bits == 8:
+            y = (raw.reshape(n_frames, ch).astype(np.float32) - np.float32(128.0)) * _INV[8]
+        elif tag == 1 and bits == 24:
+            b = raw.reshape(n_frames * ch, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            v = (v ^ 0x800000) - 0x800000
+            y = (v.astype(np.float32) * _INV[24]).reshape(n_frames, ch)
+        elif tag == 1 and bits == 32:
+            y = (raw.view("<i4").astype(np.float64) * (1.0 / 2147483648.0)).astype(np.float32)
+            y = y.reshape(n_frames, ch)
+        elif tag == 3 and bits == 32:
+            y = raw.view("<f4").astype(np.float32).reshape(n_frames, ch)
+        elif tag == 3 and bits == 64:
+            y = raw.view("<f8").astype(np.float32).reshape(n_frames, ch)
+        else:
+            raise ValueError("unsupported WAVE encoding tag=%d bits=%d" % (tag, bits))
+        if ch == 1:
+            out = y[:, 0]
+        elif ms_channel is not None:
+            out = y[:, ms_channel]
+        else:
+            out = np.mean(y.T, axis=0)          # librosa.to_mono on the [ch, n] float32 array
+        return np.ascontiguousarray(out, dtype=np.float32), int(sr)
+    except Exception:
+        raise ValueError("Could not load file {}".format(path))
+
+
+def write_wav_pcm16(path, pcm, sr):
+    """Write int16 samples, shape [n] (mono) or [n, ch]."""
+    pcm = np.ascontiguousarray(pcm, dtype="<i2")
+    ch = 1 if pcm.ndim == 1 else pcm.shape[1]
+    data = pcm.tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack(
+        "<IHHIIHH", 16, 1, ch, sr, sr * ch * 2, ch * 2, 16) + b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr)
+        f.write(data)
+
+
+def write_wav_f32(path, y, sr):
+    y = np.ascontiguousarray(y, dtype="<f4")
+    ch = 1 if y.ndim == 1 else y.shape[1]
+    data = y.tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack(
+        "<IHHIIHH", 16, 3, ch, sr, sr * ch * 4, ch * 4, 32) + b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr)
+        f.write(data)

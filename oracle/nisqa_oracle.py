@@ -1,0 +1,265 @@
+"""CPU oracle for the NISQA predict hot path (wav samples -> MOS / dimension scores).
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+CPU-baseline / ``--impl reference`` legs may import this module, and only as the checker or
+as the CPU baseline being timed.  The product path (``nisqa_b200/``) never imports it.
+
+What it is: a per-clip, unpadded restatement of the reference's predict path in NumPy +
+torch-CPU functional ops (the same arithmetic library the reference uses on the CPU), each
+function citing the reference ``file:line`` it follows (``lib`` = nisqa/NISQA_lib.py).
+
+Pinning status
+  * model half (segments -> scores): PINNED against the unmodified reference modules imported
+    from ``/root/reference`` (``oracle/make_golden.py`` -> ``tests/golden/*.npz``,
+    checked by ``tests/test_oracle_golden.py``).
+  * front-end half (samples -> mel dB): PARITY UNPINNED - see ``oracle/librosa_compat.py``.
+
+The reference pads every clip to ``ms_max_segments`` and masks; per-clip results do not depend
+on the batch composition (re-checked by ``tests/test_oracle_golden.py``),
+so the oracle processes one clip at a time with no padding.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import librosa_compat as lb
+
+STATUS_OK, STATUS_TOO_SHORT, STATUS_TOO_LONG = 0, 1, 2
+
+
+def load_checkpoint(path):
+    """reference model:938-942 - ``torch.load`` of {'args', 'model_state_dict'}."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    sd = {k: v.detach().clone() for k, v in ck["model_state_dict"].items()}
+    return dict(ck["args"]), sd
+
+
+# ------------------------------------------------------------------ front-end (a1-a6)
+def hop_win(sr, args):
+    """lib:2308-2309: int() truncation of sr * seconds (double arithmetic)."""
+    return int(sr * args["ms_hop_length"]), int(sr * args["ms_win_length"])
+
+
+def mel_db(y, sr, args):
+    """lib:2311-2330 - melspectrogram(power=1) then amplitude_to_db(amin=1e-4, top_db=80)."""
+    hop, win = hop_win(sr, args)
+    S = lb.melspectrogram(y=y, sr=sr, S=None, n_fft=args["ms_n_fft"], hop_length=hop,
+                          win_length=win, window="hann", center=True, pad_mode="reflect",
+                          power=1.0, n_mels=args["ms_n_mels"], fmin=0.0,
+                          fmax=args["ms_fmax"], htk=False, norm="slaney")
+    return lb.amplitude_to_db(S, ref=1.0, amin=1e-4, top_db=80.0)
+
+
+def segment_counts(n_samples, sr, args):
+    """Exact integer bookkeeping of lib:2308 + librosa frame count + lib:2257-2277.
+
+    Returns (n_frames, n_segments, status)."""
+    hop, _ = hop_win(sr, args)
+    n_frames = 1 + n_samples // hop
+    seg_len, seg_hop = args["ms_seg_length"], args["ms_seg_hop_length"]
+    n_wins = n_frames - (seg_len - 1)
+    if n_wins < 1:
+        return n_frames, 0, STATUS_TOO_SHORT
+    n_seg = int(math.ceil(n_wins / seg_hop)) if seg_hop > 1 else n_wins
+    if args["ms_max_segments"] is not None and n_seg > args["ms_max_segments"]:
+        return n_frames, n_seg, STATUS_TOO_LONG
+    return n_frames, n_seg, STATUS_OK
+
+
+def segments(spec, args):
+    """lib:2239-2273 without the zero-padding tail: x[i,0,m,t] = spec[m, i*seg_hop + t]."""
+    seg_len, seg_hop = args["ms_seg_length"], args["ms_seg_hop_length"]
+    spec = torch.as_tensor(np.ascontiguousarray(spec), dtype=torch.float32)
+    n_wins = spec.shape[1] - (seg_len - 1)
+    if n_wins < 1:
+        raise ValueError("Sample too short")
+    starts = torch.arange(0, n_wins, seg_hop)
+    idx = starts[:, None] + torch.arange(seg_len)[None, :]          # [S, 15]
+    x = spec[:, idx]                                                # [48, S, 15]
+    return x.permute(1, 0, 2).unsqueeze(1).contiguous()             # [S, 1, 48, 15]
+
+
+# ------------------------------------------------------------------------ CNN (a10/a15)
+def _conv_bn_relu(sd, i, x, padding):
+    p = "cnn.model."
+    x = F.conv2d(x, sd[p + "conv%d.weight" % i], sd[p + "conv%d.bias" % i], padding=padding)
+    x = F.batch_norm(x, sd[p + "bn%d.running_mean" % i], sd[p + "bn%d.running_var" % i],
+                     sd[p + "bn%d.weight" % i], sd[p + "bn%d.bias" % i],
+                     training=False, eps=1e-5)
+    return F.relu(x)
+
+
+def adapt_cnn(sd, x, args, taps=None):
+    """lib:688-710 (eval mode: Dropout2d is the identity)."""
+    x = _conv_bn_relu(sd, 1, x, (1, 1))
+    x = F.adaptive_max_pool2d(x, output_size=tuple(args["cnn_pool_1"]))
+    if taps is not None: taps["pool1"] = x
+    x = _conv_bn_relu(sd, 2, x, (1, 1))
+    x = F.adaptive_max_pool2d(x, output_size=tuple(args["cnn_pool_2"]))
+    if taps is not None: taps["pool2"] = x
+    x = _conv_bn_relu(sd, 3, x, (1, 1))
+    if taps is not None: taps["conv3"] = x
+    x = _conv_bn_relu(sd, 4, x, (1, 1))
+    x = F.adaptive_max_pool2d(x, output_size=tuple(args["cnn_pool_3"]))
+    if taps is not None: taps["pool3"] = x
+    x = _conv_bn_relu(sd, 5, x, (1, 1))
+    if taps is not None: taps["conv5"] = x
+    x = _conv_bn_relu(sd, 6, x, (1, 0))          # kernel (3, pool_3[1]) pad (1,0): W 3 -> 1
+    return x.reshape(-1, 64 * args["cnn_pool_3"][0])
+
+
+def standard_cnn(sd, x, args, taps=None):
+    """lib:811-836: fixed MaxPool2d(2) (first with padding (0,1)), fc_out 768 -> 20."""
+    x = _conv_bn_relu(sd, 1, x, 1)
+    x = F.max_pool2d(x, 2, stride=2, padding=(0, 1))
+    if taps is not None: taps["pool1"] = x
+    x = _conv_bn_relu(sd, 2, x, 1)
+    x = F.max_pool2d(x, 2, stride=2)
+    if taps is not None: taps["pool2"] = x
+    x = _conv_bn_relu(sd, 3, x, 1)
+    if taps is not None: taps["conv3"] = x
+    x = _conv_bn_relu(sd, 4, x, 1)
+    x = F.max_pool2d(x, 2, stride=2)
+    if taps is not None: taps["pool3"] = x
+    x = _conv_bn_relu(sd, 5, x, 1)
+    if taps is not None: taps["conv5"] = x
+    x = _conv_bn_relu(sd, 6, x, 1)
+    x = x.reshape(-1, 64 * 6 * 2)
+    if "cnn.model.fc_out.weight" in sd:
+        x = F.linear(x, sd["cnn.model.fc_out.weight"], sd["cnn.model.fc_out.bias"])
+    return x
+
+
+# --------------------------------------------------------- time dependency (a11/a12/a16)
+def self_attention(sd, feats, taps=None):
+    """lib:988-996 + lib:1025-1040 for ONE clip (so no key-padding mask is needed).
+
+    nn.MultiheadAttention with one head: q,k,v = in_proj; q *= 1/sqrt(64); softmax(q k^T) v;
+    out_proj; post-norm residual blocks."""
+    p = "time_dependency.model."
+    x = F.linear(feats, sd[p + "linear.weight"], sd[p + "linear.bias"])
+    x = F.layer_norm(x, (x.shape[-1],), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    if taps is not None: taps["sa_in"] = x
+    n_layers = len({k.split(".")[3] for k in sd if k.startswith(p + "layers.")})
+    for l in range(n_layers):
+        q = p + "layers.%d." % l
+        d = x.shape[-1]
+        qkv = F.linear(x, sd[q + "self_attn.in_proj_weight"], sd[q + "self_attn.in_proj_bias"])
+        qq, kk, vv = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+        att = torch.softmax((qq * (1.0 / math.sqrt(d))) @ kk.t(), dim=-1)
+        sa = F.linear(att @ vv, sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"])
+        x = F.layer_norm(x + sa, (d,), sd[q + "norm1.weight"], sd[q + "norm1.bias"], 1e-5)
+        ff = F.linear(F.relu(F.linear(x, sd[q + "linear1.weight"], sd[q + "linear1.bias"])),
+                      sd[q + "linear2.weight"], sd[q + "linear2.bias"])
+        x = F.layer_norm(x + ff, (d,), sd[q + "norm2.weight"], sd[q + "norm2.bias"], 1e-5)
+        if taps is not None: taps["sa_l%d" % l] = x
+    return x
+
+
+def bilstm(sd, feats):
+    """lib:925-943: packed 1-layer BiLSTM for ONE clip. PyTorch gate order i,f,g,o;
+    c = f*c + i*g; h = o*tanh(c); reverse direction starts at the clip's own last step."""
+    p = "time_dependency.model.lstm."
+    S = feats.shape[0]
+    outs = []
+    for suffix, order in (("", range(S)), ("_reverse", range(S - 1, -1, -1))):
+        w_ih, w_hh = sd[p + "weight_ih_l0" + suffix], sd[p + "weight_hh_l0" + suffix]
+        b = sd[p + "bias_ih_l0" + suffix] + sd[p + "bias_hh_l0" + suffix]
+        H = w_hh.shape[1]
+        gx = feats @ w_ih.t() + b
+        h = torch.zeros(H)
+        c = torch.zeros(H)
+        out = torch.zeros(S, H)
+        for t in order:
+            g = gx[t] + w_hh @ h
+            i, f, gg, o = g[:H], g[H:2 * H], g[2 * H:3 * H], g[3 * H:]
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out[t] = h
+        outs.append(out)
+    return torch.cat(outs, dim=1)                                   # [S, 2H] fwd || bwd
+
+
+# ---------------------------------------------------------------------- pooling (a13/a17)
+def pool_attff(sd, prefix, x):
+    """lib:1171-1183 for one clip: att = W2 relu(W1 x + b1) + b2; softmax over time;
+    weighted sum of x; Linear 64 -> 1."""
+    a = F.linear(F.relu(F.linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])),
+                 sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])      # [S,1]
+    a = torch.softmax(a.t(), dim=1)                                                # [1,S]
+    pooled = a @ x                                                                 # [1,64]
+    return F.linear(pooled, sd[prefix + "linear3.weight"], sd[prefix + "linear3.bias"]).reshape(-1)
+
+
+def pool_last_step_bi(sd, prefix, x):
+    """lib:1107-1115: forward hidden at the last valid step || backward hidden at step 0."""
+    H = x.shape[1] // 2
+    v = torch.cat((x[-1, :H], x[0, H:]))[None, :]
+    return F.linear(v, sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]).reshape(-1)
+
+
+# ------------------------------------------------------------------------- whole model
+def forward_from_mel(args, sd, spec, taps=None):
+    """mel dB [n_mels, F] -> scores [1] or [5] (order mos,noi,dis,col,loud; lib:255-266)."""
+    x = segments(spec, args)
+    if taps is not None: taps["n_segments"] = x.shape[0]
+    with torch.no_grad():
+        if args["cnn_model"] == "adapt":
+            feats = adapt_cnn(sd, x, args, taps)
+        elif args["cnn_model"] == "standard":
+            feats = standard_cnn(sd, x, args, taps)
+        else:
+            raise NotImplementedError(args["cnn_model"])
+        if taps is not None: taps["cnn_feat"] = feats
+        if args["td"] == "self_att":
+            td = self_attention(sd, feats, taps)
+        elif args["td"] == "lstm":
+            td = bilstm(sd, feats)
+        else:
+            raise NotImplementedError(args["td"])
+        if taps is not None: taps["td_out"] = td
+        if args["model"] == "NISQA_DIM":
+            prefixes = ["pool_layers.%d.model." % i for i in range(5)]
+        else:
+            prefixes = ["pool.model."]
+        outs = []
+        for pf in prefixes:
+            if args["pool"] == "att":
+                outs.append(pool_attff(sd, pf, td))
+            elif args["pool"] == "last_step_bi":
+                outs.append(pool_last_step_bi(sd, pf, td))
+            else:
+                raise NotImplementedError(args["pool"])
+    return torch.cat(outs).numpy()
+
+
+def predict_pcm(args, sd, y, sr, taps=None):
+    """float32 mono samples -> (scores, n_segments, status).  Mirrors lib:2162-2233 +
+    lib:1441-1467 for one clip."""
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    _, n_seg, status = segment_counts(y.shape[0], sr, args)
+    n_out = 5 if args["model"] == "NISQA_DIM" else 1
+    if status != STATUS_OK:
+        return np.full(n_out, np.nan, dtype=np.float32), n_seg, status
+    spec = mel_db(y, sr, args)
+    if taps is not None: taps["mel_db"] = spec
+    scores = forward_from_mel(args, sd, spec, taps)
+    return scores.astype(np.float32), n_seg, STATUS_OK
+
+
+def predict_file(args, sd, path, ms_channel=None, taps=None):
+    """lib:2298-2306 + the rest of the path for one wav file."""
+    if ms_channel is not None:
+        y, sr = lb.load(path, sr=args.get("ms_sr"), mono=False)
+        if y.ndim > 1:
+            y = y[ms_channel, :]
+    else:
+        y, sr = lb.load(path, sr=args.get("ms_sr"))
+    return predict_pcm(args, sd, y, sr, taps)
+
+
+def default_weights_dir():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights")
