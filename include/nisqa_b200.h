@@ -26,6 +26,12 @@ extern "C" {
 
 #define NISQA_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define NISQA_API __attribute__((visibility("default")))
+#else
+#define NISQA_API
+#endif
+
 typedef struct nisqa_engine nisqa_engine;
 
 /* architectures of the shipped checkpoints */
@@ -88,13 +94,13 @@ typedef struct nisqa_tensor {
   int64_t      dims[4];
 } nisqa_tensor;
 
-int  nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg);
-void nisqa_destroy(nisqa_engine* e);
-const char* nisqa_last_error(const nisqa_engine* e);
+NISQA_API int  nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg);
+NISQA_API void nisqa_destroy(nisqa_engine* e);
+NISQA_API const char* nisqa_last_error(const nisqa_engine* e);
 
 /* replaces model.load_state_dict(checkpoint['model_state_dict'], strict=True), model:1023:
  * folds eval-mode BatchNorm into the convolutions, repacks to the kernel layouts, uploads. */
-int  nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n);
+NISQA_API int  nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n);
 
 /* replaces the body of predict_dim / predict_mos for n_clips clips given as mono PCM in HOST
  * memory (already channel-selected / mono-mixed by the caller, lib:2298-2304).
@@ -104,7 +110,7 @@ int  nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n);
  *   n_segments_out : [n_clips] int32 - n_wins as returned by segment_specs (lib:2282)
  *   status_out     : [n_clips] int32 - enum nisqa_clip_status
  * Synchronous: results are valid in host memory on return. */
-int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
+NISQA_API int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
                        const void* const* pcm, const int64_t* n_samples,
                        const int32_t* sample_rate, int sample_fmt,
                        float* scores_out, int32_t* n_segments_out, int32_t* status_out);
@@ -113,7 +119,7 @@ int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
  * to back, clip i starting at element offset pcm_offsets[i]); scores stay on the device
  * (scores_dev [n_clips, n_out]).  Asynchronous on the engine stream unless sync != 0.
  * Used by bench.py for the "inputs resident in HBM" throughput figure. */
-int  nisqa_predict_pcm_device(nisqa_engine* e, int n_clips,
+NISQA_API int  nisqa_predict_pcm_device(nisqa_engine* e, int n_clips,
                               const void* pcm_dev, const int64_t* pcm_offsets,
                               const int64_t* n_samples, const int32_t* sample_rate,
                               int sample_fmt, float* scores_dev,
@@ -122,36 +128,36 @@ int  nisqa_predict_pcm_device(nisqa_engine* e, int n_clips,
 /* Copy an intermediate of the LAST predict call to host memory (parity tests).  Only valid
  * when that call fitted in one internal pass.  Returns the number of floats written (>=0)
  * or a negative status; with out == NULL returns the required count. */
-int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap);
+NISQA_API int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap);
 
 /* Pure host arithmetic (no device work): frames / segments / status for a clip length,
  * exactly as lib:2308 + librosa's frame count + lib:2257-2277. */
-int  nisqa_segment_counts(const nisqa_config* cfg, int64_t n_samples, int32_t sample_rate,
+NISQA_API int  nisqa_segment_counts(const nisqa_config* cfg, int64_t n_samples, int32_t sample_rate,
                           int32_t* n_frames, int32_t* n_segments, int32_t* status);
 
 /* Host copy of the engine's mel filterbank for a sample rate: dense [n_mels, n_fft/2+1]. */
-int  nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64_t cap);
+NISQA_API int  nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64_t cap);
 
 /* Single exchange step of the multi-GPU path: gather the per-rank score rows
  * onto every rank with one ncclAllGather on the engine stream.
  *   nccl_comm : ncclComm_t of the caller (one rank per GPU)
  *   local_dev : [max_rows, n_out] fp32 device rows of this rank (padded to max_rows)
  *   global_dev: [world, max_rows, n_out] fp32 device buffer */
-int  nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm /* NULL: the engine's own */,
+NISQA_API int  nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm /* NULL: the engine's own */,
                        const float* local_dev, int max_rows, float* global_dev);
 /* Engine-owned communicator: rank 0 calls nisqa_nccl_unique_id (128 bytes), the caller ships
  * the id to every rank (torch.distributed broadcast), every rank calls nisqa_nccl_init. */
-int  nisqa_nccl_unique_id(nisqa_engine* e, void* id128);
-int  nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void* id128);
+NISQA_API int  nisqa_nccl_unique_id(nisqa_engine* e, void* id128);
+NISQA_API int  nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void* id128);
 
 /* bookkeeping for bench.py */
-int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
-void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t the engine launches on */
+NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
+NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t the engine launches on */
 /* average device time (ms) of the named kernel group during the last predict call, measured
  * with CUDA events on the engine stream when profiling was enabled; <0 if unknown.
  * groups: "frontend", "cnn", "td", "pool" */
-int    nisqa_set_profiling(nisqa_engine* e, int on);
-double nisqa_group_ms(const nisqa_engine* e, const char* group);
+NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
+NISQA_API double nisqa_group_ms(const nisqa_engine* e, const char* group);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's predict seam (reference nisqa/NISQA_lib.py:1420-1467,
+2052-2236) with the hot path replaced by the B200 engine.
+
+Same names, argument meaning and error behaviour as the reference so that
+``nisqaModel.predict()`` reads the same:
+
+* :func:`predict_dim` / :func:`predict_mos` take ``(model, ds, bs, dev, num_workers)``, return
+  ``(y_hat, y)`` and add ``mos_pred`` (+ ``noi_pred, dis_pred, col_pred, loud_pred``) to
+  ``ds.df`` in dataset row order; ``predict_mos`` stores float64, ``predict_dim`` float32.
+* ``model`` is an :class:`nisqa_b200.engine.Engine` instead of an ``nn.Module``; one batch of
+  ``bs`` clips becomes ONE C-ABI call (wav decode -> PCM pointers -> scores), there is no
+  padded ``[bs, 1300, 1, 48, 15]`` tensor and no DataLoader.  ``num_workers`` sizes the
+  wav-decode thread pool that prefetches the next batch while the GPU works on this one.
+* errors are the reference's ``ValueError``s: unreadable file (lib:2305-2306), clip shorter
+  than ``seg_length`` frames (lib:2258-2263), more than ``ms_max_segments`` segments
+  (lib:2276-2277) - a single bad file aborts the run, like the reference.
+* under ``torchrun`` (WORLD_SIZE > 1) the rows are sharded over the ranks and the scores are
+  all-gathered once (``nisqa_b200/dist.py``); every rank ends up with the full table.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import dist as nb_dist
+from . import engine as nb_engine
+from .wav import read_wav
+
+
+class SpeechQualityDataset(object):
+    """Predict-only subset of the reference Dataset (lib:2052-2236): holds the table of files
+    and the front-end parameters; ``load_pcm(index)`` replaces ``__getitem__`` (no mel, no
+    segment tensor on the host)."""
+
+    def __init__(self, df, df_con=None, data_dir="", folder_column="", filename_column="filename",
+                 mos_column="MOS", seg_length=15, max_length=None, to_memory=False,
+                 to_memory_workers=0, transform=None, seg_hop_length=1, ms_n_fft=1024,
+                 ms_hop_length=80, ms_win_length=170, ms_n_mels=32, ms_sr=48e3, ms_fmax=16e3,
+                 ms_channel=None, double_ended=False, filename_column_ref=None, dim=False):
+        if double_ended:
+            raise NotImplementedError("double-ended models are outside the B200 predict path")
+        if mos_column != "predict_only":
+            raise NotImplementedError("only predict_only datasets are on the B200 path")
+        if transform is not None or to_memory:
+            raise NotImplementedError("transform / to_memory are training-side options")
+        self.df = df
+        self.df_con = df_con
+        self.data_dir = data_dir
+        self.filename_column = filename_column
+        self.mos_column = mos_column
+        self.seg_length = seg_length
+        self.seg_hop_length = seg_hop_length
+        self.max_length = max_length
+        self.ms_n_fft, self.ms_hop_length, self.ms_win_length = ms_n_fft, ms_hop_length, ms_win_length
+        self.ms_n_mels, self.ms_sr, self.ms_fmax = ms_n_mels, ms_sr, ms_fmax
+        self.ms_channel = ms_channel
+        self.dim = dim
+
+    def __len__(self):
+        return len(self.df)
+
+    def file_path(self, index):
+        return os.path.join(self.data_dir, self.df[self.filename_column].iloc[index])
+
+    def load_pcm(self, index):
+        """-> (int16|float32 mono samples, sample_rate); ValueError('Could not load file ..')."""
+        return read_wav(self.file_path(index), self.ms_channel)
+
+
+def _raise_for_status(ds, engine, index, n_samples, sr, n_seg, status):
+    path = ds.file_path(index)
+    if status == nb_engine.CLIP_TOO_SHORT:
+        hop = int(sr * ds.ms_hop_length)
+        width = 1 + n_samples // hop if hop > 0 else 0
+        raise ValueError(
+            "Sample too short. Only {} windows available but seg_length={}. "
+            "Consider zero padding the audio sample. File: {}".format(width, ds.seg_length, path))
+    if status == nb_engine.CLIP_TOO_LONG:
+        raise ValueError(
+            "n_wins {} > max_length {} --- {}. Increase max window length ms_max_segments!".format(
+                n_seg, ds.max_length, path))
+
+
+def _predict_rows(engine, ds, rows, bs, num_workers):
+    """Scores for the given dataset rows (in that order) through the C-ABI, bs clips per call."""
+    n_out = engine.n_out
+    out = np.empty((len(rows), n_out), dtype=np.float32)
+    bs = max(1, int(bs))
+    batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
+    workers = max(1, int(num_workers) if num_workers else 1)
+
+    def load(batch):
+        return [ds.load_pcm(int(i)) for i in batch]
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        def submit(batch):
+            if workers == 1:
+                return pool.submit(load, batch)
+            futs = [pool.submit(ds.load_pcm, int(i)) for i in batch]
+            return futs
+
+        def collect(h):
+            return h.result() if not isinstance(h, list) else [f.result() for f in h]
+
+        pending = submit(batches[0]) if batches else None
+        pos = 0
+        for b, batch in enumerate(batches):
+            loaded = collect(pending)
+            pending = submit(batches[b + 1]) if b + 1 < len(batches) else None
+            clips = [c for c, _ in loaded]
+            srs = [s for _, s in loaded]
+            scores, nseg, status = engine.predict_pcm(clips, srs)
+            for j, st in enumerate(status):
+                if st != nb_engine.CLIP_OK:
+                    _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
+            out[pos:pos + len(batch)] = scores
+            pos += len(batch)
+    return out
+
+
+def _predict_all(engine, ds, bs, num_workers):
+    n = len(ds)
+    rank, world, _ = nb_dist.env_world()
+    if world > 1:
+        import torch.distributed as tdist
+        if not tdist.is_initialized():
+            nb_dist.init_process_group()
+        sizes = []
+        for i in range(n):
+            try:
+                sizes.append(os.path.getsize(ds.file_path(i)))
+            except OSError:
+                sizes.append(0)
+        shards = nb_dist.shard_rows(sizes, world)
+        local = _predict_rows(engine, ds, shards[rank], bs, num_workers)
+        return nb_dist.all_gather_scores(local, shards, n, engine=engine)
+    return _predict_rows(engine, ds, np.arange(n, dtype=np.int64), bs, num_workers)
+
+
+def predict_mos(model, ds, bs, dev, num_workers=0):
+    """MOS-only models (reference lib:1420-1439): adds ``mos_pred`` (float64) to ``ds.df``."""
+    y_hat = _predict_all(model, ds, bs, num_workers)[:, :1].reshape(-1, 1)
+    y = np.full((len(ds), 1), np.nan, dtype=np.float32)          # predict_only labels (lib:2224-2225)
+    ds.df["mos_pred"] = y_hat.astype(dtype=float)
+    return y_hat, y
+
+
+def predict_dim(model, ds, bs, dev, num_workers=0):
+    """NISQA_DIM models (reference lib:1441-1467): adds the five ``*_pred`` columns (float32)."""
+    y_hat = _predict_all(model, ds, bs, num_workers)
+    y = np.full((len(ds), 5), np.nan, dtype=np.float32)          # predict_only labels (lib:2217-2219)
+    ds.df["mos_pred"] = y_hat[:, 0].reshape(-1, 1)
+    ds.df["noi_pred"] = y_hat[:, 1].reshape(-1, 1)
+    ds.df["dis_pred"] = y_hat[:, 2].reshape(-1, 1)
+    ds.df["col_pred"] = y_hat[:, 3].reshape(-1, 1)
+    ds.df["loud_pred"] = y_hat[:, 4].reshape(-1, 1)
+    return y_hat, y

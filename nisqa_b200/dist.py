@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing for the predict path: one process per GPU, clips sharded
+across ranks with no data-path collective, ONE exchange step - an all-gather of the per-rank
+score rows (NCCL over NVLink through the engine's ``nisqa_gather_nccl``; ``gloo`` on CPU for
+the host-logic tests).  The reference's own multi-GPU mechanism is ``nn.DataParallel`` over
+the batch (reference nisqa/NISQA_model.py:56-57); clips are independent, so sharding the file
+list is result-equivalent.
+"""
+import os
+
+import numpy as np
+
+
+def env_world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process if absent)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend=None):
+    """Initialise torch.distributed from the torchrun env if WORLD_SIZE > 1.  Returns
+    (rank, world, local_rank)."""
+    rank, world, local = env_world()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(local)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_rows(weights, world):
+    """Deterministic balanced partition of row indices over ranks.
+
+    Longest-processing-time-first on ``weights`` (file sizes ~ audio seconds): rows sorted by
+    decreasing weight, each handed to the currently lightest rank.  Every rank computes the
+    same table, so no communication is needed.  Returns a list of ``world`` int64 arrays, each
+    in increasing row order."""
+    w = np.asarray(weights, dtype=np.float64)
+    order = np.argsort(-w, kind="stable")
+    load = np.zeros(world, dtype=np.float64)
+    count = np.zeros(world, dtype=np.int64)
+    owner = np.empty(len(w), dtype=np.int64)
+    for i in order:
+        r = int(np.lexsort((np.arange(world), count, load))[0])
+        owner[i] = r
+        load[r] += w[i]
+        count[r] += 1
+    return [np.flatnonzero(owner == r).astype(np.int64) for r in range(world)]
+
+
+def scatter_rows(gathered, shards, n_total):
+    """gathered: [world, max_rows, n_out]; shards: per-rank row indices -> [n_total, n_out]."""
+    gathered = np.asarray(gathered)
+    out = np.full((n_total, gathered.shape[2]), np.nan, dtype=np.float32)
+    for r, idx in enumerate(shards):
+        out[idx] = gathered[r, :len(idx)]
+    return out
+
+
+def all_gather_scores(local_scores, shards, n_total, engine=None):
+    """The single exchange step.  ``local_scores`` [n_local, n_out] float32 rows of this rank in
+    the order of ``shards[rank]``.  Returns the full [n_total, n_out] matrix on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_out = local_scores.shape[1]
+    max_rows = max(1, max(len(s) for s in shards))
+    if engine is not None and dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if getattr(engine, "_nccl_ready", False) is False:
+            uid = [engine.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            engine.nccl_init(world, rank, uid[0])
+            engine._nccl_ready = True
+        loc = torch.full((max_rows, n_out), float("nan"), dtype=torch.float32, device=dev)
+        loc[:local_scores.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_scores)).to(dev)
+        glob = torch.empty((world, max_rows, n_out), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        engine.gather_nccl(loc.data_ptr(), max_rows, glob.data_ptr())
+        gathered = glob.cpu().numpy()
+    else:
+        loc = torch.full((max_rows, n_out), float("nan"), dtype=torch.float32)
+        loc[:local_scores.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_scores))
+        parts = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        gathered = torch.stack(parts).numpy()
+    return scatter_rows(gathered, shards, n_total)
