@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py - clips/s of the NISQA predict hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): predict_dir bs=64, synthetic 10 s 48 kHz PCM16 clips,
+weights/nisqa.tar.  One "step" = one pass of the hot path (PCM -> 5 scores) over one batch of 64
+clips per GPU; for N > 1 each rank has its own batch (weak scaling) and a step ends with the
+path's single exchange step, one NCCL all-gather of the score rows.
+
+Printed JSON line (rank 0): `value` = whole-job clips/s with the PCM already resident in HBM,
+`e2e` = the same through the C-ABI call with pinned HOST buffers (H2D of the PCM and D2H of the
+scores inside the timed region), `roofline` for the dominant kernel (CUDA-event timed on the
+engine stream), `cpu_baseline` = the oracle port on the host cores on a bounded sample.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port run
+clip-parallel on all host cores) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clips/sec (48 kHz, 10 s) NISQA v2.0 predict"
+UNIT = "clips/s"
+BS, SECONDS, SR = 64, 10.0, 48000
+N_ROT = 4                      # rotating batches: 4 x 61 MB PCM16 = 245 MB > 126 MB L2
+CKPT = os.path.join(ROOT, "weights", "nisqa.tar")
+
+# algorithmic FLOPs per segment of each conv layer (SURVEY.md 8a row a10 / BASELINE.md section 3)
+CONV_FLOP_PER_SEG = {"conv1": 207360, "conv2": 1548288, "conv3": 2211840, "conv4": 4423680,
+                     "conv5": 1327104, "conv6": 442368}
+SEGS_PER_CLIP = 247
+FLOP_PER_CLIP = 2.735e9
+
+
+def make_clips(n, seed0=0):
+    """n distinct 10-s PCM16 clips: a few synthesised bases, circularly shifted (np.roll)."""
+    from nisqa_b200 import synth
+    n_base = min(n, 16)
+    bases = [synth.synth_speech_pcm16(seed0 + i, SECONDS, SR) for i in range(n_base)]
+    rng = np.random.default_rng(seed0 + 999)
+    out = []
+    for i in range(n):
+        b = bases[i % n_base]
+        out.append(b if i < n_base else np.roll(b, int(rng.integers(1, len(b) - 1))))
+    return out
+
+
+class ClockSampler(object):
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class CpuPool(object):
+    """Oracle port on the host cores, clip-parallel: `procs` worker processes with one torch
+    thread each - per-clip parallelism is the reference's own way to use cores (DataLoader
+    workers, reference lib:1425-1430)."""
+
+    def __init__(self, procs):
+        self.procs = procs
+        self.pool = None
+        if procs > 1:
+            import torch.multiprocessing as mp
+            self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init)
+            self.pool.map(_cpu_worker, list(range(4000, 4000 + procs)))   # spin-up + imports, untimed
+        else:
+            _cpu_worker_init()
+            _cpu_worker(4000)
+
+    def run(self, n_clips, seed0=5000):
+        seeds = list(range(seed0, seed0 + n_clips))
+        t0 = time.perf_counter()
+        if self.pool is None:
+            res = [_cpu_worker(s) for s in seeds]
+        else:
+            res = self.pool.map(_cpu_worker, seeds, chunksize=1)
+        dt = time.perf_counter() - t0
+        return n_clips / dt, dt, res
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+_CPU = {}
+
+
+def _cpu_worker_init():
+    import torch
+    torch.set_num_threads(1)
+    from oracle import nisqa_oracle as O
+    _CPU["O"] = O
+    _CPU["ck"] = O.load_checkpoint(CKPT)
+
+
+def _cpu_worker(seed):
+    from nisqa_b200 import synth
+    O = _CPU["O"]
+    args, sd = _CPU["ck"]
+    rng = np.random.default_rng(seed)
+    y = (rng.standard_normal(int(SECONDS * SR)) * 0.05).astype(np.float32)   # cheap synthetic input
+    sc, _, _ = O.predict_pcm(args, sd, y, SR)
+    return float(sc[0])
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, cores)
+    per_step = max(procs, 8)
+    pool = CpuPool(procs)
+    vals = []
+    for s in range(a.warmup + a.steps):
+        v, dt, _ = pool.run(per_step, seed0=5000 + 1000 * s)
+        if s >= a.warmup:
+            vals.append((v, dt))
+        if s == 0 and dt * (a.warmup + a.steps) > 240:      # keep the run within a few minutes
+            per_step = max(procs, int(per_step * 240 / (dt * (a.warmup + a.steps))))
+    pool.close()
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "predict_dir bs=64, synthetic 10 s 48 kHz clips, nisqa.tar (configs[1])",
+                       "sample": "%d clips per step" % per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": "%d x 10 s 48 kHz clips per step, %d worker processes x 1 torch thread, "
+                                       "oracle port of the reference CPU path (NumPy librosa restatement + torch CPU)"
+                                       % (per_step, procs)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a, rank, world, local):
+    import torch
+    from nisqa_b200 import engine as E
+    from oracle import nisqa_oracle as O          # checker + cpu_baseline leg only
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    args, sd = O.load_checkpoint(CKPT)
+    eng = E.Engine(E.config_from_args(args), local)
+    eng.load_state_dict(sd)
+    n_out = eng.n_out
+
+    clips = make_clips(BS * N_ROT, seed0=1000 * (rank + 1))
+    n_s = np.array([len(c) for c in clips[:BS]], dtype=np.int64)
+    srs = np.full(BS, SR, dtype=np.int32)
+    stride = (int(n_s[0]) + 15) // 16 * 16
+    offs = np.arange(BS, dtype=np.int64) * stride
+    dev_batches, pin_batches, ptr_arrays = [], [], []
+    import ctypes as C
+    for r in range(N_ROT):
+        host = torch.zeros(BS * stride, dtype=torch.int16).pin_memory()
+        hv = host.numpy()
+        for i in range(BS):
+            hv[i * stride:i * stride + n_s[i]] = clips[r * BS + i]
+        pin_batches.append(host)
+        dev_batches.append(host.cuda(non_blocking=False))
+        ptr_arrays.append((C.c_void_p * BS)(*[host.data_ptr() + 2 * i * stride for i in range(BS)]))
+    scores_dev = torch.empty((BS, n_out), dtype=torch.float32, device="cuda")
+    scores_host = np.empty((BS, n_out), dtype=np.float32)
+    stream = torch.cuda.ExternalStream(eng.stream())
+
+    gather = None
+    if world > 1:
+        uid = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(world, rank, uid[0])
+        glob = torch.empty((world, BS, n_out), dtype=torch.float32, device="cuda")
+        gather = lambda: eng.gather_nccl(scores_dev.data_ptr(), BS, glob.data_ptr())   # noqa: E731
+
+    def step_dev(i, sync=False):
+        eng.predict_pcm_device(dev_batches[i % N_ROT].data_ptr(), offs, n_s, srs, E.FMT_S16,
+                               scores_dev.data_ptr(), sync=sync and gather is None)
+        if gather is not None:
+            gather()
+
+    def step_e2e(i):
+        eng.predict_pcm_ptrs(ptr_arrays[i % N_ROT], n_s, srs, E.FMT_S16, scores_host)
+        if gather is not None:
+            scores_dev.copy_(torch.from_numpy(scores_host))
+            gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        barrier()
+        return ms, wall
+
+    # ---- parity spot check of what is being timed (rank 0, first clip of batch 0)
+    step_dev(0, sync=True)
+    torch.cuda.synchronize()
+    got = scores_dev[0].cpu().numpy()
+    parity = None
+    if rank == 0:
+        ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
+        parity = float(np.abs(got - ref).max())
+
+    for i in range(a.warmup):
+        step_dev(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches()
+    ms_dev, _ = timed(step_dev, a.steps)
+    launches = eng.kernel_launches() - l0
+    for i in range(a.warmup):
+        step_e2e(i)
+    ms_e2e, wall_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel durations (CUDA events on the engine stream), same workload
+    eng.set_profiling(True)
+    names = ["frontend", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "lin_ln", "qkv",
+             "sa_layer", "pool", "seg_table"]
+    acc = dict((k, 0.0) for k in names)
+    prof_steps = max(3, min(a.steps, 10))
+    for i in range(prof_steps):
+        eng.predict_pcm_device(dev_batches[i % N_ROT].data_ptr(), offs, n_s, srs, E.FMT_S16,
+                               scores_dev.data_ptr(), sync=True)
+        for k in names:
+            v = eng.group_ms(k)
+            if v > 0:
+                acc[k] += v
+    eng.set_profiling(False)
+    kernel_ms = dict((k, v / prof_steps) for k, v in acc.items())
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    total_clips = BS * world * a.steps
+    value = total_clips / (ms_dev / 1e3)
+    e2e_value = total_clips / (max(ms_e2e / 1e3, 1e-9))
+    e2e_wall = total_clips / max(wall_e2e, 1e-9)
+    # dominant kernel = largest measured share of the step
+    dom = max(("conv2", "conv3", "conv4", "conv5", "conv6", "conv1", "frontend"), key=lambda k: kernel_ms[k])
+    n_seg_step = BS * SEGS_PER_CLIP
+    if dom.startswith("conv"):
+        flop = CONV_FLOP_PER_SEG[dom] * n_seg_step
+        ach = flop / (kernel_ms[dom] / 1e3) / 1e12
+        fp32_peak = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "note": "fp32 FFMA implicit GEMM (parity decision, SURVEY.md 0.8): tensor pipe idle; "
+                        "against the fp32 FFMA peak of 148 SMs x 128 lanes x 2 x sm_max_mhz the fraction is frac_fp32",
+                "fp32_peak_tflops": fp32_peak, "frac_fp32": ach / fp32_peak,
+                "kernel_ms": kernel_ms[dom], "algorithmic_flop_per_launch": flop}
+    else:
+        byts = BS * (int(n_s[0]) * 2 + 1001 * 48 * 4)
+        ach = byts / (kernel_ms[dom] / 1e3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "kernel_ms": kernel_ms[dom], "algorithmic_bytes_per_launch": byts}
+    cnn_ms = sum(kernel_ms[k] for k in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"))
+    # ---- CPU baseline: oracle port, one process, all torch threads, bounded sample
+    cpu_base = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        pool = CpuPool(cores)
+        _, dt1, _ = pool.run(cores)
+        n_cpu = int(min(max(cores, cores * 12.0 / max(dt1, 1e-3)), 64 * cores))
+        vcpu, dtc, _ = pool.run(n_cpu, seed0=7000)
+        pool.close()
+        cpu_base = {"value": vcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "%d x 10 s 48 kHz white-noise clips (cost is data independent), %d worker "
+                              "processes x 1 torch thread, %.1f s of wall time; oracle port of the reference "
+                              "CPU path (NumPy librosa restatement + torch CPU)" % (n_cpu, cores, dtc)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "predict_dir bs=64, synthetic 10 s 48 kHz PCM16 clips, weights/nisqa.tar "
+                                   "(BASELINE.json configs[1]); one step = 64 clips per GPU",
+                       "clips_per_step_per_gpu": BS, "segments_per_clip": SEGS_PER_CLIP,
+                       "l2": "inputs rotate over %d resident batches (%.0f MB PCM16 > 126 MB L2); per-step "
+                             "activations ~730 MB stream through L2" % (N_ROT, N_ROT * BS * stride * 2 / 1e6),
+                       "exchange": "1 ncclAllGather of [64,5] rows per step" if world > 1 else "none (N=1)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(BS * int(n_s[0]) * 2),
+                    "d2h_bytes_per_step": int(BS * n_out * 4), "wall_clock_value": e2e_wall,
+                    "api": "nisqa_predict_pcm (C-ABI) on pinned host PCM16"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "kernel_ms_per_step": kernel_ms, "cnn_ms_per_step": cnn_ms,
+            "achieved_tflops_whole_step": FLOP_PER_CLIP * BS / (ms_dev / a.steps / 1e3) / 1e12,
+            "parity_max_abs_vs_oracle": parity,
+            "cpu_baseline": cpu_base}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 0)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", rank=rank, world_size=world)
+    try:
+        run_ours(a, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

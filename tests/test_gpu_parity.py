@@ -1,0 +1,293 @@
+"""Parity tests proper (run on a B200): the CUDA path, called through the C-ABI, against the
+oracle on the same seeded inputs, against the committed reference goldens, and - at
+BASELINE.json's full sizes - through size-independent properties.
+
+Tolerances (north_star): every predicted dimension within 1e-4 of the reference path in fp32,
+segment counts bit-exact.  Intermediate tolerances are stated next to each check.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, ROOT, WEIGHTS
+from nisqa_b200 import engine as E
+from nisqa_b200 import synth, wav
+from oracle import nisqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-4          # north_star: all five dimensions within +-1e-4
+MEL_TOL_DB = 1e-3         # front-end must hold <~1e-3 dB
+ACT_TOL = 2e-4            # CNN / time-dependency activations (values are O(1..10))
+
+
+@pytest.fixture(scope="module")
+def engines(built_lib):
+    out = {}
+    for ck in ("nisqa.tar", "nisqa_mos_only.tar", "nisqa_tts.tar"):
+        args, sd = O.load_checkpoint(os.path.join(WEIGHTS, ck))
+        eng = E.Engine(E.config_from_args(args), 0)
+        eng.load_state_dict(sd)
+        out[ck] = (eng, args, sd)
+    yield out
+    for eng, _, _ in out.values():
+        eng.close()
+
+
+def _f32(pcm):
+    return pcm.astype(np.float32) / np.float32(32768.0)
+
+
+STAGES = [("mel_db", E.STAGE_MEL_DB, MEL_TOL_DB), ("pool1", E.STAGE_POOL1, ACT_TOL), ("pool2", E.STAGE_POOL2, ACT_TOL),
+          ("conv3", E.STAGE_CONV3, ACT_TOL), ("pool3", E.STAGE_POOL3, ACT_TOL), ("conv5", E.STAGE_CONV5, ACT_TOL),
+          ("cnn_feat", E.STAGE_CNN_FEAT, ACT_TOL), ("td_out", E.STAGE_TD_OUT, ACT_TOL)]
+
+
+@pytest.mark.parametrize("ckpt,clips", [
+    ("nisqa.tar", [(1, 3.0, 48000), (2, 1.37, 48000), (3, 2.0, 16000), (4, 2.5, 44100), (5, 0.1875, 8000),
+                   (6, 1.0, 22050), (21, 0.5, 96000)]),
+    ("nisqa_mos_only.tar", [(8, 2.2, 48000), (9, 1.0, 32000)]),
+    ("nisqa_tts.tar", [(10, 2.0, 16000), (11, 1.3, 48000), (12, 0.9, 22050)]),
+])
+def test_every_stage_matches_oracle(engines, ckpt, clips):
+    eng, args, sd = engines[ckpt]
+    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
+    srs = [c[2] for c in clips]
+    scores, nseg, status = eng.predict_pcm(pcm, srs)
+    assert np.all(status == E.CLIP_OK)
+    dumps = {name: eng.stage_dump(st) for name, st, _ in STAGES}
+    off = {name: 0 for name, _, _ in STAGES}
+    for i, (p, sr) in enumerate(zip(pcm, srs)):
+        taps = {}
+        ref, ns, st = O.predict_pcm(args, sd, _f32(p), sr, taps)
+        assert st == O.STATUS_OK and int(nseg[i]) == ns            # bit-exact segment count
+        for name, _, tol in STAGES:
+            r = np.asarray(taps[name].numpy() if hasattr(taps[name], "numpy") else taps[name], dtype=np.float32).reshape(-1)
+            g = dumps[name][off[name]:off[name] + r.size]
+            off[name] += r.size
+            assert g.size == r.size
+            assert np.abs(g - r).max() <= tol, (ckpt, i, name, float(np.abs(g - r).max()))
+        assert np.abs(scores[i] - ref).max() <= SCORE_TOL
+    for name, _, _ in STAGES:
+        assert off[name] == dumps[name].size                        # no extra rows anywhere
+
+
+@pytest.mark.parametrize("name,ckpt", [("nisqa_48k_3s", "nisqa.tar"), ("nisqa_mixed", "nisqa.tar"),
+                                       ("nisqa_48k_10s", "nisqa.tar"), ("mos_only_48k", "nisqa_mos_only.tar"),
+                                       ("tts_16k", "nisqa_tts.tar")])
+def test_scores_match_reference_goldens(engines, name, ckpt):
+    """tests/golden/*.npz hold the outputs of the unmodified reference (oracle/make_golden.py)."""
+    eng, _, _ = engines[ckpt]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    pcm = [synth.synth_speech_pcm16(int(s), float(sec), int(sr)) for s, sec, sr in zip(g["seeds"], g["seconds"], g["sr"])]
+    scores, nseg, status = eng.predict_pcm(pcm, [int(x) for x in g["sr"]])
+    assert np.all(status == 0)
+    np.testing.assert_array_equal(nseg, g["n_segments"].astype(np.int32))
+    assert np.abs(scores - g["scores"]).max() <= SCORE_TOL
+
+
+def test_filterbank_matches_oracle(engines):
+    from oracle import librosa_compat as lb
+    for ck, fmax in (("nisqa.tar", 20000), ("nisqa_tts.tar", 8000)):
+        eng = engines[ck][0]
+        for sr in (48000, 44100, 16000, 8000):
+            ref = lb.mel(sr, 4096, n_mels=48, fmin=0.0, fmax=fmax, htk=False, norm="slaney")
+            np.testing.assert_allclose(eng.mel_filterbank(sr), ref, rtol=0, atol=1e-7)
+
+
+def test_edge_inputs(engines):
+    eng, args, sd = engines["nisqa.tar"]
+    sr = 48000
+    silence = np.zeros(48000, np.int16)                            # every band at the -80 dB floor
+    full = (np.sign(np.sin(np.arange(96000) * 0.05)) * 32767).astype(np.int16)   # full-scale square
+    shortest = synth.synth_speech_pcm16(31, 14 * 480 / sr, sr)     # exactly 15 frames -> 1 segment
+    too_short = shortest[:-1]                                       # 14 frames
+    f32clip = synth.synth_speech_f32(32, 1.0, sr)
+    scores, nseg, status = eng.predict_pcm([_f32(silence), _f32(full), _f32(shortest), _f32(too_short), f32clip], [sr] * 5)
+    assert status.tolist() == [0, 0, 0, E.CLIP_TOO_SHORT, 0]
+    assert nseg.tolist()[:3] == [22, 47, 1] and nseg[3] == 0
+    assert np.all(np.isnan(scores[3]))
+    for i, y in ((0, _f32(silence)), (1, _f32(full)), (2, _f32(shortest)), (4, f32clip)):
+        ref, ns, st = O.predict_pcm(args, sd, y, sr)
+        assert ns == nseg[i] and np.abs(scores[i] - ref).max() <= SCORE_TOL, i
+    mel = eng.stage_dump(E.STAGE_MEL_DB)
+    assert np.all(mel[:48 * 101] == -80.0)                          # digital silence: floor everywhere
+
+
+def test_max_length_and_too_long(engines):
+    eng, args, sd = engines["nisqa.tar"]
+    sr = 16000                                                      # 52 s at 16 kHz keeps the oracle quick
+    ok = synth.synth_speech_pcm16(41, 52.0, sr)
+    long_ = synth.synth_speech_pcm16(42, 52.2, sr)
+    scores, nseg, status = eng.predict_pcm([ok, long_], [sr, sr])
+    assert status.tolist() == [0, E.CLIP_TOO_LONG] and nseg.tolist() == [1297, 1302]
+    ref, ns, st = O.predict_pcm(args, sd, _f32(ok), sr)
+    assert ns == 1297 and np.abs(scores[0] - ref).max() <= SCORE_TOL
+    assert np.all(np.isnan(scores[1]))
+
+
+def test_ragged_batch_config3(engines):
+    """configs[2]: mixed 2-30 s clips in one call (ragged path, no padding anywhere)."""
+    eng, args, sd = engines["nisqa.tar"]
+    durs = synth.ragged_durations(24, 2.0, 30.0, seed=7)
+    pcm = [synth.synth_speech_pcm16(200 + i, float(d), 48000) for i, d in enumerate(durs)]
+    scores, nseg, status = eng.predict_pcm(pcm, [48000] * len(pcm))
+    assert np.all(status == 0)
+    for i in (0, 5, 11, 17, 23, int(np.argmax(durs)), int(np.argmin(durs))):
+        ref, ns, st = O.predict_pcm(args, sd, _f32(pcm[i]), 48000)
+        assert ns == nseg[i] and np.abs(scores[i] - ref).max() <= SCORE_TOL, i
+
+
+def test_tts_config4_full_length(engines):
+    """configs[3]: nisqa_tts.tar on 10 s 16 kHz clips (987 segments, 987 serial LSTM steps)."""
+    eng, args, sd = engines["nisqa_tts.tar"]
+    pcm = [synth.synth_speech_pcm16(300 + i, 10.0, 16000) for i in range(3)]
+    scores, nseg, status = eng.predict_pcm(pcm, [16000] * 3)
+    assert nseg.tolist() == [987] * 3 and np.all(status == 0)
+    ref, ns, st = O.predict_pcm(args, sd, _f32(pcm[1]), 16000)
+    assert np.abs(scores[1] - ref).max() <= SCORE_TOL
+
+
+def test_full_size_properties_config2(engines):
+    """BASELINE configs[1] at full size (64 x 10 s x 48 kHz): size-independent properties.
+    Per-clip arithmetic does not depend on batch composition, position or pass splitting, so
+    these must hold BIT-EXACTLY; one clip is also checked against the reference golden."""
+    eng, args, sd = engines["nisqa.tar"]
+    base = [synth.synth_speech_pcm16(400 + i, 10.0, 48000) for i in range(8)]
+    rng = np.random.default_rng(0)
+    clips = [base[i % 8] if i < 8 else np.roll(base[i % 8], int(rng.integers(1, 400000))) for i in range(62)]
+    clips += [synth.synth_speech_pcm16(0, 10.0, 48000), base[3]]      # golden clip + a duplicate
+    srs = [48000] * 64
+    s1, n1, st1 = eng.predict_pcm(clips, srs)
+    assert np.all(st1 == 0) and np.all(n1 == 247)
+    g = np.load(os.path.join(GOLDEN, "nisqa_48k_10s.npz"))
+    assert np.abs(s1[62] - g["scores"][0]).max() <= SCORE_TOL           # vs the reference itself
+    np.testing.assert_array_equal(s1[63], s1[3])                        # duplicates -> identical rows
+    perm = rng.permutation(64)
+    s2, _, _ = eng.predict_pcm([clips[j] for j in perm], srs)
+    np.testing.assert_array_equal(s2, s1[perm])                         # permutation equivariance
+    s3, _, _ = eng.predict_pcm([clips[62]], [48000])
+    np.testing.assert_array_equal(s3[0], s1[62])                        # alone == inside the batch
+    # multi-pass engine (4000 segments per pass -> 4 passes) == single pass
+    cfg = E.config_from_args(args, max_chunk_segments=4000)
+    e2 = E.Engine(cfg, 0)
+    e2.load_state_dict(sd)
+    s4, n4, _ = e2.predict_pcm(clips, srs)
+    e2.close()
+    np.testing.assert_array_equal(s4, s1)
+    assert np.all(np.isfinite(s1)) and s1.min() > 0.0 and s1.max() < 6.0
+
+
+def test_device_resident_entry_point_equals_host_entry_point(engines):
+    import torch
+    eng, args, sd = engines["nisqa.tar"]
+    clips = [synth.synth_speech_pcm16(500 + i, 2.0 + 0.37 * i, 48000) for i in range(5)]
+    s_host, n_host, _ = eng.predict_pcm(clips, [48000] * 5)
+    offs, tot = [], 0
+    for c in clips:
+        offs.append(tot); tot += (len(c) + 15) // 16 * 16
+    buf = np.zeros(tot, np.int16)
+    for o, c in zip(offs, clips):
+        buf[o:o + len(c)] = c
+    d = torch.from_numpy(buf).cuda()
+    out = torch.empty((5, 5), dtype=torch.float32, device="cuda")
+    nseg, status = eng.predict_pcm_device(d.data_ptr(), offs, [len(c) for c in clips], [48000] * 5, E.FMT_S16, out.data_ptr(), sync=True)
+    np.testing.assert_array_equal(out.cpu().numpy(), s_host)
+    np.testing.assert_array_equal(nseg, n_host)
+    assert eng.kernel_launches() > 0
+
+
+def test_single_rank_nccl_gather(engines):
+    import torch
+    eng = engines["nisqa.tar"][0]
+    eng.nccl_init(1, 0, eng.nccl_unique_id())
+    loc = torch.arange(15, dtype=torch.float32, device="cuda").reshape(3, 5)
+    glob = torch.zeros((1, 3, 5), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    eng.gather_nccl(loc.data_ptr(), 3, glob.data_ptr())
+    np.testing.assert_array_equal(glob[0].cpu().numpy(), loc.cpu().numpy())
+
+
+# ------------------------------------------------------------------ the reference-facing surface
+@pytest.fixture(scope="module")
+def wav_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("wavs")
+    specs = [(601, 2.0, 48000), (602, 3.1, 16000), (603, 1.2, 44100), (604, 4.0, 48000)]
+    for seed, sec, sr in specs:
+        wav.write_wav_pcm16(str(d / ("c%d.wav" % seed)), synth.synth_speech_pcm16(seed, sec, sr), sr)
+    st = np.stack([synth.synth_speech_pcm16(605, 1.5, 48000), synth.synth_speech_pcm16(606, 1.5, 48000)], axis=1)
+    os.makedirs(str(d / "stereo"))
+    wav.write_wav_pcm16(str(d / "stereo" / "s.wav"), st, 48000)
+    wav.write_wav_f32(str(d / "stereo" / "f.wav"), synth.synth_speech_f32(607, 1.0, 32000), 32000)
+    pd.DataFrame({"deg": ["c%d.wav" % s for s, _, _ in specs], "con": [1, 1, 2, 2]}).to_csv(str(d / "files.csv"), index=False)
+    return d
+
+
+def _oracle_file(ckpt, path, ms_channel=None):
+    args, sd = O.load_checkpoint(os.path.join(WEIGHTS, ckpt))
+    return O.predict_file(args, sd, path, ms_channel)[0]
+
+
+def test_predict_dir_csv_file_modes(wav_dir, built_lib, capsys):
+    from nisqa_b200.NISQA_model import nisqaModel
+    import run_predict
+    out_dir = str(wav_dir / "out"); os.makedirs(out_dir, exist_ok=True)
+    a = run_predict.parse_args(["--mode", "predict_dir", "--pretrained_model", os.path.join(WEIGHTS, "nisqa.tar"),
+                                "--data_dir", str(wav_dir), "--bs", "3", "--num_workers", "2", "--output_dir", out_dir])
+    df = nisqaModel(a).predict()
+    assert list(df.columns) == ["deg", "mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred", "model"]
+    assert sorted(df["deg"]) == ["c601.wav", "c602.wav", "c603.wav", "c604.wav"] and set(df["model"]) == {"NISQAv2"}
+    assert df["mos_pred"].dtype == np.float32
+    csv = pd.read_csv(os.path.join(out_dir, "NISQA_results.csv"))
+    assert list(csv.columns) == list(df.columns)
+    for _, row in df.iterrows():                                        # join on 'deg' (glob order is arbitrary)
+        ref = _oracle_file("nisqa.tar", str(wav_dir / row["deg"]))
+        got = row[["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]].to_numpy(dtype=np.float64)
+        assert np.abs(got - ref).max() <= SCORE_TOL
+    assert "---> Predicting ..." in capsys.readouterr().out
+    # predict_csv with the mos-only checkpoint: float64 column, no 'model' column without output_dir
+    a = run_predict.parse_args(["--mode", "predict_csv", "--pretrained_model", os.path.join(WEIGHTS, "nisqa_mos_only.tar"),
+                                "--data_dir", str(wav_dir), "--csv_file", "files.csv", "--csv_deg", "deg", "--bs", "8"])
+    df = nisqaModel(a).predict()
+    assert list(df.columns) == ["deg", "con", "mos_pred"] and df["mos_pred"].dtype == np.float64
+    for _, row in df.iterrows():
+        assert abs(row["mos_pred"] - _oracle_file("nisqa_mos_only.tar", str(wav_dir / row["deg"]))[0]) <= SCORE_TOL
+    # predict_file with the TTS checkpoint
+    a = run_predict.parse_args(["--mode", "predict_file", "--pretrained_model", os.path.join(WEIGHTS, "nisqa_tts.tar"),
+                                "--deg", str(wav_dir / "c602.wav")])
+    df = nisqaModel(a).predict()
+    assert len(df) == 1 and abs(df["mos_pred"].iloc[0] - _oracle_file("nisqa_tts.tar", str(wav_dir / "c602.wav"))[0]) <= SCORE_TOL
+
+
+def test_stereo_channel_pick_and_float_wav(wav_dir, built_lib):
+    from nisqa_b200.NISQA_model import nisqaModel
+    base = {"mode": "predict_dir", "pretrained_model": os.path.join(WEIGHTS, "nisqa.tar"), "data_dir": str(wav_dir / "stereo"),
+            "output_dir": None, "tr_bs_val": 4, "tr_num_workers": 0}
+    for ch in (None, 0, 1):
+        df = nisqaModel(dict(base, ms_channel=ch)).predict()
+        for _, row in df.iterrows():
+            ref = _oracle_file("nisqa.tar", str(wav_dir / "stereo" / row["deg"]), ch)
+            got = row[["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]].to_numpy(dtype=np.float64)
+            assert np.abs(got - ref).max() <= SCORE_TOL, (ch, row["deg"])
+
+
+def test_reference_error_behaviour(tmp_path, built_lib):
+    from nisqa_b200.NISQA_model import nisqaModel
+    ck = os.path.join(WEIGHTS, "nisqa.tar")
+    base = {"pretrained_model": ck, "output_dir": None, "tr_bs_val": 2, "tr_num_workers": 0, "ms_channel": None}
+    wav.write_wav_pcm16(str(tmp_path / "short.wav"), synth.synth_speech_pcm16(1, 0.1, 48000), 48000)
+    with pytest.raises(ValueError, match="Sample too short"):
+        nisqaModel(dict(base, mode="predict_file", deg=str(tmp_path / "short.wav"))).predict()
+    wav.write_wav_pcm16(str(tmp_path / "long.wav"), np.zeros(8000 * 53, np.int16), 8000)
+    with pytest.raises(ValueError, match="Increase max window length ms_max_segments"):
+        nisqaModel(dict(base, mode="predict_file", deg=str(tmp_path / "long.wav"))).predict()
+    (tmp_path / "bad.wav").write_bytes(b"RIFFxxxxWAVEjunk")
+    with pytest.raises(ValueError, match="Could not load file"):
+        nisqaModel(dict(base, mode="predict_file", deg=str(tmp_path / "bad.wav"))).predict()
+    empty = tmp_path / "empty"; empty.mkdir()
+    with pytest.raises(ValueError, match="No wav files found"):
+        nisqaModel(dict(base, mode="predict_dir", data_dir=str(empty)))
+    with pytest.raises(NotImplementedError):
+        nisqaModel(dict(base, mode="predict_nothing"))

@@ -1,0 +1,137 @@
+"""Host-side logic of the product path that needs no GPU: wav ingest vs the oracle's reader,
+CLI argument validation, rank sharding and the world_size-2 gloo exchange."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from nisqa_b200 import dist as nb_dist
+from nisqa_b200 import wav
+from oracle import librosa_compat as lb
+
+
+def _write_pcm(path, data_bytes, tag, ch, sr, bits, extensible=False):
+    ba = ch * bits // 8
+    if extensible:
+        fmt = struct.pack("<HHIIHHHHIH14s", 0xFFFE, ch, sr, sr * ba, ba, bits, 22, bits, 0, tag, b"\x00" * 14)
+    else:
+        fmt = struct.pack("<HHIIHH", tag, ch, sr, sr * ba, ba, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" \
+        + b"data" + struct.pack("<I", len(data_bytes)) + data_bytes
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def _as_float(x):
+    return x.astype(np.float32) / np.float32(32768.0) if x.dtype == np.int16 else x
+
+
+@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16"])
+def test_wav_reader_matches_oracle_loader(tmp_path, kind):
+    rng = np.random.default_rng(1)
+    p = str(tmp_path / (kind + ".wav"))
+    n = 1000
+    if kind in ("pcm16", "ext16"):
+        d = rng.integers(-32768, 32767, n).astype("<i2")
+        _write_pcm(p, d.tobytes(), 1, 1, 16000, 16, extensible=(kind == "ext16"))
+    elif kind == "pcm16_stereo":
+        d = rng.integers(-32768, 32767, (n, 2)).astype("<i2")
+        _write_pcm(p, d.tobytes(), 1, 2, 44100, 16)
+    elif kind == "pcm24":
+        v = rng.integers(-(1 << 23), (1 << 23) - 1, n)
+        b = bytearray()
+        for x in v:
+            b += int(x & 0xFFFFFF).to_bytes(3, "little")
+        _write_pcm(p, bytes(b), 1, 1, 48000, 24)
+    elif kind == "pcm32":
+        d = rng.integers(-(1 << 31), (1 << 31) - 1, n).astype("<i4")
+        _write_pcm(p, d.tobytes(), 1, 1, 48000, 32)
+    elif kind == "f32":
+        _write_pcm(p, rng.standard_normal((n, 2)).astype("<f4").tobytes(), 3, 2, 22050, 32)
+    elif kind == "f64":
+        _write_pcm(p, rng.standard_normal(n).astype("<f8").tobytes(), 3, 1, 8000, 64)
+    else:
+        _write_pcm(p, rng.integers(0, 255, n).astype(np.uint8).tobytes(), 1, 1, 8000, 8)
+    y_ref, sr_ref = lb.load(p, sr=None)
+    y, sr = wav.read_wav(p)
+    assert sr == sr_ref and y.ndim == 1
+    np.testing.assert_array_equal(_as_float(y), y_ref)
+    if kind in ("pcm16_stereo", "f32"):
+        for ch in (0, 1):
+            y2, _ = lb.load(p, sr=None, mono=False)
+            yc, _ = wav.read_wav(p, ms_channel=ch)
+            np.testing.assert_array_equal(_as_float(yc), y2[ch])
+    if kind == "pcm16":
+        assert y.dtype == np.int16           # mono PCM16 stays int16: the /32768 happens on the GPU
+
+
+def test_unreadable_file_raises_value_error(tmp_path):
+    p = tmp_path / "broken.wav"
+    p.write_bytes(b"not a wav file at all")
+    with pytest.raises(ValueError, match="Could not load file"):
+        wav.read_wav(str(p))
+    with pytest.raises(ValueError, match="Could not load file"):
+        wav.read_wav(str(tmp_path / "missing.wav"))
+
+
+def test_cli_argument_validation(monkeypatch):
+    import importlib
+    sys.path.insert(0, ROOT)
+    rp = importlib.import_module("run_predict")
+    a = rp.parse_args(["--mode", "predict_dir", "--pretrained_model", "w.tar", "--data_dir", "d", "--bs", "64", "--num_workers", "3"])
+    assert a["tr_bs_val"] == 64 and a["tr_num_workers"] == 3 and a["output_dir"] is None
+    a = rp.parse_args(["--mode", "predict_csv", "--pretrained_model", "w.tar", "--csv_file", "f.csv", "--csv_deg", "deg"])
+    assert a["data_dir"] == ""
+    with pytest.raises(ValueError):
+        rp.parse_args(["--mode", "predict_file", "--pretrained_model", "w.tar"])
+    with pytest.raises(ValueError):
+        rp.parse_args(["--mode", "predict_dir", "--pretrained_model", "w.tar"])
+    with pytest.raises(ValueError):
+        rp.parse_args(["--mode", "predict_csv", "--pretrained_model", "w.tar", "--csv_file", "f.csv"])
+    with pytest.raises(NotImplementedError):
+        rp.parse_args(["--mode", "train", "--pretrained_model", "w.tar"])
+
+
+def test_shard_rows_partition_and_balance():
+    rng = np.random.default_rng(0)
+    w = rng.uniform(2, 30, size=513)
+    for world in (1, 2, 4, 8):
+        shards = nb_dist.shard_rows(w, world)
+        allrows = np.sort(np.concatenate(shards))
+        np.testing.assert_array_equal(allrows, np.arange(513))
+        loads = np.array([w[s].sum() for s in shards])
+        assert loads.max() - loads.min() <= w.max() + 1e-9
+        assert all(np.all(np.diff(s) > 0) for s in shards if len(s) > 1)
+    g = np.zeros((2, 3, 5), np.float32)
+    g[0, :3] = 1.0; g[1, :2] = 2.0
+    out = nb_dist.scatter_rows(g, [np.array([0, 2, 4]), np.array([1, 3])], 5)
+    np.testing.assert_array_equal(out[:, 0], [1, 2, 1, 2, 1])
+
+
+def test_two_rank_gloo_exchange(tmp_path):
+    """world_size-2 run of the N>1 host path on CPU (gloo): shard, 'score', all-gather."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch.distributed as dist\n"
+        "from nisqa_b200 import dist as D\n"
+        "rank, world, _ = D.init_process_group(backend='gloo')\n"
+        "w = np.random.default_rng(3).uniform(1, 9, size=37)\n"
+        "shards = D.shard_rows(w, world)\n"
+        "local = np.stack([np.full(5, float(i), np.float32) + np.arange(5, dtype=np.float32) / 10 for i in shards[rank]])\n"
+        "full = D.all_gather_scores(local, shards, 37)\n"
+        "ref = np.arange(37, dtype=np.float32)[:, None] + np.arange(5, dtype=np.float32)[None, :] / 10\n"
+        "assert full.shape == (37, 5) and np.array_equal(full, ref), full\n"
+        "dist.barrier(); dist.destroy_process_group()\n"
+        "open(os.path.join(%r, 'ok%%d' %% rank), 'w').write('ok')\n" % (ROOT, str(tmp_path)))
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
