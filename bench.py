@@ -114,6 +114,9 @@ class CpuPool(object):
     def __init__(self, procs):
         self.procs = procs
         self.pool = None
+        # one compute thread per worker process: BLAS / OpenMP pools must not oversubscribe
+        for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+            os.environ[k] = "1"
         if procs > 1:
             import torch.multiprocessing as mp
             self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_worker_init)
@@ -141,9 +144,21 @@ class CpuPool(object):
 _CPU = {}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _cpu_worker_init():
     import torch
     torch.set_num_threads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["tpl"] = threadpool_limits(limits=1)
+    except Exception:
+        pass
     from oracle import nisqa_oracle as O
     _CPU["O"] = O
     _CPU["ck"] = O.load_checkpoint(CKPT)
@@ -162,7 +177,7 @@ def _cpu_worker(seed):
 def run_reference(a, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     procs = max(1, cores)
     per_step = max(procs, 8)
     pool = CpuPool(procs)
@@ -272,8 +287,11 @@ def run_ours(a, rank, world, local):
         ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
         parity = float(np.abs(got - ref).max())
 
-    for i in range(a.warmup):
-        step_dev(i)
+    t_w, i_w = time.perf_counter(), 0
+    while i_w < a.warmup or time.perf_counter() - t_w < a.warmup_seconds:   # clocks need ~1 s to ramp
+        step_dev(i_w); i_w += 1
+        if i_w % 8 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -336,8 +354,8 @@ def run_ours(a, rank, world, local):
     cnn_ms = sum(kernel_ms[k] for k in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"))
     # ---- CPU baseline: oracle port, one process, all torch threads, bounded sample
     cpu_base = None
-    if world == 1:
-        cores = os.cpu_count() or 1
+    if world == 1 and not a.skip_cpu:
+        cores = host_cores()
         pool = CpuPool(cores)
         _, dt1, _ = pool.run(cores)
         n_cpu = int(min(max(cores, cores * 12.0 / max(dt1, 1e-3)), 64 * cores))
@@ -370,9 +388,12 @@ def run_ours(a, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--warmup-seconds", dest="warmup_seconds", type=float, default=1.5,
+                    help="minimum duration of the untimed warm-up (in addition to --warmup steps)")
+    ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 0)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
