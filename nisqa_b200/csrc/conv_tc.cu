@@ -1,0 +1,318 @@
+// conv_tc.cu - conv3 / conv4 of the AdaptCNN / StandardCNN (reference nisqa/NISQA_lib.py:696-700,
+// 820-825) as an implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), with
+// error-compensated 3xTF32 so that the result stays within fp32 rounding noise of the reference
+// (plain TF32 moves MOS by 2e-3):
+//      a = a_hi + a_lo,  b = b_hi + b_lo   (both parts exactly representable in tf32)
+//      a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped a_lo*b_lo ~ 2^-22 |a b|)
+//
+// GEMM view:  D[pos, co] = sum_{tap, ci} X[pos + off(tap), ci] * W[tap][co][ci]
+//   M = flattened padded positions of G segments (row pitch W+1: one shared zero column per
+//       row, one shared zero row between segments), N = 64 output channels, K = 9 * CIN.
+//   A (activations) is staged ONCE per CTA in shared memory in the canonical no-swizzle K-major
+//   UMMA layout [ci/4][row][4 floats] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
+//   LBO = plane).  The 9 taps are the SAME tile addressed with a row-shifted start address, so
+//   im2col is never materialised.  B (weights, pre-split on the host) streams tap by tap with
+//   cp.async.bulk + mbarrier into a 2-stage ring.  Accumulators: 2 M-tiles x 64 fp32 columns
+//   of TMEM.  One elected thread issues the MMAs; 4 warps run the epilogue (tcgen05.ld ->
+//   bias + ReLU (+ adaptive / 2x2 max-pool through a shared-memory staging tile) -> channels-last
+//   global store).
+#include "common.cuh"
+
+namespace nisqa {
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, no swizzle: ((8,m),(4,2)):((16B,SBO),(4B,LBO)); version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------ configuration
+enum { TC_POOL_NONE = 0, TC_POOL_ADAPT = 1, TC_POOL_2X2 = 2 };
+
+template <int W_, int CIN_, int POOL_>
+struct TcCfg {
+  static constexpr int H = 12, W = W_, CIN = CIN_, COUT = 64, POOL = POOL_;
+  static constexpr int P = W + 1;                 // row pitch: W interior columns + 1 shared zero column
+  static constexpr int BLK = (H + 1) * P;         // rows per segment: H interior rows + 1 shared zero row
+  static constexpr int G = 256 / BLK;             // segments per CTA (2 M-tiles of 128 rows)
+  static constexpr int HALO = P + 1;              // |row offset| of the farthest tap
+  static constexpr int AROWS = ((256 + 2 * HALO) | 1);    // odd: conflict-free staging stores
+  static constexpr int NCH = CIN / 4;             // 16-byte K chunks
+  static constexpr int A_BYTES = NCH * AROWS * 16;        // per hi / lo
+  static constexpr int B_HALF = NCH * COUT * 16;          // per hi / lo
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int NSTAGE = 2;
+  static constexpr int POW = (POOL == TC_POOL_ADAPT) ? 3 : (W / 2);    // pooled width (5->3 adaptive, 4->2)
+  static constexpr int STG_STRIDE = 68;           // floats per staged row (64 + 4: conflict-free float4)
+  static constexpr int OFF_A_HI = 0;
+  static constexpr int OFF_A_LO = A_BYTES;
+  static constexpr int OFF_B = 2 * A_BYTES;
+  static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static_assert(G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES, "staging tile must fit in the A region");
+  static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0, "alignment");
+};
+
+constexpr uint32_t kIdescTf32M128N64 =
+    (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=tf32, K-major
+
+template <class C>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
+               const float* __restrict__ wtc /*[9][hi|lo][CIN/4][64][4]*/,
+               const float* __restrict__ bias, float* __restrict__ out, int n_seg) {
+  constexpr int H = C::H, W = C::W, CIN = C::CIN, P = C::P, BLK = C::BLK, G = C::G;
+  constexpr int HALO = C::HALO, AROWS = C::AROWS, NCH = C::NCH;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t a_hi = sbase + C::OFF_A_HI, a_lo = sbase + C::OFF_A_LO, b_base = sbase + C::OFF_B;
+  const uint32_t bar_full = sbase + C::OFF_BAR;          // [2]
+  const uint32_t bar_empty = bar_full + 16;              // [2]
+  const uint32_t bar_acc = bar_full + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seg0 = blockIdx.x * G;
+
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+  if (tid == 32) {
+    mbar_init(bar_full, 1); mbar_init(bar_full + 8, 1);
+    mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- weight producer: first two taps in flight while the activation tile is staged
+  if (tid == 160) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      mbar_expect_tx(bar_full + 8 * t, C::B_STAGE);
+      bulk_g2s(b_base + t * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 4), C::B_STAGE, bar_full + 8 * t);
+    }
+  }
+
+  // ---- stage A: channels-last global -> [ci/4][row][4] hi / lo, zero halo
+  {
+    float4* ah = reinterpret_cast<float4*>(smem + C::OFF_A_HI);
+    float4* al = reinterpret_cast<float4*>(smem + C::OFF_A_LO);
+    for (int it = tid; it < AROWS * NCH; it += 192) {
+      const int c4 = it % NCH, b = it / NCH;
+      const int r = b - HALO;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r >= 0 && r < G * BLK) {
+        const int s = r / BLK, q = r - s * BLK;
+        const int hh = q / P, ww = q - hh * P;
+        if (hh >= 1 && ww >= 1 && seg0 + s < n_seg)
+          v = __ldg(reinterpret_cast<const float4*>(
+              in + ((size_t)(seg0 + s) * (H * W) + (hh - 1) * W + (ww - 1)) * CIN + c4 * 4));
+      }
+      float4 hi, lo;
+      hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+      lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+      ah[c4 * AROWS + b] = hi;
+      al[c4 * AROWS + b] = lo;
+    }
+  }
+  fence_proxy_async();          // generic-proxy stores -> visible to the tensor-core (async) proxy
+  __syncthreads();
+
+  if (warp == 5) {
+    // ===== weight producer (one lane) =====
+    if (lane == 0) {
+      for (int t = 2; t < 9; ++t) {
+        const int s = t & 1;
+        mbar_wait(bar_empty + 8 * s, ((t >> 1) - 1) & 1);     // MMAs of tap t-2 have drained the stage
+        mbar_expect_tx(bar_full + 8 * s, C::B_STAGE);
+        bulk_g2s(b_base + s * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 4), C::B_STAGE, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      tc_fence_after();
+      for (int t = 0; t < 9; ++t) {
+        const int s = t & 1;
+        mbar_wait(bar_full + 8 * s, (t >> 1) & 1);
+        tc_fence_after();
+        const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
+        const uint32_t bh = b_base + s * C::B_STAGE, bl = bh + C::B_HALF;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff);
+          const uint32_t d = tmem + mt * 64;
+#pragma unroll
+          for (int ks = 0; ks < CIN / 8; ++ks) {
+            const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
+            const uint64_t dah = make_desc(a_hi + aoff, AROWS * 16, 128);
+            const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
+            const uint32_t boff = (uint32_t)(2 * ks) * (64 * 16);
+            const uint64_t dbh = make_desc(bh + boff, 64 * 16, 128);
+            const uint64_t dbl = make_desc(bl + boff, 64 * 16, 128);
+            umma_tf32(d, dah, dbh, kIdescTf32M128N64, (t | ks) != 0);
+            umma_tf32(d, dah, dbl, kIdescTf32M128N64, 1);
+            umma_tf32(d, dal, dbh, kIdescTf32M128N64, 1);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
+      }
+      umma_commit(bar_acc);                      // all accumulators final
+    }
+  } else {
+    // ===== epilogue: warps 0..3 <-> TMEM lanes 32w..32w+31 =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem);          // reuses the A region (all MMAs retired)
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 128 + warp * 32 + lane;
+      const int s = r / BLK, q = r - s * BLK;
+      const int hh = q / P, ww = q - hh * P;
+      const bool valid = (s < G) && hh >= 1 && ww >= 1 && (seg0 + s < n_seg);
+      const int h = hh - 1, w = ww - 1;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * 64 + half * 32, v);
+        if (valid) {
+          float* dst = (C::POOL == TC_POOL_NONE)
+                           ? out + ((size_t)(seg0 + s) * (H * W) + h * W + w) * 64 + half * 32
+                           : stg + ((s * H + h) * W + w) * C::STG_STRIDE + half * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = fmaxf(v[4 * j + 0] + __ldg(bias + half * 32 + 4 * j + 0), 0.f);
+            o.y = fmaxf(v[4 * j + 1] + __ldg(bias + half * 32 + 4 * j + 1), 0.f);
+            o.z = fmaxf(v[4 * j + 2] + __ldg(bias + half * 32 + 4 * j + 2), 0.f);
+            o.w = fmaxf(v[4 * j + 3] + __ldg(bias + half * 32 + 4 * j + 3), 0.f);
+            reinterpret_cast<float4*>(dst)[j] = o;
+          }
+        }
+      }
+    }
+    if (C::POOL != TC_POOL_NONE) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+      constexpr int POW = C::POW, HO = H / 2;
+      for (int it = tid; it < G * HO * POW * 16; it += 128) {
+        const int c4 = it & 15;
+        int rest = it >> 4;
+        const int pw = rest % POW; rest /= POW;
+        const int ph = rest % HO;
+        const int s = rest / HO;
+        if (seg0 + s >= n_seg) continue;
+        int x0, x1;
+        if (C::POOL == TC_POOL_ADAPT) { x0 = (pw * W) / POW; x1 = ((pw + 1) * W + POW - 1) / POW; }
+        else { x0 = 2 * pw; x1 = 2 * pw + 2; }
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);       // post-ReLU values are >= 0
+        for (int hy = 2 * ph; hy < 2 * ph + 2; ++hy)
+          for (int x = x0; x < x1; ++x) {
+            const float4 t = *reinterpret_cast<const float4*>(stg + ((s * H + hy) * W + x) * C::STG_STRIDE + c4 * 4);
+            m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
+          }
+        *reinterpret_cast<float4*>(out + ((size_t)(seg0 + s) * (HO * POW) + ph * POW + pw) * 64 + c4 * 4) = m;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// layer = 3 | 4;  std_mode selects the StandardCNN geometry (12x4, MaxPool2d(2))
+using TcConv3A = TcCfg<5, 32, TC_POOL_NONE>;
+using TcConv4A = TcCfg<5, 64, TC_POOL_ADAPT>;
+using TcConv3S = TcCfg<4, 32, TC_POOL_NONE>;
+using TcConv4S = TcCfg<4, 64, TC_POOL_2X2>;
+
+template <class C>
+static void launch_tc(cudaStream_t st, const float* in, const float* wtc, const float* b, float* out, int n_seg) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    configured = true;
+  }
+  conv_tc_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in, wtc, b, out, n_seg);
+}
+
+void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, const float* wtc,
+                    const float* b, float* out, int n_seg) {
+  if (!std_mode) {
+    if (layer == 3) launch_tc<TcConv3A>(st, in, wtc, b, out, n_seg);
+    else launch_tc<TcConv4A>(st, in, wtc, b, out, n_seg);
+  } else {
+    if (layer == 3) launch_tc<TcConv3S>(st, in, wtc, b, out, n_seg);
+    else launch_tc<TcConv4S>(st, in, wtc, b, out, n_seg);
+  }
+}
+
+}  // namespace nisqa

@@ -31,6 +31,8 @@ void launch_conv1(cudaStream_t, int, const float*, const int*, const float*, con
                   const float*, float*, int);
 void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
 void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
+// conv_tc.cu
+void launch_conv_tc(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
 // td.cu
 struct SaLayerParams {
   const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
@@ -110,6 +112,7 @@ struct nisqa_engine {
   int64_t launches = 0;
   bool weights_loaded = false;
   bool profiling = false;
+  bool conv_tc = true;     // conv3/conv4 on tcgen05 (3xTF32); false = fp32 FFMA kernels
   std::vector<TimerSlot> timers;
 
   // weights arena (device) + offsets
@@ -339,6 +342,13 @@ bool pack_conv(Packer& P, int idx, int cin, int cout) {
   return true;
 }
 
+float tf32_rna_host(float x) {      // round-to-nearest (ties away) to 10 mantissa bits
+  uint32_t u; memcpy(&u, &x, 4);
+  u += 0x1000u; u &= 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
 // dst[k][j] = src[j][perm(k)] for a [n_out][n_in] PyTorch Linear weight
 void pack_linear_T(Packer& P, size_t off, const TensorView* w, int n_out, int n_in, float scale = 1.f) {
   for (int k = 0; k < n_in; ++k)
@@ -357,6 +367,24 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
   for (int i = 1; i <= 6; ++i)
     if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+  // conv3 / conv4 for the tcgen05 path: [tap][hi|lo][ci/4][co][4], both parts exact tf32 values
+  for (int i = 3; i <= 4; ++i) {
+    char k1[32], k2[32];
+    snprintf(k1, sizeof k1, "conv%d.w", i); snprintf(k2, sizeof k2, "conv%d.wtc", i);
+    const int ci_n = cin[i], nch = ci_n / 4;
+    const size_t src = e->woff.at(k1);
+    const size_t dst = P.alloc(k2, (size_t)9 * 2 * ci_n * 64);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < ci_n; ++ci)
+        for (int co = 0; co < 64; ++co) {
+          const float w = P.arena[src + ((size_t)ci * 9 + tap) * 64 + co];
+          const float hi = tf32_rna_host(w), lo = tf32_rna_host(w - hi);
+          const size_t base = dst + (size_t)tap * 2 * ci_n * 64;
+          const size_t off = ((size_t)(ci / 4) * 64 + co) * 4 + (ci & 3);
+          P.arena[base + off] = hi;
+          P.arena[base + (size_t)nch * 64 * 4 + off] = lo;
+        }
+  }
 
   if (e->cfg.arch == NISQA_ARCH_ADAPT_SA_ATTFF) {
     const std::string td = "time_dependency.model.";
@@ -588,9 +616,11 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "conv2");
       launch_conv_layer(st, std_mode, 2, e->act1.as<float>(), W(e, "conv2.w"), W(e, "conv2.b"), e->act2.as<float>(), n_seg); }
     { Scope s(e, "conv3");
-      launch_conv_layer(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.w"), W(e, "conv3.b"), e->act3.as<float>(), n_seg); }
+      if (e->conv_tc) launch_conv_tc(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.wtc"), W(e, "conv3.b"), e->act3.as<float>(), n_seg);
+      else launch_conv_layer(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.w"), W(e, "conv3.b"), e->act3.as<float>(), n_seg); }
     { Scope s(e, "conv4");
-      launch_conv_layer(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.w"), W(e, "conv4.b"), e->act4.as<float>(), n_seg); }
+      if (e->conv_tc) launch_conv_tc(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.wtc"), W(e, "conv4.b"), e->act4.as<float>(), n_seg);
+      else launch_conv_layer(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.w"), W(e, "conv4.b"), e->act4.as<float>(), n_seg); }
     { Scope s(e, "conv5");
       launch_conv_layer(st, std_mode, 5, e->act4.as<float>(), W(e, "conv5.w"), W(e, "conv5.b"), e->act5.as<float>(), n_seg); }
     { Scope s(e, "conv6");
@@ -849,6 +879,12 @@ int nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64
 
 int64_t nisqa_kernel_launches(const nisqa_engine* e) { return e ? e->launches : 0; }
 void* nisqa_stream(const nisqa_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
+  if (!e || !name) return NISQA_ERR_INVALID;
+  if (strcmp(name, "conv_tc") == 0) { e->conv_tc = value != 0; return 0; }
+  return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
+}
 
 int nisqa_set_profiling(nisqa_engine* e, int on) {
   if (!e) return NISQA_ERR_INVALID;

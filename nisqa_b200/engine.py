@@ -25,7 +25,7 @@ EXPORTS = [
     "nisqa_create", "nisqa_destroy", "nisqa_last_error", "nisqa_load_weights",
     "nisqa_predict_pcm", "nisqa_predict_pcm_device", "nisqa_stage_dump", "nisqa_segment_counts",
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
-    "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms",
+    "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library(path=None):
     lib.nisqa_stream.restype = vp
     lib.nisqa_set_profiling.argtypes = [vp, C.c_int]
     lib.nisqa_set_profiling.restype = C.c_int
+    lib.nisqa_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.nisqa_set_option.restype = C.c_int
     lib.nisqa_group_ms.argtypes = [vp, C.c_char_p]
     lib.nisqa_group_ms.restype = C.c_double
     if path is None:
@@ -294,6 +296,9 @@ class Engine(object):
 
     def set_profiling(self, on):
         self._check(self.lib.nisqa_set_profiling(self.h, 1 if on else 0), "nisqa_set_profiling")
+
+    def set_option(self, name, value):
+        self._check(self.lib.nisqa_set_option(self.h, name.encode(), int(value)), "nisqa_set_option")
 
     def group_ms(self, group):
         return float(self.lib.nisqa_group_ms(self.h, group.encode()))
