@@ -1,21 +1,27 @@
 // conv_tc.cu - conv3 / conv4 of the AdaptCNN / StandardCNN (reference nisqa/NISQA_lib.py:696-700,
-// 820-825) as an implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), with
-// error-compensated 3xTF32 so that the result stays within fp32 rounding noise of the reference
-// (plain TF32 moves MOS by 2e-3):
-//      a = a_hi + a_lo,  b = b_hi + b_lo   (both parts exactly representable in tf32)
+// 820-825) as an implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), with an
+// error-compensated two-term FP16 split so that the result stays within fp32 rounding noise of
+// the reference (plain TF32 / BF16 operands move MOS by 2e-3 / 1.7e-2):
+//      a = a_hi + a_lo,  b = b_hi + b_lo      (fp16 parts: 11 + 11 significant bits)
 //      a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped a_lo*b_lo ~ 2^-22 |a b|)
+// Products are exact in the tensor core and accumulate in fp32 (TMEM).  The weights are
+// pre-scaled by 2^S on the host (S chosen per layer so that max|w| 2^S <= 1024) to keep b_lo
+// out of the fp16 subnormal range; the epilogue multiplies by 2^-S (exact).  Compared with
+// 3xTF32 this halves shared memory, weight traffic and MMA time (kind::f16 has K = 16).
 //
 // GEMM view:  D[pos, co] = sum_{tap, ci} X[pos + off(tap), ci] * W[tap][co][ci]
 //   M = flattened padded positions of G segments (row pitch W+1: one shared zero column per
 //       row, one shared zero row between segments), N = 64 output channels, K = 9 * CIN.
 //   A (activations) is staged ONCE per CTA in shared memory in the canonical no-swizzle K-major
-//   UMMA layout [ci/4][row][4 floats] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
+//   UMMA layout [ci/8][row][8 halves] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
 //   LBO = plane).  The 9 taps are the SAME tile addressed with a row-shifted start address, so
 //   im2col is never materialised.  B (weights, pre-split on the host) streams tap by tap with
 //   cp.async.bulk + mbarrier into a 2-stage ring.  Accumulators: 2 M-tiles x 64 fp32 columns
 //   of TMEM.  One elected thread issues the MMAs; 4 warps run the epilogue (tcgen05.ld ->
 //   bias + ReLU (+ adaptive / 2x2 max-pool through a shared-memory staging tile) -> channels-last
 //   global store).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace nisqa {
@@ -55,12 +61,12 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 inputs, fp32 accumulate), one thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -82,13 +88,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// two-term fp16 split of 8 consecutive channels -> two 16-byte core-matrix rows
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x0 = fminf(x[2 * i], 60000.f), x1 = fminf(x[2 * i + 1], 60000.f);   // post-ReLU inputs (>= 0)
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// K-major, no swizzle: ((8,m),(4,2)):((16B,SBO),(4B,LBO)); version 1 (sm_100)
+// K-major, no swizzle: ((8,m),(8,2)):((16B,SBO),(2B,LBO)); version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
@@ -97,7 +113,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------ configuration
 enum { TC_POOL_NONE = 0, TC_POOL_ADAPT = 1, TC_POOL_2X2 = 2 };
 
-template <int W_, int CIN_, int POOL_>
+template <int W_, int CIN_, int POOL_, int NSTAGE_>
 struct TcCfg {
   static constexpr int H = 12, W = W_, CIN = CIN_, COUT = 64, POOL = POOL_;
   static constexpr int P = W + 1;                 // row pitch: W interior columns + 1 shared zero column
@@ -105,46 +121,48 @@ struct TcCfg {
   static constexpr int G = 256 / BLK;             // segments per CTA (2 M-tiles of 128 rows)
   static constexpr int HALO = P + 1;              // |row offset| of the farthest tap
   static constexpr int AROWS = ((256 + 2 * HALO) | 1);    // odd: conflict-free staging stores
-  static constexpr int NCH = CIN / 4;             // 16-byte K chunks
+  static constexpr int NCH = CIN / 8;             // 16-byte K chunks (8 halves)
   static constexpr int A_BYTES = NCH * AROWS * 16;        // per hi / lo
   static constexpr int B_HALF = NCH * COUT * 16;          // per hi / lo
   static constexpr int B_STAGE = 2 * B_HALF;
-  static constexpr int NSTAGE = 2;
+  static constexpr int NSTAGE = NSTAGE_;
   static constexpr int POW = (POOL == TC_POOL_ADAPT) ? 3 : (W / 2);    // pooled width (5->3 adaptive, 4->2)
   static constexpr int STG_STRIDE = 68;           // floats per staged row (64 + 4: conflict-free float4)
   static constexpr int OFF_A_HI = 0;
   static constexpr int OFF_A_LO = A_BYTES;
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128;
-  static_assert(G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES, "staging tile must fit in the A region");
+  static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32;
+  static constexpr int MINB = (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
+  static_assert(POOL == TC_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES, "staging tile must fit in the A region");
   static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0, "alignment");
 };
 
-constexpr uint32_t kIdescTf32M128N64 =
-    (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=tf32, K-major
+constexpr uint32_t kIdescF16M128N64 =
+    (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major
 
 template <class C>
-__global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
-               const float* __restrict__ wtc /*[9][hi|lo][CIN/4][64][4]*/,
-               const float* __restrict__ bias, float* __restrict__ out, int n_seg) {
+__global__ void __launch_bounds__(192, C::MINB)
+conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
+               const __half* __restrict__ wtc /*[9][hi|lo][CIN/8][64][8] fp16, scaled by 2^S*/,
+               const float* __restrict__ bias, float out_scale /*2^-S*/,
+               float* __restrict__ out, int n_seg) {
   constexpr int H = C::H, W = C::W, CIN = C::CIN, P = C::P, BLK = C::BLK, G = C::G;
-  constexpr int HALO = C::HALO, AROWS = C::AROWS, NCH = C::NCH;
+  constexpr int HALO = C::HALO, AROWS = C::AROWS, NCH = C::NCH, NS = C::NSTAGE;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t a_hi = sbase + C::OFF_A_HI, a_lo = sbase + C::OFF_A_LO, b_base = sbase + C::OFF_B;
-  const uint32_t bar_full = sbase + C::OFF_BAR;          // [2]
-  const uint32_t bar_empty = bar_full + 16;              // [2]
-  const uint32_t bar_acc = bar_full + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 64);
+  const uint32_t bar_full = sbase + C::OFF_BAR;          // [NS]
+  const uint32_t bar_empty = bar_full + 8 * NS;          // [NS]
+  const uint32_t bar_acc = bar_full + 16 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 16 * NS + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg0 = blockIdx.x * G;
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
   if (tid == 32) {
-    mbar_init(bar_full, 1); mbar_init(bar_full + 8, 1);
-    mbar_init(bar_empty, 1); mbar_init(bar_empty + 8, 1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
@@ -153,35 +171,51 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // ---- weight producer: first two taps in flight while the activation tile is staged
+  // ---- weight producer: the first NS taps are in flight while the activation tile is staged
   if (tid == 160) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NS; ++t) {
       mbar_expect_tx(bar_full + 8 * t, C::B_STAGE);
-      bulk_g2s(b_base + t * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 4), C::B_STAGE, bar_full + 8 * t);
+      bulk_g2s(b_base + t * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_full + 8 * t);
     }
   }
 
-  // ---- stage A: channels-last global -> [ci/4][row][4] hi / lo, zero halo
+  // ---- stage A: channels-last fp32 global -> [ci/8][row][8 halves] hi / lo, zero halo.
+  //      4 items per thread per round so that 8 independent 16-byte loads are in flight.
   {
-    float4* ah = reinterpret_cast<float4*>(smem + C::OFF_A_HI);
-    float4* al = reinterpret_cast<float4*>(smem + C::OFF_A_LO);
-    for (int it = tid; it < AROWS * NCH; it += 192) {
-      const int c4 = it % NCH, b = it / NCH;
-      const int r = b - HALO;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r >= 0 && r < G * BLK) {
-        const int s = r / BLK, q = r - s * BLK;
-        const int hh = q / P, ww = q - hh * P;
-        if (hh >= 1 && ww >= 1 && seg0 + s < n_seg)
-          v = __ldg(reinterpret_cast<const float4*>(
-              in + ((size_t)(seg0 + s) * (H * W) + (hh - 1) * W + (ww - 1)) * CIN + c4 * 4));
+    uint4* ah = reinterpret_cast<uint4*>(smem + C::OFF_A_HI);
+    uint4* al = reinterpret_cast<uint4*>(smem + C::OFF_A_LO);
+    constexpr int ITEMS = AROWS * NCH;
+    for (int it0 = tid; it0 < ITEMS; it0 += 192 * 4) {
+      float4 va[4], vb[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * 192;
+        va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; dst[u] = -1;
+        if (it < ITEMS) {
+          const int c8 = it % NCH, b = it / NCH;
+          dst[u] = c8 * AROWS + b;
+          const int r = b - HALO;
+          if (r >= 0 && r < G * BLK) {
+            const int s = r / BLK, q = r - s * BLK;
+            const int hh = q / P, ww = q - hh * P;
+            if (hh >= 1 && ww >= 1 && seg0 + s < n_seg) {
+              const float4* src = reinterpret_cast<const float4*>(
+                  in + ((size_t)(seg0 + s) * (H * W) + (hh - 1) * W + (ww - 1)) * CIN + c8 * 8);
+              va[u] = __ldg(src); vb[u] = __ldg(src + 1);
+            }
+          }
+        }
       }
-      float4 hi, lo;
-      hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-      lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
-      ah[c4 * AROWS + b] = hi;
-      al[c4 * AROWS + b] = lo;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (dst[u] >= 0) {
+          uint4 hi, lo;
+          split8(va[u], vb[u], hi, lo);
+          ah[dst[u]] = hi; al[dst[u]] = lo;
+        }
+      }
     }
   }
   fence_proxy_async();          // generic-proxy stores -> visible to the tensor-core (async) proxy
@@ -190,11 +224,11 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
   if (warp == 5) {
     // ===== weight producer (one lane) =====
     if (lane == 0) {
-      for (int t = 2; t < 9; ++t) {
-        const int s = t & 1;
-        mbar_wait(bar_empty + 8 * s, ((t >> 1) - 1) & 1);     // MMAs of tap t-2 have drained the stage
+      for (int t = NS; t < 9; ++t) {
+        const int s = t % NS;
+        mbar_wait(bar_empty + 8 * s, ((t / NS) - 1) & 1);     // MMAs of tap t-NS have drained the stage
         mbar_expect_tx(bar_full + 8 * s, C::B_STAGE);
-        bulk_g2s(b_base + s * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 4), C::B_STAGE, bar_full + 8 * s);
+        bulk_g2s(b_base + s * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_full + 8 * s);
       }
     }
   } else if (warp == 4) {
@@ -202,8 +236,8 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
     if (lane == 0) {
       tc_fence_after();
       for (int t = 0; t < 9; ++t) {
-        const int s = t & 1;
-        mbar_wait(bar_full + 8 * s, (t >> 1) & 1);
+        const int s = t % NS;
+        mbar_wait(bar_full + 8 * s, (t / NS) & 1);
         tc_fence_after();
         const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
         const uint32_t bh = b_base + s * C::B_STAGE, bl = bh + C::B_HALF;
@@ -212,16 +246,16 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
           const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff);
           const uint32_t d = tmem + mt * 64;
 #pragma unroll
-          for (int ks = 0; ks < CIN / 8; ++ks) {
+          for (int ks = 0; ks < CIN / 16; ++ks) {
             const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
             const uint64_t dah = make_desc(a_hi + aoff, AROWS * 16, 128);
             const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
             const uint32_t boff = (uint32_t)(2 * ks) * (64 * 16);
             const uint64_t dbh = make_desc(bh + boff, 64 * 16, 128);
             const uint64_t dbl = make_desc(bl + boff, 64 * 16, 128);
-            umma_tf32(d, dah, dbh, kIdescTf32M128N64, (t | ks) != 0);
-            umma_tf32(d, dah, dbl, kIdescTf32M128N64, 1);
-            umma_tf32(d, dal, dbh, kIdescTf32M128N64, 1);
+            umma_f16(d, dah, dbh, kIdescF16M128N64, (t | ks) != 0);
+            umma_f16(d, dah, dbl, kIdescF16M128N64, 1);
+            umma_f16(d, dal, dbh, kIdescF16M128N64, 1);
           }
         }
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
@@ -251,10 +285,10 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 o;
-            o.x = fmaxf(v[4 * j + 0] + __ldg(bias + half * 32 + 4 * j + 0), 0.f);
-            o.y = fmaxf(v[4 * j + 1] + __ldg(bias + half * 32 + 4 * j + 1), 0.f);
-            o.z = fmaxf(v[4 * j + 2] + __ldg(bias + half * 32 + 4 * j + 2), 0.f);
-            o.w = fmaxf(v[4 * j + 3] + __ldg(bias + half * 32 + 4 * j + 3), 0.f);
+            o.x = fmaxf(fmaf(v[4 * j + 0], out_scale, __ldg(bias + half * 32 + 4 * j + 0)), 0.f);
+            o.y = fmaxf(fmaf(v[4 * j + 1], out_scale, __ldg(bias + half * 32 + 4 * j + 1)), 0.f);
+            o.z = fmaxf(fmaf(v[4 * j + 2], out_scale, __ldg(bias + half * 32 + 4 * j + 2)), 0.f);
+            o.w = fmaxf(fmaf(v[4 * j + 3], out_scale, __ldg(bias + half * 32 + 4 * j + 3)), 0.f);
             reinterpret_cast<float4*>(dst)[j] = o;
           }
         }
@@ -289,29 +323,32 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN]*/,
 }
 
 // layer = 3 | 4;  std_mode selects the StandardCNN geometry (12x4, MaxPool2d(2))
-using TcConv3A = TcCfg<5, 32, TC_POOL_NONE>;
-using TcConv4A = TcCfg<5, 64, TC_POOL_ADAPT>;
-using TcConv3S = TcCfg<4, 32, TC_POOL_NONE>;
-using TcConv4S = TcCfg<4, 64, TC_POOL_2X2>;
+//                      W  CIN  POOL           NSTAGE
+using TcConv3A = TcCfg<5, 32, TC_POOL_NONE, 4>;
+using TcConv4A = TcCfg<5, 64, TC_POOL_ADAPT, 2>;
+using TcConv3S = TcCfg<4, 32, TC_POOL_NONE, 4>;
+using TcConv4S = TcCfg<4, 64, TC_POOL_2X2, 2>;
 
 template <class C>
-static void launch_tc(cudaStream_t st, const float* in, const float* wtc, const float* b, float* out, int n_seg) {
+static void launch_tc(cudaStream_t st, const float* in, const __half* wtc, const float* b, float scale,
+                      float* out, int n_seg) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     configured = true;
   }
-  conv_tc_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in, wtc, b, out, n_seg);
+  conv_tc_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in, wtc, b, scale, out, n_seg);
 }
 
-void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, const float* wtc,
-                    const float* b, float* out, int n_seg) {
+void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, const void* wtc,
+                    const float* b, float out_scale, float* out, int n_seg) {
+  const __half* w = reinterpret_cast<const __half*>(wtc);
   if (!std_mode) {
-    if (layer == 3) launch_tc<TcConv3A>(st, in, wtc, b, out, n_seg);
-    else launch_tc<TcConv4A>(st, in, wtc, b, out, n_seg);
+    if (layer == 3) launch_tc<TcConv3A>(st, in, w, b, out_scale, out, n_seg);
+    else launch_tc<TcConv4A>(st, in, w, b, out_scale, out, n_seg);
   } else {
-    if (layer == 3) launch_tc<TcConv3S>(st, in, wtc, b, out, n_seg);
-    else launch_tc<TcConv4S>(st, in, wtc, b, out, n_seg);
+    if (layer == 3) launch_tc<TcConv3S>(st, in, w, b, out_scale, out, n_seg);
+    else launch_tc<TcConv4S>(st, in, w, b, out_scale, out, n_seg);
   }
 }
 

@@ -5,6 +5,7 @@
 // reference nisqa/NISQA_lib.py:2308-2309, 2257-2277), device workspaces and launches.
 //
 // There is no CPU fallback: without a usable CUDA device nisqa_create fails.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -32,7 +33,7 @@ void launch_conv1(cudaStream_t, int, const float*, const int*, const float*, con
 void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
 void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
 // conv_tc.cu
-void launch_conv_tc(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
+void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int);
 // td.cu
 struct SaLayerParams {
   const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
@@ -119,6 +120,7 @@ struct nisqa_engine {
   DevBuf warena;
   std::map<std::string, size_t> woff;   // float offsets into warena
   float pool_bias_std = 0.f;
+  float tc_scale[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // 2^-S of the fp16 weight pre-scale, per conv layer
 
   // front-end tables
   std::vector<FbEntry*> fbs;
@@ -342,13 +344,6 @@ bool pack_conv(Packer& P, int idx, int cin, int cout) {
   return true;
 }
 
-float tf32_rna_host(float x) {      // round-to-nearest (ties away) to 10 mantissa bits
-  uint32_t u; memcpy(&u, &x, 4);
-  u += 0x1000u; u &= 0xFFFFE000u;
-  memcpy(&x, &u, 4);
-  return x;
-}
-
 // dst[k][j] = src[j][perm(k)] for a [n_out][n_in] PyTorch Linear weight
 void pack_linear_T(Packer& P, size_t off, const TensorView* w, int n_out, int n_in, float scale = 1.f) {
   for (int k = 0; k < n_in; ++k)
@@ -367,22 +362,29 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
   for (int i = 1; i <= 6; ++i)
     if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-  // conv3 / conv4 for the tcgen05 path: [tap][hi|lo][ci/4][co][4], both parts exact tf32 values
+  // conv3 / conv4 for the tcgen05 path: [tap][hi|lo][ci/8][co][8] fp16 two-term split of w * 2^S
   for (int i = 3; i <= 4; ++i) {
     char k1[32], k2[32];
     snprintf(k1, sizeof k1, "conv%d.w", i); snprintf(k2, sizeof k2, "conv%d.wtc", i);
-    const int ci_n = cin[i], nch = ci_n / 4;
+    const int ci_n = cin[i], nch = ci_n / 8;
     const size_t src = e->woff.at(k1);
-    const size_t dst = P.alloc(k2, (size_t)9 * 2 * ci_n * 64);
+    float wmax = 0.f;
+    for (size_t j = 0; j < (size_t)ci_n * 9 * 64; ++j) wmax = std::max(wmax, fabsf(P.arena[src + j]));
+    int S = 0;
+    while (S < 14 && wmax * (float)(2 << S) <= 1024.f) ++S;        // max|w| * 2^S <= 1024
+    e->tc_scale[i] = 1.0f / (float)(1 << S);
+    const size_t n_half = (size_t)9 * 2 * ci_n * 64;
+    const size_t dst = P.alloc(k2, (n_half + 1) / 2);              // fp16 payload inside the float arena
     for (int tap = 0; tap < 9; ++tap)
       for (int ci = 0; ci < ci_n; ++ci)
         for (int co = 0; co < 64; ++co) {
-          const float w = P.arena[src + ((size_t)ci * 9 + tap) * 64 + co];
-          const float hi = tf32_rna_host(w), lo = tf32_rna_host(w - hi);
-          const size_t base = dst + (size_t)tap * 2 * ci_n * 64;
-          const size_t off = ((size_t)(ci / 4) * 64 + co) * 4 + (ci & 3);
-          P.arena[base + off] = hi;
-          P.arena[base + (size_t)nch * 64 * 4 + off] = lo;
+          const float w = P.arena[src + ((size_t)ci * 9 + tap) * 64 + co] * (float)(1 << S);
+          const __half hi = __float2half_rn(w);
+          const __half lo = __float2half_rn(w - __half2float(hi));
+          __half* base = reinterpret_cast<__half*>(&P.arena[dst]) + (size_t)tap * 2 * ci_n * 64;
+          const size_t off = ((size_t)(ci / 8) * 64 + co) * 8 + (ci & 7);
+          base[off] = hi;
+          base[(size_t)nch * 64 * 8 + off] = lo;
         }
   }
 
@@ -616,10 +618,10 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "conv2");
       launch_conv_layer(st, std_mode, 2, e->act1.as<float>(), W(e, "conv2.w"), W(e, "conv2.b"), e->act2.as<float>(), n_seg); }
     { Scope s(e, "conv3");
-      if (e->conv_tc) launch_conv_tc(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.wtc"), W(e, "conv3.b"), e->act3.as<float>(), n_seg);
+      if (e->conv_tc) launch_conv_tc(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.wtc"), W(e, "conv3.b"), e->tc_scale[3], e->act3.as<float>(), n_seg);
       else launch_conv_layer(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.w"), W(e, "conv3.b"), e->act3.as<float>(), n_seg); }
     { Scope s(e, "conv4");
-      if (e->conv_tc) launch_conv_tc(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.wtc"), W(e, "conv4.b"), e->act4.as<float>(), n_seg);
+      if (e->conv_tc) launch_conv_tc(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.wtc"), W(e, "conv4.b"), e->tc_scale[4], e->act4.as<float>(), n_seg);
       else launch_conv_layer(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.w"), W(e, "conv4.b"), e->act4.as<float>(), n_seg); }
     { Scope s(e, "conv5");
       launch_conv_layer(st, std_mode, 5, e->act4.as<float>(), W(e, "conv5.w"), W(e, "conv5.b"), e->act5.as<float>(), n_seg); }
