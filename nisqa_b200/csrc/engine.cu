@@ -757,11 +757,18 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(e, NISQA_ERR_CUDA, "libnisqa_b200 is compiled for sm_100a only");
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  std::vector<float2> tw(4096);
-  for (int j = 0; j < 4096; ++j) {
-    const double a = -2.0 * M_PI * (double)j / 4096.0;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
-  }
+  // twiddles laid out per lane so that every warp load is coalesced:
+  //   tw1[r-1][j][lane] = W_4096^(r*(lane+32j)),  tw2[q][lane] = W_1024^(lane*q)
+  std::vector<float2> tw(4 * 1024);
+  auto w4096 = [](long k) {
+    const double a = -2.0 * M_PI * (double)(k & 4095) / 4096.0;
+    return make_float2((float)cos(a), (float)sin(a));
+  };
+  for (int r = 1; r <= 3; ++r)
+    for (int j = 0; j < 32; ++j)
+      for (int l = 0; l < 32; ++l) tw[((r - 1) * 32 + j) * 32 + l] = w4096((long)r * (l + 32 * j));
+  for (int q = 0; q < 32; ++q)
+    for (int l = 0; l < 32; ++l) tw[3 * 1024 + q * 32 + l] = w4096(4L * l * q);
   CK(e->tw4096.reserve(tw.size() * sizeof(float2)));
   CK(cudaMemcpy(e->tw4096.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   return 0;

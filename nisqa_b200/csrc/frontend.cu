@@ -67,6 +67,7 @@ __device__ __forceinline__ void fft32(float2 (&x)[32]) {
 __device__ __forceinline__ int reflect_index(int i, int n) {
   // numpy.pad(mode='reflect') index map, valid for any i (repeated reflection when the pad
   // is longer than the signal)
+  if ((unsigned)i < (unsigned)n) return i;      // interior frames: no reflection
   if (n <= 1) return 0;
   const int period = 2 * n - 2;
   int m = i % period;
@@ -81,7 +82,8 @@ template <> __device__ __forceinline__ float sample_to_float<short>(short v) {
 template <> __device__ __forceinline__ float sample_to_float<float>(float v) { return v; }
 
 constexpr int kFeThreads = 128;
-constexpr int kScratchPerWarp = 32 * 33;          // float2 elements, padded transpose tile
+constexpr int kScratchPerWarp = 32 * 33 + 4;      // float2 elements: padded transpose tile (+4: the
+                                                  // four residue planes start 8 banks apart)
 constexpr int kMagStride = 2052;
 
 __host__ __device__ constexpr int fe_region0_bytes(int Q) {
@@ -93,7 +95,8 @@ template <typename T>
 __global__ void __launch_bounds__(kFeThreads)
 frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
                 const int* __restrict__ pair_prefix, const FbTables* __restrict__ fbs,
-                const float2* __restrict__ tw4096, float* __restrict__ mel,
+                const float2* __restrict__ tw1 /*[3][32][32]: W4096^(r*(lane+32j))*/,
+                const float2* __restrict__ tw2 /*[32][32]: W1024^(lane*q)*/, float* __restrict__ mel,
                 unsigned* __restrict__ clipmax, int Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* zin = reinterpret_cast<float2*>(smem_raw);                     // [1024*Q] packed input
@@ -140,7 +143,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
           default: v.x -= u.y; v.y += u.x; break;
         }
       }
-      if (r != 0) v = cmul(v, __ldg(tw4096 + ((r * n) & 4095)));
+      if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));   // coalesced per-lane table
       x[j] = v;
     }
     fft32(x);                                      // A_l[q] at x[rev5(q)]
@@ -148,7 +151,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
       float2 v = x[rev5(q)];
-      if (q != 0) v = cmul(v, __ldg(tw4096 + ((4 * lane * q) & 4095)));   // W_1024^(l q)
+      if (q != 0) v = cmul(v, __ldg(tw2 + q * 32 + lane));                   // W_1024^(l q), coalesced
       tile[lane * 33 + q] = v;
     }
     __syncwarp();
@@ -228,16 +231,22 @@ __global__ void mel_dump_kernel(const float* __restrict__ mel, const ClipDesc* _
 // ------------------------------------------------------------------ host launchers
 void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDesc* clips,
                      int n_clips, const int* pair_prefix, int n_pairs, const FbTables* fbs,
-                     const float2* tw4096, float* mel, unsigned* clipmax, int Q) {
+                     const float2* tw, float* mel, unsigned* clipmax, int Q) {
+  const float2* tw1 = tw;               // [3][32][32]
+  const float2* tw2 = tw + 3 * 1024;    // [32][32]
   const int smem = frontend_smem_bytes(Q);
-  if (fmt_f32) {
+  static int configured_q = 0;
+  if (Q > configured_q) {
     cudaFuncSetAttribute(frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    frontend_kernel<float><<<n_pairs, kFeThreads, smem, st>>>(
-        (const float*)pcm, clips, n_clips, pair_prefix, fbs, tw4096, mel, clipmax, Q);
-  } else {
     cudaFuncSetAttribute(frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured_q = Q;
+  }
+  if (fmt_f32) {
+    frontend_kernel<float><<<n_pairs, kFeThreads, smem, st>>>(
+        (const float*)pcm, clips, n_clips, pair_prefix, fbs, tw1, tw2, mel, clipmax, Q);
+  } else {
     frontend_kernel<short><<<n_pairs, kFeThreads, smem, st>>>(
-        (const short*)pcm, clips, n_clips, pair_prefix, fbs, tw4096, mel, clipmax, Q);
+        (const short*)pcm, clips, n_clips, pair_prefix, fbs, tw1, tw2, mel, clipmax, Q);
   }
 }
 
