@@ -22,7 +22,7 @@
 
 namespace nisqa {
 // frontend.cu
-void launch_frontend(cudaStream_t, const void*, int, const ClipDesc*, int, const int*, int,
+void launch_frontend(cudaStream_t, const void*, int, const ClipDesc*, int, int,
                      const FbTables*, const float2*, float*, unsigned*, int);
 void launch_seg_table(cudaStream_t, const ClipDesc*, int, const int*, const unsigned*, int, int,
                       int*, float*, int*);
@@ -528,7 +528,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   cl.assign(n, ClipDesc());
   std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0);
   long long pcm_elems = 0;
-  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0;
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
@@ -545,6 +545,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     pair_prefix[i] = n_pairs; seg_prefix[i] = n_seg; qt_prefix[i] = n_qt;
     n_frames += d.n_frames; n_seg += d.n_seg;
     n_pairs += (d.n_frames + 1) / 2;
+    max_pairs = std::max(max_pairs, (d.n_frames + 1) / 2);
     n_qt += (d.n_seg + 127) / 128;
     if (ok) Q = std::max(Q, (p.win + 1023) / 1024);
   }
@@ -606,7 +607,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     int* seg_clip = seg_frame0 + 2 * (size_t)n_seg;
 
     { Scope s(e, "frontend");
-      launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, d_pair, n_pairs,
+      launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, max_pairs,
                       e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), e->mel.as<float>(),
                       e->clipmax.as<unsigned>(), Q); }
     { Scope s(e, "seg_table");

@@ -94,7 +94,7 @@ int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWar
 template <typename T>
 __global__ void __launch_bounds__(kFeThreads)
 frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
-                const int* __restrict__ pair_prefix, const FbTables* __restrict__ fbs,
+                const FbTables* __restrict__ fbs,
                 const float2* __restrict__ tw1 /*[3][32][32]: W4096^(r*(lane+32j))*/,
                 const float2* __restrict__ tw2 /*[32][32]: W1024^(lane*q)*/, float* __restrict__ mel,
                 unsigned* __restrict__ clipmax, int Q) {
@@ -102,27 +102,40 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   float2* zin = reinterpret_cast<float2*>(smem_raw);                     // [1024*Q] packed input
   float* mags = reinterpret_cast<float*>(smem_raw);                      // aliases zin later
   float2* scratch = reinterpret_cast<float2*>(smem_raw + fe_region0_bytes(Q));
+  __shared__ int band_meta[2 * kMels + 1];        // [0..48] CSR offsets, [49..96] first bin per band
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int P = blockIdx.x;
-  const int c = upper_slot(pair_prefix, n_clips, P);
+  // grid: x = frame pair within the clip, y = clip (no search, no dependent loads)
+  const int c = blockIdx.y;
   const ClipDesc cd = clips[c];
+  const int tA = 2 * blockIdx.x;
+  if (tA >= cd.n_frames) return;
   const FbTables fb = fbs[cd.fb_id];
-  const int tA = 2 * (P - cd.pair_off);
   const int tB = tA + 1;
   const bool validB = tB < cd.n_frames;
   const T* y = pcm + cd.pcm_off;
+  if (tid <= kMels) band_meta[tid] = __ldg(fb.band_start + tid);
+  else if (tid < 2 * kMels + 1) band_meta[tid] = __ldg(fb.band_k0 + tid - kMels - 1);
 
-  // ---- a. windowed, reflect-padded frame pair -> zin
-  for (int n = tid; n < 1024 * Q; n += kFeThreads) {
-    float a = 0.f, b = 0.f;
-    if (n < cd.win) {
-      const float wv = __ldg(fb.window + n);
-      const int ia = cd.s0 + tA * cd.hop + n;
-      a = wv * sample_to_float<T>(y[reflect_index(ia, cd.n_samples)]);
-      if (validB) b = wv * sample_to_float<T>(y[reflect_index(ia + cd.hop, cd.n_samples)]);
+  // ---- a. windowed, reflect-padded frame pair -> zin  (8 elements per thread per 1024 chunk,
+  //         all loads of a chunk issued before they are consumed)
+  for (int q0 = 0; q0 < Q; ++q0) {
+    float wv[8], sa[8], sb[8];
+    const int ia0 = cd.s0 + tA * cd.hop + q0 * 1024 + tid;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = q0 * 1024 + tid + i * kFeThreads;
+      wv[i] = 0.f; sa[i] = 0.f; sb[i] = 0.f;
+      if (n < cd.win) {
+        wv[i] = __ldg(fb.window + n);
+        const int ia = ia0 + i * kFeThreads;
+        sa[i] = sample_to_float<T>(y[reflect_index(ia, cd.n_samples)]);
+        if (validB) sb[i] = sample_to_float<T>(y[reflect_index(ia + cd.hop, cd.n_samples)]);
+      }
     }
-    zin[n] = make_float2(a, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      zin[q0 * 1024 + tid + i * kFeThreads] = make_float2(wv[i] * sa[i], wv[i] * sb[i]);
   }
   __syncthreads();
 
@@ -176,24 +189,33 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   }
   __syncthreads();
 
-  // ---- d. sparse mel + dB + clip max
+  // ---- d. sparse mel + dB + clip max: one warp item = one band of BOTH frames
   float wmax = -INFINITY;
-  for (int item = warp; item < 2 * kMels; item += kFeThreads / 32) {
-    const int f = item / kMels, b = item - f * kMels;
-    if (f == 1 && !validB) continue;
-    const int beg = __ldg(fb.band_start + b), len = __ldg(fb.band_start + b + 1) - beg;
-    const int k0 = __ldg(fb.band_k0 + b);
-    const float* mg = mags + f * kMagStride + k0;
-    float s = 0.f;
-    for (int i = lane; i < len; i += 32) s = fmaf(__ldg(fb.weights + beg + i), mg[i], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      const float p = s * s;
-      const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
-      mel[(size_t)(cd.frame_off + tA + f) * kMels + b] = db;
-      wmax = fmaxf(wmax, db);
+  for (int b = warp; b < kMels; b += kFeThreads / 32) {
+    const int beg = band_meta[b], len = band_meta[b + 1] - beg;
+    const float* mg = mags + band_meta[kMels + 1 + b];
+    const float* wt = fb.weights + beg;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = lane; i < len; i += 64) {
+      const int i2 = i + 32;
+      const float w0 = __ldg(wt + i);
+      const float w1 = (i2 < len) ? __ldg(wt + i2) : 0.f;
+      const int j2 = (i2 < len) ? i2 : i;
+      s0 = fmaf(w0, mg[i], s0);              s1 = fmaf(w0, mg[kMagStride + i], s1);
+      s0 = fmaf(w1, mg[j2], s0);             s1 = fmaf(w1, mg[kMagStride + j2], s1);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (lane < 2) {
+      const float sv = lane ? s1 : s0;
+      if (lane == 0 || validB) {
+        const float p = sv * sv;
+        const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
+        mel[(size_t)(cd.frame_off + tA + lane) * kMels + b] = db;
+        wmax = fmaxf(wmax, db);
+      }
     }
   }
+  wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
   if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
 }
 
@@ -230,7 +252,7 @@ __global__ void mel_dump_kernel(const float* __restrict__ mel, const ClipDesc* _
 
 // ------------------------------------------------------------------ host launchers
 void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDesc* clips,
-                     int n_clips, const int* pair_prefix, int n_pairs, const FbTables* fbs,
+                     int n_clips, int max_pairs, const FbTables* fbs,
                      const float2* tw, float* mel, unsigned* clipmax, int Q) {
   const float2* tw1 = tw;               // [3][32][32]
   const float2* tw2 = tw + 3 * 1024;    // [32][32]
@@ -241,12 +263,13 @@ void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDe
     cudaFuncSetAttribute(frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured_q = Q;
   }
+  const dim3 grid(max_pairs, n_clips);
   if (fmt_f32) {
-    frontend_kernel<float><<<n_pairs, kFeThreads, smem, st>>>(
-        (const float*)pcm, clips, n_clips, pair_prefix, fbs, tw1, tw2, mel, clipmax, Q);
+    frontend_kernel<float><<<grid, kFeThreads, smem, st>>>(
+        (const float*)pcm, clips, n_clips, fbs, tw1, tw2, mel, clipmax, Q);
   } else {
-    frontend_kernel<short><<<n_pairs, kFeThreads, smem, st>>>(
-        (const short*)pcm, clips, n_clips, pair_prefix, fbs, tw1, tw2, mel, clipmax, Q);
+    frontend_kernel<short><<<grid, kFeThreads, smem, st>>>(
+        (const short*)pcm, clips, n_clips, fbs, tw1, tw2, mel, clipmax, Q);
   }
 }
 
