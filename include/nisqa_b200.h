@@ -157,8 +157,9 @@ NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_
  * with CUDA events on the engine stream when profiling was enabled; <0 if unknown.
  * groups: "frontend", "cnn", "td", "pool" */
 NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
-/* kernel-variant switches for A/B measurements: "conv_tc" = 1 (default): conv3/conv4 as 3xTF32
- * tcgen05 implicit GEMMs; 0: the fp32 FFMA kernels. */
+/* kernel-variant switches for A/B measurements: "conv_tc" = bit mask of the conv layers (2..6) that
+ * run as tcgen05 implicit GEMMs with the fp16 two-term split (default / 1 = all of them); a cleared
+ * bit selects the fp32 FFMA kernel of that layer. */
 NISQA_API int    nisqa_set_option(nisqa_engine* e, const char* name, int value);
 NISQA_API double nisqa_group_ms(const nisqa_engine* e, const char* group);
 

@@ -113,9 +113,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------ configuration
 enum { TC_POOL_NONE = 0, TC_POOL_ADAPT = 1, TC_POOL_2X2 = 2 };
 
-template <int W_, int CIN_, int POOL_, int NSTAGE_>
+template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, bool CENTER_ = false>
 struct TcCfg {
-  static constexpr int H = 12, W = W_, CIN = CIN_, COUT = 64, POOL = POOL_;
+  static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, POOL = POOL_, POW = POW_;
+  static constexpr bool CENTER = CENTER_;         // conv6 of the AdaptCNN: kernel (3,3), padding (1,0) on a
+                                                  // 3-wide map == the padded conv evaluated at column 1 only
   static constexpr int P = W + 1;                 // row pitch: W interior columns + 1 shared zero column
   static constexpr int BLK = (H + 1) * P;         // rows per segment: H interior rows + 1 shared zero row
   static constexpr int G = 256 / BLK;             // segments per CTA (2 M-tiles of 128 rows)
@@ -126,28 +128,30 @@ struct TcCfg {
   static constexpr int B_HALF = NCH * COUT * 16;          // per hi / lo
   static constexpr int B_STAGE = 2 * B_HALF;
   static constexpr int NSTAGE = NSTAGE_;
-  static constexpr int POW = (POOL == TC_POOL_ADAPT) ? 3 : (W / 2);    // pooled width (5->3 adaptive, 4->2)
-  static constexpr int STG_STRIDE = 68;           // floats per staged row (64 + 4: conflict-free float4)
+  static constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : 128);
+  static constexpr int HO = (POOL == TC_POOL_NONE) ? H : H / 2;
+  static constexpr int STG_STRIDE = COUT + 4;     // floats per staged row (conflict-free float4)
   static constexpr int OFF_A_HI = 0;
   static constexpr int OFF_A_LO = A_BYTES;
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
   static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32;
-  static constexpr int MINB = (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
-  static_assert(POOL == TC_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES, "staging tile must fit in the A region");
-  static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0, "alignment");
+  static constexpr int MINB = (SMEM_BYTES <= 56 * 1024) ? 4 : (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
+  static constexpr uint32_t IDESC =                        // D=f32, A=B=f16, both K-major, M=128, N=COUT
+      (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+  static_assert(POOL == TC_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES + NSTAGE * B_STAGE,
+                "pool staging tile must fit in the A+B region");
+  static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0 && CIN % 16 == 0 && COUT % 32 == 0, "shape");
+  static_assert(G >= 1 && MINB * TMEM_COLS <= 512, "tile / TMEM budget");
 };
-
-constexpr uint32_t kIdescF16M128N64 =
-    (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major
 
 template <class C>
 __global__ void __launch_bounds__(192, C::MINB)
-conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
-               const __half* __restrict__ wtc /*[9][hi|lo][CIN/8][64][8] fp16, scaled by 2^S*/,
+conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
+               const __half* __restrict__ wtc /*[9][hi|lo][CIN/8][COUT][8] fp16, scaled by 2^S*/,
                const float* __restrict__ bias, float out_scale /*2^-S*/,
                float* __restrict__ out, int n_seg) {
-  constexpr int H = C::H, W = C::W, CIN = C::CIN, P = C::P, BLK = C::BLK, G = C::G;
+  constexpr int H = C::H, W = C::W, CIN = C::CIN, COUT = C::COUT, P = C::P, BLK = C::BLK, G = C::G;
   constexpr int HALO = C::HALO, AROWS = C::AROWS, NCH = C::NCH, NS = C::NSTAGE;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -159,7 +163,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg0 = blockIdx.x * G;
 
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
   if (tid == 32) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -244,18 +248,18 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff);
-          const uint32_t d = tmem + mt * 64;
+          const uint32_t d = tmem + mt * COUT;
 #pragma unroll
           for (int ks = 0; ks < CIN / 16; ++ks) {
             const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
             const uint64_t dah = make_desc(a_hi + aoff, AROWS * 16, 128);
             const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
-            const uint32_t boff = (uint32_t)(2 * ks) * (64 * 16);
-            const uint64_t dbh = make_desc(bh + boff, 64 * 16, 128);
-            const uint64_t dbl = make_desc(bl + boff, 64 * 16, 128);
-            umma_f16(d, dah, dbh, kIdescF16M128N64, (t | ks) != 0);
-            umma_f16(d, dah, dbl, kIdescF16M128N64, 1);
-            umma_f16(d, dal, dbh, kIdescF16M128N64, 1);
+            const uint32_t boff = (uint32_t)(2 * ks) * (COUT * 16);
+            const uint64_t dbh = make_desc(bh + boff, COUT * 16, 128);
+            const uint64_t dbl = make_desc(bl + boff, COUT * 16, 128);
+            umma_f16(d, dah, dbh, C::IDESC, (t | ks) != 0);
+            umma_f16(d, dah, dbl, C::IDESC, 1);
+            umma_f16(d, dal, dbh, C::IDESC, 1);
           }
         }
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
@@ -266,40 +270,42 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
     // ===== epilogue: warps 0..3 <-> TMEM lanes 32w..32w+31 =====
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem);          // reuses the A region (all MMAs retired)
+    float* stg = reinterpret_cast<float*>(smem);          // reuses the A/B region (all MMAs retired)
+    constexpr int WOUT = C::CENTER ? 1 : W;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int r = mt * 128 + warp * 32 + lane;
       const int s = r / BLK, q = r - s * BLK;
       const int hh = q / P, ww = q - hh * P;
-      const bool valid = (s < G) && hh >= 1 && ww >= 1 && (seg0 + s < n_seg);
-      const int h = hh - 1, w = ww - 1;
+      bool valid = (s < G) && hh >= 1 && ww >= 1 && (seg0 + s < n_seg);
+      if (C::CENTER) valid = valid && (ww == 2);
+      const int h = hh - 1, w = C::CENTER ? 0 : ww - 1;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int part = 0; part < COUT / 32; ++part) {
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * 64 + half * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * COUT + part * 32, v);
         if (valid) {
           float* dst = (C::POOL == TC_POOL_NONE)
-                           ? out + ((size_t)(seg0 + s) * (H * W) + h * W + w) * 64 + half * 32
-                           : stg + ((s * H + h) * W + w) * C::STG_STRIDE + half * 32;
+                           ? out + ((size_t)(seg0 + s) * (H * WOUT) + h * WOUT + w) * COUT + part * 32
+                           : stg + ((s * H + h) * W + w) * C::STG_STRIDE + part * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 o;
-            o.x = fmaxf(fmaf(v[4 * j + 0], out_scale, __ldg(bias + half * 32 + 4 * j + 0)), 0.f);
-            o.y = fmaxf(fmaf(v[4 * j + 1], out_scale, __ldg(bias + half * 32 + 4 * j + 1)), 0.f);
-            o.z = fmaxf(fmaf(v[4 * j + 2], out_scale, __ldg(bias + half * 32 + 4 * j + 2)), 0.f);
-            o.w = fmaxf(fmaf(v[4 * j + 3], out_scale, __ldg(bias + half * 32 + 4 * j + 3)), 0.f);
+            o.x = fmaxf(fmaf(v[4 * j + 0], out_scale, __ldg(bias + part * 32 + 4 * j + 0)), 0.f);
+            o.y = fmaxf(fmaf(v[4 * j + 1], out_scale, __ldg(bias + part * 32 + 4 * j + 1)), 0.f);
+            o.z = fmaxf(fmaf(v[4 * j + 2], out_scale, __ldg(bias + part * 32 + 4 * j + 2)), 0.f);
+            o.w = fmaxf(fmaf(v[4 * j + 3], out_scale, __ldg(bias + part * 32 + 4 * j + 3)), 0.f);
             reinterpret_cast<float4*>(dst)[j] = o;
           }
         }
       }
     }
-    if (C::POOL != TC_POOL_NONE) {
+    if constexpr (C::POOL != TC_POOL_NONE) {
       asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
-      constexpr int POW = C::POW, HO = H / 2;
-      for (int it = tid; it < G * HO * POW * 16; it += 128) {
-        const int c4 = it & 15;
-        int rest = it >> 4;
+      constexpr int POW = C::POW, HO = H / 2, C4 = COUT / 4;
+      for (int it = tid; it < G * HO * POW * C4; it += 128) {
+        const int c4 = it % C4;
+        int rest = it / C4;
         const int pw = rest % POW; rest /= POW;
         const int ph = rest % HO;
         const int s = rest / HO;
@@ -313,21 +319,26 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][12][W][CIN] fp32*/,
             const float4 t = *reinterpret_cast<const float4*>(stg + ((s * H + hy) * W + x) * C::STG_STRIDE + c4 * 4);
             m.x = fmaxf(m.x, t.x); m.y = fmaxf(m.y, t.y); m.z = fmaxf(m.z, t.z); m.w = fmaxf(m.w, t.w);
           }
-        *reinterpret_cast<float4*>(out + ((size_t)(seg0 + s) * (HO * POW) + ph * POW + pw) * 64 + c4 * 4) = m;
+        *reinterpret_cast<float4*>(out + ((size_t)(seg0 + s) * (HO * POW) + ph * POW + pw) * COUT + c4 * 4) = m;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
-// layer = 3 | 4;  std_mode selects the StandardCNN geometry (12x4, MaxPool2d(2))
-//                      W  CIN  POOL           NSTAGE
-using TcConv3A = TcCfg<5, 32, TC_POOL_NONE, 4>;
-using TcConv4A = TcCfg<5, 64, TC_POOL_ADAPT, 2>;
-using TcConv3S = TcCfg<4, 32, TC_POOL_NONE, 4>;
-using TcConv4S = TcCfg<4, 64, TC_POOL_2X2, 2>;
+// layers 2..6; std_mode selects the StandardCNN geometry (W 8/4/2, MaxPool2d(2))
+//                      H   W  CIN COUT POOL           POW NSTAGE CENTER
+using TcConv2A = TcCfg<24, 7, 16, 32, TC_POOL_ADAPT, 5, 9>;
+using TcConv3A = TcCfg<12, 5, 32, 64, TC_POOL_NONE, 0, 4>;
+using TcConv4A = TcCfg<12, 5, 64, 64, TC_POOL_ADAPT, 3, 2>;
+using TcConv5A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, 2>;
+using TcConv6A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, 2, true>;
+using TcConv2S = TcCfg<24, 8, 16, 32, TC_POOL_2X2, 4, 9>;
+using TcConv3S = TcCfg<12, 4, 32, 64, TC_POOL_NONE, 0, 4>;
+using TcConv4S = TcCfg<12, 4, 64, 64, TC_POOL_2X2, 2, 2>;
+using TcConv5S = TcCfg<6, 2, 64, 64, TC_POOL_NONE, 0, 2>;
 
 template <class C>
 static void launch_tc(cudaStream_t st, const float* in, const __half* wtc, const float* b, float scale,
@@ -344,11 +355,20 @@ void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, c
                     const float* b, float out_scale, float* out, int n_seg) {
   const __half* w = reinterpret_cast<const __half*>(wtc);
   if (!std_mode) {
-    if (layer == 3) launch_tc<TcConv3A>(st, in, w, b, out_scale, out, n_seg);
-    else launch_tc<TcConv4A>(st, in, w, b, out_scale, out, n_seg);
+    switch (layer) {
+      case 2: launch_tc<TcConv2A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 3: launch_tc<TcConv3A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 4: launch_tc<TcConv4A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 5: launch_tc<TcConv5A>(st, in, w, b, out_scale, out, n_seg); break;
+      default: launch_tc<TcConv6A>(st, in, w, b, out_scale, out, n_seg); break;
+    }
   } else {
-    if (layer == 3) launch_tc<TcConv3S>(st, in, w, b, out_scale, out, n_seg);
-    else launch_tc<TcConv4S>(st, in, w, b, out_scale, out, n_seg);
+    switch (layer) {
+      case 2: launch_tc<TcConv2S>(st, in, w, b, out_scale, out, n_seg); break;
+      case 3: launch_tc<TcConv3S>(st, in, w, b, out_scale, out, n_seg); break;
+      case 4: launch_tc<TcConv4S>(st, in, w, b, out_scale, out, n_seg); break;
+      default: launch_tc<TcConv5S>(st, in, w, b, out_scale, out, n_seg); break;   // conv5 and conv6 share a geometry
+    }
   }
 }
 

@@ -113,7 +113,7 @@ struct nisqa_engine {
   int64_t launches = 0;
   bool weights_loaded = false;
   bool profiling = false;
-  bool conv_tc = true;     // conv3/conv4 on tcgen05 (3xTF32); false = fp32 FFMA kernels
+  int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
   // weights arena (device) + offsets
@@ -362,29 +362,29 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
   for (int i = 1; i <= 6; ++i)
     if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-  // conv3 / conv4 for the tcgen05 path: [tap][hi|lo][ci/8][co][8] fp16 two-term split of w * 2^S
-  for (int i = 3; i <= 4; ++i) {
+  // conv2..conv6 for the tcgen05 path: [tap][hi|lo][ci/8][co][8] fp16 two-term split of w * 2^S
+  for (int i = 2; i <= 6; ++i) {
     char k1[32], k2[32];
     snprintf(k1, sizeof k1, "conv%d.w", i); snprintf(k2, sizeof k2, "conv%d.wtc", i);
-    const int ci_n = cin[i], nch = ci_n / 8;
+    const int ci_n = cin[i], co_n = cout[i], nch = ci_n / 8;
     const size_t src = e->woff.at(k1);
     float wmax = 0.f;
-    for (size_t j = 0; j < (size_t)ci_n * 9 * 64; ++j) wmax = std::max(wmax, fabsf(P.arena[src + j]));
+    for (size_t j = 0; j < (size_t)ci_n * 9 * co_n; ++j) wmax = std::max(wmax, fabsf(P.arena[src + j]));
     int S = 0;
     while (S < 14 && wmax * (float)(2 << S) <= 1024.f) ++S;        // max|w| * 2^S <= 1024
     e->tc_scale[i] = 1.0f / (float)(1 << S);
-    const size_t n_half = (size_t)9 * 2 * ci_n * 64;
+    const size_t n_half = (size_t)9 * 2 * ci_n * co_n;
     const size_t dst = P.alloc(k2, (n_half + 1) / 2);              // fp16 payload inside the float arena
     for (int tap = 0; tap < 9; ++tap)
       for (int ci = 0; ci < ci_n; ++ci)
-        for (int co = 0; co < 64; ++co) {
-          const float w = P.arena[src + ((size_t)ci * 9 + tap) * 64 + co] * (float)(1 << S);
+        for (int co = 0; co < co_n; ++co) {
+          const float w = P.arena[src + ((size_t)ci * 9 + tap) * co_n + co] * (float)(1 << S);
           const __half hi = __float2half_rn(w);
           const __half lo = __float2half_rn(w - __half2float(hi));
-          __half* base = reinterpret_cast<__half*>(&P.arena[dst]) + (size_t)tap * 2 * ci_n * 64;
-          const size_t off = ((size_t)(ci / 8) * 64 + co) * 8 + (ci & 7);
+          __half* base = reinterpret_cast<__half*>(&P.arena[dst]) + (size_t)tap * 2 * ci_n * co_n;
+          const size_t off = ((size_t)(ci / 8) * co_n + co) * 8 + (ci & 7);
           base[off] = hi;
-          base[(size_t)nch * 64 * 8 + off] = lo;
+          base[(size_t)nch * co_n * 8 + off] = lo;
         }
   }
 
@@ -616,18 +616,22 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "conv1");
       launch_conv1(st, std_mode, e->mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
                    W(e, "conv1.b"), e->act1.as<float>(), n_seg); }
-    { Scope s(e, "conv2");
-      launch_conv_layer(st, std_mode, 2, e->act1.as<float>(), W(e, "conv2.w"), W(e, "conv2.b"), e->act2.as<float>(), n_seg); }
-    { Scope s(e, "conv3");
-      if (e->conv_tc) launch_conv_tc(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.wtc"), W(e, "conv3.b"), e->tc_scale[3], e->act3.as<float>(), n_seg);
-      else launch_conv_layer(st, std_mode, 3, e->act2.as<float>(), W(e, "conv3.w"), W(e, "conv3.b"), e->act3.as<float>(), n_seg); }
-    { Scope s(e, "conv4");
-      if (e->conv_tc) launch_conv_tc(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.wtc"), W(e, "conv4.b"), e->tc_scale[4], e->act4.as<float>(), n_seg);
-      else launch_conv_layer(st, std_mode, 4, e->act3.as<float>(), W(e, "conv4.w"), W(e, "conv4.b"), e->act4.as<float>(), n_seg); }
-    { Scope s(e, "conv5");
-      launch_conv_layer(st, std_mode, 5, e->act4.as<float>(), W(e, "conv5.w"), W(e, "conv5.b"), e->act5.as<float>(), n_seg); }
-    { Scope s(e, "conv6");
-      launch_conv_layer(st, std_mode, 6, e->act5.as<float>(), W(e, "conv6.w"), W(e, "conv6.b"), e->feats.as<float>(), n_seg); }
+    {
+      const float* cin_[7] = {nullptr, nullptr, e->act1.as<float>(), e->act2.as<float>(), e->act3.as<float>(),
+                              e->act4.as<float>(), e->act5.as<float>()};
+      float* cout_[7] = {nullptr, nullptr, e->act2.as<float>(), e->act3.as<float>(), e->act4.as<float>(),
+                         e->act5.as<float>(), e->feats.as<float>()};
+      for (int l = 2; l <= 6; ++l) {
+        char nm[16], kw[24], kt[24], kb[24];
+        snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
+        snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
+        Scope s(e, nm);
+        if (e->conv_tc & (1 << l))
+          launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg);
+        else
+          launch_conv_layer(st, std_mode, l, cin_[l], W(e, kw), W(e, kb), cout_[l], n_seg);
+      }
+    }
 
     if (!std_mode) {
       CK(e->xa.reserve((size_t)n_seg * 64 * 4));
@@ -892,7 +896,7 @@ void* nisqa_stream(const nisqa_engine* e) { return e ? (void*)e->stream : nullpt
 
 int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
-  if (strcmp(name, "conv_tc") == 0) { e->conv_tc = value != 0; return 0; }
+  if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }
 

@@ -84,11 +84,8 @@ template <> __device__ __forceinline__ float sample_to_float<float>(float v) { r
 constexpr int kFeThreads = 128;
 constexpr int kScratchPerWarp = 32 * 33 + 4;      // float2 elements: padded transpose tile (+4: the
                                                   // four residue planes start 8 banks apart)
-constexpr int kMagStride = 2052;
 
-__host__ __device__ constexpr int fe_region0_bytes(int Q) {
-  return (1024 * Q * 8 > 2 * kMagStride * 4) ? 1024 * Q * 8 : 2 * kMagStride * 4;
-}
+__host__ __device__ constexpr int fe_region0_bytes(int Q) { return 1024 * Q * 8; }
 int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWarp * 8; }
 
 template <typename T>
@@ -100,7 +97,6 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
                 unsigned* __restrict__ clipmax, int Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* zin = reinterpret_cast<float2*>(smem_raw);                     // [1024*Q] packed input
-  float* mags = reinterpret_cast<float*>(smem_raw);                      // aliases zin later
   float2* scratch = reinterpret_cast<float2*>(smem_raw + fe_region0_bytes(Q));
   __shared__ int band_meta[2 * kMels + 1];        // [0..48] CSR offsets, [49..96] first bin per band
 
@@ -177,32 +173,26 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   }
   __syncthreads();
 
-  // ---- c. unpack the two real spectra, magnitudes (bins 0..2048)
-  for (int k = tid; k < kBins; k += kFeThreads) {
-    const int kk = (kNfft - k) & (kNfft - 1);
-    const float2 zk = scratch[(k & 3) * kScratchPerWarp + (k >> 2)];
-    const float2 zn = scratch[(kk & 3) * kScratchPerWarp + (kk >> 2)];
-    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-    const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
-    mags[k] = sqrtf(ar * ar + ai * ai);
-    mags[kMagStride + k] = sqrtf(br * br + bi * bi);
-  }
-  __syncthreads();
-
-  // ---- d. sparse mel + dB + clip max: one warp item = one band of BOTH frames
+  // ---- c. fused: unpack the two real spectra, |.|, sparse mel, dB, clip max.
+  //         One warp item = one band of BOTH frames; lanes stride over the band's bins.  A bin
+  //         belongs to two adjacent triangles, so its magnitudes are formed twice - cheaper
+  //         than a shared-memory round trip (and it frees 16 KB: 5 CTAs / SM instead of 4).
   float wmax = -INFINITY;
   for (int b = warp; b < kMels; b += kFeThreads / 32) {
     const int beg = band_meta[b], len = band_meta[b + 1] - beg;
-    const float* mg = mags + band_meta[kMels + 1 + b];
+    const int k0 = band_meta[kMels + 1 + b];
     const float* wt = fb.weights + beg;
     float s0 = 0.f, s1 = 0.f;
-    for (int i = lane; i < len; i += 64) {
-      const int i2 = i + 32;
-      const float w0 = __ldg(wt + i);
-      const float w1 = (i2 < len) ? __ldg(wt + i2) : 0.f;
-      const int j2 = (i2 < len) ? i2 : i;
-      s0 = fmaf(w0, mg[i], s0);              s1 = fmaf(w0, mg[kMagStride + i], s1);
-      s0 = fmaf(w1, mg[j2], s0);             s1 = fmaf(w1, mg[kMagStride + j2], s1);
+    for (int i = lane; i < len; i += 32) {
+      const int k = k0 + i;
+      const int kk = (kNfft - k) & (kNfft - 1);
+      const float w = __ldg(wt + i);
+      const float2 zk = scratch[(k & 3) * kScratchPerWarp + (k >> 2)];
+      const float2 zn = scratch[(kk & 3) * kScratchPerWarp + (kk >> 2)];
+      const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+      const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zk.x - zn.x);
+      s0 = fmaf(w, sqrtf(ar * ar + ai * ai), s0);
+      s1 = fmaf(w, sqrtf(br * br + bi * bi), s1);
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
     if (lane < 2) {

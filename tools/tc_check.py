@@ -16,9 +16,9 @@ def run(ckpt, clips):
     for tc in (0, 1):
         eng.set_option("conv_tc", tc)
         sc, nseg, st = eng.predict_pcm(pcm, srs)
-        res[tc] = (sc.copy(), eng.stage_dump(E.STAGE_CONV3), eng.stage_dump(E.STAGE_POOL3), eng.stage_dump(E.STAGE_CNN_FEAT))
+        res[tc] = (sc.copy(), eng.stage_dump(E.STAGE_POOL2), eng.stage_dump(E.STAGE_CONV3), eng.stage_dump(E.STAGE_POOL3), eng.stage_dump(E.STAGE_CONV5), eng.stage_dump(E.STAGE_CNN_FEAT))
         print(ckpt, "conv_tc=%d" % tc, "scores[0]", sc[0].tolist(), flush=True)
-    for i, nm in enumerate(["scores", "conv3", "pool3", "feat"]):
+    for i, nm in enumerate(["scores", "pool2", "conv3", "pool3", "conv5", "feat"]):
         a, b = res[0][i], res[1][i]
         print("  %s: max|tc-ffma| = %.3e  (max |ffma| %.3e)" % (nm, np.abs(a - b).max(), np.abs(a).max()))
     worst = 0
