@@ -7,9 +7,10 @@
 // 4096-point DFT is computed as a radix-4 decimation-in-frequency step whose butterflies
 // collapse to a twiddle multiply, followed by four independent 1024-point FFTs (one per warp,
 // residue r = k mod 4).  Each 1024-point FFT is two in-register radix-32 passes with one
-// shared-memory transpose.  Then: unpack the two real spectra, |.|, sparse mel (band-major
-// CSR), 10*log10(max(1e-8, M^2)), and a per-clip atomic max for the top_db clamp, which is
-// applied by the consumers (conv1 / stage dump) as max(dB, clipmax - 80).
+// shared-memory transpose.  Then, fused per mel band: unpack the two real spectra, |.|, sparse
+// mel (band-major CSR), 10*log10(max(1e-8, M^2)), and a per-clip atomic max for the top_db
+// clamp, which is applied by the consumers (conv1 / stage dump) as max(dB, clipmax - 80).
+// Grid: x = frame pair, y = clip.
 #include "common.cuh"
 
 namespace nisqa {
@@ -89,7 +90,7 @@ __host__ __device__ constexpr int fe_region0_bytes(int Q) { return 1024 * Q * 8;
 int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWarp * 8; }
 
 template <typename T>
-__global__ void __launch_bounds__(kFeThreads)
+__global__ void __launch_bounds__(kFeThreads, 5)
 frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
                 const FbTables* __restrict__ fbs,
                 const float2* __restrict__ tw1 /*[3][32][32]: W4096^(r*(lane+32j))*/,
@@ -177,35 +178,49 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   //         One warp item = one band of BOTH frames; lanes stride over the band's bins.  A bin
   //         belongs to two adjacent triangles, so its magnitudes are formed twice - cheaper
   //         than a shared-memory round trip (and it frees 16 KB: 5 CTAs / SM instead of 4).
-  float wmax = -INFINITY;
-  for (int b = warp; b < kMels; b += kFeThreads / 32) {
+  // Band sums of this warp's 12 bands are parked in lanes 0..23 (lane = 2*slot + frame) so
+  // that the dB conversion (log10f) runs once per warp instead of once per band.
+  float mine = 0.f;
+  int slot = 0;
+  for (int b = warp; b < kMels; b += kFeThreads / 32, ++slot) {
     const int beg = band_meta[b], len = band_meta[b + 1] - beg;
-    const int k0 = band_meta[kMels + 1 + b];
-    const float* wt = fb.weights + beg;
+    const int k = band_meta[kMels + 1 + b] + lane;
+    const int kk = (kNfft - k) & (kNfft - 1);
+    // Z planes: bin k lives at plane (k & 3), slot (k >> 2); k advances by 32 per iteration,
+    // so both indices move by +-8 and the plane never changes.
+    const float2* pk = scratch + (k & 3) * kScratchPerWarp + (k >> 2);
+    const float2* pn = scratch + (kk & 3) * kScratchPerWarp + (kk >> 2);
+    const float* wt = fb.weights + beg + lane;
     float s0 = 0.f, s1 = 0.f;
     for (int i = lane; i < len; i += 32) {
-      const int k = k0 + i;
-      const int kk = (kNfft - k) & (kNfft - 1);
-      const float w = __ldg(wt + i);
-      const float2 zk = scratch[(k & 3) * kScratchPerWarp + (k >> 2)];
-      const float2 zn = scratch[(kk & 3) * kScratchPerWarp + (kk >> 2)];
-      const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-      const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zk.x - zn.x);
-      s0 = fmaf(w, sqrtf(ar * ar + ai * ai), s0);
-      s1 = fmaf(w, sqrtf(br * br + bi * bi), s1);
+      const float w = __ldg(wt);
+      const float2 zk = *pk, zn = *pn;
+      wt += 32; pk += 8; pn -= 8;
+      const float ar = zk.x + zn.x, ai = zk.y - zn.y;      // 2 * X_a[k]
+      const float br = zk.y + zn.y, bi = zk.x - zn.x;      // 2 * X_b[k] (up to a unit factor)
+      float ma, mb;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
+      s0 = fmaf(w, ma, s0);
+      s1 = fmaf(w, mb, s1);
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (lane < 2) {
-      const float sv = lane ? s1 : s0;
-      if (lane == 0 || validB) {
-        const float p = sv * sv;
-        const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
-        mel[(size_t)(cd.frame_off + tA + lane) * kMels + b] = db;
-        wmax = fmaxf(wmax, db);
-      }
+    if (lane == 2 * slot) mine = s0;
+    if (lane == 2 * slot + 1) mine = s1;
+  }
+  float wmax = -INFINITY;
+  {
+    const int my_slot = lane >> 1, f = lane & 1;
+    const int b = warp + my_slot * (kFeThreads / 32);
+    if (my_slot < slot && (f == 0 || validB)) {
+      const float sv = 0.5f * mine;                        // the 1/2 of the real-pair unpacking
+      const float p = sv * sv;
+      const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
+      mel[(size_t)(cd.frame_off + tA + f) * kMels + b] = db;
+      wmax = db;
     }
   }
-  wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));
+  wmax = warp_max(wmax);
   if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
 }
 
