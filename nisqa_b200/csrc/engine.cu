@@ -128,9 +128,16 @@ struct nisqa_engine {
   DevBuf tw4096;         // float2[4096]
 
   // per-pass workspaces
-  DevBuf pcm, clips, prefixes, clipmax, mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
+  // host->device staging is double buffered (slot = pass & 1) and fed by a dedicated copy
+  // stream, so the upload of pass p+1 overlaps the kernels of pass p
+  DevBuf pcm[2], clips[2], prefixes[2], clipmax[2];
+  HostBuf h_tables[2], h_scores;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
+  int last_slot = 0;
+  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
       qkv, logits, feats20, tdout, partial, scores, dump;
-  HostBuf h_tables, h_scores;
 
   // description of the last pass (stage dumps)
   std::vector<ClipDesc> last_clips;
@@ -144,11 +151,17 @@ struct nisqa_engine {
 
   ~nisqa_engine() {
     for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); delete f; }
-    DevBuf* all[] = {&warena, &fb_table, &tw4096, &pcm, &clips, &prefixes, &clipmax, &mel, &segtab, &act1,
+    DevBuf* all[] = {&warena, &fb_table, &tw4096, &pcm[0], &pcm[1], &clips[0], &clips[1], &prefixes[0],
+                     &prefixes[1], &clipmax[0], &clipmax[1], &mel, &segtab, &act1,
                      &act2, &act3, &act4, &act5, &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout,
                      &partial, &scores, &dump};
     for (auto* b : all) b->release();
-    h_tables.release(); h_scores.release();
+    h_tables[0].release(); h_tables[1].release(); h_scores.release();
+    for (int i = 0; i < 2; ++i) {
+      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto& t : timers) for (auto& e : t.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (stream) cudaStreamDestroy(stream);
   }
@@ -514,8 +527,8 @@ struct PassInput {
   const void* const* host_pcm;        // per-clip host pointers, or
   const void* dev_pcm; const int64_t* dev_off;   // packed device buffer + element offsets
   int fmt;
-  float* scores_dev_out;              // optional device destination [n_clips][n_out]
-  float* scores_host_out;             // optional host destination
+  float* scores_dev_out;              // device destination [n_clips][n_out]
+  int slot;                           // staging slot (pass & 1)
 };
 
 int run_pass(nisqa_engine* e, const PassInput& in) {
@@ -553,44 +566,52 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   e->last_n_seg = n_seg; e->last_n_frames = n_frames;
   const int n_out = c.n_out;
 
-  CK(e->scores.reserve((size_t)n * n_out * 4));
-  float* scores = in.scores_dev_out ? in.scores_dev_out : e->scores.as<float>();
+  float* scores = in.scores_dev_out;
+  const int slot = in.slot;
+  cudaStream_t st = e->stream, cs = e->copy_stream;
+  // the slot (pinned tables, device tables, PCM buffer) is reused every second pass
+  if (e->slot_busy[slot]) { CK(cudaEventSynchronize(e->ev_done[slot])); e->slot_busy[slot] = false; }
 
   // ---- upload tables (one pinned block: ClipDesc[n] | 3 prefix arrays)
   const size_t tb_clips = (size_t)n * sizeof(ClipDesc);
   const size_t tb_pref = (size_t)(n + 1) * 4;
-  CK(e->h_tables.reserve(tb_clips + 3 * tb_pref));
-  CK(cudaStreamSynchronize(e->stream));        // pinned block may still be in flight from the last pass
-  char* ht = e->h_tables.as<char>();
+  CK(e->h_tables[slot].reserve(tb_clips + 3 * tb_pref));
+  char* ht = e->h_tables[slot].as<char>();
   memcpy(ht, cl.data(), tb_clips);
   memcpy(ht + tb_clips, pair_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + tb_pref, seg_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + 2 * tb_pref, qt_prefix.data(), tb_pref);
-  CK(e->clips.reserve(tb_clips));
-  CK(e->prefixes.reserve(3 * tb_pref));
-  CK(e->clipmax.reserve((size_t)n * 4));
-  cudaStream_t st = e->stream;
-  CK(cudaMemcpyAsync(e->clips.p, ht, tb_clips, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(e->clipmax.p, 0, (size_t)n * 4, st));
-  const ClipDesc* d_clips = e->clips.as<ClipDesc>();
-  const int* d_pair = e->prefixes.as<int>();
+  CK(e->clips[slot].reserve(tb_clips));
+  CK(e->prefixes[slot].reserve(3 * tb_pref));
+  CK(e->clipmax[slot].reserve((size_t)n * 4));
+  CK(cudaMemcpyAsync(e->clips[slot].p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(e->prefixes[slot].p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemsetAsync(e->clipmax[slot].p, 0, (size_t)n * 4, cs));
+  const ClipDesc* d_clips = e->clips[slot].as<ClipDesc>();
+  unsigned* d_clipmax = e->clipmax[slot].as<unsigned>();
+  const int* d_pair = e->prefixes[slot].as<int>();
+  (void)d_pair;
+  e->last_slot = slot;
   const int* d_seg = d_pair + (n + 1);
   const int* d_qt = d_pair + 2 * (n + 1);
 
   if (n_seg == 0) {   // nothing valid in this pass: NaN scores
+    CK(cudaEventRecord(e->ev_copied[slot], cs));
+    CK(cudaStreamWaitEvent(st, e->ev_copied[slot], 0));
     CK(cudaMemsetAsync(scores, 0xFF, (size_t)n * n_out * 4, st));
   } else {
-    // ---- PCM
+    // ---- PCM (copy stream), then hand over to the compute stream
     const void* d_pcm = in.dev_pcm;
     if (in.host_pcm) {
-      CK(e->pcm.reserve((size_t)pcm_elems * esz));
+      CK(e->pcm[slot].reserve((size_t)pcm_elems * esz));
       for (int i = 0; i < n; ++i)
         if (cl[i].n_frames > 0)
-          CK(cudaMemcpyAsync(e->pcm.as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
-                             (size_t)in.n_samples[i] * esz, cudaMemcpyHostToDevice, st));
-      d_pcm = e->pcm.p;
+          CK(cudaMemcpyAsync(e->pcm[slot].as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
+                             (size_t)in.n_samples[i] * esz, cudaMemcpyHostToDevice, cs));
+      d_pcm = e->pcm[slot].p;
     }
+    CK(cudaEventRecord(e->ev_copied[slot], cs));
+    CK(cudaStreamWaitEvent(st, e->ev_copied[slot], 0));
     // ---- workspaces
     const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
     const int FEAT = std_mode ? 768 : 384;
@@ -609,9 +630,9 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "frontend");
       launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, max_pairs,
                       e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), e->mel.as<float>(),
-                      e->clipmax.as<unsigned>(), Q); }
+                      d_clipmax, Q); }
     { Scope s(e, "seg_table");
-      launch_seg_table(st, d_clips, n, d_seg, e->clipmax.as<unsigned>(), c.seg_hop, n_seg,
+      launch_seg_table(st, d_clips, n, d_seg, d_clipmax, c.seg_hop, n_seg,
                        seg_frame0, seg_thr, seg_clip); }
     { Scope s(e, "conv1");
       launch_conv1(st, std_mode, e->mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
@@ -674,12 +695,8 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     }
   }
   CK(cudaGetLastError());
-  if (in.scores_host_out) {
-    CK(e->h_scores.reserve((size_t)n * n_out * 4));
-    CK(cudaMemcpyAsync(e->h_scores.p, scores, (size_t)n * n_out * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(in.scores_host_out, e->h_scores.p, (size_t)n * n_out * 4);
-  }
+  CK(cudaEventRecord(e->ev_done[slot], st));
+  e->slot_busy[slot] = true;
   return 0;
 }
 
@@ -705,7 +722,20 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     if (n_seg_out) n_seg_out[i] = plan[i].n_seg;
     if (status_out) status_out[i] = plan[i].status;
   }
-  const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
+  int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
+  if (host_pcm && e->cfg.max_chunk_segments <= 0) {
+    // host input: cut the call into ~4 passes (>= 2048 segments each) so that the upload of the
+    // next pass overlaps the kernels of the current one
+    long long total = 0;
+    for (int i = 0; i < n_clips; ++i) total += plan[i].status == NISQA_CLIP_OK ? plan[i].n_seg : 0;
+    const long long want = std::max<long long>(2048, (total + 3) / 4);
+    max_seg = (int)std::min<long long>(max_seg, want);
+  }
+  float* scores_all = scores_dev;
+  if (!scores_all) {
+    CK(e->scores.reserve((size_t)std::max(n_clips, 1) * e->cfg.n_out * 4));
+    scores_all = e->scores.as<float>();
+  }
   int i0 = 0;
   e->last_passes = 0;
   while (i0 < n_clips) {
@@ -720,12 +750,19 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     in.host_pcm = host_pcm ? host_pcm + i0 : nullptr;
     in.dev_pcm = dev_pcm; in.dev_off = dev_off ? dev_off + i0 : nullptr;
     in.fmt = fmt;
-    in.scores_dev_out = scores_dev ? scores_dev + (size_t)i0 * e->cfg.n_out : nullptr;
-    in.scores_host_out = scores_host ? scores_host + (size_t)i0 * e->cfg.n_out : nullptr;
+    in.scores_dev_out = scores_all + (size_t)i0 * e->cfg.n_out;
+    in.slot = e->last_passes & 1;
     int rc = run_pass(e, in);
     if (rc) return rc;
     ++e->last_passes;
     i0 = i1;
+  }
+  if (scores_host && n_clips > 0) {
+    const size_t bytes = (size_t)n_clips * e->cfg.n_out * 4;
+    CK(e->h_scores.reserve(bytes));
+    CK(cudaMemcpyAsync(e->h_scores.p, scores_all, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(scores_host, e->h_scores.p, bytes);
   }
   if (sync || scores_host || e->profiling) CK(cudaStreamSynchronize(e->stream));
   if (e->profiling) collect_timers(e);
@@ -762,6 +799,11 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(e, NISQA_ERR_CUDA, "libnisqa_b200 is compiled for sm_100a only");
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+  }
   // twiddles laid out per lane so that every warp load is coalesced:
   //   tw1[r-1][j][lane] = W_4096^(r*(lane+32j)),  tw2[q][lane] = W_1024^(lane*q)
   std::vector<float2> tw(4 * 1024);
@@ -782,6 +824,7 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
 void nisqa_destroy(nisqa_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
   delete e;
 }
@@ -851,8 +894,8 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   cudaStream_t st = e->stream;
   if (stage == NISQA_STAGE_MEL_DB) {
     CK(e->dump.reserve((size_t)count * 4));
-    launch_mel_dump(st, e->mel.as<float>(), e->clips.as<ClipDesc>(), (int)e->last_clips.size(),
-                    e->clipmax.as<unsigned>(), e->dump.as<float>());
+    launch_mel_dump(st, e->mel.as<float>(), e->clips[e->last_slot].as<ClipDesc>(), (int)e->last_clips.size(),
+                    e->clipmax[e->last_slot].as<unsigned>(), e->dump.as<float>());
     src = e->dump.as<float>();
   } else if (ch > 0) {
     CK(e->dump.reserve((size_t)count * 4));
