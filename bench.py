@@ -249,24 +249,42 @@ def run_ours(a, rank, world, local):
         if gather is not None:
             gather()
 
+    # e2e: the public streaming API - submit batch i (pinned host PCM16 -> H2D -> kernels -> D2H of the
+    # scores), then collect batch i-1; two batches in flight, every step's copies inside the timed region
+    e2e_scores = [np.empty((BS, n_out), dtype=np.float32) for _ in range(2)]
+    e2e_aux = [(np.empty(BS, np.int32), np.empty(BS, np.int32)) for _ in range(2)]
+    tickets = [None, None]
+
     def step_e2e(i):
-        eng.predict_pcm_ptrs(ptr_arrays[i % N_ROT], n_s, srs, E.FMT_S16, scores_host)
-        if gather is not None:
-            scores_dev.copy_(torch.from_numpy(scores_host))
-            gather()
+        k = i & 1
+        if tickets[k] is not None:
+            eng.wait_ticket(tickets[k])
+        tickets[k] = eng.submit_pcm_ptrs(ptr_arrays[i % N_ROT], n_s, srs, E.FMT_S16, e2e_scores[k], e2e_aux[k][0], e2e_aux[k][1])
+        if tickets[k ^ 1] is not None:
+            eng.wait_ticket(tickets[k ^ 1]); tickets[k ^ 1] = None
+            if gather is not None:
+                scores_dev.copy_(torch.from_numpy(e2e_scores[k ^ 1]))
+                gather()
+
+    def drain_e2e():
+        for k in (0, 1):
+            if tickets[k] is not None:
+                eng.wait_ticket(tickets[k]); tickets[k] = None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
         for i in range(steps):
             fn(i)
+        if drain is not None:
+            drain()
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -299,9 +317,10 @@ def run_ours(a, rank, world, local):
     l0 = eng.kernel_launches()
     ms_dev, _ = timed(step_dev, a.steps)
     launches = eng.kernel_launches() - l0
-    for i in range(a.warmup):
+    for i in range(max(a.warmup, 4)):
         step_e2e(i)
-    ms_e2e, wall_e2e = timed(step_e2e, a.steps)
+    drain_e2e()
+    ms_e2e, wall_e2e = timed(step_e2e, a.steps, drain_e2e)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel durations (CUDA events on the engine stream), same workload
@@ -325,8 +344,8 @@ def run_ours(a, rank, world, local):
     peaks = measured_peaks()
     total_clips = BS * world * a.steps
     value = total_clips / (ms_dev / 1e3)
-    e2e_value = total_clips / (max(ms_e2e / 1e3, 1e-9))
     e2e_wall = total_clips / max(wall_e2e, 1e-9)
+    e2e_value = min(total_clips / (max(ms_e2e / 1e3, 1e-9)), e2e_wall)
     # dominant kernel = largest measured share of the step
     dom = max(("conv2", "conv3", "conv4", "conv5", "conv6", "conv1", "frontend"), key=lambda k: kernel_ms[k])
     n_seg_step = BS * SEGS_PER_CLIP
@@ -376,7 +395,7 @@ def run_ours(a, rank, world, local):
                        "exchange": "1 ncclAllGather of [64,5] rows per step" if world > 1 else "none (N=1)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(BS * int(n_s[0]) * 2),
                     "d2h_bytes_per_step": int(BS * n_out * 4), "wall_clock_value": e2e_wall,
-                    "api": "nisqa_predict_pcm (C-ABI) on pinned host PCM16"},
+                    "api": "nisqa_submit_pcm / nisqa_wait (C-ABI, two batches in flight) on pinned host PCM16; value is wall-clock based"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "kernel_ms_per_step": kernel_ms, "cnn_ms_per_step": cnn_ms,
             "achieved_tflops_whole_step": FLOP_PER_CLIP * BS / (ms_dev / a.steps / 1e3) / 1e12,

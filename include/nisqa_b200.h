@@ -115,6 +115,19 @@ NISQA_API int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
                        const int32_t* sample_rate, int sample_fmt,
                        float* scores_out, int32_t* n_segments_out, int32_t* status_out);
 
+/* Asynchronous form of nisqa_predict_pcm for streams of batches (what the reference gets from
+ * DataLoader prefetching, lib:1425-1430): returns as soon as the copies and kernels are enqueued;
+ * up to two submissions are in flight, so the host->device copy of batch k+1 overlaps the kernels
+ * of batch k.  n_segments_out / status_out are valid on return (host arithmetic); scores_out and the
+ * PCM buffers must stay alive until nisqa_wait(ticket) returns.  Submitting a third batch first
+ * waits for the oldest one. */
+NISQA_API int  nisqa_submit_pcm(nisqa_engine* e, int n_clips,
+                                const void* const* pcm, const int64_t* n_samples,
+                                const int32_t* sample_rate, int sample_fmt,
+                                float* scores_out, int32_t* n_segments_out, int32_t* status_out,
+                                int64_t* ticket);
+NISQA_API int  nisqa_wait(nisqa_engine* e, int64_t ticket);
+
 /* Same computation with the packed PCM already resident in device memory (clips laid back
  * to back, clip i starting at element offset pcm_offsets[i]); scores stay on the device
  * (scores_dev [n_clips, n_out]).  Asynchronous on the engine stream unless sync != 0.

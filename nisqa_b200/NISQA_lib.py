@@ -102,19 +102,29 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
         def collect(h):
             return h.result() if not isinstance(h, list) else [f.result() for f in h]
 
+        def finish(job):
+            handle, batch, clips, srs, pos = job
+            scores, nseg, status = engine.wait(handle)
+            for j, st in enumerate(status):
+                if st != nb_engine.CLIP_OK:
+                    _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
+            out[pos:pos + len(batch)] = scores
+
         pending = submit(batches[0]) if batches else None
         pos = 0
+        in_flight = None              # the batch whose kernels are running while we decode / upload the next
         for b, batch in enumerate(batches):
             loaded = collect(pending)
             pending = submit(batches[b + 1]) if b + 1 < len(batches) else None
             clips = [c for c, _ in loaded]
             srs = [s for _, s in loaded]
-            scores, nseg, status = engine.predict_pcm(clips, srs)
-            for j, st in enumerate(status):
-                if st != nb_engine.CLIP_OK:
-                    _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
-            out[pos:pos + len(batch)] = scores
+            handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
+            if in_flight is not None:
+                finish(in_flight)
+            in_flight = (handle, batch, clips, srs, pos)
             pos += len(batch)
+        if in_flight is not None:
+            finish(in_flight)
     return out
 
 

@@ -96,6 +96,15 @@ struct ClipPlan {
   int hop, win, n_frames, n_seg, status, fb_id;
 };
 
+struct Ticket {          // one asynchronous nisqa_submit_pcm call
+  bool active = false;
+  int64_t id = 0;
+  size_t bytes = 0;
+  float* user_scores = nullptr;
+  HostBuf pinned;
+  cudaEvent_t done = nullptr;
+};
+
 struct TimerSlot {
   std::string name;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
@@ -136,6 +145,9 @@ struct nisqa_engine {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   int last_slot = 0;
+  int64_t pass_counter = 0;
+  Ticket tickets[2];
+  int64_t next_ticket = 1;
   DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
       qkv, logits, feats20, tdout, partial, scores, dump;
 
@@ -161,6 +173,7 @@ struct nisqa_engine {
       if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
     }
+    for (auto& tk : tickets) { tk.pinned.release(); if (tk.done) cudaEventDestroy(tk.done); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto& t : timers) for (auto& e : t.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (stream) cudaStreamDestroy(stream);
@@ -703,7 +716,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
 int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, const void* dev_pcm,
                    const int64_t* dev_off, const int64_t* n_samples, const int32_t* sample_rate,
                    int fmt, float* scores_host, float* scores_dev, int32_t* n_seg_out,
-                   int32_t* status_out, int sync) {
+                   int32_t* status_out, int sync, int64_t* ticket_out = nullptr) {
   if (!e) return NISQA_ERR_INVALID;
   if (!e->weights_loaded) return fail(e, NISQA_ERR_STATE, "nisqa_load_weights has not been called");
   if (n_clips < 0 || (n_clips > 0 && (!n_samples || !sample_rate)))
@@ -722,15 +735,7 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     if (n_seg_out) n_seg_out[i] = plan[i].n_seg;
     if (status_out) status_out[i] = plan[i].status;
   }
-  int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
-  if (host_pcm && e->cfg.max_chunk_segments <= 0) {
-    // host input: cut the call into ~4 passes (>= 2048 segments each) so that the upload of the
-    // next pass overlaps the kernels of the current one
-    long long total = 0;
-    for (int i = 0; i < n_clips; ++i) total += plan[i].status == NISQA_CLIP_OK ? plan[i].n_seg : 0;
-    const long long want = std::max<long long>(2048, (total + 3) / 4);
-    max_seg = (int)std::min<long long>(max_seg, want);
-  }
+  const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
   float* scores_all = scores_dev;
   if (!scores_all) {
     CK(e->scores.reserve((size_t)std::max(n_clips, 1) * e->cfg.n_out * 4));
@@ -751,11 +756,25 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     in.dev_pcm = dev_pcm; in.dev_off = dev_off ? dev_off + i0 : nullptr;
     in.fmt = fmt;
     in.scores_dev_out = scores_all + (size_t)i0 * e->cfg.n_out;
-    in.slot = e->last_passes & 1;
+    in.slot = (int)(e->pass_counter++ & 1);
     int rc = run_pass(e, in);
     if (rc) return rc;
     ++e->last_passes;
     i0 = i1;
+  }
+  if (ticket_out) {
+    // asynchronous completion: scores land in the ticket's pinned block; nisqa_wait hands them over
+    Ticket& tk = e->tickets[e->next_ticket & 1];
+    tk.bytes = (size_t)n_clips * e->cfg.n_out * 4;
+    tk.user_scores = scores_host;
+    CK(tk.pinned.reserve(std::max<size_t>(tk.bytes, 16)));
+    if (tk.bytes) CK(cudaMemcpyAsync(tk.pinned.p, scores_all, tk.bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (!tk.done) CK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
+    CK(cudaEventRecord(tk.done, e->stream));
+    tk.active = true;
+    tk.id = e->next_ticket++;
+    *ticket_out = tk.id;
+    return 0;
   }
   if (scores_host && n_clips > 0) {
     const size_t bytes = (size_t)n_clips * e->cfg.n_out * 4;
@@ -766,6 +785,14 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   }
   if (sync || scores_host || e->profiling) CK(cudaStreamSynchronize(e->stream));
   if (e->profiling) collect_timers(e);
+  return 0;
+}
+
+int finish_ticket(nisqa_engine* e, Ticket& tk) {
+  if (!tk.active) return 0;
+  CK(cudaEventSynchronize(tk.done));
+  if (tk.bytes && tk.user_scores) memcpy(tk.user_scores, tk.pinned.p, tk.bytes);
+  tk.active = false;
   return 0;
 }
 
@@ -847,8 +874,31 @@ int nisqa_predict_pcm(nisqa_engine* e, int n_clips, const void* const* pcm, cons
                       int32_t* n_segments_out, int32_t* status_out) {
   if (!e) return NISQA_ERR_INVALID;
   if (n_clips > 0 && (!pcm || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
+  for (auto& tk : e->tickets) { int rc = finish_ticket(e, tk); if (rc) return rc; }
   return predict_common(e, n_clips, pcm, nullptr, nullptr, n_samples, sample_rate, sample_fmt,
                         scores_out, nullptr, n_segments_out, status_out, 1);
+}
+
+int nisqa_submit_pcm(nisqa_engine* e, int n_clips, const void* const* pcm, const int64_t* n_samples,
+                     const int32_t* sample_rate, int sample_fmt, float* scores_out,
+                     int32_t* n_segments_out, int32_t* status_out, int64_t* ticket) {
+  if (!e || !ticket) return NISQA_ERR_INVALID;
+  if (n_clips > 0 && (!pcm || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
+  if (e->profiling) return fail(e, NISQA_ERR_STATE, "profiling needs the synchronous entry points");
+  int rc = finish_ticket(e, e->tickets[e->next_ticket & 1]);      // at most two submissions in flight
+  if (rc) return rc;
+  return predict_common(e, n_clips, pcm, nullptr, nullptr, n_samples, sample_rate, sample_fmt,
+                        scores_out, nullptr, n_segments_out, status_out, 0, ticket);
+}
+
+int nisqa_wait(nisqa_engine* e, int64_t ticket) {
+  if (!e) return NISQA_ERR_INVALID;
+  CK(cudaSetDevice(e->device));
+  // tickets complete in submission order: finish everything up to and including `ticket`
+  for (int pass = 0; pass < 2; ++pass)
+    for (auto& tk : e->tickets)
+      if (tk.active && tk.id <= ticket && (pass == 1 || tk.id < ticket)) { int rc = finish_ticket(e, tk); if (rc) return rc; }
+  return 0;
 }
 
 int nisqa_predict_pcm_device(nisqa_engine* e, int n_clips, const void* pcm_dev, const int64_t* pcm_offsets,

@@ -26,6 +26,7 @@ EXPORTS = [
     "nisqa_predict_pcm", "nisqa_predict_pcm_device", "nisqa_stage_dump", "nisqa_segment_counts",
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
+    "nisqa_submit_pcm", "nisqa_wait",
 ]
 
 
@@ -71,6 +72,10 @@ def load_library(path=None):
     lib.nisqa_load_weights.restype = C.c_int
     lib.nisqa_predict_pcm.argtypes = [vp, C.c_int, C.POINTER(vp), i64p, i32p, C.c_int, f32p, i32p, i32p]
     lib.nisqa_predict_pcm.restype = C.c_int
+    lib.nisqa_submit_pcm.argtypes = [vp, C.c_int, C.POINTER(vp), i64p, i32p, C.c_int, f32p, i32p, i32p, i64p]
+    lib.nisqa_submit_pcm.restype = C.c_int
+    lib.nisqa_wait.argtypes = [vp, C.c_int64]
+    lib.nisqa_wait.restype = C.c_int
     lib.nisqa_predict_pcm_device.argtypes = [vp, C.c_int, vp, i64p, i64p, i32p, C.c_int, vp, i32p, i32p, C.c_int]
     lib.nisqa_predict_pcm_device.restype = C.c_int
     lib.nisqa_stage_dump.argtypes = [vp, C.c_int, f32p, C.c_int64]
@@ -239,6 +244,50 @@ class Engine(object):
             status.ctypes.data_as(C.POINTER(C.c_int32)))
         self._check(rc, "nisqa_predict_pcm")
         return scores, nseg, status
+
+    def submit_pcm(self, clips, sample_rates):
+        """Asynchronous predict_pcm: returns a handle; ``wait(handle)`` -> (scores, n_segments, status).
+        Up to two submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
+        n = len(clips)
+        dt = clips[0].dtype if n else np.dtype(np.int16)
+        if any(c.dtype != dt for c in clips):
+            clips = [c if c.dtype == np.float32 else c.astype(np.float32) / np.float32(32768.0) for c in clips]
+            dt = np.dtype(np.float32)
+        if dt not in (np.dtype(np.int16), np.dtype(np.float32)):
+            raise ValueError("clips must be int16 or float32")
+        fmt = FMT_S16 if dt == np.int16 else FMT_F32
+        clips = [np.ascontiguousarray(c) for c in clips]
+        ptrs = (C.c_void_p * max(n, 1))(*[c.ctypes.data for c in clips])
+        ns = np.array([c.shape[0] for c in clips], dtype=np.int64)
+        sr = np.ascontiguousarray(sample_rates, dtype=np.int32)
+        scores = np.empty((n, self.n_out), dtype=np.float32)
+        nseg = np.empty(n, dtype=np.int32)
+        status = np.empty(n, dtype=np.int32)
+        ticket = C.c_int64(0)
+        rc = self.lib.nisqa_submit_pcm(
+            self.h, n, ptrs, ns.ctypes.data_as(C.POINTER(C.c_int64)), sr.ctypes.data_as(C.POINTER(C.c_int32)),
+            fmt, scores.ctypes.data_as(C.POINTER(C.c_float)), nseg.ctypes.data_as(C.POINTER(C.c_int32)),
+            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ticket))
+        self._check(rc, "nisqa_submit_pcm")
+        return (ticket.value, scores, nseg, status, clips, ptrs, ns, sr)      # keeps the buffers alive
+
+    def wait(self, handle):
+        self._check(self.lib.nisqa_wait(self.h, handle[0]), "nisqa_wait")
+        return handle[1], handle[2], handle[3]
+
+    def submit_pcm_ptrs(self, ptrs, n_samples, sample_rates, fmt, scores_out, nseg, status):
+        """Raw-pointer asynchronous variant (bench e2e).  Returns the ticket."""
+        ticket = C.c_int64(0)
+        rc = self.lib.nisqa_submit_pcm(
+            self.h, len(n_samples), ptrs, n_samples.ctypes.data_as(C.POINTER(C.c_int64)),
+            sample_rates.ctypes.data_as(C.POINTER(C.c_int32)), fmt,
+            scores_out.ctypes.data_as(C.POINTER(C.c_float)), nseg.ctypes.data_as(C.POINTER(C.c_int32)),
+            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ticket))
+        self._check(rc, "nisqa_submit_pcm")
+        return ticket.value
+
+    def wait_ticket(self, ticket):
+        self._check(self.lib.nisqa_wait(self.h, int(ticket)), "nisqa_wait")
 
     def predict_pcm_ptrs(self, ptrs, n_samples, sample_rates, fmt, scores_out):
         """Raw-pointer variant (bench e2e: pinned host buffers).  ptrs: ctypes array of void*."""

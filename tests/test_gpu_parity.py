@@ -291,3 +291,24 @@ def test_reference_error_behaviour(tmp_path, built_lib):
         nisqaModel(dict(base, mode="predict_dir", data_dir=str(empty)))
     with pytest.raises(NotImplementedError):
         nisqaModel(dict(base, mode="predict_nothing"))
+
+
+def test_async_submit_wait_equals_sync(engines):
+    """nisqa_submit_pcm / nisqa_wait (two batches in flight) return exactly what the synchronous
+    entry point returns, in submission order, also when collected late or out of order."""
+    eng, args, sd = engines["nisqa.tar"]
+    batches = [[synth.synth_speech_pcm16(700 + 10 * b + i, 1.0 + 0.3 * i + 0.1 * b, 48000) for i in range(4)] for b in range(5)]
+    ref = [eng.predict_pcm(bt, [48000] * 4) for bt in batches]
+    handles = []
+    got = {}
+    for b, bt in enumerate(batches):
+        handles.append(eng.submit_pcm(bt, [48000] * 4))       # third submit waits for the oldest internally
+        if b >= 2:
+            got[b - 2] = eng.wait(handles[b - 2])
+    got[4] = eng.wait(handles[4])                               # newest first ...
+    got[3] = eng.wait(handles[3])                               # ... then an already finished one
+    for b in range(5):
+        np.testing.assert_array_equal(got[b][0], ref[b][0])
+        np.testing.assert_array_equal(got[b][1], ref[b][1])
+    s, n, st = eng.predict_pcm(batches[0], [48000] * 4)         # sync call after async traffic
+    np.testing.assert_array_equal(s, ref[0][0])
