@@ -110,6 +110,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 
+#ifdef NISQA_TC_TIMING
+__device__ long long g_tc_timing[8 * 8192];
+#endif
+__device__ __forceinline__ void tc_stamp(int slot, int who) {
+#ifdef NISQA_TC_TIMING
+  if ((int)threadIdx.x == who && blockIdx.x < 8192) g_tc_timing[blockIdx.x * 8 + slot] = clock64();
+#endif
+}
+
 // ------------------------------------------------------------------ configuration
 enum { TC_POOL_NONE = 0, TC_POOL_ADAPT = 1, TC_POOL_2X2 = 2 };
 
@@ -162,6 +171,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 16 * NS + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg0 = blockIdx.x * G;
+  tc_stamp(0, 0);
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
   if (tid == 32) {
@@ -174,6 +184,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  tc_stamp(1, 0);
 
   // ---- weight producer: the first NS taps are in flight while the activation tile is staged
   if (tid == 160) {
@@ -224,6 +235,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
   }
   fence_proxy_async();          // generic-proxy stores -> visible to the tensor-core (async) proxy
   __syncthreads();
+  tc_stamp(2, 0);
 
   if (warp == 5) {
     // ===== weight producer (one lane) =====
@@ -242,6 +254,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
       for (int t = 0; t < 9; ++t) {
         const int s = t % NS;
         mbar_wait(bar_full + 8 * s, (t / NS) & 1);
+        if (t == 0) tc_stamp(6, 128);
         tc_fence_after();
         const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
         const uint32_t bh = b_base + s * C::B_STAGE, bl = bh + C::B_HALF;
@@ -265,11 +278,13 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
       }
       umma_commit(bar_acc);                      // all accumulators final
+      tc_stamp(7, 128);
     }
   } else {
     // ===== epilogue: warps 0..3 <-> TMEM lanes 32w..32w+31 =====
     mbar_wait(bar_acc, 0);
     tc_fence_after();
+    tc_stamp(3, 0);
     float* stg = reinterpret_cast<float*>(smem);          // reuses the A/B region (all MMAs retired)
     constexpr int WOUT = C::CENTER ? 1 : W;
 #pragma unroll 1
@@ -323,18 +338,29 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
       }
     }
   }
+  tc_stamp(4, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+  tc_stamp(5, 0);
 }
 
+#ifndef NISQA_TC_NS4
+#define NISQA_TC_NS4 2
+#endif
+#ifndef NISQA_TC_NS5
+#define NISQA_TC_NS5 2
+#endif
+#ifndef NISQA_TC_NS3
+#define NISQA_TC_NS3 4
+#endif
 // layers 2..6; std_mode selects the StandardCNN geometry (W 8/4/2, MaxPool2d(2))
 //                      H   W  CIN COUT POOL           POW NSTAGE CENTER
 using TcConv2A = TcCfg<24, 7, 16, 32, TC_POOL_ADAPT, 5, 9>;
-using TcConv3A = TcCfg<12, 5, 32, 64, TC_POOL_NONE, 0, 4>;
-using TcConv4A = TcCfg<12, 5, 64, 64, TC_POOL_ADAPT, 3, 2>;
-using TcConv5A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, 2>;
-using TcConv6A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, 2, true>;
+using TcConv3A = TcCfg<12, 5, 32, 64, TC_POOL_NONE, 0, NISQA_TC_NS3>;
+using TcConv4A = TcCfg<12, 5, 64, 64, TC_POOL_ADAPT, 3, NISQA_TC_NS4>;
+using TcConv5A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5>;
+using TcConv6A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5, true>;
 using TcConv2S = TcCfg<24, 8, 16, 32, TC_POOL_2X2, 4, 9>;
 using TcConv3S = TcCfg<12, 4, 32, 64, TC_POOL_NONE, 0, 4>;
 using TcConv4S = TcCfg<12, 4, 64, 64, TC_POOL_2X2, 2, 2>;
@@ -371,5 +397,11 @@ void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, c
     }
   }
 }
+
+#ifdef NISQA_TC_TIMING
+int tc_timing_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_tc_timing, sizeof(long long) * n);
+}
+#endif
 
 }  // namespace nisqa

@@ -34,6 +34,9 @@ void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const
 void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
 // conv_tc.cu
 void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int);
+#ifdef NISQA_TC_TIMING
+int tc_timing_read(long long*, int);
+#endif
 // td.cu
 struct SaLayerParams {
   const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
@@ -1096,3 +1099,9 @@ int nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm, const float* local_dev, 
 }
 
 }  // extern "C"
+
+#ifdef NISQA_TC_TIMING
+extern "C" __attribute__((visibility("default"))) int nisqa_debug_tc_timing(long long* host, int n) {
+  return nisqa::tc_timing_read(host, n);
+}
+#endif
