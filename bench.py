@@ -264,12 +264,17 @@ def run_ours(a, rank, world, local):
             eng.wait_ticket(tickets[k ^ 1]); tickets[k ^ 1] = None
             if gather is not None:
                 scores_dev.copy_(torch.from_numpy(e2e_scores[k ^ 1]))
+                torch.cuda.current_stream().synchronize()
                 gather()
 
     def drain_e2e():
         for k in (0, 1):
             if tickets[k] is not None:
                 eng.wait_ticket(tickets[k]); tickets[k] = None
+                if gather is not None:
+                    scores_dev.copy_(torch.from_numpy(e2e_scores[k]))
+                    torch.cuda.current_stream().synchronize()
+                    gather()
 
     def barrier():
         if world > 1:
@@ -305,10 +310,21 @@ def run_ours(a, rank, world, local):
         ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
         parity = float(np.abs(got - ref).max())
 
-    t_w, i_w = time.perf_counter(), 0
-    while i_w < a.warmup or time.perf_counter() - t_w < a.warmup_seconds:   # clocks need ~1 s to ramp
-        step_dev(i_w); i_w += 1
-        if i_w % 8 == 0:
+    # warm-up: W steps, then as many more as ~warmup_seconds needs (clocks take ~1 s to ramp).  The
+    # step count is agreed across ranks (every step holds a collective when N > 1).
+    t_w = time.perf_counter()
+    for i in range(a.warmup):
+        step_dev(i)
+    torch.cuda.synchronize()
+    per_step = max((time.perf_counter() - t_w) / max(a.warmup, 1), 1e-4)
+    n_extra = int(min(max(a.warmup_seconds / per_step, 0), 5000))
+    if world > 1:
+        t = torch.tensor([n_extra], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_extra = int(t[0])
+    for i in range(n_extra):
+        step_dev(a.warmup + i)
+        if i % 8 == 7:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
