@@ -343,7 +343,7 @@ def run_ours(a, rank, world, local):
 
     # ---- per-kernel durations (CUDA events on the engine stream), same workload
     eng.set_profiling(True)
-    names = ["frontend", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "lin_ln",
+    names = ["frontend", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "lin_ln", "qkv",
              "sa_layer", "pool", "seg_table"]
     acc = dict((k, 0.0) for k in names)
     prof_steps = max(3, min(a.steps, 10))

@@ -44,13 +44,12 @@ struct SaLayerParams {
 };
 struct PoolHeadParams { const float* W1T; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3; };
 struct LstmParams { const float* w_ih; const float* w_hh; const float* b; const float* w_pool; };
+void launch_lin_ln(cudaStream_t, const float*, const float*, const float*, const float*, const float*, float*, int);
 void launch_fc20(cudaStream_t, const float*, const float*, const float*, float*, int);
-void launch_lin_ln_qkv(cudaStream_t, const float*, const float*, const float*, const float*, const float*,
-                       const float*, const float*, float*, float*, int);
-void launch_sa_layer4(cudaStream_t, int, const float*, const float*, const ClipDesc*, int, int,
-                      const SaLayerParams&, const float*, const float*, float*, const PoolHeadParams&, int,
-                      float*, float*);
-void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
+void launch_qkv(cudaStream_t, const float*, const float*, const float*, float*, int);
+void launch_sa_layer(cudaStream_t, const float*, const float*, const ClipDesc*, int, const int*, int,
+                     const SaLayerParams&, float*);
+void launch_pool_att(cudaStream_t, const float*, const ClipDesc*, int, int, const PoolHeadParams&, int, float*, float*);
 void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmParams&, float*, float*, float, float*);
 }  // namespace nisqa
 
@@ -153,7 +152,7 @@ struct nisqa_engine {
   Ticket tickets[2];
   int64_t next_ticket = 1;
   DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
-      qkv, qkv2, logits, feats20, tdout, partial, scores, dump;
+      qkv, logits, feats20, tdout, partial, scores, dump;
 
   // description of the last pass (stage dumps)
   std::vector<ClipDesc> last_clips;
@@ -169,7 +168,7 @@ struct nisqa_engine {
     for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); delete f; }
     DevBuf* all[] = {&warena, &fb_table, &tw4096, &pcm[0], &pcm[1], &clips[0], &clips[1], &prefixes[0],
                      &prefixes[1], &clipmax[0], &clipmax[1], &mel, &segtab, &act1,
-                     &act2, &act3, &act4, &act5, &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout,
+                     &act2, &act3, &act4, &act5, &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout,
                      &partial, &scores, &dump};
     for (auto* b : all) b->release();
     h_tables[0].release(); h_tables[1].release(); h_scores.release();
@@ -558,7 +557,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   cl.assign(n, ClipDesc());
   std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0);
   long long pcm_elems = 0;
-  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0, max_seg_clip = 0;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0;
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
@@ -576,7 +575,6 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     n_frames += d.n_frames; n_seg += d.n_seg;
     n_pairs += (d.n_frames + 1) / 2;
     max_pairs = std::max(max_pairs, (d.n_frames + 1) / 2);
-    max_seg_clip = std::max(max_seg_clip, d.n_seg);
     n_qt += (d.n_seg + 127) / 128;
     if (ok) Q = std::max(Q, (p.win + 1023) / 1024);
   }
@@ -611,6 +609,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   (void)d_pair;
   e->last_slot = slot;
   const int* d_seg = d_pair + (n + 1);
+  const int* d_qt = d_pair + 2 * (n + 1);
 
   if (n_seg == 0) {   // nothing valid in this pass: NaN scores
     CK(cudaEventRecord(e->ev_copied[slot], cs));
@@ -675,35 +674,29 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       CK(e->xa.reserve((size_t)n_seg * 64 * 4));
       CK(e->xb.reserve((size_t)n_seg * 64 * 4));
       CK(e->qkv.reserve((size_t)n_seg * 192 * 4));
-      CK(e->qkv2.reserve((size_t)n_seg * 192 * 4));
       CK(e->logits.reserve((size_t)n_seg * n_out * 4));
       CK(e->tdout.reserve((size_t)n_seg * 64 * 4));
-      auto K = [&](int l, const char* s2) { char k[32]; snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
-      PoolHeadParams H;
-      H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
-      H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
-      float* qk[2] = {e->qkv.as<float>(), e->qkv2.as<float>()};
-      { Scope s(e, "lin_ln");      // Linear 384->64 + LayerNorm + layer-0 q|k|v
-        launch_lin_ln_qkv(st, e->feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"),
-                          W(e, K(0, "qkvT")), W(e, K(0, "qkvb")), e->tdout.as<float>(), qk[0], n_seg); }
+      { Scope s(e, "lin_ln");
+        launch_lin_ln(st, e->feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), e->tdout.as<float>(), n_seg); }
       e->last_td_in = e->tdout.as<float>();
       const float* cur = e->tdout.as<float>();
       float* pp[2] = {e->xa.as<float>(), e->xb.as<float>()};
       for (int l = 0; l < c.sa_layers; ++l) {
-        const int last = (l == c.sa_layers - 1);
+        char k[32];
+        auto K = [&](const char* s2) { snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
+        { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, K("qkvT")), W(e, K("qkvb")), e->qkv.as<float>(), n_seg); }
         SaLayerParams P;
-        P.WoT = W(e, K(l, "woT")); P.bo = W(e, K(l, "bo")); P.W1T = W(e, K(l, "w1T")); P.b1 = W(e, K(l, "b1"));
-        P.W2T = W(e, K(l, "w2T")); P.b2 = W(e, K(l, "b2")); P.ln1_g = W(e, K(l, "ln1g")); P.ln1_b = W(e, K(l, "ln1b"));
-        P.ln2_g = W(e, K(l, "ln2g")); P.ln2_b = W(e, K(l, "ln2b"));
-        const float* nW = last ? nullptr : W(e, K(l + 1, "qkvT"));
-        const float* nb = last ? nullptr : W(e, K(l + 1, "qkvb"));
-        { Scope s(e, "sa_layer");   // attention + out_proj + LN + FFN + LN, then next q|k|v or the pool logits
-          launch_sa_layer4(st, last, cur, qk[l & 1], d_clips, n, max_seg_clip, P, nW, nb, qk[(l + 1) & 1], H, n_out,
-                           e->logits.as<float>(), pp[l & 1]); }
+        P.WoT = W(e, K("woT")); P.bo = W(e, K("bo")); P.W1T = W(e, K("w1T")); P.b1 = W(e, K("b1"));
+        P.W2T = W(e, K("w2T")); P.b2 = W(e, K("b2")); P.ln1_g = W(e, K("ln1g")); P.ln1_b = W(e, K("ln1b"));
+        P.ln2_g = W(e, K("ln2g")); P.ln2_b = W(e, K("ln2b"));
+        { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, e->qkv.as<float>(), d_clips, n, d_qt, n_qt, P, pp[l & 1]); }
         cur = pp[l & 1];
       }
       e->last_td_out = cur;
-      { Scope s(e, "pool"); launch_pool_final(st, cur, e->logits.as<float>(), d_clips, n, H, n_out, scores); }
+      PoolHeadParams H;
+      H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
+      H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
+      { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, e->logits.as<float>(), scores); }
     } else {
       CK(e->feats20.reserve((size_t)n_seg * 20 * 4));
       CK(e->tdout.reserve((size_t)n_seg * 256 * 4));
@@ -1015,7 +1008,7 @@ double nisqa_group_ms(const nisqa_engine* e, const char* group) {
   double total = 0.0; bool found = false;
   for (const auto& t : e->timers) {
     const bool cnn = t.name.compare(0, 4, "conv") == 0;
-    const bool td = t.name == "lin_ln" || t.name == "sa_layer" || t.name == "fc_out" || t.name == "lstm";
+    const bool td = t.name == "lin_ln" || t.name == "qkv" || t.name == "sa_layer" || t.name == "fc_out" || t.name == "lstm";
     const bool match = t.name == g || (g == "cnn" && cnn) || (g == "td" && td) ||
                        (g == "frontend" && t.name == "seg_table");
     if (match) { total += t.ms; found = true; }

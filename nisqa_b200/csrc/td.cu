@@ -91,112 +91,38 @@ linear_rows_kernel(const float* __restrict__ in, int K, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// Row kernels, second generation: FOUR threads per time step (row), each owning 16 of the 64
-// columns, 32 rows per CTA.  The [n_seg, 64] matrices are small (15.8k rows per 64 clips), so one
-// thread per row leaves the GPU at 6 % occupancy; a 4-way column split gives 4x the warps with
-// the same shared-memory weight tiles.  Lane = 4 * (row in warp) + part, so the LayerNorm and
-// dot-product reductions over a row are two xor-shuffles.
-constexpr int kR4 = 32;            // rows per CTA
-constexpr int kT4 = 128;           // threads per CTA
-
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-
-// acc[j] += sum_k xrow[k] * ws[k*LD + j],  j in this thread's 16-column slice (ws pre-offset)
-template <int LD>
-__device__ __forceinline__ void rowgemm16(float (&acc)[16], const float* xrow, const float* ws, int kc) {
-#pragma unroll 4
-  for (int k = 0; k < kc; ++k) {
-    const float xv = xrow[k];
-    const float4* w4 = reinterpret_cast<const float4*>(ws + k * LD);
+// qkv[row] = [ (Wq x + bq)/8 | Wk x + bk | Wv x + bv ]   (1/sqrt(64) folded into Wq,bq on the host)
+__global__ void __launch_bounds__(kRows)
+qkv_kernel(const float* __restrict__ x, const float* __restrict__ WT3 /*[3][64][64]*/,
+           const float* __restrict__ b3 /*[192]*/, float* __restrict__ qkv, int n_rows) {
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;
+  float* ws = sm + kRows * kXS;         // [64][64]
+  const int row0 = blockIdx.x * kRows, tid = threadIdx.x;
+  for (int i = tid; i < kRows * 64; i += kRows) {
+    const int r = i >> 6, k = i & 63;
+    xs[r * kXS + k] = (row0 + r < n_rows) ? __ldg(x + (size_t)(row0 + r) * 64 + k) : 0.f;
+  }
+  for (int part = 0; part < 3; ++part) {
+    __syncthreads();
+    stage_f4(ws, WT3 + part * 4096, 4096);
+    __syncthreads();
+    float acc[64];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 w = w4[q];
-      acc[q * 4 + 0] = fmaf(xv, w.x, acc[q * 4 + 0]);
-      acc[q * 4 + 1] = fmaf(xv, w.y, acc[q * 4 + 1]);
-      acc[q * 4 + 2] = fmaf(xv, w.z, acc[q * 4 + 2]);
-      acc[q * 4 + 3] = fmaf(xv, w.w, acc[q * 4 + 3]);
+    for (int j = 0; j < 64; ++j) acc[j] = __ldg(b3 + part * 64 + j);
+    rowgemm<64>(acc, xs + tid * kXS, ws, 64);
+    if (row0 + tid < n_rows) {
+      float4* o = reinterpret_cast<float4*>(qkv + (size_t)(row0 + tid) * 192 + part * 64);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) o[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
     }
   }
 }
 
-// LayerNorm(64) of a row held as 4 x 16 columns (biased variance, eps 1e-5)
-__device__ __forceinline__ void layernorm_quad(float (&v)[16], const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, int part) {
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) s += v[j];
-  const float mean = quad_sum(s) * (1.0f / 64.0f);
-  float q = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
-  const float rstd = 1.0f / sqrtf(quad_sum(q) * (1.0f / 64.0f) + 1e-5f);
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    v[j] = (v[j] - mean) * rstd * __ldg(gamma + part * 16 + j) + __ldg(beta + part * 16 + j);
-}
-
-__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-}
-
-// q | k | v projection of the row currently in xrow (smem), weights staged through wbuf [64][64]
-__device__ __forceinline__ void qkv_rows(const float* xrow, float* wbuf, const float* __restrict__ WT3,
-                                         const float* __restrict__ b3, float* __restrict__ qkv_row,
-                                         int part, bool store) {
-  for (int p3 = 0; p3 < 3; ++p3) {
-    __syncthreads();
-    stage_f4(wbuf, WT3 + p3 * 4096, 4096);
-    __syncthreads();
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = __ldg(b3 + p3 * 64 + part * 16 + j);
-    rowgemm16<64>(acc, xrow, wbuf + part * 16, 64);
-    if (store) store16(qkv_row + p3 * 64 + part * 16, acc);
-  }
-}
-
-// ---- A: x0 = LayerNorm(Linear 384->64 (feats)), then the layer-0 q|k|v projection
-__global__ void __launch_bounds__(kT4)
-lin_ln_qkv_kernel(const float* __restrict__ feats, const float* __restrict__ WT /*[384][64]*/,
-                  const float* __restrict__ bias, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, const float* __restrict__ WT3, const float* __restrict__ b3,
-                  float* __restrict__ x0, float* __restrict__ qkv, int n_rows) {
-  __shared__ __align__(16) float xs[kR4 * kXS];
-  __shared__ __align__(16) float wbuf[64 * 64];
-  const int tid = threadIdx.x, r = tid >> 2, part = tid & 3;
-  const int row0 = blockIdx.x * kR4, row = row0 + r;
-  const bool live = row < n_rows;
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(bias + part * 16 + j);
-  for (int k0 = 0; k0 < 384; k0 += 64) {
-    __syncthreads();
-    for (int i = tid; i < kR4 * 64; i += kT4) {
-      const int rr = i >> 6, k = i & 63;
-      xs[rr * kXS + k] = (row0 + rr < n_rows) ? __ldg(feats + (size_t)(row0 + rr) * 384 + k0 + k) : 0.f;
-    }
-    stage_f4(wbuf, WT + (size_t)k0 * 64, 4096);
-    __syncthreads();
-    rowgemm16<64>(acc, xs + r * kXS, wbuf + part * 16, 64);
-  }
-  layernorm_quad(acc, gamma, beta, part);
-  if (live) store16(x0 + (size_t)row * 64 + part * 16, acc);
-  __syncthreads();                               // all reads of xs (last chunk) are done
-#pragma unroll
-  for (int j = 0; j < 16; ++j) xs[r * kXS + part * 16 + j] = acc[j];
-  qkv_rows(xs + r * kXS, wbuf, WT3, b3, qkv + (size_t)(live ? row : 0) * 192, part, live);
-}
-
-// ---- B: one encoder layer for 32 queries of one clip per CTA (grid: x = query tile, y = clip):
-//   flash-style softmax(q k^T) v over the clip's keys -> out_proj -> +x -> LN1 -> FFN(ReLU) -> + -> LN2
-//   (reference lib:1032-1038), then either the NEXT layer's q|k|v projection or the PoolAttFF
-//   logits (lib:1173) of the finished rows.
+// ---------------------------------------------------------------------------------------
+// One encoder layer minus the QKV projection, for 128 queries of one clip per CTA:
+//   flash-style softmax(q k^T) v over the clip's own keys (online max/sum, keys in blocks of 8)
+//   -> out_proj -> +x -> LN1 -> FFN(ReLU) -> + -> LN2          (reference lib:1032-1038)
 struct SaLayerParams {
   const float* WoT; const float* bo;         // [64][64] k-major, [64]
   const float* W1T; const float* b1;
@@ -204,51 +130,43 @@ struct SaLayerParams {
   const float* ln1_g; const float* ln1_b;
   const float* ln2_g; const float* ln2_b;
 };
-struct PoolHeadParams {      // device pointers, heads concatenated
-  const float* W1T;   // [n_heads][64 k][128 j]
-  const float* b1;    // [n_heads][128]
-  const float* w2;    // [n_heads][128]
-  const float* b2;    // [n_heads]
-  const float* w3;    // [n_heads][64]
-  const float* b3;    // [n_heads]
-};
 
 constexpr int kKeyTile = 64;
-constexpr int kSa4SmemFloats = 2 * kKeyTile * 64 + 64 * 128 + kR4 * kXS;   // K,V tile | weight stage | rows
+constexpr int kSaSmemFloats = 3 * 4096 + 2 * kKeyTile * 64 + kRows * kXS;
 
-template <bool LAST>
-__global__ void __launch_bounds__(kT4, 3)
-sa_layer4_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv,
-                 const ClipDesc* __restrict__ clips, SaLayerParams P,
-                 const float* __restrict__ nWT3, const float* __restrict__ nb3, float* __restrict__ qkv_next,
-                 PoolHeadParams H, int n_heads, float* __restrict__ logits, float* __restrict__ x_out) {
+__global__ void __launch_bounds__(kRows, 2)
+sa_layer_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv,
+                const ClipDesc* __restrict__ clips, int n_clips, const int* __restrict__ qtile_prefix,
+                SaLayerParams P, float* __restrict__ x_out) {
   extern __shared__ __align__(16) float sm[];
-  float* ks = sm;                              // [64 keys][64]
+  float* wo = sm; float* w1 = sm + 4096; float* w2 = sm + 8192;
+  float* ks = sm + 12288;                      // [64 keys][64]
   float* vs = ks + kKeyTile * 64;
-  float* wbuf = vs + kKeyTile * 64;            // [64][64] or [64][128]
-  float* xs = wbuf + 64 * 128;                 // [32][65]
-  const int tid = threadIdx.x, r = tid >> 2, part = tid & 3;
-  const ClipDesc cd = clips[blockIdx.y];
+  float* xs = vs + kKeyTile * 64;              // per-thread rows, stride 65
+  const int tid = threadIdx.x;
+  const int c = upper_slot(qtile_prefix, n_clips, blockIdx.x);
+  const ClipDesc cd = clips[c];
   const int S = cd.n_seg;
-  const int q0 = blockIdx.x * kR4;
-  if (q0 >= S) return;
-  const int qi = q0 + r;
-  const bool live = qi < S;
-  const size_t rowg = (size_t)cd.seg_off + (live ? qi : 0);
+  const int q0 = (blockIdx.x - __ldg(qtile_prefix + c)) * kRows;
+  const int qi = q0 + tid;
+  const bool active = qi < S;
+  const size_t rowg = (size_t)cd.seg_off + (active ? qi : 0);
 
-  float q[16], o[16];
+  stage_f4(wo, P.WoT, 4096); stage_f4(w1, P.W1T, 4096); stage_f4(w2, P.W2T, 4096);
+
+  float q[64], o[64];
   {
-    const float4* qp = reinterpret_cast<const float4*>(qkv + rowg * 192 + part * 16);
+    const float4* qp = reinterpret_cast<const float4*>(qkv + rowg * 192);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const float4 t = __ldg(qp + i); q[4*i] = t.x; q[4*i+1] = t.y; q[4*i+2] = t.z; q[4*i+3] = t.w; }
+    for (int i = 0; i < 16; ++i) { const float4 t = __ldg(qp + i); q[4*i] = t.x; q[4*i+1] = t.y; q[4*i+2] = t.z; q[4*i+3] = t.w; }
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = 0.f;
+  for (int j = 0; j < 64; ++j) o[j] = 0.f;
   float m = -INFINITY, l = 0.f;
 
   for (int j0 = 0; j0 < S; j0 += kKeyTile) {
     __syncthreads();
-    for (int i = tid; i < kKeyTile * 16; i += kT4) {       // float4 granules of the k and v rows
+    for (int i = tid; i < kKeyTile * 16; i += kRows) {       // float4 granules of k and v rows
       const int kr = i >> 4, g = i & 15;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (j0 + kr < S) {
@@ -263,37 +181,32 @@ sa_layer4_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv,
       float s[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4* kr = reinterpret_cast<const float4*>(ks + (jb + u) * 64 + part * 16);
-        float a0 = 0.f, a1 = 0.f;
+        const float4* kr = reinterpret_cast<const float4*>(ks + (jb + u) * 64);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 16; ++g) {
           const float4 kk = kr[g];
           a0 = fmaf(q[4*g], kk.x, a0); a1 = fmaf(q[4*g+1], kk.y, a1);
-          a0 = fmaf(q[4*g+2], kk.z, a0); a1 = fmaf(q[4*g+3], kk.w, a1);
+          a2 = fmaf(q[4*g+2], kk.z, a2); a3 = fmaf(q[4*g+3], kk.w, a3);
         }
-        s[u] = a0 + a1;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        s[u] = quad_sum(s[u]);
-        if (jb + u >= nk) s[u] = -INFINITY;
+        s[u] = (jb + u < nk) ? (a0 + a1) + (a2 + a3) : -INFINITY;
       }
       float bm = s[0];
 #pragma unroll
       for (int u = 1; u < 8; ++u) bm = fmaxf(bm, s[u]);
       const float mn = fmaxf(m, bm);
-      const float sc = expf(m - mn);          // first block: expf(-inf) = 0
+      const float sc = expf(m - mn);          // m == -inf on the first block: expf(-inf) = 0
       l *= sc;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] *= sc;
+      for (int j = 0; j < 64; ++j) o[j] *= sc;
       m = mn;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float p = expf(s[u] - mn);      // masked tail: expf(-inf) = 0
         l += p;
-        const float4* vr = reinterpret_cast<const float4*>(vs + (jb + u) * 64 + part * 16);
+        const float4* vr = reinterpret_cast<const float4*>(vs + (jb + u) * 64);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 16; ++g) {
           const float4 vv = vr[g];
           o[4*g] = fmaf(p, vv.x, o[4*g]); o[4*g+1] = fmaf(p, vv.y, o[4*g+1]);
           o[4*g+2] = fmaf(p, vv.z, o[4*g+2]); o[4*g+3] = fmaf(p, vv.w, o[4*g+3]);
@@ -302,70 +215,86 @@ sa_layer4_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv,
     }
   }
   const float inv = 1.0f / l;
-  float* xrow = xs + r * kXS;
+  float* xrow = xs + tid * kXS;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) xrow[part * 16 + j] = o[j] * inv;
+  for (int j = 0; j < 64; ++j) xrow[j] = o[j] * inv;
 
-  // out_proj + residual + LN1
-  __syncthreads();
-  stage_f4(wbuf, P.WoT, 4096);
-  __syncthreads();
-  float acc[16];
+  // out_proj + residual + LN1   (q[] reused as the accumulator, o[] as the residual stream)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.bo + part * 16 + j);
-  rowgemm16<64>(acc, xrow, wbuf + part * 16, 64);
+  for (int j = 0; j < 64; ++j) q[j] = __ldg(P.bo + j);
+  rowgemm<64>(q, xrow, wo, 64);
   {
-    const float4* xp = reinterpret_cast<const float4*>(x_in + rowg * 64 + part * 16);
+    const float4* xp = reinterpret_cast<const float4*>(x_in + rowg * 64);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const float4 t = __ldg(xp + i); o[4*i] = t.x + acc[4*i]; o[4*i+1] = t.y + acc[4*i+1]; o[4*i+2] = t.z + acc[4*i+2]; o[4*i+3] = t.w + acc[4*i+3]; }
+    for (int i = 0; i < 16; ++i) { const float4 t = __ldg(xp + i); o[4*i] = t.x + q[4*i]; o[4*i+1] = t.y + q[4*i+1]; o[4*i+2] = t.z + q[4*i+2]; o[4*i+3] = t.w + q[4*i+3]; }
   }
-  layernorm_quad(o, P.ln1_g, P.ln1_b, part);
+  layernorm64(o, P.ln1_g, P.ln1_b);
   // FFN
-  __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) xrow[part * 16 + j] = o[j];
-  stage_f4(wbuf, P.W1T, 4096);
-  __syncthreads();
+  for (int j = 0; j < 64; ++j) { xrow[j] = o[j]; q[j] = __ldg(P.b1 + j); }
+  rowgemm<64>(q, xrow, w1, 64);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.b1 + part * 16 + j);
-  rowgemm16<64>(acc, xrow, wbuf + part * 16, 64);
-  __syncthreads();
+  for (int j = 0; j < 64; ++j) { xrow[j] = fmaxf(q[j], 0.f); q[j] = __ldg(P.b2 + j); }
+  rowgemm<64>(q, xrow, w2, 64);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) xrow[part * 16 + j] = fmaxf(acc[j], 0.f);
-  stage_f4(wbuf, P.W2T, 4096);
-  __syncthreads();
+  for (int j = 0; j < 64; ++j) o[j] += q[j];
+  layernorm64(o, P.ln2_g, P.ln2_b);
+  if (active) {
+    float4* op = reinterpret_cast<float4*>(x_out + rowg * 64);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.b2 + part * 16 + j);
-  rowgemm16<64>(acc, xrow, wbuf + part * 16, 64);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] += acc[j];
-  layernorm_quad(o, P.ln2_g, P.ln2_b, part);
-  if (live) store16(x_out + rowg * 64 + part * 16, o);
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) xrow[part * 16 + j] = o[j];
+    for (int i = 0; i < 16; ++i) op[i] = make_float4(o[4*i], o[4*i+1], o[4*i+2], o[4*i+3]);
+  }
+}
 
-  if constexpr (!LAST) {
-    qkv_rows(xrow, wbuf, nWT3, nb3, qkv_next + rowg * 192, part, live);
-  } else {
-    // PoolAttFF logits: logit[h] = w2_h . relu(W1_h x + b1_h) + b2_h ; each thread owns 32 of the 128 hidden units
-    for (int h = 0; h < n_heads; ++h) {
-      __syncthreads();
-      stage_f4(wbuf, H.W1T + (size_t)h * 64 * 128, 64 * 128);
-      __syncthreads();
-      float part_logit = 0.f;
+// ---------------------------------------------------------------------------------------
+// PoolAttFF logits: logit[row][h] = w2_h . relu(W1_h x + b1_h) + b2_h      (lib:1173)
+struct PoolHeadParams {      // device pointers, heads concatenated
+  const float* W1T;   // [n_heads][64 k][128 j]
+  const float* b1;    // [n_heads][128]
+  const float* w2;    // [n_heads][128]
+  const float* b2;    // [n_heads]
+  const float* w3;    // [n_heads][64]
+  const float* b3;    // [n_heads]
+};
+
+__global__ void __launch_bounds__(kRows)
+pool_logits_kernel(const float* __restrict__ x, PoolHeadParams P, int n_heads,
+                   float* __restrict__ logits, int n_rows) {
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;
+  float* ws = sm + kRows * kXS;         // [64][128]
+  const int row0 = blockIdx.x * kRows, tid = threadIdx.x;
+  for (int i = tid; i < kRows * 64; i += kRows) {
+    const int r = i >> 6, k = i & 63;
+    xs[r * kXS + k] = (row0 + r < n_rows) ? __ldg(x + (size_t)(row0 + r) * 64 + k) : 0.f;
+  }
+  for (int h = 0; h < n_heads; ++h) {
+    __syncthreads();
+    stage_f4(ws, P.W1T + (size_t)h * 64 * 128, 64 * 128);
+    __syncthreads();
+    float logit = __ldg(P.b2 + h);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float acc[64];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int c0 = part * 32 + half * 16;
+      for (int j = 0; j < 64; ++j) acc[j] = __ldg(P.b1 + h * 128 + half * 64 + j);
+      // columns [half*64, half*64+64) of the [64][128] tile: row stride 128
+      const float* xrow = xs + tid * kXS;
+#pragma unroll 4
+      for (int k = 0; k < 64; ++k) {
+        const float xv = xrow[k];
+        const float4* w4 = reinterpret_cast<const float4*>(ws + k * 128 + half * 64);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = __ldg(H.b1 + h * 128 + c0 + j);
-        rowgemm16<128>(acc, xrow, wbuf + c0, 64);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) part_logit = fmaf(__ldg(H.w2 + h * 128 + c0 + j), fmaxf(acc[j], 0.f), part_logit);
+        for (int qd = 0; qd < 16; ++qd) {
+          const float4 w = w4[qd];
+          acc[qd*4] = fmaf(xv, w.x, acc[qd*4]); acc[qd*4+1] = fmaf(xv, w.y, acc[qd*4+1]);
+          acc[qd*4+2] = fmaf(xv, w.z, acc[qd*4+2]); acc[qd*4+3] = fmaf(xv, w.w, acc[qd*4+3]);
+        }
       }
-      part_logit = quad_sum(part_logit);
-      if (live && part == 0) logits[rowg * n_heads + h] = part_logit + __ldg(H.b2 + h);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) logit = fmaf(__ldg(P.w2 + h * 128 + half * 64 + j), fmaxf(acc[j], 0.f), logit);
     }
+    if (row0 + tid < n_rows) logits[(size_t)(row0 + tid) * n_heads + h] = logit;
   }
 }
 
@@ -504,32 +433,37 @@ __global__ void lastbi_final_kernel(const float* __restrict__ partial, const Cli
 }
 
 // ------------------------------------------------------------------ host launchers
+constexpr int kRowSmem64 = (kRows * kXS + 64 * 64) * 4;
 constexpr int kRowSmem20 = (kRows * kXS + 64 * 20) * 4;
+constexpr int kRowSmem128 = (kRows * kXS + 64 * 128) * 4;
 
+void launch_lin_ln(cudaStream_t st, const float* feats, const float* WT, const float* b,
+                   const float* g, const float* be, float* out, int n_rows) {
+  static bool cfg = false;
+  if (!cfg) { cudaFuncSetAttribute(linear_rows_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); cfg = true; }
+  linear_rows_kernel<64, true><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(feats, 384, WT, b, g, be, out, n_rows);
+}
 void launch_fc20(cudaStream_t st, const float* feats, const float* WT, const float* b, float* out, int n_rows) {
   linear_rows_kernel<20, false><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem20, st>>>(feats, 768, WT, b, nullptr, nullptr, out, n_rows);
 }
-void launch_lin_ln_qkv(cudaStream_t st, const float* feats, const float* WT, const float* b, const float* g,
-                       const float* be, const float* WT3, const float* b3, float* x0, float* qkv, int n_rows) {
-  lin_ln_qkv_kernel<<<(n_rows + kR4 - 1) / kR4, kT4, 0, st>>>(feats, WT, b, g, be, WT3, b3, x0, qkv, n_rows);
-}
-// one encoder layer; last == 0: also projects q|k|v of the next layer, last == 1: also the pool logits
-void launch_sa_layer4(cudaStream_t st, int last, const float* x_in, const float* qkv, const ClipDesc* clips,
-                      int n_clips, int max_seg, const SaLayerParams& P, const float* nWT3, const float* nb3,
-                      float* qkv_next, const PoolHeadParams& H, int n_heads, float* logits, float* x_out) {
+void launch_qkv(cudaStream_t st, const float* x, const float* WT3, const float* b3, float* qkv, int n_rows) {
   static bool cfg = false;
-  const int smem = kSa4SmemFloats * 4;
-  if (!cfg) {
-    cudaFuncSetAttribute(sa_layer4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sa_layer4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cfg = true;
-  }
-  const dim3 grid((max_seg + kR4 - 1) / kR4, n_clips);
-  if (last) sa_layer4_kernel<true><<<grid, kT4, smem, st>>>(x_in, qkv, clips, P, nWT3, nb3, qkv_next, H, n_heads, logits, x_out);
-  else sa_layer4_kernel<false><<<grid, kT4, smem, st>>>(x_in, qkv, clips, P, nWT3, nb3, qkv_next, H, n_heads, logits, x_out);
+  if (!cfg) { cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); cfg = true; }
+  qkv_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(x, WT3, b3, qkv, n_rows);
 }
-void launch_pool_final(cudaStream_t st, const float* x, const float* logits, const ClipDesc* clips, int n_clips,
-                       const PoolHeadParams& P, int n_heads, float* scores) {
+void launch_sa_layer(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips,
+                     int n_clips, const int* qtile_prefix, int n_qtiles, const SaLayerParams& P,
+                     float* x_out) {
+  static bool cfg = false;
+  const int smem = kSaSmemFloats * 4;
+  if (!cfg) { cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
+  sa_layer_kernel<<<n_qtiles, kRows, smem, st>>>(x_in, qkv, clips, n_clips, qtile_prefix, P, x_out);
+}
+void launch_pool_att(cudaStream_t st, const float* x, const ClipDesc* clips, int n_clips, int n_rows,
+                     const PoolHeadParams& P, int n_heads, float* logits, float* scores) {
+  static bool cfg = false;
+  if (!cfg) { cudaFuncSetAttribute(pool_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem128); cfg = true; }
+  pool_logits_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem128, st>>>(x, P, n_heads, logits, n_rows);
   pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
 }
 void launch_lstm(cudaStream_t st, const float* feats20, const ClipDesc* clips, int n_clips,
