@@ -4,6 +4,10 @@
 // the reference (plain TF32 / BF16 operands move MOS by 2e-3 / 1.7e-2):
 //      a = a_hi + a_lo,  b = b_hi + b_lo      (fp16 parts: 11 + 11 significant bits)
 //      a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped a_lo*b_lo ~ 2^-22 |a b|)
+// Issued as TWO MMAs per K-step: A_hi x [B_hi | B_lo] with N = 2*C_out (accumulator columns
+// [0,C) = hi*hi, [C,2C) = hi*lo) and A_lo x B_hi with N = C_out into columns [0,C); the epilogue
+// adds the two column halves.  Every A element is thus fetched from shared memory twice per tap
+// instead of three times - operand fetch, not the MMA issue rate, bounds these kernels.
 // Products are exact in the tensor core and accumulate in fp32 (TMEM).  The weights are
 // pre-scaled by 2^S on the host (S chosen per layer so that max|w| 2^S <= 1024) to keep b_lo
 // out of the fp16 subnormal range; the epilogue multiplies by 2^-S (exact).  Compared with
@@ -137,7 +141,7 @@ struct TcCfg {
   static constexpr int B_HALF = NCH * COUT * 16;          // per hi / lo
   static constexpr int B_STAGE = 2 * B_HALF;
   static constexpr int NSTAGE = NSTAGE_;
-  static constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : 128);
+  static constexpr int TMEM_COLS = (4 * COUT <= 64) ? 64 : (4 * COUT <= 128 ? 128 : 256);   // 2 M-tiles x 2*COUT
   static constexpr int HO = (POOL == TC_POOL_NONE) ? H : H / 2;
   static constexpr int STG_STRIDE = COUT + 4;     // floats per staged row (conflict-free float4)
   static constexpr int OFF_A_HI = 0;
@@ -145,9 +149,11 @@ struct TcCfg {
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
   static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32;
-  static constexpr int MINB = (SMEM_BYTES <= 56 * 1024) ? 4 : (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
-  static constexpr uint32_t IDESC =                        // D=f32, A=B=f16, both K-major, M=128, N=COUT
-      (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr int MINB_SMEM = (SMEM_BYTES <= 56 * 1024) ? 4 : (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
+  static constexpr int MINB = (MINB_SMEM * TMEM_COLS <= 512) ? MINB_SMEM : 512 / TMEM_COLS;
+  // D=f32, A=B=f16, both K-major, M=128; N = 2*COUT ([b_hi|b_lo]) and N = COUT (b_hi only)
+  static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * COUT) >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(POOL == TC_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES + NSTAGE * B_STAGE,
                 "pool staging tile must fit in the A+B region");
   static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0 && CIN % 16 == 0 && COUT % 32 == 0, "shape");
@@ -157,7 +163,7 @@ struct TcCfg {
 template <class C>
 __global__ void __launch_bounds__(192, C::MINB)
 conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
-               const __half* __restrict__ wtc /*[9][hi|lo][CIN/8][COUT][8] fp16, scaled by 2^S*/,
+               const __half* __restrict__ wtc /*[9][CIN/8][hi co | lo co][8] fp16, scaled by 2^S*/,
                const float* __restrict__ bias, float out_scale /*2^-S*/,
                float* __restrict__ out, int n_seg) {
   constexpr int H = C::H, W = C::W, CIN = C::CIN, COUT = C::COUT, P = C::P, BLK = C::BLK, G = C::G;
@@ -257,22 +263,19 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
         if (t == 0) tc_stamp(6, 128);
         tc_fence_after();
         const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
-        const uint32_t bh = b_base + s * C::B_STAGE, bl = bh + C::B_HALF;
+        const uint32_t bst = b_base + s * C::B_STAGE;       // [ci/8][2*COUT rows: hi then lo][8 halves]
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff);
-          const uint32_t d = tmem + mt * COUT;
+          const uint32_t d = tmem + mt * (2 * COUT);
 #pragma unroll
           for (int ks = 0; ks < CIN / 16; ++ks) {
             const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
             const uint64_t dah = make_desc(a_hi + aoff, AROWS * 16, 128);
             const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
-            const uint32_t boff = (uint32_t)(2 * ks) * (COUT * 16);
-            const uint64_t dbh = make_desc(bh + boff, COUT * 16, 128);
-            const uint64_t dbl = make_desc(bl + boff, COUT * 16, 128);
-            umma_f16(d, dah, dbh, C::IDESC, (t | ks) != 0);
-            umma_f16(d, dah, dbl, C::IDESC, 1);
-            umma_f16(d, dal, dbh, C::IDESC, 1);
+            const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
+            umma_f16(d, dah, db, C::IDESC_2N, (t | ks) != 0);     // [0,C) += hi*hi ; [C,2C) += hi*lo
+            umma_f16(d, dal, db, C::IDESC_1N, 1);                 // [0,C) += lo*hi
           }
         }
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
@@ -297,8 +300,11 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
       const int h = hh - 1, w = C::CENTER ? 0 : ww - 1;
 #pragma unroll 1
       for (int part = 0; part < COUT / 32; ++part) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * COUT + part * 32, v);
+        float v[32], v2[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + part * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + COUT + part * 32, v2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
         if (valid) {
           float* dst = (C::POOL == TC_POOL_NONE)
                            ? out + ((size_t)(seg0 + s) * (H * WOUT) + h * WOUT + w) * COUT + part * 32

@@ -391,7 +391,7 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
   for (int i = 1; i <= 6; ++i)
     if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-  // conv2..conv6 for the tcgen05 path: [tap][hi|lo][ci/8][co][8] fp16 two-term split of w * 2^S
+  // conv2..conv6 for the tcgen05 path: [tap][ci/8][hi co | lo co][8] fp16 two-term split of w * 2^S
   for (int i = 2; i <= 6; ++i) {
     char k1[32], k2[32];
     snprintf(k1, sizeof k1, "conv%d.w", i); snprintf(k2, sizeof k2, "conv%d.wtc", i);
@@ -411,9 +411,11 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
           const __half hi = __float2half_rn(w);
           const __half lo = __float2half_rn(w - __half2float(hi));
           __half* base = reinterpret_cast<__half*>(&P.arena[dst]) + (size_t)tap * 2 * ci_n * co_n;
-          const size_t off = ((size_t)(ci / 8) * co_n + co) * 8 + (ci & 7);
+          // per 16-byte K chunk: rows [0,co_n) = hi, rows [co_n, 2 co_n) = lo  (one N = 2*C_out operand)
+          const size_t off = ((size_t)(ci / 8) * (2 * co_n) + co) * 8 + (ci & 7);
           base[off] = hi;
-          base[(size_t)nch * co_n * 8 + off] = lo;
+          base[off + (size_t)co_n * 8] = lo;
+          (void)nch;
         }
   }
 
