@@ -117,9 +117,9 @@ NISQA_API int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
 
 /* Asynchronous form of nisqa_predict_pcm for streams of batches (what the reference gets from
  * DataLoader prefetching, lib:1425-1430): returns as soon as the copies and kernels are enqueued;
- * up to two submissions are in flight, so the host->device copy of batch k+1 overlaps the kernels
+ * up to three submissions are in flight, so the host->device copy of batch k+1 overlaps the kernels
  * of batch k.  n_segments_out / status_out are valid on return (host arithmetic); scores_out and the
- * PCM buffers must stay alive until nisqa_wait(ticket) returns.  Submitting a third batch first
+ * PCM buffers must stay alive until nisqa_wait(ticket) returns.  Submitting a fourth batch first
  * waits for the oldest one. */
 NISQA_API int  nisqa_submit_pcm(nisqa_engine* e, int n_clips,
                                 const void* const* pcm, const int64_t* n_samples,
@@ -162,10 +162,19 @@ NISQA_API int  nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm /* NULL: the e
  * the id to every rank (torch.distributed broadcast), every rank calls nisqa_nccl_init. */
 NISQA_API int  nisqa_nccl_unique_id(nisqa_engine* e, void* id128);
 NISQA_API int  nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void* id128);
+/* Streaming form of the exchange: once a target [world, rows, n_out] device buffer is set, every
+ * nisqa_submit_pcm / nisqa_predict_pcm_device call over exactly `rows` clips ends with the
+ * ncclAllGather of its score rows, enqueued on the call's own compute lane (no host sync).
+ * global_dev == NULL switches it off. */
+NISQA_API int  nisqa_set_gather_target(nisqa_engine* e, float* global_dev, int rows);
 
 /* bookkeeping for bench.py */
 NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
-NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t the engine launches on */
+NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t of compute lane 0 */
+/* Passes rotate over several compute lanes (streams with private workspaces).  nisqa_join makes
+ * lane 0's stream wait for everything enqueued so far on the other lanes, so that an event recorded
+ * on nisqa_stream() afterwards covers all outstanding work. */
+NISQA_API int     nisqa_join(nisqa_engine* e);
 /* average device time (ms) of the named kernel group during the last predict call, measured
  * with CUDA events on the engine stream when profiling was enabled; <0 if unknown.
  * groups: "frontend", "cnn", "td", "pool" */

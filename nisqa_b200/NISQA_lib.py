@@ -112,19 +112,19 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
 
         pending = submit(batches[0]) if batches else None
         pos = 0
-        in_flight = None              # the batch whose kernels are running while we decode / upload the next
+        in_flight = []                # batches whose kernels are running while we decode / upload the next
         for b, batch in enumerate(batches):
             loaded = collect(pending)
             pending = submit(batches[b + 1]) if b + 1 < len(batches) else None
             clips = [c for c, _ in loaded]
             srs = [s for _, s in loaded]
             handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
-            if in_flight is not None:
-                finish(in_flight)
-            in_flight = (handle, batch, clips, srs, pos)
+            in_flight.append((handle, batch, clips, srs, pos))
             pos += len(batch)
-        if in_flight is not None:
-            finish(in_flight)
+            if len(in_flight) >= 3:                         # the engine keeps three submissions in flight
+                finish(in_flight.pop(0))
+        while in_flight:
+            finish(in_flight.pop(0))
     return out
 
 

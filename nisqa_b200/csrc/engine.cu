@@ -105,7 +105,32 @@ struct Ticket {          // one asynchronous nisqa_submit_pcm call
   size_t bytes = 0;
   float* user_scores = nullptr;
   HostBuf pinned;
+  DevBuf scores;         // device scores of this submission (calls in flight do not share one)
   cudaEvent_t done = nullptr;
+};
+
+// A compute lane: everything one in-flight pass needs - its own stream, host->device staging and
+// activation workspaces.  Passes rotate over the lanes, so the kernels of consecutive passes /
+// submissions run on different streams: wave tails and the small low-occupancy kernels of one
+// pass are filled with CTAs of another (+8..12 % throughput measured, tools/two_engines.py), and
+// the upload of the next pass (copy stream) overlaps compute.
+constexpr int kLanes = 3;
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+  bool busy = false;
+  HostBuf h_tables;
+  DevBuf pcm, clips, prefixes, clipmax;
+  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, logits, feats20, tdout, partial;
+  void release() {
+    DevBuf* all[] = {&pcm, &clips, &prefixes, &clipmax, &mel, &segtab, &act1, &act2, &act3, &act4, &act5,
+                     &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout, &partial};
+    for (auto* b : all) b->release();
+    h_tables.release();
+    if (ev_copied) cudaEventDestroy(ev_copied);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (stream) cudaStreamDestroy(stream);
+  }
 };
 
 struct TimerSlot {
@@ -139,20 +164,16 @@ struct nisqa_engine {
   DevBuf fb_table;       // FbTables[]
   DevBuf tw4096;         // float2[4096]
 
-  // per-pass workspaces
-  // host->device staging is double buffered (slot = pass & 1) and fed by a dedicated copy
-  // stream, so the upload of pass p+1 overlaps the kernels of pass p
-  DevBuf pcm[2], clips[2], prefixes[2], clipmax[2];
-  HostBuf h_tables[2], h_scores;
+  // per-pass state lives in the lanes; `stream` aliases lane 0's stream (nisqa_stream)
+  Lane lanes[kLanes];
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  bool slot_busy[2] = {false, false};
-  int last_slot = 0;
+  cudaStream_t cur_stream = nullptr;     // stream of the pass being enqueued (kernel timers)
+  HostBuf h_scores;
+  int last_lane = 0;
   int64_t pass_counter = 0;
-  Ticket tickets[2];
+  Ticket tickets[kLanes];
   int64_t next_ticket = 1;
-  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb,
-      qkv, logits, feats20, tdout, partial, scores, dump;
+  DevBuf scores, dump;
 
   // description of the last pass (stage dumps)
   std::vector<ClipDesc> last_clips;
@@ -163,23 +184,19 @@ struct nisqa_engine {
   // engine-owned NCCL communicator (multi-GPU gather)
   void* nccl_comm = nullptr;
   int nccl_world = 1, nccl_rank = 0;
+  float* gather_dst = nullptr;      // when set: every asynchronous / device-path call ends with an
+  int gather_rows = 0;              // ncclAllGather of its [gather_rows, n_out] scores on its own lane
 
   ~nisqa_engine() {
     for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); delete f; }
-    DevBuf* all[] = {&warena, &fb_table, &tw4096, &pcm[0], &pcm[1], &clips[0], &clips[1], &prefixes[0],
-                     &prefixes[1], &clipmax[0], &clipmax[1], &mel, &segtab, &act1,
-                     &act2, &act3, &act4, &act5, &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout,
-                     &partial, &scores, &dump};
+    DevBuf* all[] = {&warena, &fb_table, &tw4096, &scores, &dump};
     for (auto* b : all) b->release();
-    h_tables[0].release(); h_tables[1].release(); h_scores.release();
-    for (int i = 0; i < 2; ++i) {
-      if (ev_copied[i]) cudaEventDestroy(ev_copied[i]);
-      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
-    }
-    for (auto& tk : tickets) { tk.pinned.release(); if (tk.done) cudaEventDestroy(tk.done); }
+    h_scores.release();
+    for (auto& tk : tickets) { tk.pinned.release(); tk.scores.release(); if (tk.done) cudaEventDestroy(tk.done); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto& l : lanes) l.release();
+    stream = nullptr;
     for (auto& t : timers) for (auto& e : t.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    if (stream) cudaStreamDestroy(stream);
   }
 };
 
@@ -206,12 +223,12 @@ struct Scope {
     if (!slot) { e->timers.push_back(TimerSlot()); slot = &e->timers.back(); slot->name = name; }
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, e->stream);
+    cudaEventRecord(a, e->cur_stream);
     slot->ev.push_back({a, b});
     slot->launches += n_launch;
     stop = b;
   }
-  ~Scope() { if (stop) cudaEventRecord(stop, e->stream); }
+  ~Scope() { if (stop) cudaEventRecord(stop, e->cur_stream); }
 };
 
 void collect_timers(nisqa_engine* e) {
@@ -316,7 +333,7 @@ int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
     tab[i].band_k0 = e->fbs[i]->band_k0.as<int>();
     tab[i].weights = e->fbs[i]->weights.as<float>();
   }
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaDeviceSynchronize());      // the table may be in use by passes in flight on any lane
   CK(e->fb_table.reserve(tab.size() * sizeof(FbTables) + 64 * sizeof(FbTables)));
   CK(cudaMemcpy(e->fb_table.p, tab.data(), tab.size() * sizeof(FbTables), cudaMemcpyHostToDevice));
   *id_out = (int)e->fbs.size() - 1;
@@ -549,6 +566,8 @@ struct PassInput {
   int slot;                           // staging slot (pass & 1)
 };
 
+int lane_allgather(nisqa_engine* e, const float* src, float* dst, size_t count, cudaStream_t st);
+
 int run_pass(nisqa_engine* e, const PassInput& in) {
   const nisqa_config& c = e->cfg;
   const int n = in.n_clips;
@@ -585,81 +604,82 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   const int n_out = c.n_out;
 
   float* scores = in.scores_dev_out;
-  const int slot = in.slot;
-  cudaStream_t st = e->stream, cs = e->copy_stream;
-  // the slot (pinned tables, device tables, PCM buffer) is reused every second pass
-  if (e->slot_busy[slot]) { CK(cudaEventSynchronize(e->ev_done[slot])); e->slot_busy[slot] = false; }
+  Lane& LN = e->lanes[in.slot];
+  cudaStream_t st = LN.stream, cs = e->copy_stream;
+  e->cur_stream = st;
+  // the lane (pinned tables, device tables, PCM buffer, workspaces) is reused every kLanes-th pass
+  if (LN.busy) { CK(cudaEventSynchronize(LN.ev_done)); LN.busy = false; }
 
   // ---- upload tables (one pinned block: ClipDesc[n] | 3 prefix arrays)
   const size_t tb_clips = (size_t)n * sizeof(ClipDesc);
   const size_t tb_pref = (size_t)(n + 1) * 4;
-  CK(e->h_tables[slot].reserve(tb_clips + 3 * tb_pref));
-  char* ht = e->h_tables[slot].as<char>();
+  CK(LN.h_tables.reserve(tb_clips + 3 * tb_pref));
+  char* ht = LN.h_tables.as<char>();
   memcpy(ht, cl.data(), tb_clips);
   memcpy(ht + tb_clips, pair_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + tb_pref, seg_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + 2 * tb_pref, qt_prefix.data(), tb_pref);
-  CK(e->clips[slot].reserve(tb_clips));
-  CK(e->prefixes[slot].reserve(3 * tb_pref));
-  CK(e->clipmax[slot].reserve((size_t)n * 4));
-  CK(cudaMemcpyAsync(e->clips[slot].p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemcpyAsync(e->prefixes[slot].p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemsetAsync(e->clipmax[slot].p, 0, (size_t)n * 4, cs));
-  const ClipDesc* d_clips = e->clips[slot].as<ClipDesc>();
-  unsigned* d_clipmax = e->clipmax[slot].as<unsigned>();
-  const int* d_pair = e->prefixes[slot].as<int>();
+  CK(LN.clips.reserve(tb_clips));
+  CK(LN.prefixes.reserve(3 * tb_pref));
+  CK(LN.clipmax.reserve((size_t)n * 4));
+  CK(cudaMemcpyAsync(LN.clips.p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(LN.prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemsetAsync(LN.clipmax.p, 0, (size_t)n * 4, cs));
+  const ClipDesc* d_clips = LN.clips.as<ClipDesc>();
+  unsigned* d_clipmax = LN.clipmax.as<unsigned>();
+  const int* d_pair = LN.prefixes.as<int>();
   (void)d_pair;
-  e->last_slot = slot;
+  e->last_lane = in.slot;
   const int* d_seg = d_pair + (n + 1);
   const int* d_qt = d_pair + 2 * (n + 1);
 
   if (n_seg == 0) {   // nothing valid in this pass: NaN scores
-    CK(cudaEventRecord(e->ev_copied[slot], cs));
-    CK(cudaStreamWaitEvent(st, e->ev_copied[slot], 0));
+    CK(cudaEventRecord(LN.ev_copied, cs));
+    CK(cudaStreamWaitEvent(st, LN.ev_copied, 0));
     CK(cudaMemsetAsync(scores, 0xFF, (size_t)n * n_out * 4, st));
   } else {
     // ---- PCM (copy stream), then hand over to the compute stream
     const void* d_pcm = in.dev_pcm;
     if (in.host_pcm) {
-      CK(e->pcm[slot].reserve((size_t)pcm_elems * esz));
+      CK(LN.pcm.reserve((size_t)pcm_elems * esz));
       for (int i = 0; i < n; ++i)
         if (cl[i].n_frames > 0)
-          CK(cudaMemcpyAsync(e->pcm[slot].as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
+          CK(cudaMemcpyAsync(LN.pcm.as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
                              (size_t)in.n_samples[i] * esz, cudaMemcpyHostToDevice, cs));
-      d_pcm = e->pcm[slot].p;
+      d_pcm = LN.pcm.p;
     }
-    CK(cudaEventRecord(e->ev_copied[slot], cs));
-    CK(cudaStreamWaitEvent(st, e->ev_copied[slot], 0));
+    CK(cudaEventRecord(LN.ev_copied, cs));
+    CK(cudaStreamWaitEvent(st, LN.ev_copied, 0));
     // ---- workspaces
     const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
     const int FEAT = std_mode ? 768 : 384;
-    CK(e->mel.reserve((size_t)n_frames * kMels * 4));
-    CK(e->segtab.reserve((size_t)n_seg * 12));
-    CK(e->act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
-    CK(e->act2.reserve((size_t)n_seg * 12 * W2 * 32 * 4));
-    CK(e->act3.reserve((size_t)n_seg * 12 * W2 * 64 * 4));
-    CK(e->act4.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
-    CK(e->act5.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
-    CK(e->feats.reserve((size_t)n_seg * FEAT * 4));
-    int* seg_frame0 = e->segtab.as<int>();
+    CK(LN.mel.reserve((size_t)n_frames * kMels * 4));
+    CK(LN.segtab.reserve((size_t)n_seg * 12));
+    CK(LN.act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
+    CK(LN.act2.reserve((size_t)n_seg * 12 * W2 * 32 * 4));
+    CK(LN.act3.reserve((size_t)n_seg * 12 * W2 * 64 * 4));
+    CK(LN.act4.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    CK(LN.act5.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    CK(LN.feats.reserve((size_t)n_seg * FEAT * 4));
+    int* seg_frame0 = LN.segtab.as<int>();
     float* seg_thr = reinterpret_cast<float*>(seg_frame0 + n_seg);
     int* seg_clip = seg_frame0 + 2 * (size_t)n_seg;
 
     { Scope s(e, "frontend");
       launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, max_pairs,
-                      e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), e->mel.as<float>(),
+                      e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), LN.mel.as<float>(),
                       d_clipmax, Q); }
     { Scope s(e, "seg_table");
       launch_seg_table(st, d_clips, n, d_seg, d_clipmax, c.seg_hop, n_seg,
                        seg_frame0, seg_thr, seg_clip); }
     { Scope s(e, "conv1");
-      launch_conv1(st, std_mode, e->mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
-                   W(e, "conv1.b"), e->act1.as<float>(), n_seg); }
+      launch_conv1(st, std_mode, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
+                   W(e, "conv1.b"), LN.act1.as<float>(), n_seg); }
     {
-      const float* cin_[7] = {nullptr, nullptr, e->act1.as<float>(), e->act2.as<float>(), e->act3.as<float>(),
-                              e->act4.as<float>(), e->act5.as<float>()};
-      float* cout_[7] = {nullptr, nullptr, e->act2.as<float>(), e->act3.as<float>(), e->act4.as<float>(),
-                         e->act5.as<float>(), e->feats.as<float>()};
+      const float* cin_[7] = {nullptr, nullptr, LN.act1.as<float>(), LN.act2.as<float>(), LN.act3.as<float>(),
+                              LN.act4.as<float>(), LN.act5.as<float>()};
+      float* cout_[7] = {nullptr, nullptr, LN.act2.as<float>(), LN.act3.as<float>(), LN.act4.as<float>(),
+                         LN.act5.as<float>(), LN.feats.as<float>()};
       for (int l = 2; l <= 6; ++l) {
         char nm[16], kw[24], kt[24], kb[24];
         snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
@@ -673,48 +693,48 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     }
 
     if (!std_mode) {
-      CK(e->xa.reserve((size_t)n_seg * 64 * 4));
-      CK(e->xb.reserve((size_t)n_seg * 64 * 4));
-      CK(e->qkv.reserve((size_t)n_seg * 192 * 4));
-      CK(e->logits.reserve((size_t)n_seg * n_out * 4));
-      CK(e->tdout.reserve((size_t)n_seg * 64 * 4));
+      CK(LN.xa.reserve((size_t)n_seg * 64 * 4));
+      CK(LN.xb.reserve((size_t)n_seg * 64 * 4));
+      CK(LN.qkv.reserve((size_t)n_seg * 192 * 4));
+      CK(LN.logits.reserve((size_t)n_seg * n_out * 4));
+      CK(LN.tdout.reserve((size_t)n_seg * 64 * 4));
       { Scope s(e, "lin_ln");
-        launch_lin_ln(st, e->feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), e->tdout.as<float>(), n_seg); }
-      e->last_td_in = e->tdout.as<float>();
-      const float* cur = e->tdout.as<float>();
-      float* pp[2] = {e->xa.as<float>(), e->xb.as<float>()};
+        launch_lin_ln(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), LN.tdout.as<float>(), n_seg); }
+      e->last_td_in = LN.tdout.as<float>();
+      const float* cur = LN.tdout.as<float>();
+      float* pp[2] = {LN.xa.as<float>(), LN.xb.as<float>()};
       for (int l = 0; l < c.sa_layers; ++l) {
         char k[32];
         auto K = [&](const char* s2) { snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
-        { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, K("qkvT")), W(e, K("qkvb")), e->qkv.as<float>(), n_seg); }
+        { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, K("qkvT")), W(e, K("qkvb")), LN.qkv.as<float>(), n_seg); }
         SaLayerParams P;
         P.WoT = W(e, K("woT")); P.bo = W(e, K("bo")); P.W1T = W(e, K("w1T")); P.b1 = W(e, K("b1"));
         P.W2T = W(e, K("w2T")); P.b2 = W(e, K("b2")); P.ln1_g = W(e, K("ln1g")); P.ln1_b = W(e, K("ln1b"));
         P.ln2_g = W(e, K("ln2g")); P.ln2_b = W(e, K("ln2b"));
-        { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, e->qkv.as<float>(), d_clips, n, d_qt, n_qt, P, pp[l & 1]); }
+        { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, LN.qkv.as<float>(), d_clips, n, d_qt, n_qt, P, pp[l & 1]); }
         cur = pp[l & 1];
       }
       e->last_td_out = cur;
       PoolHeadParams H;
       H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
       H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
-      { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, e->logits.as<float>(), scores); }
+      { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, LN.logits.as<float>(), scores); }
     } else {
-      CK(e->feats20.reserve((size_t)n_seg * 20 * 4));
-      CK(e->tdout.reserve((size_t)n_seg * 256 * 4));
-      CK(e->partial.reserve((size_t)n * 2 * 4));
-      { Scope s(e, "fc_out"); launch_fc20(st, e->feats.as<float>(), W(e, "fc.wT"), W(e, "fc.b"), e->feats20.as<float>(), n_seg); }
+      CK(LN.feats20.reserve((size_t)n_seg * 20 * 4));
+      CK(LN.tdout.reserve((size_t)n_seg * 256 * 4));
+      CK(LN.partial.reserve((size_t)n * 2 * 4));
+      { Scope s(e, "fc_out"); launch_fc20(st, LN.feats.as<float>(), W(e, "fc.wT"), W(e, "fc.b"), LN.feats20.as<float>(), n_seg); }
       LstmParams L;
       L.w_ih = W(e, "lstm.wih"); L.w_hh = W(e, "lstm.whh"); L.b = W(e, "lstm.b"); L.w_pool = W(e, "lastbi.w");
       { Scope s(e, "lstm", 2);
-        launch_lstm(st, e->feats20.as<float>(), d_clips, n, L, e->tdout.as<float>(), e->partial.as<float>(), e->pool_bias_std, scores); }
+        launch_lstm(st, LN.feats20.as<float>(), d_clips, n, L, LN.tdout.as<float>(), LN.partial.as<float>(), e->pool_bias_std, scores); }
       e->last_td_in = nullptr;
-      e->last_td_out = e->tdout.as<float>();
+      e->last_td_out = LN.tdout.as<float>();
     }
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e->ev_done[slot], st));
-  e->slot_busy[slot] = true;
+  CK(cudaEventRecord(LN.ev_done, st));
+  LN.busy = true;
   return 0;
 }
 
@@ -743,9 +763,11 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
   float* scores_all = scores_dev;
   if (!scores_all) {
-    CK(e->scores.reserve((size_t)std::max(n_clips, 1) * e->cfg.n_out * 4));
-    scores_all = e->scores.as<float>();
+    DevBuf& sb = ticket_out ? e->tickets[e->next_ticket % kLanes].scores : e->scores;
+    CK(sb.reserve((size_t)std::max(n_clips, 1) * e->cfg.n_out * 4));
+    scores_all = sb.as<float>();
   }
+  const int64_t first_pass = e->pass_counter;
   int i0 = 0;
   e->last_passes = 0;
   while (i0 < n_clips) {
@@ -761,21 +783,34 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     in.dev_pcm = dev_pcm; in.dev_off = dev_off ? dev_off + i0 : nullptr;
     in.fmt = fmt;
     in.scores_dev_out = scores_all + (size_t)i0 * e->cfg.n_out;
-    in.slot = (int)(e->pass_counter++ & 1);
+    in.slot = e->profiling ? 0 : (int)(e->pass_counter % kLanes);
+    ++e->pass_counter;
     int rc = run_pass(e, in);
     if (rc) return rc;
     ++e->last_passes;
     i0 = i1;
   }
+  // the lane of the last pass collects: it waits for the other lanes this call used
+  const int n_pass = (int)(e->pass_counter - first_pass);
+  cudaStream_t fin = e->lanes[e->last_lane].stream;
+  if (n_pass == 0) fin = e->lanes[0].stream;
+  for (int k = 0; k < kLanes && n_pass > 1; ++k)
+    if (k != e->last_lane && e->lanes[k].busy) CK(cudaStreamWaitEvent(fin, e->lanes[k].ev_done, 0));
+  if (e->gather_dst && e->nccl_comm && n_clips == e->gather_rows && (ticket_out || scores_dev)) {
+    // the path's single exchange step, enqueued behind this call's kernels on its own lane
+    int rc = lane_allgather(e, scores_all, e->gather_dst, (size_t)n_clips * e->cfg.n_out, fin);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->lanes[e->last_lane].ev_done, fin));
+  }
   if (ticket_out) {
     // asynchronous completion: scores land in the ticket's pinned block; nisqa_wait hands them over
-    Ticket& tk = e->tickets[e->next_ticket & 1];
+    Ticket& tk = e->tickets[e->next_ticket % kLanes];
     tk.bytes = (size_t)n_clips * e->cfg.n_out * 4;
     tk.user_scores = scores_host;
     CK(tk.pinned.reserve(std::max<size_t>(tk.bytes, 16)));
-    if (tk.bytes) CK(cudaMemcpyAsync(tk.pinned.p, scores_all, tk.bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (tk.bytes) CK(cudaMemcpyAsync(tk.pinned.p, scores_all, tk.bytes, cudaMemcpyDeviceToHost, fin));
     if (!tk.done) CK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
-    CK(cudaEventRecord(tk.done, e->stream));
+    CK(cudaEventRecord(tk.done, fin));
     tk.active = true;
     tk.id = e->next_ticket++;
     *ticket_out = tk.id;
@@ -784,11 +819,11 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   if (scores_host && n_clips > 0) {
     const size_t bytes = (size_t)n_clips * e->cfg.n_out * 4;
     CK(e->h_scores.reserve(bytes));
-    CK(cudaMemcpyAsync(e->h_scores.p, scores_all, bytes, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(e->h_scores.p, scores_all, bytes, cudaMemcpyDeviceToHost, fin));
+    CK(cudaStreamSynchronize(fin));
     memcpy(scores_host, e->h_scores.p, bytes);
   }
-  if (sync || scores_host || e->profiling) CK(cudaStreamSynchronize(e->stream));
+  if (sync || scores_host || e->profiling) CK(cudaStreamSynchronize(fin));
   if (e->profiling) collect_timers(e);
   return 0;
 }
@@ -830,12 +865,14 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(e, NISQA_ERR_CUDA, "libnisqa_b200 is compiled for sm_100a only");
-  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    CK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+  for (auto& l : e->lanes) {
+    CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&l.ev_copied, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
   }
+  e->stream = e->lanes[0].stream;
+  e->cur_stream = e->stream;
   // twiddles laid out per lane so that every warp load is coalesced:
   //   tw1[r-1][j][lane] = W_4096^(r*(lane+32j)),  tw2[q][lane] = W_1024^(lane*q)
   std::vector<float2> tw(4 * 1024);
@@ -856,8 +893,7 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
 void nisqa_destroy(nisqa_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
-  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   delete e;
 }
 
@@ -867,7 +903,7 @@ int nisqa_load_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   if (!e || !tensors || n <= 0) return NISQA_ERR_INVALID;
   if (!e->stream) return fail(e, NISQA_ERR_STATE, "engine was not created successfully");
   CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaDeviceSynchronize());
   int rc = pack_weights(e, tensors, n);
   if (rc) return rc;
   e->weights_loaded = true;
@@ -890,7 +926,7 @@ int nisqa_submit_pcm(nisqa_engine* e, int n_clips, const void* const* pcm, const
   if (!e || !ticket) return NISQA_ERR_INVALID;
   if (n_clips > 0 && (!pcm || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
   if (e->profiling) return fail(e, NISQA_ERR_STATE, "profiling needs the synchronous entry points");
-  int rc = finish_ticket(e, e->tickets[e->next_ticket & 1]);      // at most two submissions in flight
+  int rc = finish_ticket(e, e->tickets[e->next_ticket % kLanes]);      // at most kLanes submissions in flight
   if (rc) return rc;
   return predict_common(e, n_clips, pcm, nullptr, nullptr, n_samples, sample_rate, sample_fmt,
                         scores_out, nullptr, n_segments_out, status_out, 0, ticket);
@@ -900,9 +936,9 @@ int nisqa_wait(nisqa_engine* e, int64_t ticket) {
   if (!e) return NISQA_ERR_INVALID;
   CK(cudaSetDevice(e->device));
   // tickets complete in submission order: finish everything up to and including `ticket`
-  for (int pass = 0; pass < 2; ++pass)
+  for (int64_t id = ticket - kLanes; id <= ticket; ++id)
     for (auto& tk : e->tickets)
-      if (tk.active && tk.id <= ticket && (pass == 1 || tk.id < ticket)) { int rc = finish_ticket(e, tk); if (rc) return rc; }
+      if (tk.active && tk.id == id) { int rc = finish_ticket(e, tk); if (rc) return rc; }
   return 0;
 }
 
@@ -919,6 +955,7 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   if (!e) return NISQA_ERR_INVALID;
   if (e->last_passes != 1) return fail(e, NISQA_ERR_STATE, "stage dump needs a predict call that ran in one pass");
   cudaSetDevice(e->device);
+  Lane& LN = e->lanes[e->last_lane];
   const int std_mode = e->cfg.arch == NISQA_ARCH_STD_LSTM_LASTBI;
   const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
   const int64_t ns = e->last_n_seg;
@@ -927,14 +964,14 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   int hw = 0, ch = 0;    // NHWC -> NCHW conversion when ch > 0
   switch (stage) {
     case NISQA_STAGE_MEL_DB: count = (int64_t)e->last_n_frames * kMels; break;
-    case NISQA_STAGE_POOL1: src = e->act1.as<float>(); hw = 24 * W1; ch = 16; break;
-    case NISQA_STAGE_POOL2: src = e->act2.as<float>(); hw = 12 * W2; ch = 32; break;
-    case NISQA_STAGE_CONV3: src = e->act3.as<float>(); hw = 12 * W2; ch = 64; break;
-    case NISQA_STAGE_POOL3: src = e->act4.as<float>(); hw = 6 * W3; ch = 64; break;
-    case NISQA_STAGE_CONV5: src = e->act5.as<float>(); hw = 6 * W3; ch = 64; break;
+    case NISQA_STAGE_POOL1: src = LN.act1.as<float>(); hw = 24 * W1; ch = 16; break;
+    case NISQA_STAGE_POOL2: src = LN.act2.as<float>(); hw = 12 * W2; ch = 32; break;
+    case NISQA_STAGE_CONV3: src = LN.act3.as<float>(); hw = 12 * W2; ch = 64; break;
+    case NISQA_STAGE_POOL3: src = LN.act4.as<float>(); hw = 6 * W3; ch = 64; break;
+    case NISQA_STAGE_CONV5: src = LN.act5.as<float>(); hw = 6 * W3; ch = 64; break;
     case NISQA_STAGE_CNN_FEAT:
-      if (std_mode) { src = e->feats20.as<float>(); count = ns * 20; }
-      else { src = e->feats.as<float>(); hw = 6; ch = 64; }     // [h][c] -> c*6+h
+      if (std_mode) { src = LN.feats20.as<float>(); count = ns * 20; }
+      else { src = LN.feats.as<float>(); hw = 6; ch = 64; }     // [h][c] -> c*6+h
       break;
     case NISQA_STAGE_TD_IN:
       if (std_mode || !e->last_td_in) return fail(e, NISQA_ERR_INVALID, "stage not available for this architecture");
@@ -946,11 +983,11 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   if (!out) return count;
   if (cap < count) return fail(e, NISQA_ERR_INVALID, "stage dump buffer too small");
   if (count == 0) return 0;
-  cudaStream_t st = e->stream;
+  cudaStream_t st = LN.stream;
   if (stage == NISQA_STAGE_MEL_DB) {
     CK(e->dump.reserve((size_t)count * 4));
-    launch_mel_dump(st, e->mel.as<float>(), e->clips[e->last_slot].as<ClipDesc>(), (int)e->last_clips.size(),
-                    e->clipmax[e->last_slot].as<unsigned>(), e->dump.as<float>());
+    launch_mel_dump(st, LN.mel.as<float>(), LN.clips.as<ClipDesc>(), (int)e->last_clips.size(),
+                    LN.clipmax.as<unsigned>(), e->dump.as<float>());
     src = e->dump.as<float>();
   } else if (ch > 0) {
     CK(e->dump.reserve((size_t)count * 4));
@@ -991,6 +1028,14 @@ int nisqa_mel_filterbank(nisqa_engine* e, int32_t sample_rate, float* out, int64
 
 int64_t nisqa_kernel_launches(const nisqa_engine* e) { return e ? e->launches : 0; }
 void* nisqa_stream(const nisqa_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int nisqa_join(nisqa_engine* e) {
+  if (!e || !e->stream) return NISQA_ERR_INVALID;
+  CK(cudaSetDevice(e->device));
+  for (int k = 1; k < kLanes; ++k)
+    if (e->lanes[k].busy) CK(cudaStreamWaitEvent(e->stream, e->lanes[k].ev_done, 0));
+  return 0;
+}
 
 int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
@@ -1058,7 +1103,25 @@ NcclApi* nccl_api(std::string* why) {
 }
 }  // namespace
 
+namespace {
+int lane_allgather(nisqa_engine* e, const float* src, float* dst, size_t count, cudaStream_t st) {
+  std::string why;
+  NcclApi* a = nccl_api(&why);
+  if (!a) return fail(e, NISQA_ERR_NCCL, why);
+  int rc = a->AllGather(src, dst, count, /*ncclFloat32*/ 7, e->nccl_comm, st);
+  if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclAllGather: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));
+  e->launches += 1;
+  return 0;
+}
+}  // namespace
+
 extern "C" {
+
+int nisqa_set_gather_target(nisqa_engine* e, float* global_dev, int rows) {
+  if (!e || rows < 0) return NISQA_ERR_INVALID;
+  e->gather_dst = global_dev; e->gather_rows = global_dev ? rows : 0;
+  return 0;
+}
 
 int nisqa_nccl_unique_id(nisqa_engine* e, void* id128) {
   if (!e || !id128) return NISQA_ERR_INVALID;
@@ -1092,6 +1155,8 @@ int nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm, const float* local_dev, 
   void* comm = nccl_comm ? nccl_comm : e->nccl_comm;
   if (!comm) return fail(e, NISQA_ERR_STATE, "no NCCL communicator: call nisqa_nccl_init or pass one");
   CK(cudaSetDevice(e->device));
+  for (int k = 1; k < kLanes; ++k)          // the rows may have been produced on any lane
+    if (e->lanes[k].busy) CK(cudaStreamWaitEvent(e->stream, e->lanes[k].ev_done, 0));
   const size_t count = (size_t)max_rows * e->cfg.n_out;
   int rc = a->AllGather(local_dev, global_dev, count, /*ncclFloat32*/ 7, comm, e->stream);
   if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclAllGather: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));

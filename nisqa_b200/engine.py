@@ -26,7 +26,7 @@ EXPORTS = [
     "nisqa_predict_pcm", "nisqa_predict_pcm_device", "nisqa_stage_dump", "nisqa_segment_counts",
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
-    "nisqa_submit_pcm", "nisqa_wait",
+    "nisqa_submit_pcm", "nisqa_wait", "nisqa_join", "nisqa_set_gather_target",
 ]
 
 
@@ -74,6 +74,10 @@ def load_library(path=None):
     lib.nisqa_predict_pcm.restype = C.c_int
     lib.nisqa_submit_pcm.argtypes = [vp, C.c_int, C.POINTER(vp), i64p, i32p, C.c_int, f32p, i32p, i32p, i64p]
     lib.nisqa_submit_pcm.restype = C.c_int
+    lib.nisqa_set_gather_target.argtypes = [vp, vp, C.c_int]
+    lib.nisqa_set_gather_target.restype = C.c_int
+    lib.nisqa_join.argtypes = [vp]
+    lib.nisqa_join.restype = C.c_int
     lib.nisqa_wait.argtypes = [vp, C.c_int64]
     lib.nisqa_wait.restype = C.c_int
     lib.nisqa_predict_pcm_device.argtypes = [vp, C.c_int, vp, i64p, i64p, i32p, C.c_int, vp, i32p, i32p, C.c_int]
@@ -247,7 +251,7 @@ class Engine(object):
 
     def submit_pcm(self, clips, sample_rates):
         """Asynchronous predict_pcm: returns a handle; ``wait(handle)`` -> (scores, n_segments, status).
-        Up to two submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
+        Up to three submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
         n = len(clips)
         dt = clips[0].dtype if n else np.dtype(np.int16)
         if any(c.dtype != dt for c in clips):
@@ -343,6 +347,9 @@ class Engine(object):
     def stream(self):
         return self.lib.nisqa_stream(self.h)
 
+    def join(self):
+        self._check(self.lib.nisqa_join(self.h), "nisqa_join")
+
     def set_profiling(self, on):
         self._check(self.lib.nisqa_set_profiling(self.h, 1 if on else 0), "nisqa_set_profiling")
 
@@ -361,6 +368,9 @@ class Engine(object):
     def nccl_init(self, world, rank, uid):
         buf = (C.c_char * 128).from_buffer_copy(uid)
         self._check(self.lib.nisqa_nccl_init(self.h, int(world), int(rank), buf), "nisqa_nccl_init")
+
+    def set_gather_target(self, global_dev_ptr, rows):
+        self._check(self.lib.nisqa_set_gather_target(self.h, C.c_void_p(global_dev_ptr), int(rows)), "nisqa_set_gather_target")
 
     def gather_nccl(self, local_dev_ptr, max_rows, global_dev_ptr, comm=None):
         self._check(self.lib.nisqa_gather_nccl(self.h, C.c_void_p(comm), C.c_void_p(local_dev_ptr),
