@@ -642,10 +642,22 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     const void* d_pcm = in.dev_pcm;
     if (in.host_pcm) {
       CK(LN.pcm.reserve((size_t)pcm_elems * esz));
-      for (int i = 0; i < n; ++i)
-        if (cl[i].n_frames > 0)
-          CK(cudaMemcpyAsync(LN.pcm.as<char>() + (size_t)cl[i].pcm_off * esz, in.host_pcm[i],
-                             (size_t)in.n_samples[i] * esz, cudaMemcpyHostToDevice, cs));
+      // clips that are back to back in host memory with the same 16-element alignment as the
+      // device packing travel as ONE copy (a pinned batch buffer becomes a single large DMA)
+      for (int i = 0; i < n;) {
+        if (cl[i].n_frames <= 0) { ++i; continue; }
+        const char* h0 = static_cast<const char*>(in.host_pcm[i]);
+        const long long o0 = cl[i].pcm_off;
+        size_t bytes = (size_t)in.n_samples[i] * esz;
+        int j = i + 1;
+        while (j < n && cl[j].n_frames > 0 &&
+               static_cast<const char*>(in.host_pcm[j]) == h0 + (size_t)(cl[j].pcm_off - o0) * esz) {
+          bytes = (size_t)(cl[j].pcm_off - o0) * esz + (size_t)in.n_samples[j] * esz;
+          ++j;
+        }
+        CK(cudaMemcpyAsync(LN.pcm.as<char>() + (size_t)o0 * esz, h0, bytes, cudaMemcpyHostToDevice, cs));
+        i = j;
+      }
       d_pcm = LN.pcm.p;
     }
     CK(cudaEventRecord(LN.ev_copied, cs));
