@@ -334,53 +334,61 @@ __global__ void pool_final_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------
-// BiLSTM(20 -> 128), one CTA per (clip, direction), 512 threads = 512 gate rows (PyTorch order
-// i,f,g,o).  W_hh row: first 64 taps in registers, last 64 in shared memory [k][512].
+// BiLSTM(20 -> 128), one CTA per (clip, direction), 512 threads = 512 gate rows.  The four gates
+// of hidden unit j live in one lane quad (thread t: unit t>>2, gate t&3 in PyTorch order i,f,g,o),
+// so the gate exchange is four shuffles, the cell update is replicated in the quad, and a step
+// needs ONE barrier (h and x are double buffered).  W_hh row: first 64 taps in registers, last 64
+// in shared memory [k][512].
 struct LstmParams {
   const float* w_ih;   // [2][512][20]
   const float* w_hh;   // [2][512][128]
   const float* b;      // [2][512]   (bias_ih + bias_hh)
   const float* w_pool; // [256]
 };
-constexpr int kLstmSmemFloats = 64 * 512 + 512 + 2 * 128 + 32;
+constexpr int kLstmSmemFloats = 64 * 512 + 2 * 128 + 2 * 32 + 128;
 
 __global__ void __launch_bounds__(512, 1)
 lstm_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipDesc* __restrict__ clips,
             LstmParams P, float* __restrict__ td_out /*[n_seg][256]*/, float* __restrict__ partial /*[n_clips][2]*/) {
   extern __shared__ __align__(16) float sm[];
-  float* whs = sm;                   // [64][512]  taps 64..127
-  float* gates = sm + 64 * 512;      // [512]
-  float* hbuf = gates + 512;         // [2][128]
-  float* xt = hbuf + 256;            // [32] current input (20 used)
+  float* whs = sm;                   // [64][512]  taps 64..127, indexed by thread
+  float* hbuf = sm + 64 * 512;       // [2][128]
+  float* xbuf = hbuf + 256;          // [2][32] input of the current / next step (20 used)
+  float* red = xbuf + 64;            // [128]
   const int clip = blockIdx.x >> 1, dir = blockIdx.x & 1;
   const ClipDesc cd = clips[clip];
   const int S = cd.n_seg;
-  const int g = threadIdx.x;
-  if (S <= 0) { if (g == 0) partial[clip * 2 + dir] = 0.f; return; }
+  const int t = threadIdx.x, lane = t & 31;
+  const int unit = t >> 2, gate = t & 3;
+  const int grow = gate * 128 + unit;          // row of the PyTorch gate matrices
+  if (S <= 0) { if (t == 0) partial[clip * 2 + dir] = 0.f; return; }
 
   float wr[64], wi[20];
   {
-    const float* wrow = P.w_hh + ((size_t)dir * 512 + g) * 128;
+    const float* wrow = P.w_hh + ((size_t)dir * 512 + grow) * 128;
 #pragma unroll
     for (int k = 0; k < 64; ++k) wr[k] = __ldg(wrow + k);
-    for (int k = 0; k < 64; ++k) whs[k * 512 + g] = __ldg(wrow + 64 + k);
-    const float* irow = P.w_ih + ((size_t)dir * 512 + g) * 20;
+    for (int k = 0; k < 64; ++k) whs[k * 512 + t] = __ldg(wrow + 64 + k);
+    const float* irow = P.w_ih + ((size_t)dir * 512 + grow) * 20;
 #pragma unroll
     for (int k = 0; k < 20; ++k) wi[k] = __ldg(irow + k);
   }
-  const float bias = __ldg(P.b + dir * 512 + g);
-  if (g < 256) hbuf[g] = 0.f;
-  float cstate = 0.f;
+  const float bias = __ldg(P.b + dir * 512 + grow);
+  if (t < 256) hbuf[t] = 0.f;
+  if (t < 64) xbuf[t] = 0.f;
+  float cstate = 0.f, hlast = 0.f;
   const float* fb = feats + (size_t)cd.seg_off * 20;
-  {
-    const int t0 = dir ? S - 1 : 0;
-    if (g < 20) xt[g] = __ldg(fb + (size_t)t0 * 20 + g);
-  }
+  __syncthreads();
+  if (t < 20) xbuf[t] = __ldg(fb + (size_t)(dir ? S - 1 : 0) * 20 + t);
   __syncthreads();
 
   for (int step = 0; step < S; ++step) {
-    const int t = dir ? S - 1 - step : step;
+    const int tt = dir ? S - 1 - step : step;
     const float* h = hbuf + (step & 1) * 128;
+    const float* xt = xbuf + (step & 1) * 32;
+    // prefetch the next input row while this step computes
+    float xnext = 0.f;
+    if (t < 20 && step + 1 < S) xnext = __ldg(fb + (size_t)(dir ? S - 2 - step : step + 1) * 20 + t);
     float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int k = 0; k < 20; k += 4) {
@@ -392,35 +400,36 @@ lstm_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipDesc* __r
       const float4 hv = *reinterpret_cast<const float4*>(h + k);
       a0 = fmaf(wr[k], hv.x, a0); a1 = fmaf(wr[k+1], hv.y, a1); a2 = fmaf(wr[k+2], hv.z, a2); a3 = fmaf(wr[k+3], hv.w, a3);
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < 64; k += 4) {
       const float4 hv = *reinterpret_cast<const float4*>(h + 64 + k);
-      a0 = fmaf(whs[(k) * 512 + g], hv.x, a0); a1 = fmaf(whs[(k+1) * 512 + g], hv.y, a1);
-      a2 = fmaf(whs[(k+2) * 512 + g], hv.z, a2); a3 = fmaf(whs[(k+3) * 512 + g], hv.w, a3);
+      a0 = fmaf(whs[(k) * 512 + t], hv.x, a0); a1 = fmaf(whs[(k+1) * 512 + t], hv.y, a1);
+      a2 = fmaf(whs[(k+2) * 512 + t], hv.z, a2); a3 = fmaf(whs[(k+3) * 512 + t], hv.w, a3);
     }
     const float pre = (a0 + a1) + (a2 + a3);
-    // gate nonlinearity: rows 256..383 are the cell candidate (tanh), the rest sigmoid
-    gates[g] = ((g >> 7) == 2) ? tanhf(pre) : 1.0f / (1.0f + expf(-pre));
-    __syncthreads();
-    if (g < 128) {
-      const float ig = gates[g], fg = gates[128 + g], gg = gates[256 + g], og = gates[384 + g];
-      cstate = fmaf(fg, cstate, ig * gg);
-      const float hn = og * tanhf(cstate);
-      hbuf[((step + 1) & 1) * 128 + g] = hn;
-      td_out[((size_t)cd.seg_off + t) * 256 + dir * 128 + g] = hn;
-    } else if (g >= 480 && g < 500 && step + 1 < S) {
-      const int tn = dir ? S - 2 - step : step + 1;
-      xt[g - 480] = __ldg(fb + (size_t)tn * 20 + (g - 480));
+    // gate nonlinearity: gate 2 is the cell candidate (tanh), the others sigmoid
+    const float act = (gate == 2) ? tanhf(pre) : 1.0f / (1.0f + expf(-pre));
+    const int q0 = lane & ~3;
+    const float ig = __shfl_sync(0xffffffffu, act, q0);
+    const float fg = __shfl_sync(0xffffffffu, act, q0 + 1);
+    const float gg = __shfl_sync(0xffffffffu, act, q0 + 2);
+    const float og = __shfl_sync(0xffffffffu, act, q0 + 3);
+    cstate = fmaf(fg, cstate, ig * gg);
+    hlast = og * tanhf(cstate);
+    if (gate == 0) {
+      hbuf[((step + 1) & 1) * 128 + unit] = hlast;
+      td_out[((size_t)cd.seg_off + tt) * 256 + dir * 128 + unit] = hlast;
     }
+    if (t < 20) xbuf[((step + 1) & 1) * 32 + t] = xnext;
     __syncthreads();
   }
   // PoolLastStepBi: this direction's final hidden state . w_pool half
-  if (g < 128) gates[g] = hbuf[(S & 1) * 128 + g] * __ldg(P.w_pool + dir * 128 + g);
+  if (gate == 0) red[unit] = hlast * __ldg(P.w_pool + dir * 128 + unit);
   __syncthreads();
-  if (g < 32) {
-    float v = gates[g] + gates[g + 32] + gates[g + 64] + gates[g + 96];
+  if (t < 32) {
+    float v = red[t] + red[t + 32] + red[t + 64] + red[t + 96];
     v = warp_sum(v);
-    if (g == 0) partial[clip * 2 + dir] = v;
+    if (t == 0) partial[clip * 2 + dir] = v;
   }
 }
 
