@@ -168,6 +168,17 @@ NISQA_API int  nisqa_nccl_init(nisqa_engine* e, int world, int rank, const void*
  * global_dev == NULL switches it off. */
 NISQA_API int  nisqa_set_gather_target(nisqa_engine* e, float* global_dev, int rows);
 
+/* ---- native WAV ingest (replaces lb.load + channel pick, lib:2298-2306) -----------
+ * Host-only, thread-safe, no engine handle: probe the header, then decode straight into caller-owned
+ * (ideally pinned) memory.  kind_out / out_fmt use enum nisqa_sample_fmt: S16 when the clip can be
+ * delivered as int16 without loss (PCM16, mono or channel pick), else F32 (libsndfile conversion,
+ * float32 mean over channels when ms_channel < 0).  Any failure is what the reference reports as
+ * "Could not load file". */
+NISQA_API int     nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t* sample_rate,
+                                  int64_t* n_frames, int32_t* channels, int32_t* kind_out);
+NISQA_API int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst,
+                                   int64_t cap_frames);
+
 /* bookkeeping for bench.py */
 NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
 NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t of compute lane 0 */

@@ -9,8 +9,9 @@ Same names, argument meaning and error behaviour as the reference so that
   ``ds.df`` in dataset row order; ``predict_mos`` stores float64, ``predict_dim`` float32.
 * ``model`` is an :class:`nisqa_b200.engine.Engine` instead of an ``nn.Module``; one batch of
   ``bs`` clips becomes ONE C-ABI call (wav decode -> PCM pointers -> scores), there is no
-  padded ``[bs, 1300, 1, 48, 15]`` tensor and no DataLoader.  ``num_workers`` sizes the
-  wav-decode thread pool that prefetches the next batch while the GPU works on this one.
+  padded ``[bs, 1300, 1, 48, 15]`` tensor and no DataLoader.  ``num_workers`` sizes the thread pool
+  that drives the native wav reader (csrc/wavio.cpp) straight into pinned batch buffers while the
+  GPU works on earlier batches.
 * errors are the reference's ``ValueError``s: unreadable file (lib:2305-2306), clip shorter
   than ``seg_length`` frames (lib:2258-2263), more than ``ms_max_segments`` segments
   (lib:2276-2277) - a single bad file aborts the run, like the reference.
@@ -24,7 +25,7 @@ import numpy as np
 
 from . import dist as nb_dist
 from . import engine as nb_engine
-from .wav import read_wav
+from .wav import decode_wav_into, probe_wav, read_wav
 
 
 class SpeechQualityDataset(object):
@@ -81,43 +82,70 @@ def _raise_for_status(ds, engine, index, n_samples, sr, n_seg, status):
                 n_seg, ds.max_length, path))
 
 
+class _PinnedPool(object):
+    """Grow-only ring of pinned host buffers: a batch is decoded straight into one of them (native
+    reader, csrc/wavio.cpp), clips back to back at the engine's 16-sample alignment, so the whole
+    batch travels to the GPU as ONE asynchronous copy."""
+
+    def __init__(self, n):
+        self.bufs = [None] * n
+
+    def get(self, slot, nbytes):
+        import torch
+        cur = self.bufs[slot]
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
+            self.bufs[slot] = cur
+        return cur.numpy()
+
+
+def _load_batch(ds, batch, pool, slot, workers):
+    """wav files of one batch -> (list of 1-D views into a pinned buffer, sample rates)."""
+    paths = [ds.file_path(int(i)) for i in batch]
+    probes = list(workers.map(lambda p: probe_wav(p, ds.ms_channel), paths))
+    dtype = np.int16 if all(k == 0 for _, _, _, k in probes) else np.float32
+    offs, total = [], 0
+    for _, nf, _, _ in probes:
+        offs.append(total)
+        total += (int(nf) + 15) // 16 * 16
+    buf = pool.get(slot, max(total, 16) * np.dtype(dtype).itemsize)[:max(total, 16) * np.dtype(dtype).itemsize].view(dtype)
+
+    def dec(j):
+        view = buf[offs[j]:offs[j] + int(probes[j][1])]
+        decode_wav_into(paths[j], view, ds.ms_channel)
+        return view
+
+    clips = list(workers.map(dec, range(len(paths))))
+    return clips, [int(p[0]) for p in probes]
+
+
 def _predict_rows(engine, ds, rows, bs, num_workers):
-    """Scores for the given dataset rows (in that order) through the C-ABI, bs clips per call."""
+    """Scores for the given dataset rows (in that order) through the C-ABI, bs clips per call.
+    Pipeline: decode batch b+1 (thread pool, native reader -> pinned memory) while the engine has up
+    to three earlier batches in flight (H2D on the copy stream, kernels on rotating compute lanes)."""
     n_out = engine.n_out
     out = np.empty((len(rows), n_out), dtype=np.float32)
     bs = max(1, int(bs))
     batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
-    workers = max(1, int(num_workers) if num_workers else 1)
+    n_threads = max(1, int(num_workers) if num_workers else 1)
+    pool = _PinnedPool(6)             # 3 in flight + 1 being decoded + slack
 
-    def load(batch):
-        return [ds.load_pcm(int(i)) for i in batch]
+    def finish(job):
+        handle, batch, clips, srs, pos = job
+        scores, nseg, status = engine.wait(handle)
+        for j, st in enumerate(status):
+            if st != nb_engine.CLIP_OK:
+                _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
+        out[pos:pos + len(batch)] = scores
 
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        def submit(batch):
-            if workers == 1:
-                return pool.submit(load, batch)
-            futs = [pool.submit(ds.load_pcm, int(i)) for i in batch]
-            return futs
-
-        def collect(h):
-            return h.result() if not isinstance(h, list) else [f.result() for f in h]
-
-        def finish(job):
-            handle, batch, clips, srs, pos = job
-            scores, nseg, status = engine.wait(handle)
-            for j, st in enumerate(status):
-                if st != nb_engine.CLIP_OK:
-                    _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
-            out[pos:pos + len(batch)] = scores
-
-        pending = submit(batches[0]) if batches else None
+    with ThreadPoolExecutor(max_workers=n_threads) as workers, ThreadPoolExecutor(max_workers=1) as feeder:
+        pending = feeder.submit(_load_batch, ds, batches[0], pool, 0, workers) if batches else None
         pos = 0
-        in_flight = []                # batches whose kernels are running while we decode / upload the next
+        in_flight = []                # batches whose kernels are running while the next one is decoded
         for b, batch in enumerate(batches):
-            loaded = collect(pending)
-            pending = submit(batches[b + 1]) if b + 1 < len(batches) else None
-            clips = [c for c, _ in loaded]
-            srs = [s for _, s in loaded]
+            clips, srs = pending.result()
+            pending = (feeder.submit(_load_batch, ds, batches[b + 1], pool, (b + 1) % 6, workers)
+                       if b + 1 < len(batches) else None)
             handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
             in_flight.append((handle, batch, clips, srs, pos))
             pos += len(batch)

@@ -1,0 +1,169 @@
+// wavio.cpp - native RIFF/WAVE ingest (the caller side of the hot path).
+// Replaces what lb.load(path, sr=None[, mono=False]) + the ms_channel pick do at reference
+// nisqa/NISQA_lib.py:2298-2306 (libsndfile conversion rules, float32 mean over channels).
+//
+// Two-step C ABI so that the CALLER owns the memory: nisqa_wav_probe() parses the header,
+// nisqa_wav_decode() reads the samples straight into the caller's (pinned) batch buffer - mono
+// PCM16 is a single fread into place, no intermediate copy.  Both are thread-safe and are driven
+// from a Python thread pool (ctypes releases the GIL), one file per task.
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/nisqa_b200.h"
+
+namespace {
+
+struct WavInfo {
+  int tag = 0, channels = 0, bits = 0;
+  int32_t sample_rate = 0;
+  int64_t data_off = 0, n_frames = 0;
+};
+
+bool parse_header(FILE* f, WavInfo* w) {
+  unsigned char h[12];
+  if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) return false;
+  bool have_fmt = false;
+  int64_t pos = 12;
+  for (;;) {
+    unsigned char ck[8];
+    if (fseek(f, pos, SEEK_SET) != 0 || fread(ck, 1, 8, f) != 8) return false;
+    const uint32_t sz = (uint32_t)ck[4] | ((uint32_t)ck[5] << 8) | ((uint32_t)ck[6] << 16) | ((uint32_t)ck[7] << 24);
+    if (memcmp(ck, "fmt ", 4) == 0) {
+      unsigned char b[40] = {0};
+      const size_t want = sz < 40 ? sz : 40;
+      if (sz < 16 || fread(b, 1, want, f) != want) return false;
+      w->tag = b[0] | (b[1] << 8);
+      w->channels = b[2] | (b[3] << 8);
+      w->sample_rate = (int32_t)((uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24));
+      w->bits = b[14] | (b[15] << 8);
+      if (w->tag == 0xFFFE && sz >= 26) w->tag = b[24] | (b[25] << 8);   // WAVE_FORMAT_EXTENSIBLE
+      have_fmt = true;
+    } else if (memcmp(ck, "data", 4) == 0) {
+      if (!have_fmt || w->channels < 1) return false;
+      const int width = w->bits / 8;
+      if (width < 1) return false;
+      // clamp to the real file size (streamed files may carry a bogus length)
+      fseek(f, 0, SEEK_END);
+      const int64_t fsize = ftell(f);
+      int64_t bytes = sz;
+      if (pos + 8 + bytes > fsize) bytes = fsize - (pos + 8);
+      if (bytes < 0) return false;
+      w->data_off = pos + 8;
+      w->n_frames = bytes / ((int64_t)width * w->channels);
+      return true;
+    }
+    pos += 8 + (int64_t)sz + (sz & 1);
+  }
+}
+
+bool supported(const WavInfo& w) {
+  if (w.tag == 1) return w.bits == 8 || w.bits == 16 || w.bits == 24 || w.bits == 32;
+  if (w.tag == 3) return w.bits == 32 || w.bits == 64;
+  return false;
+}
+
+// libsndfile's conversion of one stored sample to float32
+inline float sample_f32(const unsigned char* p, const WavInfo& w) {
+  if (w.tag == 1) {
+    switch (w.bits) {
+      case 8: return ((float)p[0] - 128.0f) * (1.0f / 128.0f);
+      case 16: return (float)(int16_t)(p[0] | (p[1] << 8)) * (1.0f / 32768.0f);
+      case 24: {
+        int32_t v = p[0] | (p[1] << 8) | (p[2] << 16);
+        v = (v ^ 0x800000) - 0x800000;
+        return (float)v * (1.0f / 8388608.0f);
+      }
+      default: {
+        const int32_t v = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+        return (float)((double)v * (1.0 / 2147483648.0));
+      }
+    }
+  }
+  if (w.bits == 32) { float v; memcpy(&v, p, 4); return v; }
+  double d; memcpy(&d, p, 8); return (float)d;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Header only.  kind_out: NISQA_FMT_S16 if the clip can be delivered as int16 without loss (PCM16 and
+// either mono or a channel pick), else NISQA_FMT_F32.  Returns 0, or NISQA_ERR_INVALID for anything
+// the reference would answer with "Could not load file".
+int nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t* sample_rate, int64_t* n_frames,
+                    int32_t* channels, int32_t* kind_out) {
+  if (!path) return NISQA_ERR_INVALID;
+  FILE* f = fopen(path, "rb");
+  if (!f) return NISQA_ERR_INVALID;
+  WavInfo w;
+  const bool ok = parse_header(f, &w) && supported(w);
+  fclose(f);
+  if (!ok) return NISQA_ERR_INVALID;
+  if (ms_channel >= 0 && w.channels > 1 && ms_channel >= w.channels) return NISQA_ERR_INVALID;
+  if (sample_rate) *sample_rate = w.sample_rate;
+  if (n_frames) *n_frames = w.n_frames;
+  if (channels) *channels = w.channels;
+  if (kind_out) *kind_out = (w.tag == 1 && w.bits == 16 && (w.channels == 1 || ms_channel >= 0)) ? NISQA_FMT_S16 : NISQA_FMT_F32;
+  return 0;
+}
+
+// Decode into dst (capacity cap_frames samples of out_fmt).  out_fmt NISQA_FMT_S16 is only legal when
+// probe reported S16; NISQA_FMT_F32 is always legal (PCM16 is then scaled by 1/32768).
+// ms_channel < 0: mono mix = float32 mean over the channels (librosa.to_mono); else that channel
+// (ignored for mono files, lib:2301).  Returns the number of frames written, or a negative status.
+int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
+  if (!path || !dst) return NISQA_ERR_INVALID;
+  FILE* f = fopen(path, "rb");
+  if (!f) return NISQA_ERR_INVALID;
+  WavInfo w;
+  if (!parse_header(f, &w) || !supported(w) || w.n_frames > cap_frames ||
+      (ms_channel >= 0 && w.channels > 1 && ms_channel >= w.channels)) { fclose(f); return NISQA_ERR_INVALID; }
+  const int width = w.bits / 8, ch = w.channels;
+  const int pick = (ch > 1 && ms_channel >= 0) ? ms_channel : -1;
+  if (fseek(f, w.data_off, SEEK_SET) != 0) { fclose(f); return NISQA_ERR_INVALID; }
+  int64_t done = 0;
+  if (out_fmt == NISQA_FMT_S16) {
+    if (!(w.tag == 1 && w.bits == 16 && (ch == 1 || pick >= 0))) { fclose(f); return NISQA_ERR_INVALID; }
+    int16_t* o = static_cast<int16_t*>(dst);
+    if (ch == 1) {                                   // straight into place (little-endian host)
+      done = (int64_t)fread(o, 2, (size_t)w.n_frames, f);
+    } else {
+      std::vector<int16_t> buf((size_t)8192 * ch);
+      while (done < w.n_frames) {
+        const int64_t want = std::min<int64_t>(8192, w.n_frames - done);
+        const int64_t got = (int64_t)fread(buf.data(), (size_t)2 * ch, (size_t)want, f);
+        if (got <= 0) break;
+        for (int64_t i = 0; i < got; ++i) o[done + i] = buf[(size_t)i * ch + pick];
+        done += got;
+      }
+    }
+  } else if (out_fmt == NISQA_FMT_F32) {
+    float* o = static_cast<float*>(dst);
+    std::vector<unsigned char> buf((size_t)8192 * ch * width);
+    while (done < w.n_frames) {
+      const int64_t want = std::min<int64_t>(8192, w.n_frames - done);
+      const int64_t got = (int64_t)fread(buf.data(), (size_t)width * ch, (size_t)want, f);
+      if (got <= 0) break;
+      for (int64_t i = 0; i < got; ++i) {
+        const unsigned char* p = buf.data() + (size_t)i * ch * width;
+        if (ch == 1) o[done + i] = sample_f32(p, w);
+        else if (pick >= 0) o[done + i] = sample_f32(p + (size_t)pick * width, w);
+        else {
+          // numpy.mean(axis=0) over float32 channels: sequential float32 sum, then / n
+          float s = 0.f;
+          for (int c = 0; c < ch; ++c) s += sample_f32(p + (size_t)c * width, w);
+          o[done + i] = s / (float)ch;
+        }
+      }
+      done += got;
+    }
+  } else { fclose(f); return NISQA_ERR_INVALID; }
+  fclose(f);
+  return done == w.n_frames ? done : (int64_t)NISQA_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -27,6 +27,7 @@ EXPORTS = [
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
     "nisqa_submit_pcm", "nisqa_wait", "nisqa_join", "nisqa_set_gather_target",
+    "nisqa_wav_probe", "nisqa_wav_decode",
 ]
 
 
@@ -74,6 +75,10 @@ def load_library(path=None):
     lib.nisqa_predict_pcm.restype = C.c_int
     lib.nisqa_submit_pcm.argtypes = [vp, C.c_int, C.POINTER(vp), i64p, i32p, C.c_int, f32p, i32p, i32p, i64p]
     lib.nisqa_submit_pcm.restype = C.c_int
+    lib.nisqa_wav_probe.argtypes = [C.c_char_p, C.c_int32, i32p, i64p, i32p, i32p]
+    lib.nisqa_wav_probe.restype = C.c_int
+    lib.nisqa_wav_decode.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int64]
+    lib.nisqa_wav_decode.restype = C.c_int64
     lib.nisqa_set_gather_target.argtypes = [vp, vp, C.c_int]
     lib.nisqa_set_gather_target.restype = C.c_int
     lib.nisqa_join.argtypes = [vp]

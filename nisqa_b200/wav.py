@@ -10,6 +10,7 @@ Returns ``(samples, sample_rate)`` where samples is a contiguous 1-D ``int16`` o
 array.  Any parse problem raises ``ValueError('Could not load file ...')`` exactly like the
 reference's bare ``except`` (lib:2305-2306).
 """
+import os
 import struct
 
 import numpy as np
@@ -81,6 +82,41 @@ def read_wav(path, ms_channel=None):
         return np.ascontiguousarray(out, dtype=np.float32), int(sr)
     except Exception:
         raise ValueError("Could not load file {}".format(path))
+
+
+def probe_wav(path, ms_channel=None):
+    """Native header probe (csrc/wavio.cpp) -> (sample_rate, n_frames, channels, kind) with kind
+    0 = deliverable as int16, 1 = float32.  ValueError('Could not load file ...') on failure."""
+    import ctypes as C
+    from . import engine as _e
+    lib = _e.load_library()
+    sr, nf, ch, kind = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+    rc = lib.nisqa_wav_probe(os.fsencode(path), -1 if ms_channel is None else int(ms_channel),
+                             C.byref(sr), C.byref(nf), C.byref(ch), C.byref(kind))
+    if rc != 0:
+        raise ValueError("Could not load file {}".format(path))
+    return sr.value, nf.value, ch.value, kind.value
+
+
+def decode_wav_into(path, dst, ms_channel=None):
+    """Native decode straight into ``dst`` (1-D int16 or float32 array / pinned tensor view with room
+    for the clip).  Returns the number of samples written."""
+    from . import engine as _e
+    lib = _e.load_library()
+    fmt = _e.FMT_S16 if dst.dtype == np.int16 else _e.FMT_F32
+    n = lib.nisqa_wav_decode(os.fsencode(path), -1 if ms_channel is None else int(ms_channel), fmt,
+                             dst.ctypes.data, dst.shape[0])
+    if n < 0:
+        raise ValueError("Could not load file {}".format(path))
+    return int(n)
+
+
+def read_wav_native(path, ms_channel=None):
+    """read_wav through the native reader (same return contract)."""
+    sr, nf, _, kind = probe_wav(path, ms_channel)
+    out = np.empty(nf, dtype=np.int16 if kind == 0 else np.float32)
+    decode_wav_into(path, out, ms_channel)
+    return out, sr
 
 
 def write_wav_pcm16(path, pcm, sr):

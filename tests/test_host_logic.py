@@ -135,3 +135,46 @@ def test_two_rank_gloo_exchange(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16"])
+def test_native_wav_reader_matches_oracle_loader(tmp_path, kind, built_lib):
+    """csrc/wavio.cpp (nisqa_wav_probe / nisqa_wav_decode, host-only entry points of the C-ABI)."""
+    rng = np.random.default_rng(2)
+    p = str(tmp_path / (kind + ".wav"))
+    n = 20011
+    if kind in ("pcm16", "ext16"):
+        _write_pcm(p, rng.integers(-32768, 32767, n).astype("<i2").tobytes(), 1, 1, 16000, 16, extensible=(kind == "ext16"))
+    elif kind == "pcm16_stereo":
+        _write_pcm(p, rng.integers(-32768, 32767, (n, 3)).astype("<i2").tobytes(), 1, 3, 44100, 16)
+    elif kind == "pcm24":
+        b = bytearray()
+        for x in rng.integers(-(1 << 23), (1 << 23) - 1, n):
+            b += int(x & 0xFFFFFF).to_bytes(3, "little")
+        _write_pcm(p, bytes(b), 1, 1, 48000, 24)
+    elif kind == "pcm32":
+        _write_pcm(p, rng.integers(-(1 << 31), (1 << 31) - 1, n).astype("<i4").tobytes(), 1, 1, 48000, 32)
+    elif kind == "f32":
+        _write_pcm(p, rng.standard_normal((n, 2)).astype("<f4").tobytes(), 3, 2, 22050, 32)
+    elif kind == "f64":
+        _write_pcm(p, rng.standard_normal(n).astype("<f8").tobytes(), 3, 1, 8000, 64)
+    else:
+        _write_pcm(p, rng.integers(0, 255, n).astype(np.uint8).tobytes(), 1, 1, 8000, 8)
+    y_ref, sr_ref = lb.load(p, sr=None)
+    y, sr = wav.read_wav_native(p)
+    assert sr == sr_ref
+    np.testing.assert_array_equal(_as_float(y), y_ref)
+    y2, _ = lb.load(p, sr=None, mono=False)
+    if y2.ndim > 1:
+        for ch in range(y2.shape[0]):
+            yc, _ = wav.read_wav_native(p, ms_channel=ch)
+            np.testing.assert_array_equal(_as_float(yc), y2[ch])
+    if kind == "pcm16":
+        assert y.dtype == np.int16
+
+
+def test_native_wav_reader_errors(tmp_path, built_lib):
+    (tmp_path / "bad.wav").write_bytes(b"RIFFxxxxWAVEjunk")
+    for name in ("bad.wav", "missing.wav"):
+        with pytest.raises(ValueError, match="Could not load file"):
+            wav.read_wav_native(str(tmp_path / name))
