@@ -178,6 +178,14 @@ NISQA_API int     nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t*
                                   int64_t* n_frames, int32_t* channels, int32_t* kind_out);
 NISQA_API int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst,
                                    int64_t cap_frames);
+/* whole-batch forms: one call per batch, files spread over n_threads native threads; status[i] per
+ * file, return value = number of files that failed (or a negative status for bad arguments) */
+NISQA_API int     nisqa_wav_probe_batch(int n, const char* const* paths, int32_t ms_channel, int n_threads,
+                                        int32_t* sample_rate, int64_t* n_frames, int32_t* kind,
+                                        int32_t* status);
+NISQA_API int     nisqa_wav_decode_batch(int n, const char* const* paths, int32_t ms_channel, int32_t out_fmt,
+                                         void* base, const int64_t* elem_offsets, const int64_t* cap_frames,
+                                         int n_threads, int32_t* status);
 
 /* bookkeeping for bench.py */
 NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import dist as nb_dist
 from . import engine as nb_engine
-from .wav import decode_wav_into, probe_wav, read_wav
+from .wav import decode_batch, probe_batch, read_wav
 
 
 class SpeechQualityDataset(object):
@@ -99,24 +99,21 @@ class _PinnedPool(object):
         return cur.numpy()
 
 
-def _load_batch(ds, batch, pool, slot, workers):
-    """wav files of one batch -> (list of 1-D views into a pinned buffer, sample rates)."""
+def _load_batch(ds, batch, pool, slot, n_threads):
+    """wav files of one batch -> (list of 1-D views into a pinned buffer, sample rates).  Two native
+    calls per batch (probe, decode), each spread over ``n_threads`` C++ threads."""
     paths = [ds.file_path(int(i)) for i in batch]
-    probes = list(workers.map(lambda p: probe_wav(p, ds.ms_channel), paths))
-    dtype = np.int16 if all(k == 0 for _, _, _, k in probes) else np.float32
-    offs, total = [], 0
-    for _, nf, _, _ in probes:
-        offs.append(total)
-        total += (int(nf) + 15) // 16 * 16
-    buf = pool.get(slot, max(total, 16) * np.dtype(dtype).itemsize)[:max(total, 16) * np.dtype(dtype).itemsize].view(dtype)
-
-    def dec(j):
-        view = buf[offs[j]:offs[j] + int(probes[j][1])]
-        decode_wav_into(paths[j], view, ds.ms_channel)
-        return view
-
-    clips = list(workers.map(dec, range(len(paths))))
-    return clips, [int(p[0]) for p in probes]
+    sr, nf, kind, arr = probe_batch(paths, ds.ms_channel, n_threads)
+    dtype = np.int16 if not kind.any() else np.float32
+    offs = np.zeros(len(paths), np.int64)
+    if len(paths) > 1:
+        offs[1:] = np.cumsum((nf[:-1] + 15) // 16 * 16)
+    total = int(offs[-1] + (nf[-1] + 15) // 16 * 16) if len(paths) else 0
+    nbytes = max(total, 16) * np.dtype(dtype).itemsize
+    buf = pool.get(slot, nbytes)[:nbytes].view(dtype)
+    decode_batch(arr, len(paths), buf, offs, nf, ds.ms_channel, n_threads, paths)
+    clips = [buf[int(o):int(o) + int(n)] for o, n in zip(offs, nf)]
+    return clips, [int(x) for x in sr]
 
 
 def _predict_rows(engine, ds, rows, bs, num_workers):
@@ -127,7 +124,7 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
     out = np.empty((len(rows), n_out), dtype=np.float32)
     bs = max(1, int(bs))
     batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
-    n_threads = max(1, int(num_workers) if num_workers else 1)
+    n_threads = max(1, int(num_workers) if num_workers else 1)     # native decode threads per batch
     pool = _PinnedPool(6)             # 3 in flight + 1 being decoded + slack
 
     def finish(job):
@@ -138,13 +135,13 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
                 _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
         out[pos:pos + len(batch)] = scores
 
-    with ThreadPoolExecutor(max_workers=n_threads) as workers, ThreadPoolExecutor(max_workers=1) as feeder:
-        pending = feeder.submit(_load_batch, ds, batches[0], pool, 0, workers) if batches else None
+    with ThreadPoolExecutor(max_workers=1) as feeder:
+        pending = feeder.submit(_load_batch, ds, batches[0], pool, 0, n_threads) if batches else None
         pos = 0
         in_flight = []                # batches whose kernels are running while the next one is decoded
         for b, batch in enumerate(batches):
             clips, srs = pending.result()
-            pending = (feeder.submit(_load_batch, ds, batches[b + 1], pool, (b + 1) % 6, workers)
+            pending = (feeder.submit(_load_batch, ds, batches[b + 1], pool, (b + 1) % 6, n_threads)
                        if b + 1 < len(batches) else None)
             handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
             in_flight.append((handle, batch, clips, srs, pos))

@@ -9,8 +9,12 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "../../include/nisqa_b200.h"
@@ -129,8 +133,15 @@ int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, 
   if (out_fmt == NISQA_FMT_S16) {
     if (!(w.tag == 1 && w.bits == 16 && (ch == 1 || pick >= 0))) { fclose(f); return NISQA_ERR_INVALID; }
     int16_t* o = static_cast<int16_t*>(dst);
-    if (ch == 1) {                                   // straight into place (little-endian host)
-      done = (int64_t)fread(o, 2, (size_t)w.n_frames, f);
+    if (ch == 1) {                                   // straight into place (little-endian host), no stdio copy
+      const int fd = fileno(f);
+      size_t want = (size_t)w.n_frames * 2, off = 0;
+      while (off < want) {
+        const ssize_t got = pread(fd, reinterpret_cast<char*>(o) + off, want - off, (off_t)(w.data_off + (int64_t)off));
+        if (got <= 0) break;
+        off += (size_t)got;
+      }
+      done = (int64_t)(off / 2);
     } else {
       std::vector<int16_t> buf((size_t)8192 * ch);
       while (done < w.n_frames) {
@@ -164,6 +175,47 @@ int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, 
   } else { fclose(f); return NISQA_ERR_INVALID; }
   fclose(f);
   return done == w.n_frames ? done : (int64_t)NISQA_ERR_INVALID;
+}
+
+
+// ---- whole-batch forms: one call per batch, the files are spread over n_threads native threads
+// (per-file calls from Python are bound by interpreter overhead at a few thousand files per second).
+static void run_parallel(int n, int n_threads, const std::function<void(int)>& fn) {
+  n_threads = std::max(1, std::min(n_threads, n));
+  if (n_threads == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_threads; ++t)
+    pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
+  for (auto& th : pool) th.join();
+}
+
+// status[i] = 0 or NISQA_ERR_INVALID per file; returns the number of files that failed.
+int nisqa_wav_probe_batch(int n, const char* const* paths, int32_t ms_channel, int n_threads,
+                          int32_t* sample_rate, int64_t* n_frames, int32_t* kind, int32_t* status) {
+  if (n < 0 || (n > 0 && (!paths || !sample_rate || !n_frames || !kind || !status))) return NISQA_ERR_INVALID;
+  std::atomic<int> bad(0);
+  run_parallel(n, n_threads, [&](int i) {
+    int32_t ch = 0;
+    status[i] = nisqa_wav_probe(paths[i], ms_channel, &sample_rate[i], &n_frames[i], &ch, &kind[i]);
+    if (status[i] != 0) { sample_rate[i] = 0; n_frames[i] = 0; kind[i] = NISQA_FMT_F32; bad.fetch_add(1); }
+  });
+  return bad.load();
+}
+
+// clip i is decoded to base + elem_offsets[i] * sizeof(out_fmt element), capacity cap_frames[i]
+int nisqa_wav_decode_batch(int n, const char* const* paths, int32_t ms_channel, int32_t out_fmt, void* base,
+                           const int64_t* elem_offsets, const int64_t* cap_frames, int n_threads,
+                           int32_t* status) {
+  if (n < 0 || (n > 0 && (!paths || !base || !elem_offsets || !cap_frames || !status))) return NISQA_ERR_INVALID;
+  const size_t esz = out_fmt == NISQA_FMT_S16 ? 2 : 4;
+  std::atomic<int> bad(0);
+  run_parallel(n, n_threads, [&](int i) {
+    const int64_t got = nisqa_wav_decode(paths[i], ms_channel, out_fmt, static_cast<char*>(base) + (size_t)elem_offsets[i] * esz, cap_frames[i]);
+    status[i] = got < 0 ? (int32_t)got : 0;
+    if (got < 0) bad.fetch_add(1);
+  });
+  return bad.load();
 }
 
 }  // extern "C"

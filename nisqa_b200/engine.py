@@ -27,7 +27,7 @@ EXPORTS = [
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
     "nisqa_submit_pcm", "nisqa_wait", "nisqa_join", "nisqa_set_gather_target",
-    "nisqa_wav_probe", "nisqa_wav_decode",
+    "nisqa_wav_probe", "nisqa_wav_decode", "nisqa_wav_probe_batch", "nisqa_wav_decode_batch",
 ]
 
 
@@ -79,6 +79,11 @@ def load_library(path=None):
     lib.nisqa_wav_probe.restype = C.c_int
     lib.nisqa_wav_decode.argtypes = [C.c_char_p, C.c_int32, C.c_int32, vp, C.c_int64]
     lib.nisqa_wav_decode.restype = C.c_int64
+    cpp = C.POINTER(C.c_char_p)
+    lib.nisqa_wav_probe_batch.argtypes = [C.c_int, cpp, C.c_int32, C.c_int, i32p, i64p, i32p, i32p]
+    lib.nisqa_wav_probe_batch.restype = C.c_int
+    lib.nisqa_wav_decode_batch.argtypes = [C.c_int, cpp, C.c_int32, C.c_int32, vp, i64p, i64p, C.c_int, i32p]
+    lib.nisqa_wav_decode_batch.restype = C.c_int
     lib.nisqa_set_gather_target.argtypes = [vp, vp, C.c_int]
     lib.nisqa_set_gather_target.restype = C.c_int
     lib.nisqa_join.argtypes = [vp]

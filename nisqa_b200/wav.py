@@ -111,6 +111,41 @@ def decode_wav_into(path, dst, ms_channel=None):
     return int(n)
 
 
+def probe_batch(paths, ms_channel=None, n_threads=1):
+    """One native call for a whole batch -> (sample_rate int32[n], n_frames int64[n], kind int32[n]).
+    Raises ValueError('Could not load file <first bad path>')."""
+    import ctypes as C
+    from . import engine as _e
+    lib = _e.load_library()
+    n = len(paths)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    sr = np.zeros(n, np.int32); nf = np.zeros(n, np.int64); kind = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+    bad = lib.nisqa_wav_probe_batch(n, arr, -1 if ms_channel is None else int(ms_channel), int(n_threads),
+                                    sr.ctypes.data_as(C.POINTER(C.c_int32)), nf.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    kind.ctypes.data_as(C.POINTER(C.c_int32)), st.ctypes.data_as(C.POINTER(C.c_int32)))
+    if bad != 0:
+        i = int(np.flatnonzero(st)[0]) if bad > 0 and st.any() else 0
+        raise ValueError("Could not load file {}".format(paths[i]))
+    return sr, nf, kind, arr
+
+
+def decode_batch(path_array, n, dst, offsets, n_frames, ms_channel=None, n_threads=1, paths=None):
+    """Decode the whole batch into ``dst`` (1-D int16 / float32 pinned array) at element ``offsets``."""
+    import ctypes as C
+    from . import engine as _e
+    lib = _e.load_library()
+    st = np.zeros(n, np.int32)
+    offsets = np.ascontiguousarray(offsets, np.int64); caps = np.ascontiguousarray(n_frames, np.int64)
+    fmt = _e.FMT_S16 if dst.dtype == np.int16 else _e.FMT_F32
+    bad = lib.nisqa_wav_decode_batch(n, path_array, -1 if ms_channel is None else int(ms_channel), fmt,
+                                     dst.ctypes.data, offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                     caps.ctypes.data_as(C.POINTER(C.c_int64)), int(n_threads),
+                                     st.ctypes.data_as(C.POINTER(C.c_int32)))
+    if bad != 0:
+        i = int(np.flatnonzero(st)[0]) if bad > 0 and st.any() else 0
+        raise ValueError("Could not load file {}".format(paths[i] if paths else "<batch>"))
+
+
 def read_wav_native(path, ms_channel=None):
     """read_wav through the native reader (same return contract)."""
     sr, nf, _, kind = probe_wav(path, ms_channel)
