@@ -125,7 +125,6 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
     bs = max(1, int(bs))
     batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
     n_threads = max(1, int(num_workers) if num_workers else 1)     # native decode threads per batch
-    pool = _PinnedPool(6)             # 3 in flight + 1 being decoded + slack
 
     def finish(job):
         handle, batch, clips, srs, pos = job
@@ -135,19 +134,29 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
                 _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
         out[pos:pos + len(batch)] = scores
 
-    with ThreadPoolExecutor(max_workers=1) as feeder:
-        pending = feeder.submit(_load_batch, ds, batches[0], pool, 0, n_threads) if batches else None
+    DEPTH = 3                         # batches being decoded ahead of the GPU
+    pool = _PinnedPool(3 + DEPTH + 1) # 3 in flight on the engine + DEPTH being decoded + slack
+    with ThreadPoolExecutor(max_workers=DEPTH) as feeder:
+        pending = []
+        nxt = 0
+
+        def top_up():
+            nonlocal nxt
+            while nxt < len(batches) and len(pending) < DEPTH:
+                pending.append(feeder.submit(_load_batch, ds, batches[nxt], pool, nxt % len(pool.bufs), n_threads))
+                nxt += 1
+
+        top_up()
         pos = 0
-        in_flight = []                # batches whose kernels are running while the next one is decoded
+        in_flight = []                # batches whose kernels are running while later ones are decoded
         for b, batch in enumerate(batches):
-            clips, srs = pending.result()
-            pending = (feeder.submit(_load_batch, ds, batches[b + 1], pool, (b + 1) % 6, n_threads)
-                       if b + 1 < len(batches) else None)
+            clips, srs = pending.pop(0).result()
             handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
             in_flight.append((handle, batch, clips, srs, pos))
             pos += len(batch)
             if len(in_flight) >= 3:                         # the engine keeps three submissions in flight
                 finish(in_flight.pop(0))
+            top_up()                                        # a pinned slot is recycled only after its batch finished
         while in_flight:
             finish(in_flight.pop(0))
     return out
