@@ -117,10 +117,10 @@ NISQA_API int  nisqa_predict_pcm(nisqa_engine* e, int n_clips,
 
 /* Asynchronous form of nisqa_predict_pcm for streams of batches (what the reference gets from
  * DataLoader prefetching, lib:1425-1430): returns as soon as the copies and kernels are enqueued;
- * up to three submissions are in flight, so the host->device copy of batch k+1 overlaps the kernels
+ * up to six submissions are in flight (their uploads run ahead on the copy stream, their kernels
+ * rotate over three compute lanes), so the host->device copy of batch k+1 overlaps the kernels
  * of batch k.  n_segments_out / status_out are valid on return (host arithmetic); scores_out and the
- * PCM buffers must stay alive until nisqa_wait(ticket) returns.  Submitting a fourth batch first
- * waits for the oldest one. */
+ * PCM buffers must stay alive until nisqa_wait(ticket) returns.  Submitting a seventh batch first waits for the oldest one. */
 NISQA_API int  nisqa_submit_pcm(nisqa_engine* e, int n_clips,
                                 const void* const* pcm, const int64_t* n_samples,
                                 const int32_t* sample_rate, int sample_fmt,

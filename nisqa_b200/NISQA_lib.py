@@ -119,7 +119,7 @@ def _load_batch(ds, batch, pool, slot, n_threads):
 def _predict_rows(engine, ds, rows, bs, num_workers):
     """Scores for the given dataset rows (in that order) through the C-ABI, bs clips per call.
     Pipeline: decode batch b+1 (thread pool, native reader -> pinned memory) while the engine has up
-    to three earlier batches in flight (H2D on the copy stream, kernels on rotating compute lanes)."""
+    to five earlier batches in flight (H2D on the copy stream, kernels on rotating compute lanes)."""
     n_out = engine.n_out
     out = np.empty((len(rows), n_out), dtype=np.float32)
     bs = max(1, int(bs))
@@ -135,7 +135,8 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
         out[pos:pos + len(batch)] = scores
 
     DEPTH = 3                         # batches being decoded ahead of the GPU
-    pool = _PinnedPool(3 + DEPTH + 1) # 3 in flight on the engine + DEPTH being decoded + slack
+    FLIGHT = 5                        # submissions kept in flight on the engine (it has 6 staging slots)
+    pool = _PinnedPool(FLIGHT + DEPTH + 1)
     with ThreadPoolExecutor(max_workers=DEPTH) as feeder:
         pending = []
         nxt = 0
@@ -154,7 +155,7 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
             handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
             in_flight.append((handle, batch, clips, srs, pos))
             pos += len(batch)
-            if len(in_flight) >= 3:                         # the engine keeps three submissions in flight
+            if len(in_flight) >= FLIGHT:
                 finish(in_flight.pop(0))
             top_up()                                        # a pinned slot is recycled only after its batch finished
         while in_flight:

@@ -115,21 +115,31 @@ struct Ticket {          // one asynchronous nisqa_submit_pcm call
 // pass are filled with CTAs of another (+8..12 % throughput measured, tools/two_engines.py), and
 // the upload of the next pass (copy stream) overlaps compute.
 constexpr int kLanes = 3;
+constexpr int kStages = 6;     // staging slots / submissions in flight (uploads run ahead of the lanes)
 struct Lane {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
-  bool busy = false;
-  HostBuf h_tables;
-  DevBuf pcm, clips, prefixes, clipmax;
   DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, logits, feats20, tdout, partial;
   void release() {
-    DevBuf* all[] = {&pcm, &clips, &prefixes, &clipmax, &mel, &segtab, &act1, &act2, &act3, &act4, &act5,
+    DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
                      &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout, &partial};
+    for (auto* b : all) b->release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+// Host->device staging of one pass: pinned tables, device tables, packed PCM, and the two events that
+// order it (copied: upload finished on the copy stream; done: the pass's kernels finished on its lane).
+struct Stage {
+  cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+  bool busy = false;
+  int lane = 0;
+  HostBuf h_tables;
+  DevBuf pcm, clips, prefixes, clipmax;
+  void release() {
+    DevBuf* all[] = {&pcm, &clips, &prefixes, &clipmax};
     for (auto* b : all) b->release();
     h_tables.release();
     if (ev_copied) cudaEventDestroy(ev_copied);
     if (ev_done) cudaEventDestroy(ev_done);
-    if (stream) cudaStreamDestroy(stream);
   }
 };
 
@@ -166,12 +176,14 @@ struct nisqa_engine {
 
   // per-pass state lives in the lanes; `stream` aliases lane 0's stream (nisqa_stream)
   Lane lanes[kLanes];
+  Stage stages[kStages];
+  int last_stage = 0;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t cur_stream = nullptr;     // stream of the pass being enqueued (kernel timers)
   HostBuf h_scores;
   int last_lane = 0;
   int64_t pass_counter = 0;
-  Ticket tickets[kLanes];
+  Ticket tickets[kStages];
   int64_t next_ticket = 1;
   DevBuf scores, dump;
 
@@ -195,6 +207,7 @@ struct nisqa_engine {
     for (auto& tk : tickets) { tk.pinned.release(); tk.scores.release(); if (tk.done) cudaEventDestroy(tk.done); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto& l : lanes) l.release();
+    for (auto& g : stages) g.release();
     stream = nullptr;
     for (auto& t : timers) for (auto& e : t.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   }
@@ -563,7 +576,8 @@ struct PassInput {
   const void* dev_pcm; const int64_t* dev_off;   // packed device buffer + element offsets
   int fmt;
   float* scores_dev_out;              // device destination [n_clips][n_out]
-  int slot;                           // staging slot (pass & 1)
+  int slot;                           // compute lane
+  int stage;                          // staging slot
 };
 
 int lane_allgather(nisqa_engine* e, const float* src, float* dst, size_t count, cudaStream_t st);
@@ -605,43 +619,47 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
 
   float* scores = in.scores_dev_out;
   Lane& LN = e->lanes[in.slot];
+  Stage& SG = e->stages[in.stage];
   cudaStream_t st = LN.stream, cs = e->copy_stream;
   e->cur_stream = st;
-  // the lane (pinned tables, device tables, PCM buffer, workspaces) is reused every kLanes-th pass
-  if (LN.busy) { CK(cudaEventSynchronize(LN.ev_done)); LN.busy = false; }
+  // the staging slot (pinned tables, device tables, PCM buffer) is reused every kStages-th pass; the
+  // lane's activation workspaces are protected by stream order alone
+  if (SG.busy) { CK(cudaEventSynchronize(SG.ev_done)); SG.busy = false; }
+  SG.lane = in.slot;
 
   // ---- upload tables (one pinned block: ClipDesc[n] | 3 prefix arrays)
   const size_t tb_clips = (size_t)n * sizeof(ClipDesc);
   const size_t tb_pref = (size_t)(n + 1) * 4;
-  CK(LN.h_tables.reserve(tb_clips + 3 * tb_pref));
-  char* ht = LN.h_tables.as<char>();
+  CK(SG.h_tables.reserve(tb_clips + 3 * tb_pref));
+  char* ht = SG.h_tables.as<char>();
   memcpy(ht, cl.data(), tb_clips);
   memcpy(ht + tb_clips, pair_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + tb_pref, seg_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + 2 * tb_pref, qt_prefix.data(), tb_pref);
-  CK(LN.clips.reserve(tb_clips));
-  CK(LN.prefixes.reserve(3 * tb_pref));
-  CK(LN.clipmax.reserve((size_t)n * 4));
-  CK(cudaMemcpyAsync(LN.clips.p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemcpyAsync(LN.prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemsetAsync(LN.clipmax.p, 0, (size_t)n * 4, cs));
-  const ClipDesc* d_clips = LN.clips.as<ClipDesc>();
-  unsigned* d_clipmax = LN.clipmax.as<unsigned>();
-  const int* d_pair = LN.prefixes.as<int>();
+  CK(SG.clips.reserve(tb_clips));
+  CK(SG.prefixes.reserve(3 * tb_pref));
+  CK(SG.clipmax.reserve((size_t)n * 4));
+  CK(cudaMemcpyAsync(SG.clips.p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(SG.prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemsetAsync(SG.clipmax.p, 0, (size_t)n * 4, cs));
+  const ClipDesc* d_clips = SG.clips.as<ClipDesc>();
+  unsigned* d_clipmax = SG.clipmax.as<unsigned>();
+  const int* d_pair = SG.prefixes.as<int>();
   (void)d_pair;
   e->last_lane = in.slot;
+  e->last_stage = in.stage;
   const int* d_seg = d_pair + (n + 1);
   const int* d_qt = d_pair + 2 * (n + 1);
 
   if (n_seg == 0) {   // nothing valid in this pass: NaN scores
-    CK(cudaEventRecord(LN.ev_copied, cs));
-    CK(cudaStreamWaitEvent(st, LN.ev_copied, 0));
+    CK(cudaEventRecord(SG.ev_copied, cs));
+    CK(cudaStreamWaitEvent(st, SG.ev_copied, 0));
     CK(cudaMemsetAsync(scores, 0xFF, (size_t)n * n_out * 4, st));
   } else {
     // ---- PCM (copy stream), then hand over to the compute stream
     const void* d_pcm = in.dev_pcm;
     if (in.host_pcm) {
-      CK(LN.pcm.reserve((size_t)pcm_elems * esz));
+      CK(SG.pcm.reserve((size_t)pcm_elems * esz));
       // clips that are back to back in host memory with the same 16-element alignment as the
       // device packing travel as ONE copy (a pinned batch buffer becomes a single large DMA)
       for (int i = 0; i < n;) {
@@ -655,13 +673,13 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
           bytes = (size_t)(cl[j].pcm_off - o0) * esz + (size_t)in.n_samples[j] * esz;
           ++j;
         }
-        CK(cudaMemcpyAsync(LN.pcm.as<char>() + (size_t)o0 * esz, h0, bytes, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(SG.pcm.as<char>() + (size_t)o0 * esz, h0, bytes, cudaMemcpyHostToDevice, cs));
         i = j;
       }
-      d_pcm = LN.pcm.p;
+      d_pcm = SG.pcm.p;
     }
-    CK(cudaEventRecord(LN.ev_copied, cs));
-    CK(cudaStreamWaitEvent(st, LN.ev_copied, 0));
+    CK(cudaEventRecord(SG.ev_copied, cs));
+    CK(cudaStreamWaitEvent(st, SG.ev_copied, 0));
     // ---- workspaces
     const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
     const int FEAT = std_mode ? 768 : 384;
@@ -745,8 +763,8 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     }
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(LN.ev_done, st));
-  LN.busy = true;
+  CK(cudaEventRecord(SG.ev_done, st));
+  SG.busy = true;
   return 0;
 }
 
@@ -775,7 +793,7 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
   float* scores_all = scores_dev;
   if (!scores_all) {
-    DevBuf& sb = ticket_out ? e->tickets[e->next_ticket % kLanes].scores : e->scores;
+    DevBuf& sb = ticket_out ? e->tickets[e->next_ticket % kStages].scores : e->scores;
     CK(sb.reserve((size_t)std::max(n_clips, 1) * e->cfg.n_out * 4));
     scores_all = sb.as<float>();
   }
@@ -796,6 +814,7 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     in.fmt = fmt;
     in.scores_dev_out = scores_all + (size_t)i0 * e->cfg.n_out;
     in.slot = e->profiling ? 0 : (int)(e->pass_counter % kLanes);
+    in.stage = (int)(e->pass_counter % kStages);
     ++e->pass_counter;
     int rc = run_pass(e, in);
     if (rc) return rc;
@@ -806,17 +825,17 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   const int n_pass = (int)(e->pass_counter - first_pass);
   cudaStream_t fin = e->lanes[e->last_lane].stream;
   if (n_pass == 0) fin = e->lanes[0].stream;
-  for (int k = 0; k < kLanes && n_pass > 1; ++k)
-    if (k != e->last_lane && e->lanes[k].busy) CK(cudaStreamWaitEvent(fin, e->lanes[k].ev_done, 0));
+  for (int k = 0; k < kStages && n_pass > 1; ++k)      // passes of this call that ran on other lanes
+    if (e->stages[k].busy && e->stages[k].lane != e->last_lane) CK(cudaStreamWaitEvent(fin, e->stages[k].ev_done, 0));
   if (e->gather_dst && e->nccl_comm && n_clips == e->gather_rows && (ticket_out || scores_dev)) {
     // the path's single exchange step, enqueued behind this call's kernels on its own lane
     int rc = lane_allgather(e, scores_all, e->gather_dst, (size_t)n_clips * e->cfg.n_out, fin);
     if (rc) return rc;
-    CK(cudaEventRecord(e->lanes[e->last_lane].ev_done, fin));
+    CK(cudaEventRecord(e->stages[e->last_stage].ev_done, fin));
   }
   if (ticket_out) {
     // asynchronous completion: scores land in the ticket's pinned block; nisqa_wait hands them over
-    Ticket& tk = e->tickets[e->next_ticket % kLanes];
+    Ticket& tk = e->tickets[e->next_ticket % kStages];
     tk.bytes = (size_t)n_clips * e->cfg.n_out * 4;
     tk.user_scores = scores_host;
     CK(tk.pinned.reserve(std::max<size_t>(tk.bytes, 16)));
@@ -878,10 +897,10 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(e, NISQA_ERR_CUDA, "libnisqa_b200 is compiled for sm_100a only");
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  for (auto& l : e->lanes) {
-    CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&l.ev_copied, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+  for (auto& l : e->lanes) CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  for (auto& g : e->stages) {
+    CK(cudaEventCreateWithFlags(&g.ev_copied, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming));
   }
   e->stream = e->lanes[0].stream;
   e->cur_stream = e->stream;
@@ -938,7 +957,7 @@ int nisqa_submit_pcm(nisqa_engine* e, int n_clips, const void* const* pcm, const
   if (!e || !ticket) return NISQA_ERR_INVALID;
   if (n_clips > 0 && (!pcm || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
   if (e->profiling) return fail(e, NISQA_ERR_STATE, "profiling needs the synchronous entry points");
-  int rc = finish_ticket(e, e->tickets[e->next_ticket % kLanes]);      // at most kLanes submissions in flight
+  int rc = finish_ticket(e, e->tickets[e->next_ticket % kStages]);      // at most kStages submissions in flight
   if (rc) return rc;
   return predict_common(e, n_clips, pcm, nullptr, nullptr, n_samples, sample_rate, sample_fmt,
                         scores_out, nullptr, n_segments_out, status_out, 0, ticket);
@@ -948,7 +967,7 @@ int nisqa_wait(nisqa_engine* e, int64_t ticket) {
   if (!e) return NISQA_ERR_INVALID;
   CK(cudaSetDevice(e->device));
   // tickets complete in submission order: finish everything up to and including `ticket`
-  for (int64_t id = ticket - kLanes; id <= ticket; ++id)
+  for (int64_t id = ticket - kStages; id <= ticket; ++id)
     for (auto& tk : e->tickets)
       if (tk.active && tk.id == id) { int rc = finish_ticket(e, tk); if (rc) return rc; }
   return 0;
@@ -968,6 +987,7 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   if (e->last_passes != 1) return fail(e, NISQA_ERR_STATE, "stage dump needs a predict call that ran in one pass");
   cudaSetDevice(e->device);
   Lane& LN = e->lanes[e->last_lane];
+  Stage& SG = e->stages[e->last_stage];
   const int std_mode = e->cfg.arch == NISQA_ARCH_STD_LSTM_LASTBI;
   const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
   const int64_t ns = e->last_n_seg;
@@ -998,8 +1018,8 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   cudaStream_t st = LN.stream;
   if (stage == NISQA_STAGE_MEL_DB) {
     CK(e->dump.reserve((size_t)count * 4));
-    launch_mel_dump(st, LN.mel.as<float>(), LN.clips.as<ClipDesc>(), (int)e->last_clips.size(),
-                    LN.clipmax.as<unsigned>(), e->dump.as<float>());
+    launch_mel_dump(st, LN.mel.as<float>(), SG.clips.as<ClipDesc>(), (int)e->last_clips.size(),
+                    SG.clipmax.as<unsigned>(), e->dump.as<float>());
     src = e->dump.as<float>();
   } else if (ch > 0) {
     CK(e->dump.reserve((size_t)count * 4));
@@ -1044,8 +1064,8 @@ void* nisqa_stream(const nisqa_engine* e) { return e ? (void*)e->stream : nullpt
 int nisqa_join(nisqa_engine* e) {
   if (!e || !e->stream) return NISQA_ERR_INVALID;
   CK(cudaSetDevice(e->device));
-  for (int k = 1; k < kLanes; ++k)
-    if (e->lanes[k].busy) CK(cudaStreamWaitEvent(e->stream, e->lanes[k].ev_done, 0));
+  for (auto& g : e->stages)
+    if (g.busy && g.lane != 0) CK(cudaStreamWaitEvent(e->stream, g.ev_done, 0));
   return 0;
 }
 
@@ -1167,8 +1187,8 @@ int nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm, const float* local_dev, 
   void* comm = nccl_comm ? nccl_comm : e->nccl_comm;
   if (!comm) return fail(e, NISQA_ERR_STATE, "no NCCL communicator: call nisqa_nccl_init or pass one");
   CK(cudaSetDevice(e->device));
-  for (int k = 1; k < kLanes; ++k)          // the rows may have been produced on any lane
-    if (e->lanes[k].busy) CK(cudaStreamWaitEvent(e->stream, e->lanes[k].ev_done, 0));
+  for (auto& g : e->stages)                 // the rows may have been produced on any lane
+    if (g.busy && g.lane != 0) CK(cudaStreamWaitEvent(e->stream, g.ev_done, 0));
   const size_t count = (size_t)max_rows * e->cfg.n_out;
   int rc = a->AllGather(local_dev, global_dev, count, /*ncclFloat32*/ 7, comm, e->stream);
   if (rc) return fail(e, NISQA_ERR_NCCL, std::string("ncclAllGather: ") + (a->GetErrorString ? a->GetErrorString(rc) : "error"));

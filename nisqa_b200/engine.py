@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnisqa_b200.so")
 
 ABI_VERSION = 1
+MAX_IN_FLIGHT = 6          # staging slots of the engine (nisqa_submit_pcm)
 ARCH_ADAPT_SA_ATTFF, ARCH_STD_LSTM_LASTBI = 0, 1
 FMT_S16, FMT_F32 = 0, 1
 CLIP_OK, CLIP_TOO_SHORT, CLIP_TOO_LONG = 0, 1, 2
@@ -261,7 +262,7 @@ class Engine(object):
 
     def submit_pcm(self, clips, sample_rates):
         """Asynchronous predict_pcm: returns a handle; ``wait(handle)`` -> (scores, n_segments, status).
-        Up to three submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
+        Up to six submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
         n = len(clips)
         dt = clips[0].dtype if n else np.dtype(np.int16)
         if any(c.dtype != dt for c in clips):
