@@ -211,6 +211,9 @@ def run_ours(a, rank, world, local):
     import torch.distributed as dist
 
     torch.cuda.set_device(local)
+    from nisqa_b200 import dist as nb_dist
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = nb_dist.bind_to_gpu_numa(local)      # pinned PCM buffers next to the GPU's PCIe root
     args, sd = O.load_checkpoint(CKPT)
     eng = E.Engine(E.config_from_args(args), local)
     eng.load_state_dict(sd)
@@ -399,6 +402,7 @@ def run_ours(a, rank, world, local):
     cnn_ms = sum(kernel_ms[k] for k in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"))
     # ---- CPU baseline: oracle port, one process, all torch threads, bounded sample
     cpu_base = None
+    os.sched_setaffinity(0, all_cpus)               # the CPU baseline may use every host core again
     if world == 1 and not a.skip_cpu:
         cores = host_cores()
         pool = CpuPool(cores)
@@ -421,7 +425,7 @@ def run_ours(a, rank, world, local):
                        "exchange": "1 ncclAllGather of [64,5] rows per step" if world > 1 else "none (N=1)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(BS * int(n_s[0]) * 2),
                     "d2h_bytes_per_step": int(BS * n_out * 4), "wall_clock_value": e2e_wall,
-                    "api": "nisqa_submit_pcm / nisqa_wait (C-ABI, five batches in flight) on pinned host PCM16; value is wall-clock based"},
+                    "api": "nisqa_submit_pcm / nisqa_wait (C-ABI, five batches in flight) on pinned host PCM16; value is wall-clock based", "numa_node": numa_node},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_kernels": roofs,
             "kernel_ms_per_step": kernel_ms, "cnn_ms_per_step": cnn_ms,
             "achieved_tflops_whole_step": FLOP_PER_CLIP * BS / (ms_dev / a.steps / 1e3) / 1e12,

@@ -89,3 +89,34 @@ def all_gather_scores(local_scores, shards, n_total, engine=None):
         dist.all_gather(parts, loc)
         gathered = torch.stack(parts).numpy()
     return scatter_rows(gathered, shards, n_total)
+
+
+def bind_to_gpu_numa(device_index=0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers
+    are allocated next to the GPU's PCIe root (a remote node roughly halves H2D bandwidth).
+    Best effort: returns the node number, or None when the topology is not visible."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
