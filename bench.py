@@ -75,12 +75,16 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
         if self.proc is not None:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[lo:hi] if len(self.rows[lo:hi]) >= 2 else self.rows[max(0, lo - 3):]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -211,6 +215,9 @@ def run_ours(a, rank, world, local):
     import torch.distributed as dist
 
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()               # nvidia-smi needs a second or two to come up
     from nisqa_b200 import dist as nb_dist
     all_cpus = os.sched_getaffinity(0)
     numa_node = nb_dist.bind_to_gpu_numa(local)      # pinned PCM buffers next to the GPU's PCIe root
@@ -308,9 +315,6 @@ def run_ours(a, rank, world, local):
         ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
         parity = float(np.abs(got - ref).max())
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # warm-up: W steps, then as many more as ~warmup_seconds needs (clocks take ~1 s to ramp).  The
     # step count is agreed across ranks (every step holds a collective when N > 1).
     t_w = time.perf_counter()
@@ -329,13 +333,14 @@ def run_ours(a, rank, world, local):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     l0 = eng.kernel_launches()
+    mark0 = sampler.mark()
     ms_dev, _ = timed(step_dev, a.steps)
     launches = eng.kernel_launches() - l0
     for i in range(max(a.warmup, 4)):
         step_e2e(i)
     drain_e2e()
     ms_e2e, wall_e2e = timed(step_e2e, a.steps, drain_e2e)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
 
     # ---- per-kernel durations (CUDA events on the engine stream), same workload
     eng.set_profiling(True)
@@ -437,7 +442,7 @@ def run_ours(a, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--warmup-seconds", dest="warmup_seconds", type=float, default=1.5,
