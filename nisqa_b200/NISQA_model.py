@@ -164,7 +164,6 @@ class nisqaModel(object):
         _, world, local = nb_dist.env_world()
         idx = local if world > 1 else torch.cuda.current_device()
         torch.cuda.set_device(idx)
-        nb_dist.bind_to_gpu_numa(idx)          # pinned batch buffers next to the GPU's PCIe root
         self.dev = torch.device("cuda", idx)
         if nb_dist.env_world()[0] == 0:
             print("Device: {}".format(torch.device("cuda")))

@@ -47,5 +47,9 @@ def parse_args(argv=None):
 
 
 if __name__ == "__main__":
+    import os
+    from nisqa_b200 import dist as nb_dist
+    # the CLI process only feeds the GPU: keep it (and its pinned batch buffers) on the GPU's NUMA node
+    nb_dist.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
     nisqa = nisqaModel(parse_args())
     nisqa.predict()
