@@ -442,13 +442,15 @@ def run_ours(a, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200, or 20 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--warmup-seconds", dest="warmup_seconds", type=float, default=1.5,
                     help="minimum duration of the untimed warm-up (in addition to --warmup steps)")
     ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 200 if a.impl == "ours" else 20
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 0)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if a.impl == "reference":
