@@ -1,48 +1,55 @@
 # -*- coding: utf-8 -*-
-"""Command line of the B200 NISQA engine - same flags and modes as the reference
-``run_predict.py`` (reference run_predict.py:8-43): predict_file / predict_dir / predict_csv.
+"""Command line of the B200 NISQA engine.
+
+Flag-compatible with the reference CLI (reference run_predict.py:8-43): the three predict modes
+and the same option names, so existing invocations keep working:
 
     python run_predict.py --mode predict_file --pretrained_model weights/nisqa.tar --deg a.wav
     python run_predict.py --mode predict_dir  --pretrained_model weights/nisqa.tar --data_dir d --bs 64
-    torchrun --nproc-per-node 8 run_predict.py --mode predict_csv ... (one rank per GPU)
+    torchrun --nproc-per-node 8 run_predict.py --mode predict_csv ...   (one rank per GPU)
 """
 import argparse
 
 from nisqa_b200.NISQA_model import nisqaModel
 
+# option name -> (type, default, what it is)
+_OPTIONS = {
+    "mode": (str, None, "predict_file | predict_dir | predict_csv"),
+    "pretrained_model": (str, None, "checkpoint (.tar) to load; relative paths resolve against the working directory"),
+    "deg": (str, None, "wav file to score (predict_file)"),
+    "data_dir": (str, None, "directory holding the wav files (predict_dir) / base directory of the csv paths"),
+    "output_dir": (str, None, "if given, NISQA_results.csv is written here"),
+    "csv_file": (str, None, "table of files to score (predict_csv)"),
+    "csv_deg": (str, None, "name of the csv column with the file paths"),
+    "num_workers": (int, 0, "native wav-decode threads per batch"),
+    "bs": (int, 1, "clips per engine call"),
+    "ms_channel": (int, None, "channel to use for multi-channel files (default: mono mix)"),
+}
+_REQUIRED = {"mode", "pretrained_model"}
+# what each mode cannot run without, with the complaint raised when it is missing
+_NEEDS = {
+    "predict_file": [("deg", "predict_file needs --deg <wav file>")],
+    "predict_dir": [("data_dir", "predict_dir needs --data_dir <folder of wav files>")],
+    "predict_csv": [("csv_file", "predict_csv needs --csv_file <table>"),
+                    ("csv_deg", "predict_csv needs --csv_deg <column holding the file names>")],
+}
+
 
 def parse_args(argv=None):
-    p = argparse.ArgumentParser()
-    p.add_argument("--mode", required=True, type=str, help="either predict_file, predict_dir, or predict_csv")
-    p.add_argument("--pretrained_model", required=True, type=str, help="file name of pretrained model (must be in current working folder)")
-    p.add_argument("--deg", type=str, help="path to speech file")
-    p.add_argument("--data_dir", type=str, help="folder with speech files")
-    p.add_argument("--output_dir", type=str, help="folder to ouput results.csv")
-    p.add_argument("--csv_file", type=str, help="file name of csv (must be in current working folder)")
-    p.add_argument("--csv_deg", type=str, help="column in csv with files name/path")
-    p.add_argument("--num_workers", type=int, default=0, help="number of wav-decode worker threads")
-    p.add_argument("--bs", type=int, default=1, help="batch size for predicting")
-    p.add_argument("--ms_channel", type=int, help="audio channel in case of stereo file")
-    args = vars(p.parse_args(argv))
+    parser = argparse.ArgumentParser(description="NISQA speech quality prediction on B200")
+    for name, (typ, default, text) in _OPTIONS.items():
+        parser.add_argument("--" + name, type=typ, default=default, required=name in _REQUIRED, help=text)
+    args = vars(parser.parse_args(argv))
 
-    mode = args["mode"]
-    if mode == "predict_file":
-        if args["deg"] is None:
-            raise ValueError("--deg argument with path to input file needed")
-    elif mode == "predict_dir":
-        if args["data_dir"] is None:
-            raise ValueError("--data_dir argument with folder with input files needed")
-    elif mode == "predict_csv":
-        if args["csv_file"] is None:
-            raise ValueError("--csv_file argument with csv file name needed")
-        if args["csv_deg"] is None:
-            raise ValueError("--csv_deg argument with csv column name of the filenames needed")
-        if args["data_dir"] is None:
-            args["data_dir"] = ""
-    else:
-        raise NotImplementedError("--mode given not available")
-    args["tr_bs_val"] = args["bs"]
-    args["tr_num_workers"] = args["num_workers"]
+    if args["mode"] not in _NEEDS:
+        raise NotImplementedError("unknown --mode %r" % args["mode"])
+    for key, complaint in _NEEDS[args["mode"]]:
+        if args[key] is None:
+            raise ValueError(complaint)
+    if args["mode"] == "predict_csv" and args["data_dir"] is None:
+        args["data_dir"] = ""                     # csv paths are then taken as given
+    # the driver class reads the batch size / worker count under their training-config names
+    args["tr_bs_val"], args["tr_num_workers"] = args["bs"], args["num_workers"]
     return args
 
 
@@ -51,5 +58,4 @@ if __name__ == "__main__":
     from nisqa_b200 import dist as nb_dist
     # the CLI process only feeds the GPU: keep it (and its pinned batch buffers) on the GPU's NUMA node
     nb_dist.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
-    nisqa = nisqaModel(parse_args())
-    nisqa.predict()
+    nisqaModel(parse_args()).predict()

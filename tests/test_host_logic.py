@@ -178,3 +178,18 @@ def test_native_wav_reader_errors(tmp_path, built_lib):
     for name in ("bad.wav", "missing.wav"):
         with pytest.raises(ValueError, match="Could not load file"):
             wav.read_wav_native(str(tmp_path / name))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints the contract's JSON line."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
