@@ -178,11 +178,18 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   //         One warp item = one band of BOTH frames; lanes stride over the band's bins.  A bin
   //         belongs to two adjacent triangles, so its magnitudes are formed twice - cheaper
   //         than a shared-memory round trip (and it frees 16 KB: 5 CTAs / SM instead of 4).
-  // Band sums of this warp's 12 bands are parked in lanes 0..23 (lane = 2*slot + frame) so
-  // that the dB conversion (log10f) runs once per warp instead of once per band.
-  float mine = 0.f;
-  int slot = 0;
-  for (int b = warp; b < kMels; b += kFeThreads / 32, ++slot) {
+  // Each warp owns 12 bands (b = warp + 4*slot); lanes stride over a band's bins and keep one
+  // partial sum per (slot, frame) in registers.  The 24 partials are then reduced across the warp
+  // with ONE multi-value butterfly (16+8+4+2+1 = 31 shuffles instead of 24 x 5): after the step
+  // with offset o, a lane keeps the half of its values whose index bit matches its lane bit, so
+  // lane L ends up holding the total of value index L.  Lane L < 24 then owns (slot L>>1, frame L&1):
+  // one log10f per warp.
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int slot = 0; slot < kMels / (kFeThreads / 32); ++slot) {
+    const int b = warp + slot * (kFeThreads / 32);
     const int beg = band_meta[b], len = band_meta[b + 1] - beg;
     const int k = band_meta[kMels + 1 + b] + lane;
     const int kk = (kNfft - k) & (kNfft - 1);
@@ -204,15 +211,30 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
       s0 = fmaf(w, ma, s0);
       s1 = fmaf(w, mb, s1);
     }
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (lane == 2 * slot) mine = s0;
-    if (lane == 2 * slot + 1) mine = s1;
+    v[2 * slot] = s0;
+    v[2 * slot + 1] = s1;
+  }
+  // multi-value butterfly: at the step with offset o the 2*o live values are paired (i, i+o); a lane
+  // whose bit o is set keeps the upper one and sends the lower one, so bit o of the surviving
+  // value index equals bit o of the lane.
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
   }
   float wmax = -INFINITY;
   {
+    // after the butterfly v[0] of lane L is the total of value index L (bit o of the index was
+    // selected by bit o of the lane at every step)
+    const float mine = v[0];
     const int my_slot = lane >> 1, f = lane & 1;
     const int b = warp + my_slot * (kFeThreads / 32);
-    if (my_slot < slot && (f == 0 || validB)) {
+    if (lane < 2 * (kMels / (kFeThreads / 32)) && (f == 0 || validB)) {
       const float sv = 0.5f * mine;                        // the 1/2 of the real-pair unpacking
       const float p = sv * sv;
       const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
