@@ -23,7 +23,7 @@
 namespace nisqa {
 // frontend.cu
 void launch_frontend(cudaStream_t, const void*, int, const ClipDesc*, int, int,
-                     const FbTables*, const float2*, float*, unsigned*, int);
+                     const FbTables*, const float2*, float*, unsigned*, int, int);
 void launch_seg_table(cudaStream_t, const ClipDesc*, int, const int*, const unsigned*, int, int,
                       int*, float*, int*);
 void launch_mel_dump(cudaStream_t, const float*, const ClipDesc*, int, const unsigned*, float*);
@@ -592,7 +592,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   cl.assign(n, ClipDesc());
   std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0);
   long long pcm_elems = 0;
-  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0, max_span = 0;
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
@@ -611,7 +611,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     n_pairs += (d.n_frames + 1) / 2;
     max_pairs = std::max(max_pairs, (d.n_frames + 1) / 2);
     n_qt += (d.n_seg + 127) / 128;
-    if (ok) Q = std::max(Q, (p.win + 1023) / 1024);
+    if (ok) { Q = std::max(Q, (p.win + 1023) / 1024); max_span = std::max(max_span, p.hop + p.win); }
   }
   pair_prefix[n] = n_pairs; seg_prefix[n] = n_seg; qt_prefix[n] = n_qt;
   e->last_n_seg = n_seg; e->last_n_frames = n_frames;
@@ -698,7 +698,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "frontend");
       launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, max_pairs,
                       e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), LN.mel.as<float>(),
-                      d_clipmax, Q); }
+                      d_clipmax, Q, max_span); }
     { Scope s(e, "seg_table");
       launch_seg_table(st, d_clips, n, d_seg, d_clipmax, c.seg_hop, n_seg,
                        seg_frame0, seg_thr, seg_clip); }

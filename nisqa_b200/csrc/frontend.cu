@@ -89,6 +89,90 @@ constexpr int kScratchPerWarp = 32 * 33 + 4;      // float2 elements: padded tra
 __host__ __device__ constexpr int fe_region0_bytes(int Q) { return 1024 * Q * 8; }
 int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWarp * 8; }
 
+// ---- shared pieces of the two front-end kernels ---------------------------------------------
+// 1024-point FFT of one residue plane: x[j] = input n = lane + 32 j (already twiddled by
+// W_4096^(r n)); result Z_r[m] is left in tile[m] (m = 0..1023).
+__device__ __forceinline__ void fft1024_plane(float2 (&x)[32], float2* tile, int lane,
+                                              const float2* __restrict__ tw2) {
+  fft32(x);                                      // A_l[q] at x[rev5(q)]
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    float2 v = x[rev5(q)];
+    if (q != 0) v = cmul(v, __ldg(tw2 + q * 32 + lane));                   // W_1024^(l q), coalesced
+    tile[lane * 33 + q] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int l = 0; l < 32; ++l) x[l] = tile[l * 33 + lane];
+  __syncwarp();
+  fft32(x);                                      // Z_r[lane + 32 p] at x[rev5(p)]
+#pragma unroll
+  for (int p = 0; p < 32; ++p) tile[lane + 32 * p] = x[rev5(p)];
+}
+
+// Fused unpack of the two real spectra, |.|, sparse mel, dB for the 12 bands of this warp
+// (b = warp + 4*slot).  Lanes stride over a band's bins and keep one partial sum per (slot, frame);
+// the 24 partials are reduced across the warp with ONE multi-value butterfly (31 shuffles instead of
+// 24 x 5): at the step with offset o the 2*o live values are paired (i, i+o), a lane whose bit o is set
+// keeps the upper one and sends the lower one, so lane L ends up with the total of value index L =
+// (slot L>>1, frame L&1) and one log10f serves the whole warp.  A bin belongs to two adjacent
+// triangles, so its magnitudes are formed twice - cheaper than a shared-memory round trip.
+// Returns this lane's dB value (or -inf) for the clip maximum.
+__device__ __forceinline__ float mel_bands(const float2* scratch, const int* band_meta,
+                                           const float* __restrict__ weights, int warp, int lane,
+                                           bool validB, float* __restrict__ mel_row0 /*frame A row*/) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int slot = 0; slot < kMels / 4; ++slot) {
+    const int b = warp + slot * 4;
+    const int beg = band_meta[b], len = band_meta[b + 1] - beg;
+    const int k = band_meta[kMels + 1 + b] + lane;
+    const int kk = (kNfft - k) & (kNfft - 1);
+    // Z planes: bin k lives at plane (k & 3), slot (k >> 2); k advances by 32 per iteration,
+    // so both indices move by +-8 and the plane never changes.
+    const float2* pk = scratch + (k & 3) * kScratchPerWarp + (k >> 2);
+    const float2* pn = scratch + (kk & 3) * kScratchPerWarp + (kk >> 2);
+    const float* wt = weights + beg + lane;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = lane; i < len; i += 32) {
+      const float w = __ldg(wt);
+      const float2 zk = *pk, zn = *pn;
+      wt += 32; pk += 8; pn -= 8;
+      const float ar = zk.x + zn.x, ai = zk.y - zn.y;      // 2 * X_a[k]
+      const float br = zk.y + zn.y, bi = zk.x - zn.x;      // 2 * X_b[k] (up to a unit factor)
+      float ma, mb;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
+      s0 = fmaf(w, ma, s0);
+      s1 = fmaf(w, mb, s1);
+    }
+    v[2 * slot] = s0;
+    v[2 * slot + 1] = s1;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float out = -INFINITY;
+  const int my_slot = lane >> 1, f = lane & 1;
+  if (lane < 2 * (kMels / 4) && (f == 0 || validB)) {
+    const float sv = 0.5f * v[0];                          // the 1/2 of the real-pair unpacking
+    const float p = sv * sv;
+    out = 10.0f * log10f(fmaxf(p, 1e-8f));
+    mel_row0[(size_t)f * kMels + warp + my_slot * 4] = out;
+  }
+  return out;
+}
+
+// ---- generic kernel: one CTA per frame pair, any window length (win <= 1024*Q <= n_fft) ------
 template <typename T>
 __global__ void __launch_bounds__(kFeThreads, 5)
 frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
@@ -156,91 +240,103 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
       if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));   // coalesced per-lane table
       x[j] = v;
     }
-    fft32(x);                                      // A_l[q] at x[rev5(q)]
-    float2* tile = scratch + r * kScratchPerWarp;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      float2 v = x[rev5(q)];
-      if (q != 0) v = cmul(v, __ldg(tw2 + q * 32 + lane));                   // W_1024^(l q), coalesced
-      tile[lane * 33 + q] = v;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int l = 0; l < 32; ++l) x[l] = tile[l * 33 + lane];
-    __syncwarp();
-    fft32(x);                                      // Z_r[lane + 32 p] at x[rev5(p)]
-#pragma unroll
-    for (int p = 0; p < 32; ++p) tile[lane + 32 * p] = x[rev5(p)];
+    fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
   }
   __syncthreads();
 
-  // ---- c. fused: unpack the two real spectra, |.|, sparse mel, dB, clip max.
-  //         One warp item = one band of BOTH frames; lanes stride over the band's bins.  A bin
-  //         belongs to two adjacent triangles, so its magnitudes are formed twice - cheaper
-  //         than a shared-memory round trip (and it frees 16 KB: 5 CTAs / SM instead of 4).
-  // Each warp owns 12 bands (b = warp + 4*slot); lanes stride over a band's bins and keep one
-  // partial sum per (slot, frame) in registers.  The 24 partials are then reduced across the warp
-  // with ONE multi-value butterfly (16+8+4+2+1 = 31 shuffles instead of 24 x 5): after the step
-  // with offset o, a lane keeps the half of its values whose index bit matches its lane bit, so
-  // lane L ends up holding the total of value index L.  Lane L < 24 then owns (slot L>>1, frame L&1):
-  // one log10f per warp.
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = 0.f;
-#pragma unroll
-  for (int slot = 0; slot < kMels / (kFeThreads / 32); ++slot) {
-    const int b = warp + slot * (kFeThreads / 32);
-    const int beg = band_meta[b], len = band_meta[b + 1] - beg;
-    const int k = band_meta[kMels + 1 + b] + lane;
-    const int kk = (kNfft - k) & (kNfft - 1);
-    // Z planes: bin k lives at plane (k & 3), slot (k >> 2); k advances by 32 per iteration,
-    // so both indices move by +-8 and the plane never changes.
-    const float2* pk = scratch + (k & 3) * kScratchPerWarp + (k >> 2);
-    const float2* pn = scratch + (kk & 3) * kScratchPerWarp + (kk >> 2);
-    const float* wt = fb.weights + beg + lane;
-    float s0 = 0.f, s1 = 0.f;
-    for (int i = lane; i < len; i += 32) {
-      const float w = __ldg(wt);
-      const float2 zk = *pk, zn = *pn;
-      wt += 32; pk += 8; pn -= 8;
-      const float ar = zk.x + zn.x, ai = zk.y - zn.y;      // 2 * X_a[k]
-      const float br = zk.y + zn.y, bi = zk.x - zn.x;      // 2 * X_b[k] (up to a unit factor)
-      float ma, mb;
-      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
-      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
-      s0 = fmaf(w, ma, s0);
-      s1 = fmaf(w, mb, s1);
-    }
-    v[2 * slot] = s0;
-    v[2 * slot + 1] = s1;
+  // ---- c. mel + dB + clip max
+  float wmax = mel_bands(scratch, band_meta, fb.weights, warp, lane, validB,
+                         mel + (size_t)(cd.frame_off + tA) * kMels);
+  wmax = warp_max(wmax);
+  if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
+}
+
+// ---- pipelined kernel for win <= 1024 and hop + win <= 1536 (every standard rate up to 51.2 kHz)
+// One CTA walks kPairsPerCta consecutive frame pairs of one clip, so the dependent prologue loads
+// (ClipDesc -> filterbank tables) are paid once per 8 pairs, and the hop + win raw samples of pair
+// p+1 are fetched with cp.async (16-byte chunks, no registers) into a two-slot shared-memory ring
+// while pair p is transformed: the global-load latency that opens every pair in the generic kernel
+// (46 % of its stall samples) is off the critical path.  Pairs that touch the reflect padding
+// (the first / last one or two of a clip) fill their slot with plain indexed loads instead.
+// The FFT input stage reads samples straight from the ring (window via the read-only path).
+constexpr int kPairsPerCta = 8;
+constexpr int kSpanMax = 1536;                    // hop + win limit of this kernel
+template <typename T> __host__ __device__ constexpr int pp_slot_bytes() {
+  return ((kSpanMax + 16 / (int)sizeof(T)) * (int)sizeof(T) + 15) / 16 * 16;
+}
+template <typename T> constexpr int pp_smem_bytes() { return 2 * pp_slot_bytes<T>() + 4 * kScratchPerWarp * 8; }
+
+template <typename T>
+__device__ __forceinline__ void pp_issue_pair(const T* __restrict__ y, int a, int span, int n_samples,
+                                              T* slot, int tid) {
+  if (a >= 0 && a + span <= n_samples) {
+    const char* src = reinterpret_cast<const char*>(y + a);
+    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    src -= mis;
+    const int chunks = (mis + span * (int)sizeof(T) + 15) >> 4;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(slot);
+    for (int i = tid; i < chunks; i += kFeThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 16 * i) : "memory");
+  } else {
+    for (int i = tid; i < span; i += kFeThreads) slot[i] = y[reflect_index(a + i, n_samples)];
   }
-  // multi-value butterfly: at the step with offset o the 2*o live values are paired (i, i+o); a lane
-  // whose bit o is set keeps the upper one and sends the lower one, so bit o of the surviving
-  // value index equals bit o of the lane.
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float keep = up ? v[i + o] : v[i];
-      const float send = up ? v[i] : v[i + o];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFeThreads, 5)
+frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips,
+                   const FbTables* __restrict__ fbs, const float2* __restrict__ tw1,
+                   const float2* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* scratch = reinterpret_cast<float2*>(smem_raw + 2 * pp_slot_bytes<T>());
+  __shared__ int band_meta[2 * kMels + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.y;
+  const ClipDesc cd = clips[c];
+  const int n_pairs = (cd.n_frames + 1) >> 1;
+  const int p0 = blockIdx.x * kPairsPerCta;
+  if (p0 >= n_pairs) return;
+  const int p1 = min(p0 + kPairsPerCta, n_pairs);
+  const T* y = pcm + cd.pcm_off;
+  const int span = cd.hop + cd.win;
+  pp_issue_pair<T>(y, cd.s0 + 2 * p0 * cd.hop, span, cd.n_samples, reinterpret_cast<T*>(smem_raw), tid);
+  const FbTables fb = fbs[cd.fb_id];
+  if (tid <= kMels) band_meta[tid] = __ldg(fb.band_start + tid);
+  else if (tid < 2 * kMels + 1) band_meta[tid] = __ldg(fb.band_k0 + tid - kMels - 1);
+
+  const int r = warp;
   float wmax = -INFINITY;
-  {
-    // after the butterfly v[0] of lane L is the total of value index L (bit o of the index was
-    // selected by bit o of the lane at every step)
-    const float mine = v[0];
-    const int my_slot = lane >> 1, f = lane & 1;
-    const int b = warp + my_slot * (kFeThreads / 32);
-    if (lane < 2 * (kMels / (kFeThreads / 32)) && (f == 0 || validB)) {
-      const float sv = 0.5f * mine;                        // the 1/2 of the real-pair unpacking
-      const float p = sv * sv;
-      const float db = 10.0f * log10f(fmaxf(p, 1e-8f));
-      mel[(size_t)(cd.frame_off + tA + f) * kMels + b] = db;
-      wmax = db;
+  for (int p = p0; p < p1; ++p) {
+    const int s = (p - p0) & 1;
+    const int a = cd.s0 + 2 * p * cd.hop;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                    // slot s complete and visible; planes of pair p-1 consumed
+    if (p + 1 < p1)
+      pp_issue_pair<T>(y, a + 2 * cd.hop, span, cd.n_samples,
+                       reinterpret_cast<T*>(smem_raw + (s ^ 1) * pp_slot_bytes<T>()), tid);
+    const bool validB = 2 * p + 1 < cd.n_frames;
+    const bool interior = a >= 0 && a + span <= cd.n_samples;
+    const int shift = interior ? (int)((reinterpret_cast<uintptr_t>(y + a) & 15) / sizeof(T)) : 0;
+    const T* src = reinterpret_cast<const T*>(smem_raw + s * pp_slot_bytes<T>()) + shift;
+    float2 x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = lane + 32 * j;
+      float2 v = make_float2(0.f, 0.f);
+      if (n < cd.win) {
+        const float w = __ldg(fb.window + n);
+        v.x = w * sample_to_float<T>(src[n]);
+        if (validB) v.y = w * sample_to_float<T>(src[n + cd.hop]);
+        if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));
+      }
+      x[j] = v;
     }
+    fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
+    __syncthreads();                    // all four planes written
+    wmax = fmaxf(wmax, mel_bands(scratch, band_meta, fb.weights, warp, lane, validB,
+                                 mel + (size_t)(cd.frame_off + 2 * p) * kMels));
   }
   wmax = warp_max(wmax);
   if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
@@ -280,9 +376,23 @@ __global__ void mel_dump_kernel(const float* __restrict__ mel, const ClipDesc* _
 // ------------------------------------------------------------------ host launchers
 void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDesc* clips,
                      int n_clips, int max_pairs, const FbTables* fbs,
-                     const float2* tw, float* mel, unsigned* clipmax, int Q) {
+                     const float2* tw, float* mel, unsigned* clipmax, int Q, int max_span) {
   const float2* tw1 = tw;               // [3][32][32]
   const float2* tw2 = tw + 3 * 1024;    // [32][32]
+  if (Q == 1 && max_span <= kSpanMax) { // the pipelined multi-pair kernel
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(frontend_pp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes<float>());
+      cudaFuncSetAttribute(frontend_pp_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes<short>());
+      configured = true;
+    }
+    const dim3 grid((max_pairs + kPairsPerCta - 1) / kPairsPerCta, n_clips);
+    if (fmt_f32)
+      frontend_pp_kernel<float><<<grid, kFeThreads, pp_smem_bytes<float>(), st>>>((const float*)pcm, clips, fbs, tw1, tw2, mel, clipmax);
+    else
+      frontend_pp_kernel<short><<<grid, kFeThreads, pp_smem_bytes<short>(), st>>>((const short*)pcm, clips, fbs, tw1, tw2, mel, clipmax);
+    return;
+  }
   const int smem = frontend_smem_bytes(Q);
   static int configured_q = 0;
   if (Q > configured_q) {
