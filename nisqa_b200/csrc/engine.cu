@@ -23,7 +23,7 @@
 namespace nisqa {
 // frontend.cu
 void launch_frontend(cudaStream_t, const void*, int, const ClipDesc*, int, int,
-                     const FbTables*, const float2*, float*, unsigned*, int, int);
+                     const FbTables*, const float2*, float*, unsigned*, int, int, int);
 void launch_seg_table(cudaStream_t, const ClipDesc*, int, const int*, const unsigned*, int, int,
                       int*, float*, int*);
 void launch_mel_dump(cudaStream_t, const float*, const ClipDesc*, int, const unsigned*, float*);
@@ -160,6 +160,7 @@ struct nisqa_engine {
   int64_t launches = 0;
   bool weights_loaded = false;
   bool profiling = false;
+  int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
@@ -326,7 +327,7 @@ int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
   band_start[n_mels] = (int)wts.size();
   if (wts.empty()) wts.push_back(0.f);
   // scipy.signal.get_window('hann', win, fftbins=True): periodic Hann in float64 -> float32
-  std::vector<float> window(win);
+  std::vector<float> window((size_t)(win + 1023) / 1024 * 1024, 0.f);   // zero-padded to the FFT sub-length
   for (int n = 0; n < win; ++n) window[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)win));
   if (win == 1) window[0] = 1.f;
   CK(fb->window.reserve(window.size() * 4));
@@ -698,7 +699,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "frontend");
       launch_frontend(st, d_pcm, in.fmt == NISQA_FMT_F32, d_clips, n, max_pairs,
                       e->fb_table.as<FbTables>(), e->tw4096.as<float2>(), LN.mel.as<float>(),
-                      d_clipmax, Q, max_span); }
+                      d_clipmax, Q, max_span, e->fe_ppc); }
     { Scope s(e, "seg_table");
       launch_seg_table(st, d_clips, n, d_seg, d_clipmax, c.seg_hop, n_seg,
                        seg_frame0, seg_thr, seg_clip); }
@@ -1072,6 +1073,7 @@ int nisqa_join(nisqa_engine* e) {
 int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
+  if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }
 

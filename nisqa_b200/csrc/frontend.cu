@@ -259,7 +259,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
 // (46 % of its stall samples) is off the critical path.  Pairs that touch the reflect padding
 // (the first / last one or two of a clip) fill their slot with plain indexed loads instead.
 // The FFT input stage reads samples straight from the ring (window via the read-only path).
-constexpr int kPairsPerCta = 8;
+constexpr int kPairsPerCta = 1;
 constexpr int kSpanMax = 1536;                    // hop + win limit of this kernel
 template <typename T> __host__ __device__ constexpr int pp_slot_bytes() {
   return ((kSpanMax + 16 / (int)sizeof(T)) * (int)sizeof(T) + 15) / 16 * 16;
@@ -287,7 +287,8 @@ template <typename T>
 __global__ void __launch_bounds__(kFeThreads, 5)
 frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips,
                    const FbTables* __restrict__ fbs, const float2* __restrict__ tw1,
-                   const float2* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax) {
+                   const float2* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax,
+                   int ppc /*frame pairs per CTA*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* scratch = reinterpret_cast<float2*>(smem_raw + 2 * pp_slot_bytes<T>());
   __shared__ int band_meta[2 * kMels + 1];
@@ -296,9 +297,9 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
   const int c = blockIdx.y;
   const ClipDesc cd = clips[c];
   const int n_pairs = (cd.n_frames + 1) >> 1;
-  const int p0 = blockIdx.x * kPairsPerCta;
+  const int p0 = blockIdx.x * ppc;
   if (p0 >= n_pairs) return;
-  const int p1 = min(p0 + kPairsPerCta, n_pairs);
+  const int p1 = min(p0 + ppc, n_pairs);
   const T* y = pcm + cd.pcm_off;
   const int span = cd.hop + cd.win;
   pp_issue_pair<T>(y, cd.s0 + 2 * p0 * cd.hop, span, cd.n_samples, reinterpret_cast<T*>(smem_raw), tid);
@@ -320,18 +321,30 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
     const bool interior = a >= 0 && a + span <= cd.n_samples;
     const int shift = interior ? (int)((reinterpret_cast<uintptr_t>(y + a) & 15) / sizeof(T)) : 0;
     const T* src = reinterpret_cast<const T*>(smem_raw + s * pp_slot_bytes<T>()) + shift;
+    // input stage, branch-free so that the loads of 4 elements are in flight together: the window
+    // table is zero-padded to 1024 and the sample index is clamped into the slot for n >= win
     float2 x[32];
+    const int hopB = validB ? cd.hop : 0;
+    constexpr int CH = 4;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int n = lane + 32 * j;
-      float2 v = make_float2(0.f, 0.f);
-      if (n < cd.win) {
-        const float w = __ldg(fb.window + n);
-        v.x = w * sample_to_float<T>(src[n]);
-        if (validB) v.y = w * sample_to_float<T>(src[n + cd.hop]);
-        if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));
+    for (int j0 = 0; j0 < 32; j0 += CH) {
+      float w[CH], sa[CH], sb[CH];
+      float2 t[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int n = lane + 32 * (j0 + u);
+        const int ni = min(n, cd.win - 1);
+        w[u] = __ldg(fb.window + n);
+        if (r != 0) t[u] = __ldg(tw1 + ((r - 1) * 32 + j0 + u) * 32 + lane);
+        sa[u] = sample_to_float<T>(src[ni]);
+        sb[u] = sample_to_float<T>(src[ni + hopB]);
       }
-      x[j] = v;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        float2 v = make_float2(w[u] * sa[u], validB ? w[u] * sb[u] : 0.f);
+        if (r != 0) v = cmul(v, t[u]);
+        x[j0 + u] = v;
+      }
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
     __syncthreads();                    // all four planes written
@@ -376,7 +389,7 @@ __global__ void mel_dump_kernel(const float* __restrict__ mel, const ClipDesc* _
 // ------------------------------------------------------------------ host launchers
 void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDesc* clips,
                      int n_clips, int max_pairs, const FbTables* fbs,
-                     const float2* tw, float* mel, unsigned* clipmax, int Q, int max_span) {
+                     const float2* tw, float* mel, unsigned* clipmax, int Q, int max_span, int ppc) {
   const float2* tw1 = tw;               // [3][32][32]
   const float2* tw2 = tw + 3 * 1024;    // [32][32]
   if (Q == 1 && max_span <= kSpanMax) { // the pipelined multi-pair kernel
@@ -386,11 +399,12 @@ void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDe
       cudaFuncSetAttribute(frontend_pp_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes<short>());
       configured = true;
     }
-    const dim3 grid((max_pairs + kPairsPerCta - 1) / kPairsPerCta, n_clips);
+    if (ppc < 1) ppc = kPairsPerCta;
+    const dim3 grid((max_pairs + ppc - 1) / ppc, n_clips);
     if (fmt_f32)
-      frontend_pp_kernel<float><<<grid, kFeThreads, pp_smem_bytes<float>(), st>>>((const float*)pcm, clips, fbs, tw1, tw2, mel, clipmax);
+      frontend_pp_kernel<float><<<grid, kFeThreads, pp_smem_bytes<float>(), st>>>((const float*)pcm, clips, fbs, tw1, tw2, mel, clipmax, ppc);
     else
-      frontend_pp_kernel<short><<<grid, kFeThreads, pp_smem_bytes<short>(), st>>>((const short*)pcm, clips, fbs, tw1, tw2, mel, clipmax);
+      frontend_pp_kernel<short><<<grid, kFeThreads, pp_smem_bytes<short>(), st>>>((const short*)pcm, clips, fbs, tw1, tw2, mel, clipmax, ppc);
     return;
   }
   const int smem = frontend_smem_bytes(Q);
