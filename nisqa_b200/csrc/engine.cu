@@ -323,6 +323,7 @@ int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
     band_start[i] = (int)wts.size();
     band_k0[i] = k0 < 0 ? 0 : k0;
     if (k0 >= 0) for (int k = k0; k <= k1; ++k) wts.push_back(fb->dense[(size_t)i * n_bins + k]);
+    while (wts.size() % 32) wts.push_back(0.f);     // rows padded to the warp width (frontend mel_bands)
   }
   band_start[n_mels] = (int)wts.size();
   if (wts.empty()) wts.push_back(0.f);

@@ -127,7 +127,9 @@ __device__ __forceinline__ float mel_bands(const float2* scratch, const int* ban
 #pragma unroll
   for (int slot = 0; slot < kMels / 4; ++slot) {
     const int b = warp + slot * 4;
-    const int beg = band_meta[b], len = band_meta[b + 1] - beg;
+    // band rows are zero-padded to a multiple of 32 weights (engine build_fb): warp-uniform trip
+    // count, no divergence, every lane loads unconditionally (the padded bins stay inside the planes)
+    const int beg = band_meta[b], iters = (band_meta[b + 1] - beg) >> 5;
     const int k = band_meta[kMels + 1 + b] + lane;
     const int kk = (kNfft - k) & (kNfft - 1);
     // Z planes: bin k lives at plane (k & 3), slot (k >> 2); k advances by 32 per iteration,
@@ -136,7 +138,8 @@ __device__ __forceinline__ float mel_bands(const float2* scratch, const int* ban
     const float2* pn = scratch + (kk & 3) * kScratchPerWarp + (kk >> 2);
     const float* wt = weights + beg + lane;
     float s0 = 0.f, s1 = 0.f;
-    for (int i = lane; i < len; i += 32) {
+#pragma unroll 2
+    for (int it = 0; it < iters; ++it) {
       const float w = __ldg(wt);
       const float2 zk = *pk, zn = *pn;
       wt += 32; pk += 8; pn -= 8;
@@ -259,7 +262,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
 // (46 % of its stall samples) is off the critical path.  Pairs that touch the reflect padding
 // (the first / last one or two of a clip) fill their slot with plain indexed loads instead.
 // The FFT input stage reads samples straight from the ring (window via the read-only path).
-constexpr int kPairsPerCta = 1;
+constexpr int kPairsPerCta = 2;
 constexpr int kSpanMax = 1536;                    // hop + win limit of this kernel
 template <typename T> __host__ __device__ constexpr int pp_slot_bytes() {
   return ((kSpanMax + 16 / (int)sizeof(T)) * (int)sizeof(T) + 15) / 16 * 16;
