@@ -33,7 +33,7 @@ void launch_conv1(cudaStream_t, int, const float*, const int*, const float*, con
 void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
 void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
 // conv_tc.cu
-void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int);
+void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int, int);
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
 #endif
@@ -161,6 +161,7 @@ struct nisqa_engine {
   bool weights_loaded = false;
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
+  int tc_swz = 0;          // bit l set: conv layer l stages its activation tile in the swizzled row-major layout
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
@@ -718,7 +719,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
         Scope s(e, nm);
         if (e->conv_tc & (1 << l))
-          launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg);
+          launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg, (e->tc_swz >> l) & 1);
         else
           launch_conv_layer(st, std_mode, l, cin_[l], W(e, kw), W(e, kb), cout_[l], n_seg);
       }
@@ -1075,6 +1076,7 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
+  if (strcmp(name, "tc_swz") == 0) { e->tc_swz = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }
 
