@@ -13,6 +13,7 @@
 //                        LDS.128), max-pool + bias + ReLU fused into the epilogue.
 // fp32 FFMA is a parity decision: TF32 operands alone move MOS by 2e-3.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace nisqa {
 
@@ -21,11 +22,14 @@ namespace nisqa {
 //   MODE 0 (adapt, lib:690-691): adaptive_max_pool2d 48x15 -> 24x7 : rows {2i,2i+1}, cols [2j,2j+3)
 //   MODE 1 (standard, lib:813-814): MaxPool2d(2, stride 2, padding (0,1)) -> 24x8 : cols {2j-1,2j}
 // thread = one pooled cell of one segment, all 16 channels.
-template <int MODE>
+// SPLIT: the output goes out as the two fp16 planes conv2's tensor-core kernel consumes (conv_split.cu:
+// padded rows of 16 halves = 32 bytes, 32-byte swizzle) instead of fp32 channels-last.
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv1_pool1_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
                    const float* __restrict__ seg_thr, const float* __restrict__ w1 /*[9][16]*/,
-                   const float* __restrict__ b1 /*[16]*/, float* __restrict__ out, int n_seg) {
+                   const float* __restrict__ b1 /*[16]*/, float* __restrict__ out,
+                   unsigned char* __restrict__ out_hi, unsigned char* __restrict__ out_lo, int n_seg) {
   constexpr int PW = (MODE == 0) ? 7 : 8;
   constexpr int NWC = (MODE == 0) ? 3 : 2;       // window columns
   constexpr int PC = NWC + 2;                    // patch columns
@@ -94,10 +98,24 @@ conv1_pool1_kernel(const float* __restrict__ mel, const int* __restrict__ seg_fr
       res[cq * 4 + c] = fmaxf(m + ws[144 + cq * 4 + c], 0.f);   // bias + ReLU commute with max
     }
   }
-  float4* o = reinterpret_cast<float4*>(out + ((size_t)seg * 24 * PW + ph * PW + pw) * 16);
+  if constexpr (SPLIT) {
+    const int g = kSplitLead + seg * (25 * (PW + 1)) + (ph + 1) * (PW + 1) + (pw + 1);
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    o[q] = make_float4(res[q * 4], res[q * 4 + 1], res[q * 4 + 2], res[q * 4 + 3]);
+    for (int c = 0; c < 2; ++c) {
+      uint4 hi, lo;
+      split8(make_float4(res[8 * c], res[8 * c + 1], res[8 * c + 2], res[8 * c + 3]),
+             make_float4(res[8 * c + 4], res[8 * c + 5], res[8 * c + 6], res[8 * c + 7]), hi, lo);
+      size_t o = (size_t)g * 32 + (size_t)c * 16;
+      o ^= (o >> 3) & 16;                          // Swizzle<1,4,3>
+      *reinterpret_cast<uint4*>(out_hi + o) = hi;
+      *reinterpret_cast<uint4*>(out_lo + o) = lo;
+    }
+  } else {
+    float4* o = reinterpret_cast<float4*>(out + ((size_t)seg * 24 * PW + ph * PW + pw) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      o[q] = make_float4(res[q * 4], res[q * 4 + 1], res[q * 4 + 2], res[q * 4 + 3]);
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -300,14 +318,20 @@ static void launch_conv(cudaStream_t st, const float* in, const float* w, const 
 }
 
 void launch_conv1(cudaStream_t st, int std_mode, const float* mel, const int* seg_frame0,
-                  const float* seg_thr, const float* w1, const float* b1, float* out, int n_seg) {
+                  const float* seg_thr, const float* w1, const float* b1, float* out, int n_seg,
+                  void* out_hi, void* out_lo) {
   const int cells = std_mode ? 24 * 8 : 24 * 7;
   const long long total = (long long)n_seg * cells;
   const int grid = (int)((total + 255) / 256);
-  if (std_mode)
-    conv1_pool1_kernel<1><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, n_seg);
-  else
-    conv1_pool1_kernel<0><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, n_seg);
+  unsigned char* oh = static_cast<unsigned char*>(out_hi);
+  unsigned char* ol = static_cast<unsigned char*>(out_lo);
+  if (out_hi) {
+    if (std_mode) conv1_pool1_kernel<1, true><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, oh, ol, n_seg);
+    else conv1_pool1_kernel<0, true><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, oh, ol, n_seg);
+  } else {
+    if (std_mode) conv1_pool1_kernel<1, false><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, oh, ol, n_seg);
+    else conv1_pool1_kernel<0, false><<<grid, 256, 0, st>>>(mel, seg_frame0, seg_thr, w1, b1, out, oh, ol, n_seg);
+  }
 }
 
 // layer = 2..6

@@ -9,6 +9,7 @@ constexpr int kMels = 48;        // ms_n_mels (asserted on the host)
 constexpr int kSegLen = 15;      // ms_seg_length
 constexpr int kNfft = 4096;      // ms_n_fft
 constexpr int kBins = kNfft / 2 + 1;
+constexpr int kSplitLead = 16;  // zero rows in front of segment 0 of an fp16 plane pair (conv_split.cu) >= the largest tap halo
 
 // One row per clip of the current pass (device copy lives in HBM).
 struct ClipDesc {

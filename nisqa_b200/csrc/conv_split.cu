@@ -1,0 +1,387 @@
+// conv_split.cu - conv2..conv6 of the AdaptCNN / StandardCNN (reference nisqa/NISQA_lib.py:692-706,
+// 816-830) on the 5th-generation tensor cores, with the activations travelling BETWEEN the layers
+// already in the form the tensor core consumes: two fp16 planes (hi, lo) of the error-compensated
+// split  x = x_hi + x_lo  (see conv_tc.cu for the arithmetic: a_hi*[b_hi|b_lo] + a_lo*b_hi in fp32,
+// results within fp32 rounding noise of the reference), laid out in HBM as the exact shared-memory
+// image of the implicit-GEMM A tile:
+//
+//   plane row g(seg, hh, ww) = kSplitLead + seg * BLK + hh * P + ww,   P = W + 1, BLK = (H + 1) * P
+//     hh = 0 / ww = 0 are the shared zero row / zero column (never written: the planes are zeroed
+//     when they are allocated), interior positions are hh = h + 1, ww = w + 1
+//   row = CIN halves (32 / 64 / 128 bytes); the 16-byte chunk c of row g sits at chunk position
+//     c ^ f(g), f = the hardware 32B / 64B / 128B swizzle of a tile whose row index is == g (mod 8)
+//
+// so that a CTA's whole activation tile (256 + 2 * HALO consecutive rows, two planes) arrives with
+// TWO cp.async.bulk copies issued by one thread (placed at row offset g0 & 7 inside a 1024-byte
+// aligned tile so that the absolute-address swizzle of the UMMA descriptors matches the image), and
+// the producing layer's epilogue does the split once, right where the fp32 value exists.  Compared
+// with conv_tc.cu (fp32 channels-last activations, register staging + split in every consumer) the
+// fill phase of a CTA drops from ~9 k cycles of LDG -> split -> STS to one asynchronous copy, the 9
+// taps are the same tile addressed through row-shifted descriptors as before, and max-pooling runs
+// on all 192 threads of the CTA.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace nisqa {
+
+#ifdef NISQA_TC_TIMING
+__device__ long long g_sp_timing[8 * 8192];
+#endif
+__device__ __forceinline__ void sp_stamp(int slot, int who, int flags) {
+#ifdef NISQA_TC_TIMING
+  if ((flags & 2) && (int)threadIdx.x == who && blockIdx.x < 8192) g_sp_timing[blockIdx.x * 8 + slot] = clock64();
+#endif
+}
+
+enum { SP_POOL_NONE = 0, SP_POOL_ADAPT = 1, SP_POOL_2X2 = 2 };
+
+// byte offset of chunk c (8 halves) of plane row g, rows of ROWB bytes: Swizzle<log2(ROWB/16), 4, 3>
+template <int ROWB>
+__device__ __forceinline__ size_t split_off(int g, int c) {
+  const size_t o = (size_t)g * ROWB + (size_t)c * 16;
+  return o ^ ((o >> 3) & (size_t)(ROWB - 16));
+}
+
+template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, bool F32OUT_ = false, bool CENTER_ = false>
+struct SpCfg {
+  static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, POOL = POOL_, POW = POW_;
+  static constexpr bool CENTER = CENTER_;         // conv6 of the AdaptCNN: kernel (3,3), padding (1,0) on a
+                                                  // 3-wide map == the padded conv evaluated at column 1 only
+  static constexpr bool OUT_SPLIT = !F32OUT_;     // the last layer writes the CNN features as fp32 channels-last
+  static constexpr int P = W + 1;                 // row pitch: W interior columns + 1 shared zero column
+  static constexpr int BLK = (H + 1) * P;         // rows per segment: H interior rows + 1 shared zero row
+  static constexpr int G = 256 / BLK;             // segments per CTA (2 M-tiles of 128 rows)
+  static constexpr int HALO = P + 1;              // |row offset| of the farthest tap
+  static constexpr int AROWS = 256 + 2 * HALO;    // rows of the tile (copied)
+  static constexpr int ROWB = CIN * 2;            // bytes per row
+  static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : (ROWB == 64 ? 4u : 6u);
+  static constexpr int A_BYTES = ((AROWS + 7) * ROWB + 1023) & ~1023;     // + placement shift (g0 & 7 rows)
+  static constexpr int NCH = CIN / 8;             // 16-byte K chunks (8 halves)
+  static constexpr int B_HALF = NCH * COUT * 16;  // per hi / lo
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int TMEM_COLS = (4 * COUT <= 64) ? 64 : (4 * COUT <= 128 ? 128 : 256);   // 2 M-tiles x 2*COUT
+  // output geometry (= the next layer's input geometry)
+  static constexpr int HO = (POOL == SP_POOL_NONE) ? H : H / 2;
+  static constexpr int WO = (POOL == SP_POOL_NONE) ? (CENTER ? 1 : W) : POW;
+  static constexpr int OP = WO + 1, OBLK = (HO + 1) * OP, OROWB = COUT * 2;
+  static constexpr int STG_STRIDE = COUT + 4;     // floats per staged row (conflict-free float4)
+  static constexpr int OFF_A_HI = 0;
+  static constexpr int OFF_A_LO = A_BYTES;
+  static constexpr int OFF_B = 2 * A_BYTES;
+  static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32 + 1024;    // + slack: the tile is aligned to 1024 B
+  static constexpr int MINB_SMEM = (SMEM_BYTES <= 56 * 1024) ? 4 : (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
+  static constexpr int MINB = (MINB_SMEM * TMEM_COLS <= 512) ? MINB_SMEM : 512 / TMEM_COLS;
+  // D=f32, A=B=f16, both K-major, M=128; N = 2*COUT ([b_hi|b_lo]) and N = COUT (b_hi only)
+  static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * COUT) >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+  static_assert(POOL == SP_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES + NSTAGE * B_STAGE,
+                "pool staging tile must fit in the A+B region");
+  static_assert(B_STAGE % 16 == 0 && CIN % 16 == 0 && COUT % 32 == 0, "shape");
+  static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "rows are 32 / 64 / 128 bytes (one swizzle atom)");
+  static_assert(HALO <= kSplitLead, "kSplitLead");
+  static_assert(!CENTER || F32OUT_, "the centre-column variant only exists as the last layer");
+  static_assert(OUT_SPLIT || POOL == SP_POOL_NONE, "fp32 output is not pooled");
+  static_assert(G >= 1 && MINB * TMEM_COLS <= 512, "tile / TMEM budget");
+};
+
+template <class C>
+__global__ void __launch_bounds__(192, C::MINB)
+conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* __restrict__ in_lo,
+                  const __half* __restrict__ wtc /*[9][CIN/8][hi co | lo co][8] fp16, scaled by 2^S*/,
+                  const float* __restrict__ bias, float out_scale /*2^-S*/,
+                  unsigned char* __restrict__ out_hi, unsigned char* __restrict__ out_lo,
+                  float* __restrict__ out_f32 /*last layer only*/, int n_seg, int flags) {
+  constexpr int H = C::H, W = C::W, CIN = C::CIN, COUT = C::COUT, P = C::P, BLK = C::BLK, G = C::G;
+  constexpr int HALO = C::HALO, NS = C::NSTAGE, ROWB = C::ROWB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms repeat every 1024 B
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t a_hi = sbase + C::OFF_A_HI, a_lo = sbase + C::OFF_A_LO, b_base = sbase + C::OFF_B;
+  const uint32_t bar_full = sbase + C::OFF_BAR;          // [NS]
+  const uint32_t bar_empty = bar_full + 8 * NS;          // [NS]
+  const uint32_t bar_acc = bar_full + 16 * NS;
+  const uint32_t bar_a = bar_acc + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 16 * NS + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seg0 = blockIdx.x * G;
+  const int g0 = kSplitLead + seg0 * BLK - HALO;         // first plane row of this CTA's tile
+  const uint32_t sh = (uint32_t)(g0 & 7);                // tile row == plane row (mod 8)
+  sp_stamp(0, 0, flags);
+
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+  if (tid == 32) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_a, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  sp_stamp(1, 0, flags);
+
+  if (warp == 5) {
+    // ===== producer (one lane): the activation tile (2 copies), then the weights tap by tap =====
+    if (lane == 0) {
+      constexpr uint32_t A_COPY = (uint32_t)C::AROWS * ROWB;
+      mbar_expect_tx(bar_a, 2 * A_COPY);
+      bulk_g2s(a_hi + sh * ROWB, in_hi + (size_t)g0 * ROWB, A_COPY, bar_a);
+      bulk_g2s(a_lo + sh * ROWB, in_lo + (size_t)g0 * ROWB, A_COPY, bar_a);
+      for (int t = 0; t < 9; ++t) {
+        const int s = t % NS;
+        if (t >= NS) mbar_wait(bar_empty + 8 * s, ((t / NS) - 1) & 1);     // MMAs of tap t-NS have drained the stage
+        mbar_expect_tx(bar_full + 8 * s, C::B_STAGE);
+        bulk_g2s(b_base + s * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      mbar_wait(bar_a, 0);
+      sp_stamp(2, 128, flags);
+      for (int t = 0; t < 9; ++t) {
+        const int s = t % NS;
+        mbar_wait(bar_full + 8 * s, (t / NS) & 1);
+        if (t == 0) sp_stamp(6, 128, flags);
+        tc_fence_after();
+        const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
+        const uint32_t bst = b_base + s * C::B_STAGE;       // [ci/8][2*COUT rows: hi then lo][8 halves]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t row = sh + (uint32_t)(HALO + mt * 128 + tapoff);
+          const uint32_t d = tmem + mt * (2 * COUT);
+#pragma unroll
+          for (int ks = 0; ks < CIN / 16; ++ks) {
+            const uint32_t aoff = row * ROWB + (uint32_t)ks * 32;
+            const uint64_t dah = make_desc_swz(a_hi + aoff, 8 * ROWB, C::LAYOUT);
+            const uint64_t dal = make_desc_swz(a_lo + aoff, 8 * ROWB, C::LAYOUT);
+            const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
+            umma_f16(d, dah, db, C::IDESC_2N, (t | ks) != 0);     // [0,C) += hi*hi ; [C,2C) += hi*lo
+            umma_f16(d, dal, db, C::IDESC_1N, 1);                 // [0,C) += lo*hi
+          }
+        }
+        umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
+      }
+      umma_commit(bar_acc);                      // all accumulators final
+      sp_stamp(7, 128, flags);
+    }
+  } else {
+    // ===== epilogue part 1: warps 0..3 <-> TMEM lanes 32w..32w+31 =====
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    sp_stamp(3, 0, flags);
+    float* stg = reinterpret_cast<float*>(smem);          // reuses the A/B region (all MMAs retired)
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 128 + warp * 32 + lane;
+      const int s = r / BLK, q = r - s * BLK;
+      const int hh = q / P, ww = q - hh * P;
+      bool valid = (s < G) && hh >= 1 && ww >= 1 && (seg0 + s < n_seg);
+      if (C::CENTER) valid = valid && (ww == 2);
+#pragma unroll 1
+      for (int part = 0; part < COUT / 32; ++part) {
+        float v[32], v2[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + part * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + COUT + part * 32, v2);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaxf(fmaf(v[j] + v2[j], out_scale, __ldg(bias + part * 32 + j)), 0.f);
+          if constexpr (C::POOL != SP_POOL_NONE) {
+            float4* dst = reinterpret_cast<float4*>(stg + ((s * H + (hh - 1)) * W + (ww - 1)) * C::STG_STRIDE + part * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if constexpr (C::OUT_SPLIT) {
+            const int g = kSplitLead + (seg0 + s) * C::OBLK + hh * C::OP + ww;     // same padded geometry as the input
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 hi, lo;
+              split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                     make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+              const size_t o = split_off<C::OROWB>(g, part * 4 + j);
+              *reinterpret_cast<uint4*>(out_hi + o) = hi;
+              *reinterpret_cast<uint4*>(out_lo + o) = lo;
+            }
+          } else {
+            constexpr int WOUT = C::CENTER ? 1 : W;
+            const int w = C::CENTER ? 0 : ww - 1;
+            float4* dst = reinterpret_cast<float4*>(out_f32 + (((size_t)(seg0 + s) * H + (hh - 1)) * WOUT + w) * COUT + part * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+  sp_stamp(4, 0, flags);
+  tc_fence_before();
+  __syncthreads();                     // accumulators read, staging tile complete; every role is done
+  if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+
+  if constexpr (C::POOL != SP_POOL_NONE) {
+    // ===== epilogue part 2 (all 192 threads): max-pool the staged tile, split, store =====
+    const float* stg = reinterpret_cast<const float*>(smem);
+    constexpr int POW = C::POW, HO = H / 2, C8 = COUT / 8;
+    for (int it = tid; it < G * HO * POW * C8; it += 192) {
+      const int c8 = it % C8;
+      int rest = it / C8;
+      const int pw = rest % POW; rest /= POW;
+      const int ph = rest % HO;
+      const int s = rest / HO;
+      if (seg0 + s >= n_seg) continue;
+      int x0, x1;
+      if (C::POOL == SP_POOL_ADAPT) { x0 = (pw * W) / POW; x1 = ((pw + 1) * W + POW - 1) / POW; }
+      else { x0 = 2 * pw; x1 = 2 * pw + 2; }
+      float4 ma = make_float4(0.f, 0.f, 0.f, 0.f), mb = ma;       // post-ReLU values are >= 0
+      for (int hy = 2 * ph; hy < 2 * ph + 2; ++hy)
+        for (int x = x0; x < x1; ++x) {
+          const float4* t = reinterpret_cast<const float4*>(stg + ((s * H + hy) * W + x) * C::STG_STRIDE + c8 * 8);
+          const float4 ta = t[0], tb = t[1];
+          ma.x = fmaxf(ma.x, ta.x); ma.y = fmaxf(ma.y, ta.y); ma.z = fmaxf(ma.z, ta.z); ma.w = fmaxf(ma.w, ta.w);
+          mb.x = fmaxf(mb.x, tb.x); mb.y = fmaxf(mb.y, tb.y); mb.z = fmaxf(mb.z, tb.z); mb.w = fmaxf(mb.w, tb.w);
+        }
+      uint4 hi, lo;
+      split8(ma, mb, hi, lo);
+      const int g = kSplitLead + (seg0 + s) * C::OBLK + (ph + 1) * C::OP + (pw + 1);
+      const size_t o = split_off<C::OROWB>(g, c8);
+      *reinterpret_cast<uint4*>(out_hi + o) = hi;
+      *reinterpret_cast<uint4*>(out_lo + o) = lo;
+    }
+  }
+  sp_stamp(5, 0, flags);
+}
+
+// planes -> fp32 channels-last [seg][H][W][C] (stage dumps for the parity tests; x_hi + x_lo == x to 2^-22)
+template <int ROWB>
+__global__ void unsplit_kernel(const unsigned char* __restrict__ hi, const unsigned char* __restrict__ lo,
+                               float* __restrict__ out, long long n_items, int H, int W) {
+  constexpr int C8 = ROWB / 16;
+  const int P = W + 1, BLK = (H + 1) * P;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(it % C8);
+    long long rest = it / C8;
+    const int w = (int)(rest % W); rest /= W;
+    const int h = (int)(rest % H);
+    const int seg = (int)(rest / H);
+    const int g = kSplitLead + seg * BLK + (h + 1) * P + (w + 1);
+    const size_t o = split_off<ROWB>(g, c8);
+    const uint4 a = *reinterpret_cast<const uint4*>(hi + o), b = *reinterpret_cast<const uint4*>(lo + o);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(ah[i]), y = __half22float2(bh[i]);
+      r[2 * i] = x.x + y.x; r[2 * i + 1] = x.y + y.y;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + it * 8);
+    dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+    dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+  }
+}
+
+#ifndef NISQA_SP_NS4
+#define NISQA_SP_NS4 2
+#endif
+#ifndef NISQA_SP_NS5
+#define NISQA_SP_NS5 2
+#endif
+#ifndef NISQA_SP_NS3
+#define NISQA_SP_NS3 4
+#endif
+// layers 2..6; std_mode selects the StandardCNN geometry (W 8/4/2, MaxPool2d(2))
+//                     H   W  CIN COUT POOL           POW NSTAGE F32OUT CENTER
+using SpConv2A = SpCfg<24, 7, 16, 32, SP_POOL_ADAPT, 5, 9>;
+using SpConv3A = SpCfg<12, 5, 32, 64, SP_POOL_NONE, 0, NISQA_SP_NS3>;
+using SpConv4A = SpCfg<12, 5, 64, 64, SP_POOL_ADAPT, 3, NISQA_SP_NS4>;
+using SpConv5A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5>;
+using SpConv6A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5, true, true>;
+using SpConv2S = SpCfg<24, 8, 16, 32, SP_POOL_2X2, 4, 9>;
+using SpConv3S = SpCfg<12, 4, 32, 64, SP_POOL_NONE, 0, 4>;
+using SpConv4S = SpCfg<12, 4, 64, 64, SP_POOL_2X2, 2, 2>;
+using SpConv5S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2>;
+using SpConv6S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2, true>;
+
+template <class C>
+static void launch_sp(cudaStream_t st, const unsigned char* in_hi, const unsigned char* in_lo, const __half* wtc,
+                      const float* b, float scale, unsigned char* out_hi, unsigned char* out_lo, float* out_f32,
+                      int n_seg, int flags) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    configured = true;
+  }
+  conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in_hi, in_lo, wtc, b, scale, out_hi,
+                                                                            out_lo, out_f32, n_seg, flags);
+}
+
+// Geometry of the plane pair that feeds conv layer `layer` (2..6): rows of the padded image per segment,
+// bytes per row, and the bytes of one plane for n_seg segments (tile over-read included).
+void split_geometry(int std_mode, int layer, int* H, int* W, int* C) {
+  static const int ha[7] = {0, 0, 24, 12, 12, 6, 6}, ca[7] = {0, 0, 16, 32, 64, 64, 64};
+  static const int wa[7] = {0, 0, 7, 5, 5, 3, 3}, ws[7] = {0, 0, 8, 4, 4, 2, 2};
+  *H = ha[layer]; *C = ca[layer]; *W = std_mode ? ws[layer] : wa[layer];
+}
+size_t split_plane_bytes(int std_mode, int layer, int n_seg) {
+  int H, W, C;
+  split_geometry(std_mode, layer, &H, &W, &C);
+  const size_t rows = (size_t)kSplitLead + (size_t)n_seg * (H + 1) * (W + 1) + 256 + 32;
+  return (rows * (size_t)C * 2 + 1023) & ~(size_t)1023;
+}
+
+// conv layer 2..6 on planes; the last layer (6) writes the fp32 CNN features (adapt: [seg][6][64];
+// standard: [seg][6][2][64])
+void launch_conv_split(cudaStream_t st, int std_mode, int layer, const void* in_hi, const void* in_lo,
+                       const void* wtc, const float* b, float out_scale, void* out_hi, void* out_lo,
+                       float* out_f32, int n_seg, int flags) {
+  const __half* w = reinterpret_cast<const __half*>(wtc);
+  const unsigned char* ih = static_cast<const unsigned char*>(in_hi);
+  const unsigned char* il = static_cast<const unsigned char*>(in_lo);
+  unsigned char* oh = static_cast<unsigned char*>(out_hi);
+  unsigned char* ol = static_cast<unsigned char*>(out_lo);
+  if (!std_mode) {
+    switch (layer) {
+      case 2: launch_sp<SpConv2A>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 3: launch_sp<SpConv3A>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 4: launch_sp<SpConv4A>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 5: launch_sp<SpConv5A>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      default: launch_sp<SpConv6A>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+    }
+  } else {
+    switch (layer) {
+      case 2: launch_sp<SpConv2S>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 3: launch_sp<SpConv3S>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 4: launch_sp<SpConv4S>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      case 5: launch_sp<SpConv5S>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+      default: launch_sp<SpConv6S>(st, ih, il, w, b, out_scale, oh, ol, out_f32, n_seg, flags); break;
+    }
+  }
+}
+
+void launch_unsplit(cudaStream_t st, int std_mode, int layer, const void* hi, const void* lo, float* out, int n_seg) {
+  int H, W, C;
+  split_geometry(std_mode, layer, &H, &W, &C);
+  const long long items = (long long)n_seg * H * W * (C / 8);
+  const unsigned char* h = static_cast<const unsigned char*>(hi);
+  const unsigned char* l = static_cast<const unsigned char*>(lo);
+  const int grid = (int)std::min<long long>((items + 255) / 256, 148 * 16);
+  if (C == 16) unsplit_kernel<32><<<grid, 256, 0, st>>>(h, l, out, items, H, W);
+  else if (C == 32) unsplit_kernel<64><<<grid, 256, 0, st>>>(h, l, out, items, H, W);
+  else unsplit_kernel<128><<<grid, 256, 0, st>>>(h, l, out, items, H, W);
+}
+
+#ifdef NISQA_TC_TIMING
+int sp_timing_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_sp_timing, sizeof(long long) * n);
+}
+#endif
+
+}  // namespace nisqa

@@ -27,101 +27,9 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace nisqa {
-
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 inputs, fp32 accumulate), one thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// two-term fp16 split of 8 consecutive channels -> two 16-byte core-matrix rows
-__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float x0 = fminf(x[2 * i], 60000.f), x1 = fminf(x[2 * i + 1], 60000.f);   // post-ReLU inputs (>= 0)
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// K-major, no swizzle: ((8,m),(8,2)):((16B,SBO),(2B,LBO)); version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-
-// K-major with hardware swizzle (rows of ROWB = 32 / 64 / 128 bytes, 8-row groups at SBO = 8 * ROWB):
-// layout type 6 / 4 / 2 = SWIZZLE_32B / 64B / 128B in bits 61..63; LBO is unused (K = 32 bytes
-// never leaves the swizzle atom).  The XOR is a function of the absolute shared-memory address, so
-// a start address shifted by whole rows (a tap) or by 32 bytes (a K-step) addresses the same tile.
-__device__ __forceinline__ uint64_t make_desc_swz(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | ((uint64_t)layout << 61);
-}
 
 #ifdef NISQA_TC_TIMING
 __device__ long long g_tc_timing[8 * 8192];
@@ -135,12 +43,8 @@ __device__ __forceinline__ void tc_stamp(int slot, int who) {
 // ------------------------------------------------------------------ configuration
 enum { TC_POOL_NONE = 0, TC_POOL_ADAPT = 1, TC_POOL_2X2 = 2 };
 
-template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, bool CENTER_ = false, bool SWZ_ = false>
+template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, bool CENTER_ = false>
 struct TcCfg {
-  static constexpr bool SWZ = SWZ_;               // activation tile row-major [row][CIN halves] with the
-                                                  // hardware 32/64/128-byte swizzle instead of K-planes
-  static constexpr int ROWB = CIN_ * 2;           // bytes per activation row (swizzled layout)
-  static constexpr uint32_t SWZ_LAYOUT = (ROWB == 128) ? 2u : (ROWB == 64 ? 4u : 6u);
   static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, POOL = POOL_, POW = POW_;
   static constexpr bool CENTER = CENTER_;         // conv6 of the AdaptCNN: kernel (3,3), padding (1,0) on a
                                                   // 3-wide map == the padded conv evaluated at column 1 only
@@ -148,9 +52,9 @@ struct TcCfg {
   static constexpr int BLK = (H + 1) * P;         // rows per segment: H interior rows + 1 shared zero row
   static constexpr int G = 256 / BLK;             // segments per CTA (2 M-tiles of 128 rows)
   static constexpr int HALO = P + 1;              // |row offset| of the farthest tap
-  static constexpr int AROWS = SWZ ? ((256 + 2 * HALO + 7) & ~7) : ((256 + 2 * HALO) | 1);   // odd: conflict-free staging stores
+  static constexpr int AROWS = ((256 + 2 * HALO) | 1);    // odd: conflict-free staging stores
   static constexpr int NCH = CIN / 8;             // 16-byte K chunks (8 halves)
-  static constexpr int A_BYTES = SWZ ? ((AROWS * ROWB + 1023) & ~1023) : NCH * AROWS * 16;        // per hi / lo
+  static constexpr int A_BYTES = NCH * AROWS * 16;        // per hi / lo
   static constexpr int B_HALF = NCH * COUT * 16;          // per hi / lo
   static constexpr int B_STAGE = 2 * B_HALF;
   static constexpr int NSTAGE = NSTAGE_;
@@ -161,7 +65,7 @@ struct TcCfg {
   static constexpr int OFF_A_LO = A_BYTES;
   static constexpr int OFF_B = 2 * A_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32 + (SWZ ? 1024 : 0);   // + slack to align the tile to 1024 B
+  static constexpr int SMEM_BYTES = OFF_BAR + 16 * NSTAGE + 32;
   static constexpr int MINB_SMEM = (SMEM_BYTES <= 56 * 1024) ? 4 : (SMEM_BYTES <= 74 * 1024) ? 3 : (SMEM_BYTES <= 112 * 1024 ? 2 : 1);
   static constexpr int MINB = (MINB_SMEM * TMEM_COLS <= 512) ? MINB_SMEM : 512 / TMEM_COLS;
   // D=f32, A=B=f16, both K-major, M=128; N = 2*COUT ([b_hi|b_lo]) and N = COUT (b_hi only)
@@ -170,7 +74,6 @@ struct TcCfg {
   static_assert(POOL == TC_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES + NSTAGE * B_STAGE,
                 "pool staging tile must fit in the A+B region");
   static_assert(A_BYTES % 16 == 0 && B_STAGE % 16 == 0 && CIN % 16 == 0 && COUT % 32 == 0, "shape");
-  static_assert(!SWZ || ROWB == 32 || ROWB == 64 || ROWB == 128, "swizzled rows are 32 / 64 / 128 bytes");
   static_assert(G >= 1 && MINB * TMEM_COLS <= 512, "tile / TMEM budget");
 };
 
@@ -182,9 +85,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
                float* __restrict__ out, int n_seg) {
   constexpr int H = C::H, W = C::W, CIN = C::CIN, COUT = C::COUT, P = C::P, BLK = C::BLK, G = C::G;
   constexpr int HALO = C::HALO, AROWS = C::AROWS, NCH = C::NCH, NS = C::NSTAGE;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* smem = smem_raw;
-  if constexpr (C::SWZ) smem += (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;     // swizzle atoms repeat every 1024 B
+  extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t a_hi = sbase + C::OFF_A_HI, a_lo = sbase + C::OFF_A_LO, b_base = sbase + C::OFF_B;
   const uint32_t bar_full = sbase + C::OFF_BAR;          // [NS]
@@ -232,12 +133,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
         va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; dst[u] = -1;
         if (it < ITEMS) {
           const int c8 = it % NCH, b = it / NCH;
-          if constexpr (C::SWZ) {
-            const int o = b * C::ROWB + c8 * 16;
-            dst[u] = (o ^ ((o >> 3) & (C::ROWB - 16))) >> 4;       // Swizzle<log2(ROWB/16), 4, 3>
-          } else {
-            dst[u] = c8 * AROWS + b;
-          }
+          dst[u] = c8 * AROWS + b;
           const int r = b - HALO;
           if (r >= 0 && r < G * BLK) {
             const int s = r / BLK, q = r - s * BLK;
@@ -287,24 +183,13 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
         const uint32_t bst = b_base + s * C::B_STAGE;       // [ci/8][2*COUT rows: hi then lo][8 halves]
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-#ifdef NISQA_TC_ALIGNHACK                     // timing experiment only (wrong results): 8-row aligned taps
-          const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff) & ~7u;
-#else
           const uint32_t row = (uint32_t)(HALO + mt * 128 + tapoff);
-#endif
           const uint32_t d = tmem + mt * (2 * COUT);
 #pragma unroll
           for (int ks = 0; ks < CIN / 16; ++ks) {
-            uint64_t dah, dal;
-            if constexpr (C::SWZ) {
-              const uint32_t aoff = row * C::ROWB + (uint32_t)ks * 32;
-              dah = make_desc_swz(a_hi + aoff, 8 * C::ROWB, C::SWZ_LAYOUT);
-              dal = make_desc_swz(a_lo + aoff, 8 * C::ROWB, C::SWZ_LAYOUT);
-            } else {
-              const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
-              dah = make_desc(a_hi + aoff, AROWS * 16, 128);
-              dal = make_desc(a_lo + aoff, AROWS * 16, 128);
-            }
+            const uint32_t aoff = ((uint32_t)(2 * ks) * AROWS + row) * 16;
+            const uint64_t dah = make_desc(a_hi + aoff, AROWS * 16, 128);
+            const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
             const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
             umma_f16(d, dah, db, C::IDESC_2N, (t | ks) != 0);     // [0,C) += hi*hi ; [C,2C) += hi*lo
             umma_f16(d, dal, db, C::IDESC_1N, 1);                 // [0,C) += lo*hi
@@ -394,15 +279,15 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
 #endif
 // layers 2..6; std_mode selects the StandardCNN geometry (W 8/4/2, MaxPool2d(2))
 //                      H   W  CIN COUT POOL           POW NSTAGE CENTER
-template <bool Z> using TcConv2A = TcCfg<24, 7, 16, 32, TC_POOL_ADAPT, 5, 9, false, Z>;
-template <bool Z> using TcConv3A = TcCfg<12, 5, 32, 64, TC_POOL_NONE, 0, NISQA_TC_NS3, false, Z>;
-template <bool Z> using TcConv4A = TcCfg<12, 5, 64, 64, TC_POOL_ADAPT, 3, NISQA_TC_NS4, false, Z>;
-template <bool Z> using TcConv5A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5, false, Z>;
-template <bool Z> using TcConv6A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5, true, Z>;
-template <bool Z> using TcConv2S = TcCfg<24, 8, 16, 32, TC_POOL_2X2, 4, 9, false, Z>;
-template <bool Z> using TcConv3S = TcCfg<12, 4, 32, 64, TC_POOL_NONE, 0, 4, false, Z>;
-template <bool Z> using TcConv4S = TcCfg<12, 4, 64, 64, TC_POOL_2X2, 2, 2, false, Z>;
-template <bool Z> using TcConv5S = TcCfg<6, 2, 64, 64, TC_POOL_NONE, 0, 2, false, Z>;
+using TcConv2A = TcCfg<24, 7, 16, 32, TC_POOL_ADAPT, 5, 9>;
+using TcConv3A = TcCfg<12, 5, 32, 64, TC_POOL_NONE, 0, NISQA_TC_NS3>;
+using TcConv4A = TcCfg<12, 5, 64, 64, TC_POOL_ADAPT, 3, NISQA_TC_NS4>;
+using TcConv5A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5>;
+using TcConv6A = TcCfg<6, 3, 64, 64, TC_POOL_NONE, 0, NISQA_TC_NS5, true>;
+using TcConv2S = TcCfg<24, 8, 16, 32, TC_POOL_2X2, 4, 9>;
+using TcConv3S = TcCfg<12, 4, 32, 64, TC_POOL_NONE, 0, 4>;
+using TcConv4S = TcCfg<12, 4, 64, 64, TC_POOL_2X2, 2, 2>;
+using TcConv5S = TcCfg<6, 2, 64, 64, TC_POOL_NONE, 0, 2>;
 
 template <class C>
 static void launch_tc(cudaStream_t st, const float* in, const __half* wtc, const float* b, float scale,
@@ -415,33 +300,25 @@ static void launch_tc(cudaStream_t st, const float* in, const __half* wtc, const
   conv_tc_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in, wtc, b, scale, out, n_seg);
 }
 
-template <bool Z>
-static void launch_conv_tc_z(cudaStream_t st, int std_mode, int layer, const float* in, const __half* w,
-                             const float* b, float out_scale, float* out, int n_seg) {
+void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, const void* wtc,
+                    const float* b, float out_scale, float* out, int n_seg) {
+  const __half* w = reinterpret_cast<const __half*>(wtc);
   if (!std_mode) {
     switch (layer) {
-      case 2: launch_tc<TcConv2A<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      case 3: launch_tc<TcConv3A<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      case 4: launch_tc<TcConv4A<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      case 5: launch_tc<TcConv5A<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      default: launch_tc<TcConv6A<Z>>(st, in, w, b, out_scale, out, n_seg); break;
+      case 2: launch_tc<TcConv2A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 3: launch_tc<TcConv3A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 4: launch_tc<TcConv4A>(st, in, w, b, out_scale, out, n_seg); break;
+      case 5: launch_tc<TcConv5A>(st, in, w, b, out_scale, out, n_seg); break;
+      default: launch_tc<TcConv6A>(st, in, w, b, out_scale, out, n_seg); break;
     }
   } else {
     switch (layer) {
-      case 2: launch_tc<TcConv2S<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      case 3: launch_tc<TcConv3S<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      case 4: launch_tc<TcConv4S<Z>>(st, in, w, b, out_scale, out, n_seg); break;
-      default: launch_tc<TcConv5S<Z>>(st, in, w, b, out_scale, out, n_seg); break;   // conv5 and conv6 share a geometry
+      case 2: launch_tc<TcConv2S>(st, in, w, b, out_scale, out, n_seg); break;
+      case 3: launch_tc<TcConv3S>(st, in, w, b, out_scale, out, n_seg); break;
+      case 4: launch_tc<TcConv4S>(st, in, w, b, out_scale, out, n_seg); break;
+      default: launch_tc<TcConv5S>(st, in, w, b, out_scale, out, n_seg); break;   // conv5 and conv6 share a geometry
     }
   }
-}
-
-// swz: activation tile in the hardware-swizzled row-major layout (1) or in K-planes without swizzle (0)
-void launch_conv_tc(cudaStream_t st, int std_mode, int layer, const float* in, const void* wtc,
-                    const float* b, float out_scale, float* out, int n_seg, int swz) {
-  const __half* w = reinterpret_cast<const __half*>(wtc);
-  if (swz) launch_conv_tc_z<true>(st, std_mode, layer, in, w, b, out_scale, out, n_seg);
-  else launch_conv_tc_z<false>(st, std_mode, layer, in, w, b, out_scale, out, n_seg);
 }
 
 #ifdef NISQA_TC_TIMING

@@ -29,13 +29,19 @@ void launch_seg_table(cudaStream_t, const ClipDesc*, int, const int*, const unsi
 void launch_mel_dump(cudaStream_t, const float*, const ClipDesc*, int, const unsigned*, float*);
 // cnn.cu
 void launch_conv1(cudaStream_t, int, const float*, const int*, const float*, const float*,
-                  const float*, float*, int);
+                  const float*, float*, int, void*, void*);
 void launch_conv_layer(cudaStream_t, int, int, const float*, const float*, const float*, float*, int);
 void launch_nhwc_to_nchw(cudaStream_t, const float*, float*, long long, int, int);
 // conv_tc.cu
-void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int, int);
+void launch_conv_tc(cudaStream_t, int, int, const float*, const void*, const float*, float, float*, int);
+// conv_split.cu
+size_t split_plane_bytes(int std_mode, int layer, int n_seg);
+void launch_conv_split(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
+                       void*, void*, float*, int, int);
+void launch_unsplit(cudaStream_t, int, int, const void*, const void*, float*, int);
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
+int sp_timing_read(long long*, int);
 #endif
 // td.cu
 struct SaLayerParams {
@@ -68,6 +74,14 @@ struct DevBuf {
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
+  }
+  // reserve; a (re)allocated buffer is zero-filled on `st` (fp16 plane pairs rely on never-written
+  // padding rows / columns being zero)
+  cudaError_t reserve_zeroed(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    cudaError_t e = reserve(bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(p, 0, cap, st);
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -119,7 +133,10 @@ constexpr int kStages = 6;     // staging slots / submissions in flight (uploads
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, logits, feats20, tdout, partial;
+  DevBuf planes[7];        // planes[l]: fp16 hi | lo plane pair feeding conv layer l (2..6), conv_split.cu
+  size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
   void release() {
+    for (auto& b : planes) b.release();
     DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
                      &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout, &partial};
     for (auto* b : all) b->release();
@@ -161,7 +178,9 @@ struct nisqa_engine {
   bool weights_loaded = false;
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
-  int tc_swz = 0;          // bit l set: conv layer l stages its activation tile in the swizzled row-major layout
+  int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
+  int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
+  bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
@@ -688,11 +707,20 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     const int FEAT = std_mode ? 768 : 384;
     CK(LN.mel.reserve((size_t)n_frames * kMels * 4));
     CK(LN.segtab.reserve((size_t)n_seg * 12));
-    CK(LN.act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
-    CK(LN.act2.reserve((size_t)n_seg * 12 * W2 * 32 * 4));
-    CK(LN.act3.reserve((size_t)n_seg * 12 * W2 * 64 * 4));
-    CK(LN.act4.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
-    CK(LN.act5.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    const bool split = e->conv_split && e->conv_tc == 0x7c;
+    e->last_split = split;
+    if (split) {
+      for (int l = 2; l <= 6; ++l) {
+        LN.plane_bytes[l] = split_plane_bytes(std_mode, l, n_seg);
+        CK(LN.planes[l].reserve_zeroed(2 * LN.plane_bytes[l], st));
+      }
+    } else {
+      CK(LN.act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
+      CK(LN.act2.reserve((size_t)n_seg * 12 * W2 * 32 * 4));
+      CK(LN.act3.reserve((size_t)n_seg * 12 * W2 * 64 * 4));
+      CK(LN.act4.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+      CK(LN.act5.reserve((size_t)n_seg * 6 * W3 * 64 * 4));
+    }
     CK(LN.feats.reserve((size_t)n_seg * FEAT * 4));
     int* seg_frame0 = LN.segtab.as<int>();
     float* seg_thr = reinterpret_cast<float*>(seg_frame0 + n_seg);
@@ -705,9 +733,12 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     { Scope s(e, "seg_table");
       launch_seg_table(st, d_clips, n, d_seg, d_clipmax, c.seg_hop, n_seg,
                        seg_frame0, seg_thr, seg_clip); }
+    auto plane_hi = [&](int l) { return LN.planes[l].as<char>(); };
+    auto plane_lo = [&](int l) { return LN.planes[l].as<char>() + LN.plane_bytes[l]; };
     { Scope s(e, "conv1");
       launch_conv1(st, std_mode, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
-                   W(e, "conv1.b"), LN.act1.as<float>(), n_seg); }
+                   W(e, "conv1.b"), split ? nullptr : LN.act1.as<float>(), n_seg,
+                   split ? plane_hi(2) : nullptr, split ? plane_lo(2) : nullptr); }
     {
       const float* cin_[7] = {nullptr, nullptr, LN.act1.as<float>(), LN.act2.as<float>(), LN.act3.as<float>(),
                               LN.act4.as<float>(), LN.act5.as<float>()};
@@ -718,8 +749,12 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
         snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
         Scope s(e, nm);
-        if (e->conv_tc & (1 << l))
-          launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg, (e->tc_swz >> l) & 1);
+        if (split)
+          launch_conv_split(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
+                            l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
+                            l == 6 ? LN.feats.as<float>() : nullptr, n_seg, e->tc_timing_layer == l ? 2 : 0);
+        else if (e->conv_tc & (1 << l))
+          launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg);
         else
           launch_conv_layer(st, std_mode, l, cin_[l], W(e, kw), W(e, kb), cout_[l], n_seg);
       }
@@ -1016,6 +1051,17 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   }
   if (ch > 0) count = ns * hw * ch;
   if (!out) return count;
+  int plane_layer = 0;          // stage lives in the plane pair feeding this conv layer
+  if (e->last_split) {
+    switch (stage) {
+      case NISQA_STAGE_POOL1: plane_layer = 2; break;
+      case NISQA_STAGE_POOL2: plane_layer = 3; break;
+      case NISQA_STAGE_CONV3: plane_layer = 4; break;
+      case NISQA_STAGE_POOL3: plane_layer = 5; break;
+      case NISQA_STAGE_CONV5: plane_layer = 6; break;
+      default: break;
+    }
+  }
   if (cap < count) return fail(e, NISQA_ERR_INVALID, "stage dump buffer too small");
   if (count == 0) return 0;
   cudaStream_t st = LN.stream;
@@ -1025,6 +1071,13 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
                     SG.clipmax.as<unsigned>(), e->dump.as<float>());
     src = e->dump.as<float>();
   } else if (ch > 0) {
+    if (plane_layer) {
+      DevBuf* tmp[7] = {nullptr, nullptr, &LN.act1, &LN.act2, &LN.act3, &LN.act4, &LN.act5};
+      CK(tmp[plane_layer]->reserve((size_t)count * 4));
+      launch_unsplit(st, std_mode, plane_layer, LN.planes[plane_layer].as<char>(),
+                     LN.planes[plane_layer].as<char>() + LN.plane_bytes[plane_layer], tmp[plane_layer]->as<float>(), (int)ns);
+      src = tmp[plane_layer]->as<float>();
+    }
     CK(e->dump.reserve((size_t)count * 4));
     launch_nhwc_to_nchw(st, src, e->dump.as<float>(), ns, hw, ch);
     src = e->dump.as<float>();
@@ -1076,7 +1129,8 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
-  if (strcmp(name, "tc_swz") == 0) { e->tc_swz = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
+  if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
+  if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }
 
@@ -1207,5 +1261,8 @@ int nisqa_gather_nccl(nisqa_engine* e, void* nccl_comm, const float* local_dev, 
 #ifdef NISQA_TC_TIMING
 extern "C" __attribute__((visibility("default"))) int nisqa_debug_tc_timing(long long* host, int n) {
   return nisqa::tc_timing_read(host, n);
+}
+extern "C" __attribute__((visibility("default"))) int nisqa_debug_sp_timing(long long* host, int n) {
+  return nisqa::sp_timing_read(host, n);
 }
 #endif

@@ -1,0 +1,10 @@
+#!/bin/bash
+# builds the experiment variants of the library (run here; the .so files travel with gpurun)
+set -e
+cd "$(dirname "$0")/.."
+F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --shared"
+S="nisqa_b200/csrc/engine.cu nisqa_b200/csrc/frontend.cu nisqa_b200/csrc/cnn.cu nisqa_b200/csrc/conv_tc.cu nisqa_b200/csrc/conv_split.cu nisqa_b200/csrc/td.cu nisqa_b200/csrc/wavio.cpp"
+mkdir -p nisqa_b200/exp
+nvcc $F -DNISQA_TC_TIMING $S -o nisqa_b200/exp/libnisqa_timing.so -ldl &
+wait
+ls -la nisqa_b200/exp
