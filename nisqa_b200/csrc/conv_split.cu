@@ -18,7 +18,7 @@
 // with conv_tc.cu (fp32 channels-last activations, register staging + split in every consumer) the
 // fill phase of a CTA drops from ~9 k cycles of LDG -> split -> STS to one asynchronous copy, the 9
 // taps are the same tile addressed through row-shifted descriptors as before, and max-pooling runs
-// on all 192 threads of the CTA.
+// on every thread of the CTA, and 8 epilogue warps (one per TMEM lane quarter and M-tile) drain the accumulators.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -46,8 +46,12 @@ __device__ __forceinline__ size_t split_off(int g, int c) {
   return o ^ ((o >> 3) & (size_t)(ROWB - 16));
 }
 
-template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, bool F32OUT_ = false, bool CENTER_ = false>
+template <int H_, int W_, int CIN_, int COUT_, int POOL_, int POW_, int NSTAGE_, int EPW_, bool F32OUT_ = false, bool CENTER_ = false>
 struct SpCfg {
+  static constexpr int EPW = EPW_;                // epilogue warps: 4 (each owns both M-tiles of its TMEM lane quarter)
+                                                  // or 8 (warp w: lane quarter w & 3, M-tile w >> 2)
+  static constexpr int NT = (EPW + 2) * 32;       // + MMA issuer warp + producer warp
+  static_assert(EPW_ == 4 || EPW_ == 8, "epilogue warps");
   static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, POOL = POOL_, POW = POW_;
   static constexpr bool CENTER = CENTER_;         // conv6 of the AdaptCNN: kernel (3,3), padding (1,0) on a
                                                   // 3-wide map == the padded conv evaluated at column 1 only
@@ -82,6 +86,10 @@ struct SpCfg {
   static constexpr uint32_t IDESC_1N = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(POOL == SP_POOL_NONE || G * H * W * STG_STRIDE * 4 <= 2 * A_BYTES + NSTAGE * B_STAGE,
                 "pool staging tile must fit in the A+B region");
+  // un-pooled layers stage their output in shared memory as the exact HBM image of the CTA's segments
+  // (plane rows incl. the zero row / column, or the fp32 feature rows) and write it with bulk stores
+  static constexpr int IMG_BYTES = OUT_SPLIT ? G * OBLK * OROWB : G * HO * WO * COUT * 4;
+  static_assert(POOL != SP_POOL_NONE || (OUT_SPLIT ? 2 : 1) * IMG_BYTES <= OFF_BAR, "output image must fit in the A+B region");
   static_assert(B_STAGE % 16 == 0 && CIN % 16 == 0 && COUT % 32 == 0, "shape");
   static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "rows are 32 / 64 / 128 bytes (one swizzle atom)");
   static_assert(HALO <= kSplitLead, "kSplitLead");
@@ -91,14 +99,14 @@ struct SpCfg {
 };
 
 template <class C>
-__global__ void __launch_bounds__(192, C::MINB)
+__global__ void __launch_bounds__(C::NT, C::MINB)
 conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* __restrict__ in_lo,
                   const __half* __restrict__ wtc /*[9][CIN/8][hi co | lo co][8] fp16, scaled by 2^S*/,
                   const float* __restrict__ bias, float out_scale /*2^-S*/,
                   unsigned char* __restrict__ out_hi, unsigned char* __restrict__ out_lo,
                   float* __restrict__ out_f32 /*last layer only*/, int n_seg, int flags) {
   constexpr int H = C::H, W = C::W, CIN = C::CIN, COUT = C::COUT, P = C::P, BLK = C::BLK, G = C::G;
-  constexpr int HALO = C::HALO, NS = C::NSTAGE, ROWB = C::ROWB;
+  constexpr int HALO = C::HALO, NS = C::NSTAGE, ROWB = C::ROWB, EPW = C::EPW, MMA_TID = C::EPW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms repeat every 1024 B
   const uint32_t sbase = smem_u32(smem);
@@ -128,7 +136,7 @@ conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* 
   const uint32_t tmem = *tmem_slot;
   sp_stamp(1, 0, flags);
 
-  if (warp == 5) {
+  if (warp == EPW + 1) {
     // ===== producer (one lane): the activation tile (2 copies), then the weights tap by tap =====
     if (lane == 0) {
       constexpr uint32_t A_COPY = (uint32_t)C::AROWS * ROWB;
@@ -142,15 +150,15 @@ conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* 
         bulk_g2s(b_base + s * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_full + 8 * s);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == EPW) {
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       mbar_wait(bar_a, 0);
-      sp_stamp(2, 128, flags);
+      sp_stamp(2, MMA_TID, flags);
       for (int t = 0; t < 9; ++t) {
         const int s = t % NS;
         mbar_wait(bar_full + 8 * s, (t / NS) & 1);
-        if (t == 0) sp_stamp(6, 128, flags);
+        if (t == 0) sp_stamp(6, MMA_TID, flags);
         tc_fence_after();
         const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
         const uint32_t bst = b_base + s * C::B_STAGE;       // [ci/8][2*COUT rows: hi then lo][8 halves]
@@ -171,66 +179,103 @@ conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* 
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
       }
       umma_commit(bar_acc);                      // all accumulators final
-      sp_stamp(7, 128, flags);
+      sp_stamp(7, MMA_TID, flags);
     }
   } else {
-    // ===== epilogue part 1: warps 0..3 <-> TMEM lanes 32w..32w+31 =====
+    // ===== epilogue part 1: warp w reads TMEM lanes 32 (w & 3) .. +31 (its M-tile(s)) =====
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     sp_stamp(3, 0, flags);
     float* stg = reinterpret_cast<float*>(smem);          // reuses the A/B region (all MMAs retired)
+    const int quarter = warp & 3;
+    const int mt_begin = (EPW == 8) ? (warp >> 2) : 0, mt_end = (EPW == 8) ? (warp >> 2) + 1 : 2;
 #pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
-      const int r = mt * 128 + warp * 32 + lane;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      const int r = mt * 128 + quarter * 32 + lane;
       const int s = r / BLK, q = r - s * BLK;
       const int hh = q / P, ww = q - hh * P;
-      bool valid = (s < G) && hh >= 1 && ww >= 1 && (seg0 + s < n_seg);
+      const bool live = (s < G) && (seg0 + s < n_seg);          // this TMEM row maps to a plane row that is stored
+      bool valid = live && hh >= 1 && ww >= 1;                  // ... and to an interior position
       if (C::CENTER) valid = valid && (ww == 2);
+      const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + mt * (2 * COUT);
 #pragma unroll 1
-      for (int part = 0; part < COUT / 32; ++part) {
-        float v[32], v2[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + part * 32, v);
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * (2 * COUT) + COUT + part * 32, v2);
-        if (valid) {
+      for (int c16 = 0; c16 < COUT / 16; ++c16) {          // 16 output channels per step
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(trow + c16 * 16, ra);             // hi*hi + lo*hi
+        tmem_ld16_nowait(trow + COUT + c16 * 16, rb);      // hi*lo
+        tmem_ld_wait();
+        float v[16];
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c16 * 16);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaxf(fmaf(v[j] + v2[j], out_scale, __ldg(bias + part * 32 + j)), 0.f);
-          if constexpr (C::POOL != SP_POOL_NONE) {
-            float4* dst = reinterpret_cast<float4*>(stg + ((s * H + (hh - 1)) * W + (ww - 1)) * C::STG_STRIDE + part * 32);
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(ra[4 * j + 0]) + __uint_as_float(rb[4 * j + 0]), out_scale, bb.x), 0.f);
+          v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(ra[4 * j + 1]) + __uint_as_float(rb[4 * j + 1]), out_scale, bb.y), 0.f);
+          v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(ra[4 * j + 2]) + __uint_as_float(rb[4 * j + 2]), out_scale, bb.z), 0.f);
+          v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(ra[4 * j + 3]) + __uint_as_float(rb[4 * j + 3]), out_scale, bb.w), 0.f);
+        }
+        if constexpr (C::POOL != SP_POOL_NONE) {
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(stg + ((s * H + (hh - 1)) * W + (ww - 1)) * C::STG_STRIDE + c16 * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else if constexpr (C::OUT_SPLIT) {
-            const int g = kSplitLead + (seg0 + s) * C::OBLK + hh * C::OP + ww;     // same padded geometry as the input
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else if constexpr (C::OUT_SPLIT) {
+          // image row r <-> plane row g = g_out0 + r (same padded geometry as the input); the zero row /
+          // column positions are written as zeros, so the whole image goes out as one contiguous block
+          if (live) {
+            const int g = kSplitLead + seg0 * BLK + r;
+            const size_t img0 = (size_t)(kSplitLead + seg0 * BLK) * C::OROWB;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 hi, lo;
-              split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-                     make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-              const size_t o = split_off<C::OROWB>(g, part * 4 + j);
-              *reinterpret_cast<uint4*>(out_hi + o) = hi;
-              *reinterpret_cast<uint4*>(out_lo + o) = lo;
+            for (int j = 0; j < 2; ++j) {
+              uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+              if (valid)
+                split8(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                       make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+              const uint32_t o = (uint32_t)(split_off<C::OROWB>(g, c16 * 2 + j) - img0);
+              *reinterpret_cast<uint4*>(smem + o) = hi;
+              *reinterpret_cast<uint4*>(smem + C::IMG_BYTES + o) = lo;
             }
-          } else {
-            constexpr int WOUT = C::CENTER ? 1 : W;
+          }
+        } else {
+          if (valid) {
             const int w = C::CENTER ? 0 : ww - 1;
-            float4* dst = reinterpret_cast<float4*>(out_f32 + (((size_t)(seg0 + s) * H + (hh - 1)) * WOUT + w) * COUT + part * 32);
+            float4* dst = reinterpret_cast<float4*>(stg + ((s * H + (hh - 1)) * C::WO + w) * COUT + c16 * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
       }
     }
+    if constexpr (C::POOL == SP_POOL_NONE) fence_proxy_async();     // staged image -> visible to the bulk store
   }
   sp_stamp(4, 0, flags);
   tc_fence_before();
   __syncthreads();                     // accumulators read, staging tile complete; every role is done
   if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
 
+  if constexpr (C::POOL == SP_POOL_NONE) {
+    // ===== epilogue part 2: one thread writes the staged image with bulk stores =====
+    if (tid == 32) {
+      const int nvalid = min(G, n_seg - seg0);
+      if constexpr (C::OUT_SPLIT) {
+        const size_t img0 = (size_t)(kSplitLead + seg0 * BLK) * C::OROWB;
+        const uint32_t bytes = (uint32_t)nvalid * C::OBLK * C::OROWB;
+        bulk_s2g(out_hi + img0, sbase, bytes);
+        bulk_s2g(out_lo + img0, sbase + C::IMG_BYTES, bytes);
+      } else {
+        const uint32_t per_seg = C::HO * C::WO * COUT * 4;
+        bulk_s2g(out_f32 + (size_t)seg0 * (per_seg / 4), sbase, (uint32_t)nvalid * per_seg);
+      }
+      bulk_commit();
+      bulk_wait_read0();               // shared memory must outlive the reads of the bulk stores
+    }
+  }
   if constexpr (C::POOL != SP_POOL_NONE) {
-    // ===== epilogue part 2 (all 192 threads): max-pool the staged tile, split, store =====
+    // ===== epilogue part 2 (all threads): max-pool the staged tile, split, store =====
     const float* stg = reinterpret_cast<const float*>(smem);
     constexpr int POW = C::POW, HO = H / 2, C8 = COUT / 8;
-    for (int it = tid; it < G * HO * POW * C8; it += 192) {
+    for (int it = tid; it < G * HO * POW * C8; it += C::NT) {
       const int c8 = it % C8;
       int rest = it / C8;
       const int pw = rest % POW; rest /= POW;
@@ -298,17 +343,20 @@ __global__ void unsplit_kernel(const unsigned char* __restrict__ hi, const unsig
 #define NISQA_SP_NS3 4
 #endif
 // layers 2..6; std_mode selects the StandardCNN geometry (W 8/4/2, MaxPool2d(2))
-//                     H   W  CIN COUT POOL           POW NSTAGE F32OUT CENTER
-using SpConv2A = SpCfg<24, 7, 16, 32, SP_POOL_ADAPT, 5, 9>;
-using SpConv3A = SpCfg<12, 5, 32, 64, SP_POOL_NONE, 0, NISQA_SP_NS3>;
-using SpConv4A = SpCfg<12, 5, 64, 64, SP_POOL_ADAPT, 3, NISQA_SP_NS4>;
-using SpConv5A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5>;
-using SpConv6A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5, true, true>;
-using SpConv2S = SpCfg<24, 8, 16, 32, SP_POOL_2X2, 4, 9>;
-using SpConv3S = SpCfg<12, 4, 32, 64, SP_POOL_NONE, 0, 4>;
-using SpConv4S = SpCfg<12, 4, 64, 64, SP_POOL_2X2, 2, 2>;
-using SpConv5S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2>;
-using SpConv6S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2, true>;
+#ifndef NISQA_SP_EPW
+#define NISQA_SP_EPW 8
+#endif
+//                     H   W  CIN COUT POOL           POW NSTAGE        EPW          F32OUT CENTER
+using SpConv2A = SpCfg<24, 7, 16, 32, SP_POOL_ADAPT, 5, 9, 4>;          // 4 CTAs / SM: registers only allow 6 warps
+using SpConv3A = SpCfg<12, 5, 32, 64, SP_POOL_NONE, 0, NISQA_SP_NS3, NISQA_SP_EPW>;
+using SpConv4A = SpCfg<12, 5, 64, 64, SP_POOL_ADAPT, 3, NISQA_SP_NS4, NISQA_SP_EPW>;
+using SpConv5A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5, NISQA_SP_EPW>;
+using SpConv6A = SpCfg<6, 3, 64, 64, SP_POOL_NONE, 0, NISQA_SP_NS5, NISQA_SP_EPW, true, true>;
+using SpConv2S = SpCfg<24, 8, 16, 32, SP_POOL_2X2, 4, 9, 4>;
+using SpConv3S = SpCfg<12, 4, 32, 64, SP_POOL_NONE, 0, 4, NISQA_SP_EPW>;
+using SpConv4S = SpCfg<12, 4, 64, 64, SP_POOL_2X2, 2, 2, NISQA_SP_EPW>;
+using SpConv5S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2, NISQA_SP_EPW>;
+using SpConv6S = SpCfg<6, 2, 64, 64, SP_POOL_NONE, 0, 2, NISQA_SP_EPW, true>;
 
 template <class C>
 static void launch_sp(cudaStream_t st, const unsigned char* in_hi, const unsigned char* in_lo, const __half* wtc,
@@ -319,7 +367,7 @@ static void launch_sp(cudaStream_t st, const unsigned char* in_hi, const unsigne
     cudaFuncSetAttribute(conv_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     configured = true;
   }
-  conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in_hi, in_lo, wtc, b, scale, out_hi,
+  conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, C::NT, C::SMEM_BYTES, st>>>(in_hi, in_lo, wtc, b, scale, out_hi,
                                                                             out_lo, out_f32, n_seg, flags);
 }
 

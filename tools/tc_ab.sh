@@ -1,8 +1,7 @@
 #!/bin/bash
-# GPU-box A/B driver; the timing build is prebuilt by tools/tc_ab_build.sh (nisqa_b200/exp/*.so)
+# GPU-box A/B driver; the variant builds are prebuilt by tools/tc_ab_build.sh (nisqa_b200/exp/*.so)
 cd "$(dirname "$0")/.."
 run() { timeout "$1" python tools/tc_ab.py "${@:2}" > /tmp/ab.log 2>&1; rc=$?; grep -v Warning /tmp/ab.log | tail -14; echo "rc=$rc"; return $rc; }
 python -c "import torch" 2>/dev/null     # page the image in outside the timeouts
 run 200 --split 1 --tag split || { echo "split variant failed - stopping"; exit 0; }
-run 150 --split 0 --skip-check --tag legacy
 run 150 --lib nisqa_b200/exp/libnisqa_timing.so --timing --skip-check --split 1 --tag T_split
