@@ -39,6 +39,7 @@ __device__ __forceinline__ void sp_stamp(int slot, int who, int flags) {
 
 enum { SP_POOL_NONE = 0, SP_POOL_ADAPT = 1, SP_POOL_2X2 = 2 };
 
+
 // byte offset of chunk c (8 halves) of plane row g, rows of ROWB bytes: Swizzle<log2(ROWB/16), 4, 3>
 template <int ROWB>
 __device__ __forceinline__ size_t split_off(int g, int c) {
@@ -367,8 +368,8 @@ static void launch_sp(cudaStream_t st, const unsigned char* in_hi, const unsigne
     cudaFuncSetAttribute(conv_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     configured = true;
   }
-  conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, C::NT, C::SMEM_BYTES, st>>>(in_hi, in_lo, wtc, b, scale, out_hi,
-                                                                            out_lo, out_f32, n_seg, flags);
+  conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, C::NT, C::SMEM_BYTES, st>>>(
+      in_hi, in_lo, wtc, b, scale, out_hi, out_lo, out_f32, n_seg, flags);
 }
 
 // Geometry of the plane pair that feeds conv layer `layer` (2..6): rows of the padded image per segment,

@@ -180,6 +180,42 @@ def test_full_size_properties_config2(engines):
     assert np.all(np.isfinite(s1)) and s1.min() > 0.0 and s1.max() < 6.0
 
 
+@pytest.mark.parametrize("ckpt,clips", [
+    ("nisqa.tar", [(31, 10.0, 48000), (32, 2.3, 48000), (33, 4.0, 16000), (34, 0.1875, 8000)]),
+    ("nisqa_tts.tar", [(35, 3.0, 16000), (36, 1.1, 48000)]),
+])
+def test_conv_paths_agree(engines, ckpt, clips):
+    """The three conv2..conv6 implementations behind nisqa_set_option: fp16-plane tcgen05 pipeline
+    (default, conv_split.cu), fp32-activation tcgen05 kernels (conv_tc.cu) and fp32 FFMA (cnn.cu).
+    Both tcgen05 paths do the same split and issue the same MMAs in the same order, so their scores and
+    features are BIT-identical; the FFMA path agrees to fp32 rounding noise; growing / shrinking batches
+    reuse the zero-padded planes (stale rows of earlier, larger passes must not leak)."""
+    eng, args, sd = engines[ckpt]
+    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
+    srs = [c[2] for c in clips]
+    out = {}
+    try:
+        for name, opts in (("planes", dict(conv_tc=1, conv_split=1)), ("tc_f32", dict(conv_tc=1, conv_split=0)),
+                           ("ffma", dict(conv_tc=0, conv_split=0))):
+            for k, v in opts.items():
+                eng.set_option(k, v)
+            sc, nseg, st = eng.predict_pcm(pcm, srs)
+            out[name] = (sc.copy(), eng.stage_dump(E.STAGE_CNN_FEAT), eng.stage_dump(E.STAGE_POOL3))
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
+        np.testing.assert_array_equal(out["planes"][0], out["tc_f32"][0])
+        np.testing.assert_array_equal(out["planes"][1], out["tc_f32"][1])
+        assert np.abs(out["planes"][2] - out["tc_f32"][2]).max() <= 1e-5      # planes dump = hi + lo (2^-22 relative)
+        assert np.abs(out["planes"][0] - out["ffma"][0]).max() <= SCORE_TOL / 4
+        assert np.abs(out["planes"][1] - out["ffma"][1]).max() <= ACT_TOL
+        # shrink, then grow again: same rows as in the first call
+        s_small, _, _ = eng.predict_pcm(pcm[1:2], srs[1:2])
+        np.testing.assert_array_equal(s_small[0], out["planes"][0][1])
+        s_again, _, _ = eng.predict_pcm(pcm[::-1], srs[::-1])
+        np.testing.assert_array_equal(s_again[::-1], out["planes"][0])
+    finally:
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
+
+
 def test_device_resident_entry_point_equals_host_entry_point(engines):
     import torch
     eng, args, sd = engines["nisqa.tar"]

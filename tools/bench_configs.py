@@ -35,6 +35,7 @@ def run(name, ckpt, durations, sr, steps=8, check=3):
     e0.record(stream)
     for _ in range(steps):
         nseg, status = eng.predict_pcm_device(d_pcm.data_ptr(), offs, ns, srs, E.FMT_S16, out.data_ptr(), sync=False)
+    eng.join()                 # lane 0 waits for the other compute lanes: e1 covers all of them
     e1.record(stream); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     got = out.cpu().numpy()

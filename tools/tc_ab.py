@@ -72,25 +72,29 @@ def step(i, sync=False):
     eng.predict_pcm_device(pcm[i % 4].data_ptr(), offs, ns, srs, E.FMT_S16, out.data_ptr(), sync=sync)
 
 
-t0 = time.time(); i = 0
-while time.time() - t0 < 1.5:
-    step(i); i += 1
-torch.cuda.synchronize()
-K = 150
-t0 = time.perf_counter()
-for i in range(K):
-    step(i)
-eng.join(); torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-eng.set_profiling(True)
-names = ["frontend", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "lin_ln", "qkv", "sa_layer", "pool"]
-acc = dict((k, 0.0) for k in names)
-for i in range(5):
-    step(i, sync=True)
-    for k in names:
-        acc[k] += max(eng.group_ms(k), 0.0) / 5
-eng.set_profiling(False)
-print("[%s] %.0f clips/s (%.3f ms/step)  kernels ms: %s" % (tag, K * BS / dt, dt / K * 1e3, "  ".join("%s %.3f" % (k, acc[k]) for k in names)), flush=True)
+def measure(tag):
+    t0 = time.time(); i = 0
+    while time.time() - t0 < 1.0:
+        step(i); i += 1
+    torch.cuda.synchronize()
+    K = 150
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(i)
+    eng.join(); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    eng.set_profiling(True)
+    names = ["frontend", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "lin_ln", "qkv", "sa_layer", "pool"]
+    acc = dict((k, 0.0) for k in names)
+    for i in range(5):
+        step(i, sync=True)
+        for k in names:
+            acc[k] += max(eng.group_ms(k), 0.0) / 5
+    eng.set_profiling(False)
+    print("[%s] %.0f clips/s (%.3f ms/step)  kernels ms: %s" % (tag, K * BS / dt, dt / K * 1e3, "  ".join("%s %.3f" % (k, acc[k]) for k in names)), flush=True)
+
+
+measure(tag)
 
 if a.timing:
     lib = E.load_library()
