@@ -198,9 +198,13 @@ NISQA_API int     nisqa_join(nisqa_engine* e);
  * with CUDA events on the engine stream when profiling was enabled; <0 if unknown.
  * groups: "frontend", "cnn", "td", "pool" */
 NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
-/* kernel-variant switches for A/B measurements: "conv_tc" = bit mask of the conv layers (2..6) that
- * run as tcgen05 implicit GEMMs with the fp16 two-term split (default / 1 = all of them); a cleared
- * bit selects the fp32 FFMA kernel of that layer. */
+/* kernel-variant switches for A/B measurements and the parity tests:
+ *   "conv_tc"    bit mask of the conv layers (2..6) that run as tcgen05 implicit GEMMs with the fp16
+ *                two-term split (default / 1 = all of them); a cleared bit selects the fp32 FFMA kernel.
+ *   "conv_split" 1 (default): with all of conv2..6 on tcgen05, activations travel between the layers as
+ *                fp16 hi/lo plane pairs (csrc/conv_split.cu); 0: fp32 channels-last activations and the
+ *                register-staged kernels of csrc/conv_tc.cu.  Results are bit-identical.
+ *   "fe_ppc"     frame pairs per front-end CTA (0 = kernel default). */
 NISQA_API int    nisqa_set_option(nisqa_engine* e, const char* name, int value);
 NISQA_API double nisqa_group_ms(const nisqa_engine* e, const char* group);
 

@@ -4,8 +4,9 @@ dict, the same ``predict()`` surface (prints, ``NISQA_results.csv``, returned Da
 same precedence of checkpoint args vs. CLI args, but with the torch modules replaced by
 :class:`nisqa_b200.engine.Engine`.
 
-Out of scope here: ``train()``, ``evaluate()``, ``mode == 'main'`` and
-double-ended models raise ``NotImplementedError``.  There is no CPU device: ``tr_device='cpu'``
+``evaluate()`` (reference model:48-52, 572-715) prints the reference's per-database statistics of the last
+``predict()`` from :mod:`nisqa_b200.evaluate`.  Out of scope here:
+``train()``, ``mode == 'main'`` and double-ended models raise ``NotImplementedError``.  There is no CPU device: ``tr_device='cpu'``
 or a machine without CUDA raises.
 """
 import datetime
@@ -19,6 +20,7 @@ pd.options.mode.chained_assignment = None
 import torch
 
 from . import NISQA_lib as NL
+from . import evaluate as EV
 from . import dist as nb_dist
 from .engine import Engine, config_from_args
 
@@ -40,8 +42,39 @@ class nisqaModel(object):
     def train(self):
         raise NotImplementedError("training is outside the B200 predict path (SURVEY.md section 2, #15)")
 
+    # ------------------------------------------------------------------ evaluate (model:48-52, 572-715)
     def evaluate(self, mapping="first_order", do_print=True, do_plot=False):
-        raise NotImplementedError("evaluation statistics are outside the B200 predict path (SURVEY.md 8f.3)")
+        """Statistics of the predictions against the labels in the csv tables.  For dimension models one
+        block per predicted dimension (db_results_val_<dim>, keys of ``self.r`` suffixed like the
+        reference), for MOS-only models ``self.db_results`` / ``self.r``."""
+        if nb_dist.env_world()[0] != 0:
+            return
+        con = self.ds_val.df_con is not None
+
+        def block(title, target):
+            print("--> %s:" % title)
+            db_results, r = EV.eval_results(
+                self.ds_val.df, dcon=self.ds_val.df_con, target_mos=target, target_ci=target + "_ci",
+                pred=target + "_pred", mapping=mapping, do_print=do_print, do_plot=do_plot)
+            if not con:
+                print("r_p_mean_file: {:0.2f}, rmse_mean_file: {:0.2f}".format(r["r_p_mean_file"], r["rmse_mean_file"]))
+            elif target == "noi":          # the reference prints two of the three numbers for this block (model:636)
+                print("r_p_mean_con: {:0.2f}, rmse_mean_con: {:0.2f}".format(r["r_p_mean_con"], r["rmse_mean_con"]))
+            else:
+                print("r_p_mean_con: {:0.2f}, rmse_mean_con: {:0.2f}, rmse_star_map_mean_con: {:0.2f}".format(
+                    r["r_p_mean_con"], r["rmse_mean_con"], r["rmse_star_map_mean_con"]))
+            return db_results, r
+
+        if self.args["dim"] != True:  # noqa: E712
+            self.db_results, self.r = block("MOS", "mos")
+            return
+        self.r = {}
+        for target in ("mos", "noi", "dis", "col", "loud"):
+            db_results, r = block(target.upper(), target)
+            setattr(self, "db_results_val_" + target, db_results)
+            self.r.update(r if target == "mos" else {k + "_" + target: v for k, v in r.items()})
+        r_mean = 1 / 5 * sum(self.r["r_p_mean_con" + sfx] for sfx in ("", "_noi", "_col", "_dis", "_loud"))
+        print("\nAverage over MOS and dimensions: r_p={:0.3f}".format(r_mean))
 
     # ------------------------------------------------------------------ predict (model:54-81)
     def predict(self):
