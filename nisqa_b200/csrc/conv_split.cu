@@ -26,6 +26,10 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef NISQA_SP_INTERLEAVE
+#define NISQA_SP_INTERLEAVE 1      // MMA issue order: alternate the two M-tile accumulators (0: tile after tile)
+#endif
+
 namespace nisqa {
 
 #ifdef NISQA_TC_TIMING
@@ -163,6 +167,22 @@ conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* 
         tc_fence_after();
         const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
         const uint32_t bst = b_base + s * C::B_STAGE;       // [ci/8][2*COUT rows: hi then lo][8 halves]
+#if NISQA_SP_INTERLEAVE
+        // Consecutive MMAs alternate between the two M-tiles: an MMA that accumulates into the tile the
+        // previous one wrote waits for it (the tensor pipe was 39 % busy = exactly the useful math while the
+        // MMA phases covered more than half of the time), so the two independent accumulators are interleaved
+        // (hi 0, hi 1, lo 0, lo 1 per K-step).  Per accumulator the order of additions is unchanged.
+        const uint32_t row0 = sh + (uint32_t)(HALO + tapoff);
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks) {
+          const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
+          const uint32_t aoff0 = row0 * ROWB + (uint32_t)ks * 32, aoff1 = aoff0 + 128u * ROWB;
+          umma_f16(tmem, make_desc_swz(a_hi + aoff0, 8 * ROWB, C::LAYOUT), db, C::IDESC_2N, (t | ks) != 0);   // tile 0: [0,C) += hi*hi ; [C,2C) += hi*lo
+          umma_f16(tmem + 2 * COUT, make_desc_swz(a_hi + aoff1, 8 * ROWB, C::LAYOUT), db, C::IDESC_2N, (t | ks) != 0);   // tile 1
+          umma_f16(tmem, make_desc_swz(a_lo + aoff0, 8 * ROWB, C::LAYOUT), db, C::IDESC_1N, 1);               // tile 0: [0,C) += lo*hi
+          umma_f16(tmem + 2 * COUT, make_desc_swz(a_lo + aoff1, 8 * ROWB, C::LAYOUT), db, C::IDESC_1N, 1);    // tile 1
+        }
+#else   // A/B: one M-tile after the other (every MMA depends on its predecessor)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const uint32_t row = sh + (uint32_t)(HALO + mt * 128 + tapoff);
@@ -170,13 +190,12 @@ conv_split_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* 
 #pragma unroll
           for (int ks = 0; ks < CIN / 16; ++ks) {
             const uint32_t aoff = row * ROWB + (uint32_t)ks * 32;
-            const uint64_t dah = make_desc_swz(a_hi + aoff, 8 * ROWB, C::LAYOUT);
-            const uint64_t dal = make_desc_swz(a_lo + aoff, 8 * ROWB, C::LAYOUT);
             const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
-            umma_f16(d, dah, db, C::IDESC_2N, (t | ks) != 0);     // [0,C) += hi*hi ; [C,2C) += hi*lo
-            umma_f16(d, dal, db, C::IDESC_1N, 1);                 // [0,C) += lo*hi
+            umma_f16(d, make_desc_swz(a_hi + aoff, 8 * ROWB, C::LAYOUT), db, C::IDESC_2N, (t | ks) != 0);
+            umma_f16(d, make_desc_swz(a_lo + aoff, 8 * ROWB, C::LAYOUT), db, C::IDESC_1N, 1);
           }
         }
+#endif
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire
       }
       umma_commit(bar_acc);                      // all accumulators final
