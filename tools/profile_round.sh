@@ -40,6 +40,6 @@ echo "bench exit $?"; cut -c1-300 $OUT/${TAG}_bench_n1.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 15 -c 30 --csv \
     --log-file $OUT/${TAG}_launches_bench_steps2.csv $BENCH_PROF > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-timeout 300 python tools/bench_configs.py > $OUT/${TAG}_bench_configs.log 2>&1
+timeout 150 python tools/bench_configs.py > $OUT/${TAG}_bench_configs.log 2>&1
 echo "bench_configs exit $?"; mv $OUT/bench_configs.json $OUT/${TAG}_bench_configs.json 2>/dev/null
 ls -la $OUT | head -30
