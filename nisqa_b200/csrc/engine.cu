@@ -134,7 +134,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, logits, feats20, tdout, partial;
   DevBuf planes[7];        // planes[l]: fp16 hi | lo plane pair feeding conv layer l (2..6), conv_split.cu
-  size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
+  size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // offset of the lo plane inside planes[l] (half of the allocation)
   void release() {
     for (auto& b : planes) b.release();
     DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
@@ -711,8 +711,10 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     e->last_split = split;
     if (split) {
       for (int l = 2; l <= 6; ++l) {
-        LN.plane_bytes[l] = split_plane_bytes(std_mode, l, n_seg);
-        CK(LN.planes[l].reserve_zeroed(2 * LN.plane_bytes[l], st));
+        // the lo plane sits at a fixed offset of the ALLOCATION (not of this pass's n_seg): the zero rows /
+        // columns of both planes must stay where they were when the buffer was cleared
+        CK(LN.planes[l].reserve_zeroed(2 * split_plane_bytes(std_mode, l, n_seg), st));
+        LN.plane_bytes[l] = (LN.planes[l].cap / 2) & ~(size_t)1023;
       }
     } else {
       CK(LN.act1.reserve((size_t)n_seg * 24 * W1 * 16 * 4));
