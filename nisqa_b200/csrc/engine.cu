@@ -39,6 +39,9 @@ size_t split_plane_bytes(int std_mode, int layer, int n_seg);
 void launch_conv_split(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
                        void*, void*, float*, int, int);
 void launch_unsplit(cudaStream_t, int, int, const void*, const void*, float*, int);
+// conv_wide.cu (experimental)
+void launch_conv_wide(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
+                      void*, void*, float*, int);
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
 int sp_timing_read(long long*, int);
@@ -179,6 +182,7 @@ struct nisqa_engine {
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
   int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
+  int conv_wide = 0;       // EXPERIMENTAL: bit l (3..6) set: layer l runs conv_wide.cu (N = 256 MMAs) instead of conv_split.cu
   int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
   bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
@@ -751,7 +755,11 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
         snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
         Scope s(e, nm);
-        if (split)
+        if (split && ((e->conv_wide >> l) & 1) && l >= 3)
+          launch_conv_wide(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
+                           l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
+                           l == 6 ? LN.feats.as<float>() : nullptr, n_seg);
+        else if (split)
           launch_conv_split(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
                             l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
                             l == 6 ? LN.feats.as<float>() : nullptr, n_seg, e->tc_timing_layer == l ? 2 : 0);
@@ -1132,6 +1140,7 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
+  if (strcmp(name, "conv_wide") == 0) { e->conv_wide = value & 0x78; return 0; }
   if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }

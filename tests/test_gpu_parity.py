@@ -216,6 +216,30 @@ def test_conv_paths_agree(engines, ckpt, clips):
         eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
 
 
+@pytest.mark.skipif(os.environ.get("NISQA_EXPERIMENTAL") != "1",
+                    reason="round-2 candidate kernel (csrc/conv_wide.cu), never run on a GPU yet: NISQA_EXPERIMENTAL=1 enables it")
+@pytest.mark.parametrize("ckpt,clips", [
+    ("nisqa.tar", [(41, 10.0, 48000), (42, 2.3, 48000), (43, 0.1875, 8000)]),
+    ("nisqa_tts.tar", [(44, 3.0, 16000)]),
+])
+def test_conv_wide_candidate(engines, ckpt, clips):
+    """conv3..6 with one N = 256 MMA per tile (weights as the M operand) against the default plane pipeline:
+    same values up to the extra w_lo * x_lo term (2^-22 relative)."""
+    eng, args, sd = engines[ckpt]
+    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
+    srs = [c[2] for c in clips]
+    try:
+        ref, _, _ = eng.predict_pcm(pcm, srs)
+        ref_feat = eng.stage_dump(E.STAGE_CNN_FEAT)
+        for mask in (0x78, 0x10, 0x08, 0x20, 0x40):
+            eng.set_option("conv_wide", mask)
+            got, _, _ = eng.predict_pcm(pcm, srs)
+            assert np.abs(got - ref).max() <= SCORE_TOL / 10, hex(mask)
+            assert np.abs(eng.stage_dump(E.STAGE_CNN_FEAT) - ref_feat).max() <= ACT_TOL / 4, hex(mask)
+    finally:
+        eng.set_option("conv_wide", 0)
+
+
 def test_device_resident_entry_point_equals_host_entry_point(engines):
     import torch
     eng, args, sd = engines["nisqa.tar"]
