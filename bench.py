@@ -42,6 +42,64 @@ SEGS_PER_CLIP = 247
 FLOP_PER_CLIP = 2.735e9
 
 
+# algorithmic FLOPs per clip of the self-attention layers (SURVEY.md 8a rows a11/a12 at S = 247, 2 layers):
+# QK^T + PV = 31.2 M (the "attention-FLOP roofline" of 8d), out-proj + FFN = 24.4 M
+ATT_FLOP_PER_CLIP = 31.2e6
+SA_LAYER_FLOP_PER_CLIP = 55.6e6
+
+
+def build_rooflines(kernel_ms, peaks, sm_max_mhz, traffic_tab, n_samples):
+    """Per-kernel rooflines from CUDA-event kernel times (ms per 64-clip step).  Returns (all, dominant):
+    `dominant` is the kernel with the largest share of the step.  Pure function (tests/test_host_logic.py
+    replays a recorded bench line through it)."""
+    n_seg_step = BS * SEGS_PER_CLIP
+    fp32_peak = 148 * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 / 1e12
+    tc_layers = ("conv2", "conv3", "conv4", "conv5", "conv6")
+    roofs = {}
+    for k in ("conv1",) + tc_layers:
+        if kernel_ms[k] <= 0:
+            continue
+        flop = CONV_FLOP_PER_SEG[k] * n_seg_step
+        ach = flop / (kernel_ms[k] / 1e3) / 1e12
+        r = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+             "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic_tab.get(k),
+             "peak_source": peaks["source"] + ", sustained 16-bit dense (kernel timed inside a long step)",
+             "kernel_ms": kernel_ms[k], "algorithmic_flop_per_launch": flop}
+        if k in tc_layers:
+            r["note"] = ("tcgen05 kind::f16 implicit GEMM with a two-term fp16 split: 3 MMAs per algorithmic MAC "
+                         "(parity: plain 16-bit operands move MOS by >1e-3), so the tensor pipe executes 3x `achieved`")
+            r["executed_tflops"] = 3 * ach
+            r["frac_executed"] = 3 * ach / peaks["bf16_tflops_sustained"]
+        else:
+            r["note"] = "conv1 (C_in=1, K=9) is direct fp32 FFMA; fraction of the fp32 FFMA peak in frac_fp32"
+            r["fp32_peak_tflops"] = fp32_peak
+            r["frac_fp32"] = ach / fp32_peak
+        roofs[k] = r
+    byts = BS * (n_samples * 2 + 1001 * 48 * 4)
+    ach = byts / (kernel_ms["frontend"] / 1e3) / 1e9
+    fft_tf = 136.7e6 * BS / (kernel_ms["frontend"] / 1e3) / 1e12
+    roofs["frontend"] = {"kernel": "frontend", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic_tab.get("frontend"),
+                         "peak_source": peaks["source"], "kernel_ms": kernel_ms["frontend"],
+                         "algorithmic_bytes_per_launch": byts,
+                         "note": "PCM16 in + mel out (SURVEY 8d 'STFT-bandwidth roofline'); the kernel is FFT issue/latency "
+                                 "bound (123 MFLOP/clip of radix-32 butterflies), not HBM bound",
+                         "fft_tflops": fft_tf, "fp32_peak_tflops": fp32_peak, "frac_fp32": fft_tf / fp32_peak}
+    if kernel_ms.get("sa_layer", 0) > 0:
+        # the two self-attention layer launches (flash-style softmax(QK^T)V + out-proj + FFN + 2 LayerNorms), fp32 FFMA
+        ms = kernel_ms["sa_layer"]
+        att = ATT_FLOP_PER_CLIP * BS / (ms / 1e3) / 1e12
+        roofs["sa_layer"] = {"kernel": "sa_layer", "bound": "tensor", "achieved": att, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": att / fp32_peak, "traffic": traffic_tab.get("sa_layer"),
+                             "peak_source": "fp32 FFMA peak 148 SM x 128 lanes x 2 x SM clock (the kernel runs on the FFMA pipe, "
+                                            "no tensor cores: fp32 parity)",
+                             "kernel_ms": ms, "algorithmic_flop_per_launch": ATT_FLOP_PER_CLIP * BS,
+                             "note": "attention-FLOP roofline of SURVEY 8d(iii): QK^T + PV only; with out-proj + FFN the same "
+                                     "launches do %.1f TFLOP/s" % (SA_LAYER_FLOP_PER_CLIP * BS / (ms / 1e3) / 1e12)}
+    dom = max(roofs, key=lambda k: kernel_ms[k])
+    return roofs, roofs[dom]
+
+
 def make_clips(n, seed0=0):
     """n distinct 10-s PCM16 clips: a few synthesised bases, circularly shifted (np.roll)."""
     from nisqa_b200 import synth
@@ -366,44 +424,11 @@ def run_ours(a, rank, world, local):
     e2e_wall = total_clips / max(wall_e2e, 1e-9)
     e2e_value = min(total_clips / (max(ms_e2e / 1e3, 1e-9)), e2e_wall)
     # ---- rooflines: every heavy kernel, `roofline` = the dominant one (largest share of the step)
-    n_seg_step = BS * SEGS_PER_CLIP
     traffic_tab = {}
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic_tab = json.load(open(tp))
-    fp32_peak = 148 * 128 * 2 * ((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-    tc_layers = ("conv2", "conv3", "conv4", "conv5", "conv6")
-    roofs = {}
-    for k in ("conv1",) + tc_layers:
-        if kernel_ms[k] <= 0:
-            continue
-        flop = CONV_FLOP_PER_SEG[k] * n_seg_step
-        ach = flop / (kernel_ms[k] / 1e3) / 1e12
-        r = {"kernel": k, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-             "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic_tab.get(k),
-             "peak_source": peaks["source"] + ", sustained 16-bit dense (kernel timed inside a long step)",
-             "kernel_ms": kernel_ms[k], "algorithmic_flop_per_launch": flop}
-        if k in tc_layers:
-            r["note"] = ("tcgen05 kind::f16 implicit GEMM with a two-term fp16 split: 3 MMAs per algorithmic MAC "
-                         "(parity: plain 16-bit operands move MOS by >1e-3), so the tensor pipe executes 3x `achieved`")
-            r["executed_tflops"] = 3 * ach
-            r["frac_executed"] = 3 * ach / peaks["bf16_tflops_sustained"]
-        else:
-            r["note"] = "conv1 (C_in=1, K=9) is direct fp32 FFMA; fraction of the fp32 FFMA peak in frac_fp32"
-            r["fp32_peak_tflops"] = fp32_peak
-            r["frac_fp32"] = ach / fp32_peak
-        roofs[k] = r
-    byts = BS * (int(n_s[0]) * 2 + 1001 * 48 * 4)
-    ach = byts / (kernel_ms["frontend"] / 1e3) / 1e9
-    roofs["frontend"] = {"kernel": "frontend", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic_tab.get("frontend"),
-                         "peak_source": peaks["source"], "kernel_ms": kernel_ms["frontend"],
-                         "algorithmic_bytes_per_launch": byts,
-                         "note": "PCM16 in + mel out (SURVEY 8d 'STFT-bandwidth roofline'); the kernel is FFT issue/latency "
-                                 "bound (123 MFLOP/clip of radix-32 butterflies), not HBM bound",
-                         "fft_tflops": 136.7e6 * BS / (kernel_ms["frontend"] / 1e3) / 1e12}
-    dom = max(roofs, key=lambda k: kernel_ms[k])
-    roof = roofs[dom]
+    roofs, roof = build_rooflines(kernel_ms, peaks, (clocks or {}).get("sm_max_mhz"), traffic_tab, int(n_s[0]))
     cnn_ms = sum(kernel_ms[k] for k in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"))
     # ---- CPU baseline: oracle port, one process, all torch threads, bounded sample
     cpu_base = None

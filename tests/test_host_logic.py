@@ -193,3 +193,33 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_bench_rooflines_replay_recorded_line():
+    """bench.build_rooflines is a pure function of the per-kernel CUDA-event times: replaying the recorded
+    r01e line (profiles/r01e_bench_n1.json, measured on a B200) must reproduce its roofline entries, name the
+    same dominant kernel, and carry the attention-FLOP roofline of SURVEY 8d(iii)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("nisqa_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r01e_bench_n1.json")))
+    peaks = {"hbm_gbs": rec["roofline"]["peak"], "bf16_tflops_sustained": rec["roofline_kernels"]["conv4"]["peak"],
+             "bf16_tflops": 0.0, "source": "measured (MEASURED_PEAKS.json)"}
+    traffic = {k: v["traffic"] for k, v in rec["roofline_kernels"].items()}
+    roofs, dom = bench.build_rooflines(rec["kernel_ms_per_step"], peaks, rec["clocks"]["sm_max_mhz"], traffic, 480000)
+    assert dom["kernel"] == rec["roofline"]["kernel"] == "frontend"
+    for k, want in rec["roofline_kernels"].items():
+        got = roofs[k]
+        for field in ("bound", "unit", "traffic"):
+            assert got[field] == want[field], (k, field)
+        for field in ("achieved", "peak", "frac", "kernel_ms"):
+            assert abs(got[field] - want[field]) <= 1e-9 * max(1.0, abs(want[field])), (k, field)
+        if "frac_executed" in want:
+            assert abs(got["frac_executed"] - want["frac_executed"]) <= 1e-12
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):           # the contract's roofline object
+        assert key in dom
+    sa = roofs["sa_layer"]
+    assert sa["unit"] == "TFLOP/s" and 0.0 < sa["frac"] < 1.0
+    assert abs(sa["achieved"] - 31.2e6 * 64 / (rec["kernel_ms_per_step"]["sa_layer"] / 1e3) / 1e12) <= 1e-9
