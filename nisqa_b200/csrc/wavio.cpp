@@ -67,7 +67,21 @@ bool parse_header(FILE* f, WavInfo* w) {
 bool supported(const WavInfo& w) {
   if (w.tag == 1) return w.bits == 8 || w.bits == 16 || w.bits == 24 || w.bits == 32;
   if (w.tag == 3) return w.bits == 32 || w.bits == 64;
+  if (w.tag == 6 || w.tag == 7) return w.bits == 8;            // G.711 A-law / mu-law (telephony corpora)
   return false;
+}
+
+// ITU-T G.711 expansion of one code to a 16-bit linear sample (the tables of libsndfile's alaw.c / ulaw.c)
+inline int g711_expand(unsigned char code, bool alaw) {
+  if (alaw) {
+    const int c = code ^ 0x55, seg = (c & 0x70) >> 4;
+    int t = (c & 0x0F) << 4;
+    t = (seg == 0) ? t + 8 : (t + 0x108) << (seg - 1);
+    return (c & 0x80) ? t : -t;
+  }
+  const int c = ~code & 0xFF;
+  const int t = (((c & 0x0F) << 3) + 0x84) << ((c & 0x70) >> 4);
+  return (c & 0x80) ? 0x84 - t : t - 0x84;
 }
 
 // libsndfile's conversion of one stored sample to float32
@@ -87,6 +101,7 @@ inline float sample_f32(const unsigned char* p, const WavInfo& w) {
       }
     }
   }
+  if (w.tag == 6 || w.tag == 7) return (float)g711_expand(p[0], w.tag == 6) * (1.0f / 32768.0f);
   if (w.bits == 32) { float v; memcpy(&v, p, 4); return v; }
   double d; memcpy(&d, p, 8); return (float)d;
 }

@@ -15,7 +15,26 @@ import struct
 
 import numpy as np
 
-_INV = {8: np.float32(1.0 / 128.0), 24: np.float32(1.0 / 8388608.0)}
+_INV = {8: np.float32(1.0 / 128.0), 16: np.float32(1.0 / 32768.0), 24: np.float32(1.0 / 8388608.0)}
+
+
+def _g711_table(alaw):
+    """8-bit G.711 code -> 16-bit linear sample (ITU-T G.711 expansion, as libsndfile's alaw.c / ulaw.c)."""
+    out = np.zeros(256, np.int16)
+    for code in range(256):
+        if alaw:
+            c = code ^ 0x55
+            t, seg = (c & 0x0F) << 4, (c & 0x70) >> 4
+            t = t + 8 if seg == 0 else (t + 0x108) << (seg - 1)
+            out[code] = t if c & 0x80 else -t
+        else:
+            c = ~code & 0xFF
+            t = (((c & 0x0F) << 3) + 0x84) << ((c & 0x70) >> 4)
+            out[code] = 0x84 - t if c & 0x80 else t - 0x84
+    return out
+
+
+_G711 = {6: _g711_table(True), 7: _g711_table(False)}       # WAVE_FORMAT_ALAW / WAVE_FORMAT_MULAW
 
 
 def _parse(buf):
@@ -67,6 +86,8 @@ def read_wav(path, ms_channel=None):
         elif tag == 1 and bits == 32:
             y = (raw.view("<i4").astype(np.float64) * (1.0 / 2147483648.0)).astype(np.float32)
             y = y.reshape(n_frames, ch)
+        elif tag in (6, 7) and bits == 8:       # G.711 A-law / mu-law: 16-bit expansion, then libsndfile's / 32768
+            y = (_G711[tag][raw].astype(np.float32) * _INV[16]).reshape(n_frames, ch)
         elif tag == 3 and bits == 32:
             y = raw.view("<f4").astype(np.float32).reshape(n_frames, ch)
         elif tag == 3 and bits == 64:

@@ -40,11 +40,26 @@ __version__ = "0.8.1-restated"
 
 
 # --------------------------------------------------------------------------- load
+def _g711_expand(codes, alaw):
+    """ITU-T G.711 expansion of 8-bit codes to 16-bit linear samples (the tables of libsndfile's alaw.c / ulaw.c)."""
+    c = codes.astype(np.int32)
+    if alaw:
+        c = c ^ 0x55
+        t = (c & 0x0F) << 4
+        seg = (c & 0x70) >> 4
+        t = np.where(seg == 0, t + 8, np.where(seg == 1, t + 0x108, (t + 0x108) << np.maximum(seg - 1, 0)))
+        return np.where(c & 0x80, t, -t)
+    c = ~c & 0xFF
+    t = (((c & 0x0F) << 3) + 0x84) << ((c & 0x70) >> 4)
+    return np.where(c & 0x80, 0x84 - t, t - 0x84)
+
+
 def _read_wav(path):
     """RIFF/WAVE reader with libsndfile's float conversion rules.
 
     PCM u8 -> (v-128)/128, PCM16 -> v/32768, PCM24 -> v/2**23, PCM32 -> v/2**31,
-    IEEE float32/float64 -> as is (cast to float32).  Returns (y[n, ch] float32, sr).
+    IEEE float32/float64 -> as is (cast to float32), G.711 A-law / mu-law (tags 6 / 7) -> the 16-bit
+    expansion / 32768 (libsndfile alaw.c / ulaw.c).  Returns (y[n, ch] float32, sr).
     """
     with open(path, "rb") as f:
         data = f.read()
@@ -84,6 +99,8 @@ def _read_wav(path):
                  / 2147483648.0).astype(np.float32)
         else:
             raise ValueError("unsupported PCM width %d" % bits)
+    elif tag in (6, 7) and bits == 8:
+        y = _g711_expand(np.frombuffer(payload, dtype=np.uint8), alaw=(tag == 6)).astype(np.float32) / 32768.0
     elif tag == 3:
         if bits == 32:
             y = np.frombuffer(payload[:len(payload) // 4 * 4], dtype="<f4").astype(np.float32)

@@ -30,7 +30,7 @@ def _as_float(x):
     return x.astype(np.float32) / np.float32(32768.0) if x.dtype == np.int16 else x
 
 
-@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16"])
+@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16", "alaw", "ulaw_stereo"])
 def test_wav_reader_matches_oracle_loader(tmp_path, kind):
     rng = np.random.default_rng(1)
     p = str(tmp_path / (kind + ".wav"))
@@ -50,6 +50,10 @@ def test_wav_reader_matches_oracle_loader(tmp_path, kind):
     elif kind == "pcm32":
         d = rng.integers(-(1 << 31), (1 << 31) - 1, n).astype("<i4")
         _write_pcm(p, d.tobytes(), 1, 1, 48000, 32)
+    elif kind == "alaw":
+        _write_pcm(p, np.arange(n, dtype=np.int64).astype(np.uint8).tobytes(), 6, 1, 8000, 8)          # every code
+    elif kind == "ulaw_stereo":
+        _write_pcm(p, rng.integers(0, 256, (n, 2)).astype(np.uint8).tobytes(), 7, 2, 8000, 8)
     elif kind == "f32":
         _write_pcm(p, rng.standard_normal((n, 2)).astype("<f4").tobytes(), 3, 2, 22050, 32)
     elif kind == "f64":
@@ -60,7 +64,16 @@ def test_wav_reader_matches_oracle_loader(tmp_path, kind):
     y, sr = wav.read_wav(p)
     assert sr == sr_ref and y.ndim == 1
     np.testing.assert_array_equal(_as_float(y), y_ref)
-    if kind in ("pcm16_stereo", "f32"):
+    if kind in ("alaw", "ulaw_stereo"):
+        # independent decoder: the standard library's G.711 tables
+        audioop = pytest.importorskip("audioop")
+        raw = open(p, "rb").read()[-n * (2 if kind == "ulaw_stereo" else 1):]
+        lin = np.frombuffer((audioop.alaw2lin if kind == "alaw" else audioop.ulaw2lin)(raw, 2), dtype="<i2")
+        want = lin.astype(np.float32) / np.float32(32768.0)
+        if kind == "ulaw_stereo":
+            want = np.mean(want.reshape(n, 2).T, axis=0)
+        np.testing.assert_array_equal(_as_float(y), want)
+    if kind in ("pcm16_stereo", "f32", "ulaw_stereo"):
         for ch in (0, 1):
             y2, _ = lb.load(p, sr=None, mono=False)
             yc, _ = wav.read_wav(p, ms_channel=ch)
@@ -137,7 +150,7 @@ def test_two_rank_gloo_exchange(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
-@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16"])
+@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16", "alaw", "ulaw_stereo"])
 def test_native_wav_reader_matches_oracle_loader(tmp_path, kind, built_lib):
     """csrc/wavio.cpp (nisqa_wav_probe / nisqa_wav_decode, host-only entry points of the C-ABI)."""
     rng = np.random.default_rng(2)
@@ -154,6 +167,10 @@ def test_native_wav_reader_matches_oracle_loader(tmp_path, kind, built_lib):
         _write_pcm(p, bytes(b), 1, 1, 48000, 24)
     elif kind == "pcm32":
         _write_pcm(p, rng.integers(-(1 << 31), (1 << 31) - 1, n).astype("<i4").tobytes(), 1, 1, 48000, 32)
+    elif kind == "alaw":
+        _write_pcm(p, np.arange(n, dtype=np.int64).astype(np.uint8).tobytes(), 6, 1, 8000, 8)          # every code
+    elif kind == "ulaw_stereo":
+        _write_pcm(p, rng.integers(0, 256, (n, 2)).astype(np.uint8).tobytes(), 7, 2, 8000, 8)
     elif kind == "f32":
         _write_pcm(p, rng.standard_normal((n, 2)).astype("<f4").tobytes(), 3, 2, 22050, 32)
     elif kind == "f64":
