@@ -187,6 +187,15 @@ NISQA_API int     nisqa_wav_decode_batch(int n, const char* const* paths, int32_
                                          void* base, const int64_t* elem_offsets, const int64_t* cap_frames,
                                          int n_threads, int32_t* status);
 
+/* ---- sample-rate conversion of the ingest (reference lib:2300-2304 with ms_sr != None: librosa 0.8.1
+ * resample(res_type='kaiser_best', fix=True) = resampy's band-limited sinc interpolation).  Host side, no
+ * engine handle.  The interpolation table (resampy's kaiser_best half window, num_table samples per zero
+ * crossing) is set once; the output has ceil(n * sr_new / sr_orig) samples. */
+NISQA_API int     nisqa_resample_set_filter(const double* half_window, int64_t n, int32_t num_table);
+NISQA_API int64_t nisqa_resample_out_len(int64_t n, int32_t sr_orig, int32_t sr_new);
+NISQA_API int64_t nisqa_resample_f32(const float* x, int64_t n, int32_t sr_orig, int32_t sr_new, float* y,
+                                     int64_t cap);
+
 /* bookkeeping for bench.py */
 NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */
 NISQA_API void*   nisqa_stream(const nisqa_engine* e);            /* cudaStream_t of compute lane 0 */

@@ -25,7 +25,8 @@ import numpy as np
 
 from . import dist as nb_dist
 from . import engine as nb_engine
-from .wav import decode_batch, probe_batch, read_wav
+from . import resample as nb_resample
+from .wav import decode_batch, decode_wav_into, probe_batch, read_wav
 
 
 class SpeechQualityDataset(object):
@@ -63,9 +64,21 @@ class SpeechQualityDataset(object):
     def file_path(self, index):
         return os.path.join(self.data_dir, self.df[self.filename_column].iloc[index])
 
+    def target_sr(self):
+        """``ms_sr`` of the checkpoint as an int, or None (= every file at its native rate, lib:2300)."""
+        return None if self.ms_sr is None else int(self.ms_sr)
+
     def load_pcm(self, index):
-        """-> (int16|float32 mono samples, sample_rate); ValueError('Could not load file ..')."""
-        return read_wav(self.file_path(index), self.ms_channel)
+        """-> (int16|float32 mono samples, sample_rate); ValueError('Could not load file ..').  With
+        ``ms_sr`` set the clip is converted to that rate (lb.load(path, sr=ms_sr), lib:2300-2304)."""
+        y, sr = read_wav(self.file_path(index), self.ms_channel)
+        target = self.target_sr()
+        if target is not None and sr != target:
+            try:
+                y, sr = nb_resample.resample(y, sr, target), target
+            except Exception:
+                raise ValueError("Could not load file {}".format(self.file_path(index)))
+        return y, sr
 
 
 def _raise_for_status(ds, engine, index, n_samples, sr, n_seg, status):
@@ -104,6 +117,9 @@ def _load_batch(ds, batch, pool, slot, n_threads):
     calls per batch (probe, decode), each spread over ``n_threads`` C++ threads."""
     paths = [ds.file_path(int(i)) for i in batch]
     sr, nf, kind, arr = probe_batch(paths, ds.ms_channel, n_threads)
+    target = ds.target_sr()
+    if target is not None and bool((sr != target).any()):
+        return _load_batch_resampled(ds, paths, sr, nf, target, pool, slot, n_threads)
     dtype = np.int16 if not kind.any() else np.float32
     offs = np.zeros(len(paths), np.int64)
     if len(paths) > 1:
@@ -114,6 +130,39 @@ def _load_batch(ds, batch, pool, slot, n_threads):
     decode_batch(arr, len(paths), buf, offs, nf, ds.ms_channel, n_threads, paths)
     clips = [buf[int(o):int(o) + int(n)] for o, n in zip(offs, nf)]
     return clips, [int(x) for x in sr]
+
+
+def _load_batch_resampled(ds, paths, sr, nf, target, pool, slot, n_threads):
+    """``ms_sr`` checkpoints (lib:2300-2304): every clip is decoded to float32 (mono mix / channel pick first, as
+    librosa does) and converted to ``target`` Hz straight into the pinned batch buffer; one native decode + one
+    native resample call per file, spread over ``n_threads`` threads (ctypes releases the GIL)."""
+    n_out = np.array([nb_resample.out_len(int(n), int(s), target) for n, s in zip(nf, sr)], np.int64)
+    offs = np.zeros(len(paths), np.int64)
+    if len(paths) > 1:
+        offs[1:] = np.cumsum((n_out[:-1] + 15) // 16 * 16)
+    total = int(offs[-1] + (n_out[-1] + 15) // 16 * 16) if len(paths) else 0
+    buf = pool.get(slot, max(total, 16) * 4)[:max(total, 16) * 4].view(np.float32)
+
+    def one(i):
+        dst = buf[int(offs[i]):int(offs[i]) + int(n_out[i])]
+        if int(sr[i]) == target:
+            decode_wav_into(paths[i], dst, ds.ms_channel)
+            return
+        tmp = np.empty(int(nf[i]), np.float32)
+        decode_wav_into(paths[i], tmp, ds.ms_channel)
+        try:
+            nb_resample.resample(tmp, int(sr[i]), target, out=dst)
+        except Exception:
+            raise ValueError("Could not load file {}".format(paths[i]))
+
+    if n_threads > 1 and len(paths) > 1:
+        with ThreadPoolExecutor(max_workers=n_threads) as ex:
+            list(ex.map(one, range(len(paths))))
+    else:
+        for i in range(len(paths)):
+            one(i)
+    clips = [buf[int(o):int(o) + int(n)] for o, n in zip(offs, n_out)]
+    return clips, [target] * len(paths)
 
 
 def _predict_rows(engine, ds, rows, bs, num_workers):

@@ -29,6 +29,7 @@ EXPORTS = [
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
     "nisqa_submit_pcm", "nisqa_wait", "nisqa_join", "nisqa_set_gather_target",
     "nisqa_wav_probe", "nisqa_wav_decode", "nisqa_wav_probe_batch", "nisqa_wav_decode_batch",
+    "nisqa_resample_set_filter", "nisqa_resample_out_len", "nisqa_resample_f32",
 ]
 
 
@@ -85,6 +86,12 @@ def load_library(path=None):
     lib.nisqa_wav_probe_batch.restype = C.c_int
     lib.nisqa_wav_decode_batch.argtypes = [C.c_int, cpp, C.c_int32, C.c_int32, vp, i64p, i64p, C.c_int, i32p]
     lib.nisqa_wav_decode_batch.restype = C.c_int
+    lib.nisqa_resample_set_filter.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_int32]
+    lib.nisqa_resample_set_filter.restype = C.c_int
+    lib.nisqa_resample_out_len.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.nisqa_resample_out_len.restype = C.c_int64
+    lib.nisqa_resample_f32.argtypes = [f32p, C.c_int64, C.c_int32, C.c_int32, f32p, C.c_int64]
+    lib.nisqa_resample_f32.restype = C.c_int64
     lib.nisqa_set_gather_target.argtypes = [vp, vp, C.c_int]
     lib.nisqa_set_gather_target.restype = C.c_int
     lib.nisqa_join.argtypes = [vp]
@@ -146,8 +153,7 @@ def config_from_args(args, max_chunk_segments=0):
     ok = ok and args["ms_n_fft"] == 4096 and args["ms_n_mels"] == 48 and args["ms_seg_length"] == 15
     if not ok:
         raise NotImplementedError("checkpoint hyper-parameters outside the shipped NISQA configurations")
-    if args.get("ms_sr") is not None:
-        raise NotImplementedError("ms_sr != None (resampling) is not on the B200 path (SURVEY.md 8f.2)")
+    # ms_sr != None: the ingest converts every clip to that rate (nisqa_b200/resample.py) before the engine sees it
     cfg = NisqaConfig()
     cfg.abi_version = ABI_VERSION
     cfg.arch = arch

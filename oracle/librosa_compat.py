@@ -130,11 +130,112 @@ def load(path, sr=22050, mono=True, offset=0.0, duration=None, dtype=np.float32,
         y = y[0]
     if mono:
         y = to_mono(y)
-    if sr is not None and int(sr) != sr_native:
-        raise NotImplementedError(
-            "resampling (ms_sr != native rate) is outside the restated path: all shipped "
-            "checkpoints carry ms_sr=None (SURVEY.md section 0.5)")
-    return np.ascontiguousarray(y, dtype=dtype), sr_native
+    if sr is not None:
+        y = resample(y, sr_native, sr, res_type=res_type)
+    else:
+        sr = sr_native
+    return np.ascontiguousarray(y, dtype=dtype), sr
+
+
+# ----------------------------------------------------------------------- resample
+# librosa 0.8.1 core/audio.py::resample -> resampy (0.2.2) core.py::resample / interpn.py::resample_f with the
+# 'kaiser_best' filter.  resampy is a further third-party dependency that is not vendored (PARITY UNPINNED, like
+# the rest of this file); restated from its published algorithm.  Its data/kaiser_best.npz is the output of
+# filters.sinc_window(num_zeros=64, precision=9, rolloff=0.9475937167399596) with a Kaiser window of
+# beta=14.769656459379492 (the parameters stated in resampy's filters.py docstring) and is regenerated here.
+_KAISER_BEST = dict(num_zeros=64, precision=9, rolloff=0.9475937167399596, beta=14.769656459379492)
+_filter_cache = {}
+
+
+def sinc_window(num_zeros, precision, rolloff, beta):
+    """resampy.filters.sinc_window with window = scipy.signal.kaiser(., beta): right half of a windowed sinc,
+    2**precision samples per zero crossing.  -> (half_window float64 [n + 1], samples per zero crossing)."""
+    from scipy.signal.windows import kaiser
+    num_bits = 2 ** precision
+    n = num_bits * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = kaiser(2 * n + 1, beta)[n:]
+    return taper * sinc_win, num_bits
+
+
+def resampy_resample(x, sr_orig, sr_new):
+    """resampy.resample(x, sr_orig, sr_new, filter='kaiser_best') for 1-D float32 x: band-limited sinc
+    interpolation (J. O. Smith) with linear interpolation between filter table entries.  The reference loop runs
+    per output sample t over the left wing (taps i = 0.. towards the past) and then the right wing (taps k), adding
+    weight (float64) * x (float32) into the float32 output EVERY iteration; here the same additions are done in
+    the same order, vectorised over t."""
+    if sr_orig <= 0 or sr_new <= 0:
+        raise ValueError("invalid sample rate")
+    x = np.asarray(x, dtype=np.float32)
+    sample_ratio = float(sr_new) / sr_orig
+    n_out = int(x.shape[0] * sample_ratio)
+    if n_out < 1:
+        raise ValueError("Input signal length is too small to resample")
+    if "kb" not in _filter_cache:
+        _filter_cache["kb"] = sinc_window(**_KAISER_BEST)
+    interp_win, num_table = _filter_cache["kb"]
+    interp_win = interp_win.copy()
+    if sample_ratio < 1:
+        interp_win *= sample_ratio
+    interp_delta = np.zeros_like(interp_win)
+    interp_delta[:-1] = np.diff(interp_win)
+    scale = min(1.0, sample_ratio)
+    time_increment = 1.0 / sample_ratio
+    index_step = int(scale * num_table)
+    nwin, n_orig = interp_win.shape[0], x.shape[0]
+    # time_register += time_increment, starting from 0.0 (sequential float64 additions)
+    steps = np.full(n_out, time_increment)
+    steps[0] = 0.0
+    time_register = np.cumsum(steps)
+    n = time_register.astype(np.int64)
+    y = np.zeros(n_out, dtype=np.float32)
+    for wing in (0, 1):
+        frac = scale * (time_register - n)
+        if wing:
+            frac = scale - frac
+        index_frac = frac * num_table
+        offset = index_frac.astype(np.int64)
+        eta = index_frac - offset
+        if wing == 0:
+            count = np.minimum(n + 1, (nwin - offset) // index_step)
+        else:
+            count = np.minimum(n_orig - n - 1, (nwin - offset) // index_step)
+        for i in range(int(count.max()) if n_out else 0):
+            live = np.nonzero(count > i)[0]
+            idx = offset[live] + i * index_step
+            weight = interp_win[idx] + eta[live] * interp_delta[idx]
+            src = n[live] - i if wing == 0 else n[live] + i + 1
+            y[live] = (y[live].astype(np.float64) + weight * x[src].astype(np.float64)).astype(np.float32)
+    return y
+
+
+def fix_length(data, size):
+    """librosa.util.fix_length on the last axis: trim, or pad with zeros."""
+    n = data.shape[-1]
+    if n > size:
+        return data[..., :size]
+    if n < size:
+        return np.pad(data, [(0, 0)] * (data.ndim - 1) + [(0, size - n)], mode="constant")
+    return data
+
+
+def resample(y, orig_sr, target_sr, res_type="kaiser_best", fix=True, scale=False):
+    """librosa.core.audio.resample (0.8.1) for mono or [ch, n] float32 input."""
+    if orig_sr == target_sr:
+        return y
+    if res_type != "kaiser_best":
+        raise NotImplementedError("only res_type='kaiser_best' (librosa.load's default) is restated")
+    ratio = float(target_sr) / orig_sr
+    n_samples = int(np.ceil(y.shape[-1] * ratio))
+    if y.ndim == 1:
+        y_hat = resampy_resample(y, orig_sr, target_sr)
+    else:
+        y_hat = np.stack([resampy_resample(c, orig_sr, target_sr) for c in y])
+    if fix:
+        y_hat = fix_length(y_hat, n_samples)
+    if scale:
+        y_hat = y_hat / np.sqrt(ratio)
+    return np.ascontiguousarray(y_hat, dtype=y.dtype)
 
 
 # ------------------------------------------------------------------------ convert

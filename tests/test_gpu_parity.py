@@ -333,6 +333,23 @@ def test_stereo_channel_pick_and_float_wav(wav_dir, built_lib):
             assert np.abs(got - ref).max() <= SCORE_TOL, (ch, row["deg"])
 
 
+@pytest.mark.skipif(os.environ.get("NISQA_EXPERIMENTAL") != "1",
+                    reason="ms_sr ingest path (SURVEY 8f.2): host side verified on the CPU (tests/test_resample.py), the "
+                           "end-to-end run has not been on a GPU yet: NISQA_EXPERIMENTAL=1 enables it")
+def test_ms_sr_checkpoint_resamples_on_ingest(wav_dir, built_lib):
+    """A checkpoint whose args carry ms_sr (here: forced through the caller's dict, model:941-942): every file
+    is converted to that rate before the engine sees it, like lb.load(path, sr=ms_sr) at lib:2300-2304."""
+    from nisqa_b200.NISQA_model import nisqaModel
+    df = nisqaModel({"mode": "predict_dir", "pretrained_model": os.path.join(WEIGHTS, "nisqa.tar"), "data_dir": str(wav_dir),
+                     "output_dir": None, "tr_bs_val": 3, "tr_num_workers": 2, "ms_sr": 16000}).predict()
+    args, sd = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa.tar"))
+    args = dict(args, ms_sr=16000)
+    for _, row in df.iterrows():
+        ref = O.predict_file(args, sd, str(wav_dir / row["deg"]))[0]
+        got = row[["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]].to_numpy(dtype=np.float64)
+        assert np.abs(got - ref).max() <= SCORE_TOL, row["deg"]
+
+
 def test_reference_error_behaviour(tmp_path, built_lib):
     from nisqa_b200.NISQA_model import nisqaModel
     ck = os.path.join(WEIGHTS, "nisqa.tar")
