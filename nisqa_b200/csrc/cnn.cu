@@ -307,11 +307,10 @@ using Conv6S = Conv5S;
 template <class C>
 static void launch_conv(cudaStream_t st, const float* in, const float* w, const float* b,
                         float* out, int n_seg) {
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_launch_on_device(configured)) {
     cudaFuncSetAttribute(conv3x3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          C::SMEM_BYTES);
-    configured = true;
   }
   const int grid = (n_seg + C::G - 1) / C::G;
   conv3x3_kernel<C><<<grid, C::NT, C::SMEM_BYTES, st>>>(in, w, b, out, n_seg);

@@ -34,6 +34,17 @@ struct FbTables {
   const float* weights;    // concatenated non-zero runs, band-major
 };
 
+// Kernel attributes (the dynamic shared-memory opt-in) are per device and several engines - one per GPU - may live
+// in one process: true the first time it is called with `mask` while the calling thread's current device is active.
+inline bool first_launch_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // order-preserving float <-> uint key (for atomicMax over signed floats)
 __device__ __forceinline__ unsigned f2key(float f) {
   unsigned b = __float_as_uint(f);

@@ -382,10 +382,9 @@ template <class C>
 static void launch_sp(cudaStream_t st, const unsigned char* in_hi, const unsigned char* in_lo, const __half* wtc,
                       const float* b, float scale, unsigned char* out_hi, unsigned char* out_lo, float* out_f32,
                       int n_seg, int flags) {
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_launch_on_device(configured)) {
     cudaFuncSetAttribute(conv_split_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    configured = true;
   }
   conv_split_kernel<C><<<(n_seg + C::G - 1) / C::G, C::NT, C::SMEM_BYTES, st>>>(
       in_hi, in_lo, wtc, b, scale, out_hi, out_lo, out_f32, n_seg, flags);

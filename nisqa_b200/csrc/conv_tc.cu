@@ -292,10 +292,9 @@ using TcConv5S = TcCfg<6, 2, 64, 64, TC_POOL_NONE, 0, 2>;
 template <class C>
 static void launch_tc(cudaStream_t st, const float* in, const __half* wtc, const float* b, float scale,
                       float* out, int n_seg) {
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_launch_on_device(configured)) {
     cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    configured = true;
   }
   conv_tc_kernel<C><<<(n_seg + C::G - 1) / C::G, 192, C::SMEM_BYTES, st>>>(in, wtc, b, scale, out, n_seg);
 }

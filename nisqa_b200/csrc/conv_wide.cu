@@ -253,10 +253,9 @@ using WdConv6S = WdCfg<6, 2, 64, WD_POOL_NONE, 0, 2, true>;
 template <class C>
 void launch_wd(cudaStream_t st, const unsigned char* ih, const unsigned char* il, const __half* w, const float* b,
                float scale, unsigned char* oh, unsigned char* ol, float* of, int n_seg) {
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_launch_on_device(configured)) {
     cudaFuncSetAttribute(conv_wide_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    configured = true;
   }
   conv_wide_kernel<C><<<(n_seg + C::G - 1) / C::G, C::NT, C::SMEM_BYTES, st>>>(ih, il, w, b, scale, oh, ol, of, n_seg);
 }

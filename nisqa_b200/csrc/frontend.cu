@@ -396,11 +396,10 @@ void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDe
   const float2* tw1 = tw;               // [3][32][32]
   const float2* tw2 = tw + 3 * 1024;    // [32][32]
   if (Q == 1 && max_span <= kSpanMax) { // the pipelined multi-pair kernel
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_launch_on_device(configured)) {
       cudaFuncSetAttribute(frontend_pp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes<float>());
       cudaFuncSetAttribute(frontend_pp_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp_smem_bytes<short>());
-      configured = true;
     }
     if (ppc < 1) ppc = kPairsPerCta;
     const dim3 grid((max_pairs + ppc - 1) / ppc, n_clips);

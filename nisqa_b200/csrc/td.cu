@@ -448,38 +448,38 @@ constexpr int kRowSmem128 = (kRows * kXS + 64 * 128) * 4;
 
 void launch_lin_ln(cudaStream_t st, const float* feats, const float* WT, const float* b,
                    const float* g, const float* be, float* out, int n_rows) {
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(linear_rows_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); cfg = true; }
+  static unsigned long long cfg = 0;
+  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(linear_rows_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); }
   linear_rows_kernel<64, true><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(feats, 384, WT, b, g, be, out, n_rows);
 }
 void launch_fc20(cudaStream_t st, const float* feats, const float* WT, const float* b, float* out, int n_rows) {
   linear_rows_kernel<20, false><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem20, st>>>(feats, 768, WT, b, nullptr, nullptr, out, n_rows);
 }
 void launch_qkv(cudaStream_t st, const float* x, const float* WT3, const float* b3, float* qkv, int n_rows) {
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); cfg = true; }
+  static unsigned long long cfg = 0;
+  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); }
   qkv_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(x, WT3, b3, qkv, n_rows);
 }
 void launch_sa_layer(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips,
                      int n_clips, const int* qtile_prefix, int n_qtiles, const SaLayerParams& P,
                      float* x_out) {
-  static bool cfg = false;
+  static unsigned long long cfg = 0;
   const int smem = kSaSmemFloats * 4;
-  if (!cfg) { cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
+  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   sa_layer_kernel<<<n_qtiles, kRows, smem, st>>>(x_in, qkv, clips, n_clips, qtile_prefix, P, x_out);
 }
 void launch_pool_att(cudaStream_t st, const float* x, const ClipDesc* clips, int n_clips, int n_rows,
                      const PoolHeadParams& P, int n_heads, float* logits, float* scores) {
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(pool_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem128); cfg = true; }
+  static unsigned long long cfg = 0;
+  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(pool_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem128); }
   pool_logits_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem128, st>>>(x, P, n_heads, logits, n_rows);
   pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
 }
 void launch_lstm(cudaStream_t st, const float* feats20, const ClipDesc* clips, int n_clips,
                  const LstmParams& P, float* td_out, float* partial, float pool_bias, float* scores) {
-  static bool cfg = false;
+  static unsigned long long cfg = 0;
   const int smem = kLstmSmemFloats * 4;
-  if (!cfg) { cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
+  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   lstm_kernel<<<2 * n_clips, 512, smem, st>>>(feats20, clips, P, td_out, partial);
   lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
 }
