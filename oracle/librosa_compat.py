@@ -20,7 +20,8 @@ anchored on the reference's own call sites:
 Independent cross-checks (``tests/test_oracle_frontend.py``): the filterbank
 against ``torchaudio.functional.melscale_fbanks`` and
 ``transformers.audio_utils.mel_filter_bank``; the STFT against ``torch.stft`` in
-float64; the window against ``scipy.signal.get_window``.
+float64; the window against ``scipy.signal.get_window``; the whole chain (STFT, mel, dB, clamp)
+against ``transformers.audio_utils.spectrogram`` + ``amplitude_to_db`` to 1e-5 dB.
 
 librosa 0.8.1 functions restated (module :: function):
   core/audio.py    :: load, to_mono

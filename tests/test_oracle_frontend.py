@@ -2,6 +2,8 @@
 front-end half is "parity unpinned" (real librosa is not installable offline and the reference
 holds no vectors for it); these tests bound it against other implementations of the same
 published definitions that ARE available offline."""
+import os
+
 import numpy as np
 import pytest
 import scipy.signal
@@ -74,3 +76,32 @@ def test_load_pcm_conversions(tmp_path):
     np.testing.assert_array_equal(y, np.mean(st.T.astype(np.float32) / 32768.0, axis=0))
     y2, _ = lb.load(p, sr=None, mono=False)
     assert y2.shape == (2, 10)
+
+
+@pytest.mark.parametrize("sr,sec", [(48000, 2.0), (16000, 1.5), (44100, 1.0), (8000, 1.0), (32000, 0.7), (96000, 0.5)])
+def test_whole_front_end_vs_transformers_spectrogram(sr, sec):
+    """End-to-end cross-check of the restated front end (reflect-padded centred STFT, n_fft 4096 with the
+    periodic Hann window of win < n_fft samples, magnitude, Slaney mel, amplitude_to_db with the 80 dB clamp)
+    against an independent implementation: transformers.audio_utils.spectrogram / mel_filter_bank /
+    amplitude_to_db, which the Hugging Face feature extractors keep equivalent to librosa.  transformers places
+    the win-sample frame at the start of the FFT buffer where librosa centres the padded window - a linear
+    phase, invisible in the magnitudes - and pads the signal by win/2 instead of n_fft/2, which selects the
+    same samples under the window for even win."""
+    from transformers import audio_utils as AU
+    from oracle import nisqa_oracle as O
+    from nisqa_b200 import synth
+    import warnings
+    args, _ = O.load_checkpoint(os.path.join(O.default_weights_dir(), "nisqa.tar"))
+    y = synth.synth_speech_pcm16(5, sec, sr).astype(np.float32) / np.float32(32768.0)
+    ref = O.mel_db(y, sr, args)
+    hop, win = int(sr * args["ms_hop_length"]), int(sr * args["ms_win_length"])
+    assert win % 2 == 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")            # all-zero filters above fmax at low sample rates
+        fb = AU.mel_filter_bank(2049, 48, 0.0, float(args["ms_fmax"]), sr, norm="slaney", mel_scale="slaney")
+    mel = AU.spectrogram(y.astype(np.float64), AU.window_function(win, "hann", periodic=True), frame_length=win,
+                         hop_length=hop, fft_length=4096, power=1.0, center=True, pad_mode="reflect",
+                         mel_filters=fb, mel_floor=0.0)
+    db = AU.amplitude_to_db(mel, reference=1.0, min_value=1e-4, db_range=80.0)
+    assert db.shape == ref.shape == (48, 1 + len(y) // hop)
+    assert np.abs(db - ref).max() <= 1e-4          # measured 1e-5 dB
