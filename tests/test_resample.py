@@ -103,3 +103,23 @@ def test_loader_converts_to_ms_sr(tmp_path, built_lib):
                                   ms_sr=16000, ms_channel=None)
     clips, srs = NL._load_batch(ds2, [0], _HostPool(), 0, 1)
     assert clips[0].dtype == np.int16 and srs == [16000]
+
+
+@pytest.mark.parametrize("so,sn,tol", [(16000, 48000, 2e-4), (8000, 16000, 2e-4), (44100, 48000, 2e-4), (48000, 44100, 5e-4),
+                                       (48000, 16000, 3e-3)])
+def test_restatement_vs_torchaudio_kaiser_sinc(so, sn, tol):
+    """Independent implementation of the same filter family: torchaudio's sinc_interp_kaiser with the parameters
+    torchaudio documents as the equivalent of resampy's kaiser_best (width 64, rolloff 0.9475937167399596, beta
+    14.769656459379492 - its built-in default beta is that very constant).  It evaluates the windowed sinc
+    exactly per polyphase branch where resampy interpolates a 512-per-zero-crossing table (a few 1e-5) and, when
+    down-sampling, strides that table by int(ratio * 512) (a few 1e-3, see above)."""
+    import torch
+    import torchaudio.functional as TF
+    from nisqa_b200 import synth
+    y = synth.synth_speech_pcm16(3, 1.0, so).astype(np.float32) / np.float32(32768.0)
+    a = lb.resample(y, so, sn)
+    b = TF.resample(torch.from_numpy(y), so, sn, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                    resampling_method="sinc_interp_kaiser", beta=14.769656459379492).numpy()
+    m = min(len(a), len(b))
+    assert abs(len(a) - len(b)) <= 1          # librosa's ceil(n * float ratio) can exceed the exact length by one
+    assert np.abs(a[200:m - 200] - b[200:m - 200]).max() <= tol
