@@ -1,7 +1,7 @@
 """GPU-box A/B of the tcgen05 conv variants (one process per variant so that a faulting variant cannot
 take the others down):
 
-    python tools/tc_ab.py [--lib path.so] [--swz MASK] [--bo 0|1] [--timing] [--tag name]
+    python tools/tc_ab.py [--lib path.so] [--split 0|1] [--wide MASK] [--timing] [--skip-check] [--tag name]
 
 Prints (1) max |variant - fp32 FFMA path| per CNN stage and the worst |score - oracle| on a few clips,
 (2) per-layer kernel times (CUDA events on the engine stream) and the device-resident throughput of

@@ -1,3 +1,4 @@
+"""One nisqa_tts.tar call on short clips (for ncu captures of the StandardCNN / BiLSTM kernels)."""
 import os, sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from nisqa_b200 import engine as E, synth

@@ -1,3 +1,4 @@
+"""GPU-box probe: nisqa_tts.tar throughput and per-group kernel times at full length (987 segments / clip)."""
 import os, sys, numpy as np, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from nisqa_b200 import engine as E, synth
