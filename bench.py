@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - clips/s of the NISQA predict hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): predict_dir bs=64, synthetic 10 s 48 kHz PCM16 clips,
@@ -15,6 +15,9 @@ scores inside the timed region), `roofline` for the dominant kernel (CUDA-event 
 engine stream), `cpu_baseline` = the oracle port on the host cores on a bounded sample.
 `--impl reference` times the reference's CPU implementation of the path (the oracle port run
 clip-parallel on all host cores) and prints the same line with "impl": "reference".
+`--impl reference-gpu` (and the `reference_gpu` key of the default line at N=1) times the UNMODIFIED
+reference torch modules in PyTorch eager on this GPU (tools/reference_gpu.py; SURVEY.md 8d's "honest thing to
+beat"), when the reference package was installed under baseline/_ref by __graft_entry__.build().
 """
 import argparse
 import json
@@ -76,15 +79,19 @@ def build_rooflines(kernel_ms, peaks, sm_max_mhz, traffic_tab, n_samples):
             r["frac_fp32"] = ach / fp32_peak
         roofs[k] = r
     byts = BS * (n_samples * 2 + 1001 * 48 * 4)
-    ach = byts / (kernel_ms["frontend"] / 1e3) / 1e9
+    hbm = byts / (kernel_ms["frontend"] / 1e3) / 1e9
     fft_tf = 136.7e6 * BS / (kernel_ms["frontend"] / 1e3) / 1e12
-    roofs["frontend"] = {"kernel": "frontend", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic_tab.get("frontend"),
-                         "peak_source": peaks["source"], "kernel_ms": kernel_ms["frontend"],
-                         "algorithmic_bytes_per_launch": byts,
-                         "note": "PCM16 in + mel out (SURVEY 8d 'STFT-bandwidth roofline'); the kernel is FFT issue/latency "
-                                 "bound (123 MFLOP/clip of radix-32 butterflies), not HBM bound",
-                         "fft_tflops": fft_tf, "fp32_peak_tflops": fp32_peak, "frac_fp32": fft_tf / fp32_peak}
+    # The front-end moves 1.2 MB per clip but executes 137 MFLOP of radix-32 butterflies + mel on the FFMA pipe: it
+    # is bound by fp32 instruction issue, so `frac` is the fraction of the fp32 FFMA peak (the HBM view of SURVEY
+    # 8d's "STFT-bandwidth roofline" is kept beside it: hbm_gbs / hbm_frac say how far it is from being a copy)
+    roofs["frontend"] = {"kernel": "frontend", "bound": "fp32-issue", "achieved": fft_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": fft_tf / fp32_peak, "traffic": traffic_tab.get("frontend"),
+                         "peak_source": "fp32 FFMA peak 148 SM x 128 lanes x 2 x SM clock", "kernel_ms": kernel_ms["frontend"],
+                         "algorithmic_flop_per_launch": 136.7e6 * BS, "algorithmic_bytes_per_launch": byts,
+                         "hbm_gbs": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": hbm / peaks["hbm_gbs"],
+                         "hbm_peak_source": peaks["source"],
+                         "note": "123 MFLOP/clip of FFT butterflies + 13.7 MFLOP magnitude / mel / log (BASELINE.md section 3), "
+                                 "PCM16 in + mel out = algorithmic_bytes_per_launch"}
     if kernel_ms.get("sa_layer", 0) > 0:
         # the two self-attention layer launches (flash-style softmax(QK^T)V + out-proj + FFN + 2 LayerNorms), fp32 FFMA
         ms = kernel_ms["sa_layer"]
@@ -236,6 +243,81 @@ def _cpu_worker(seed):
     return float(sc[0])
 
 
+def _host_info():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import reference_gpu
+    return reference_gpu.host_info()
+
+
+def load_traffic_table():
+    """Per-launch DRAM traffic (ncu dram__bytes_read + write) of the kernels, measured by tools/profile_round.sh and
+    stamped with the digest of the kernel sources it was measured on (nisqa_b200/build.py _digest).  ncu cannot run
+    inside the bench, so a table taken on OTHER sources is refused: traffic is then null, never stale."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tp):
+        return {}, "no profiles/roofline_traffic.json"
+    tab = json.load(open(tp))
+    from nisqa_b200 import build as nb_build
+    have, want = tab.get("_source_digest"), nb_build._digest()
+    if have != want:
+        return {}, "profiles/roofline_traffic.json was measured on other kernel sources (digest %s..., library %s...): traffic = null" % (
+            str(have)[:12], want[:12])
+    return tab, "profiles/roofline_traffic.json (%s), same kernel sources as this library" % tab.get("_note", "")
+
+
+def cpu_baseline_leg(target_s=6.0, repeats=3):
+    """Oracle port on every host core, clip-parallel; `repeats` bounded samples, median reported, host described
+    (the same port printed 87 and 420-460 clips/s on two '128 core' boxes in round 1: the box matters)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import reference_gpu
+    cores = host_cores()
+    pool = CpuPool(cores)
+    _, dt1, _ = pool.run(cores)
+    n_cpu = int(min(max(cores, cores * target_s / max(dt1, 1e-3)), 64 * cores))
+    runs = [pool.run(n_cpu, seed0=7000 + 100 * r) for r in range(repeats)]
+    pool.close()
+    vals = sorted(v for v, _, _ in runs)
+    return {"value": float(np.median(vals)), "unit": UNIT, "cores": cores, "kind": "port",
+            "repeats": [float(v) for v, _, _ in runs], "host": reference_gpu.host_info(),
+            "sample": "median of %d runs of %d x 10 s 48 kHz white-noise clips (cost is data independent), %d worker "
+                      "processes x 1 torch thread, %.1f s of wall time each; oracle port of the reference "
+                      "CPU path (NumPy librosa restatement + torch CPU)" % (repeats, n_cpu, cores, float(np.median([d for _, d, _ in runs])))}
+
+
+def reference_gpu_leg(eng=None):
+    """The unmodified reference modules in PyTorch eager on this GPU (tools/reference_gpu.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import reference_gpu
+    ours = None
+    if eng is not None:
+        def ours(paths):
+            from nisqa_b200 import wav
+            pcm = [wav.read_wav(p)[0] for p in paths]
+            return eng.predict_pcm(pcm, [SR] * len(pcm))[0]
+    try:
+        return reference_gpu.measure(n_clips=BS, bs=BS, seconds=SECONDS, sr=SR, ckpt=CKPT, ours=ours)
+    except Exception as exc:       # the extra arm must never take the bench line down
+        return {"unavailable": "reference-gpu arm failed: %r" % (exc,)}
+
+
+def run_reference_gpu(a, rank, world):
+    if rank != 0:
+        return
+    r = reference_gpu_leg(None)
+    if "unavailable" in r:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": r["unavailable"]}), flush=True)
+        return
+    v = r["predict_dir"]["clips_per_s"]
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": 3, "warmup": 1,
+            "ms_per_step": r["predict_dir"]["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "predict_dir bs=64, synthetic 10 s 48 kHz clips, nisqa.tar (configs[1]); unmodified "
+                                   "reference package, PyTorch eager on cuda:0, %d DataLoader workers" % r["num_workers"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(BS * 1300 * 48 * 15 * 4), "d2h_bytes_per_step": BS * 5 * 4},
+            "reference_gpu": r}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(a, rank, world):
     if rank != 0:
         return
@@ -258,7 +340,7 @@ def run_reference(a, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "predict_dir bs=64, synthetic 10 s 48 kHz clips, nisqa.tar (configs[1])",
                        "sample": "%d clips per step" % per_step},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "host": _host_info(),
                              "sample": "%d x 10 s 48 kHz clips per step, %d worker processes x 1 torch thread, "
                                        "oracle port of the reference CPU path (NumPy librosa restatement + torch CPU)"
                                        % (per_step, procs)},
@@ -269,7 +351,6 @@ def run_reference(a, rank, world):
 def run_ours(a, rank, world, local):
     import torch
     from nisqa_b200 import engine as E
-    from oracle import nisqa_oracle as O          # checker + cpu_baseline leg only
     import torch.distributed as dist
 
     torch.cuda.set_device(local)
@@ -279,7 +360,8 @@ def run_ours(a, rank, world, local):
     from nisqa_b200 import dist as nb_dist
     all_cpus = os.sched_getaffinity(0)
     numa_node = nb_dist.bind_to_gpu_numa(local)      # pinned PCM buffers next to the GPU's PCIe root
-    args, sd = O.load_checkpoint(CKPT)
+    ck = torch.load(CKPT, map_location="cpu", weights_only=False)     # as nisqaModel._loadModel does (model:938-942)
+    args, sd = ck["args"], ck["model_state_dict"]
     eng = E.Engine(E.config_from_args(args), local)
     eng.load_state_dict(sd)
     n_out = eng.n_out
@@ -368,10 +450,6 @@ def run_ours(a, rank, world, local):
     step_dev(0, sync=True)
     torch.cuda.synchronize()
     got = scores_ring[0][0].cpu().numpy()
-    parity = None
-    if rank == 0:
-        ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
-        parity = float(np.abs(got - ref).max())
 
     # warm-up: W steps, then as many more as ~warmup_seconds needs (clocks take ~1 s to ramp).  The
     # step count is agreed across ranks (every step holds a collective when N > 1).
@@ -424,26 +502,20 @@ def run_ours(a, rank, world, local):
     e2e_wall = total_clips / max(wall_e2e, 1e-9)
     e2e_value = min(total_clips / (max(ms_e2e / 1e3, 1e-9)), e2e_wall)
     # ---- rooflines: every heavy kernel, `roofline` = the dominant one (largest share of the step)
-    traffic_tab = {}
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic_tab = json.load(open(tp))
+    traffic_tab, traffic_note = load_traffic_table()
     roofs, roof = build_rooflines(kernel_ms, peaks, (clocks or {}).get("sm_max_mhz"), traffic_tab, int(n_s[0]))
     cnn_ms = sum(kernel_ms[k] for k in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6"))
-    # ---- CPU baseline: oracle port, one process, all torch threads, bounded sample
+    # ---- checker legs (the only place this arm touches oracle/): parity of what was timed, then the CPU baseline
+    from oracle import nisqa_oracle as O
+    ref, _, _ = O.predict_pcm(args, sd, clips[0].astype(np.float32) / 32768.0, SR)
+    parity = float(np.abs(got - ref).max())
     cpu_base = None
     os.sched_setaffinity(0, all_cpus)               # the CPU baseline may use every host core again
     if world == 1 and not a.skip_cpu:
-        cores = host_cores()
-        pool = CpuPool(cores)
-        _, dt1, _ = pool.run(cores)
-        n_cpu = int(min(max(cores, cores * 12.0 / max(dt1, 1e-3)), 64 * cores))
-        vcpu, dtc, _ = pool.run(n_cpu, seed0=7000)
-        pool.close()
-        cpu_base = {"value": vcpu, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": "%d x 10 s 48 kHz white-noise clips (cost is data independent), %d worker "
-                              "processes x 1 torch thread, %.1f s of wall time; oracle port of the reference "
-                              "CPU path (NumPy librosa restatement + torch CPU)" % (n_cpu, cores, dtc)}
+        cpu_base = cpu_baseline_leg()
+    ref_gpu = None
+    if world == 1 and not a.skip_cpu and not a.skip_reference_gpu:
+        ref_gpu = reference_gpu_leg(eng)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -457,10 +529,11 @@ def run_ours(a, rank, world, local):
                     "d2h_bytes_per_step": int(BS * n_out * 4), "wall_clock_value": e2e_wall,
                     "api": "nisqa_submit_pcm / nisqa_wait (C-ABI, five batches in flight) on pinned host PCM16; value is wall-clock based", "numa_node": numa_node},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_kernels": roofs,
+            "roofline_traffic_source": traffic_note,
             "kernel_ms_per_step": kernel_ms, "cnn_ms_per_step": cnn_ms,
             "achieved_tflops_whole_step": FLOP_PER_CLIP * BS / (ms_dev / a.steps / 1e3) / 1e12,
             "parity_max_abs_vs_oracle": parity,
-            "cpu_baseline": cpu_base}
+            "cpu_baseline": cpu_base, "reference_gpu": ref_gpu}
     print(json.dumps(line), flush=True)
 
 
@@ -469,7 +542,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200, or 20 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--skip-reference-gpu", dest="skip_reference_gpu", action="store_true",
+                    help="omit the reference_gpu key (the reference torch modules in eager mode on this GPU)")
     ap.add_argument("--warmup-seconds", dest="warmup_seconds", type=float, default=1.5,
                     help="minimum duration of the untimed warm-up (in addition to --warmup steps)")
     ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
@@ -480,6 +555,9 @@ def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if a.impl == "reference":
         run_reference(a, rank, world)
+        return
+    if a.impl == "reference-gpu":
+        run_reference_gpu(a, rank, world)
         return
     if world > 1:
         import torch

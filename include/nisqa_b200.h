@@ -127,6 +127,10 @@ NISQA_API int  nisqa_submit_pcm(nisqa_engine* e, int n_clips,
                                 float* scores_out, int32_t* n_segments_out, int32_t* status_out,
                                 int64_t* ticket);
 NISQA_API int  nisqa_wait(nisqa_engine* e, int64_t ticket);
+/* Abandon every submission still in flight (error paths of the caller: a later batch failed on the host side and
+ * the loop is being unwound): waits until the device is idle, then forgets the tickets WITHOUT writing their
+ * scores - after it returns the scores_out / PCM buffers of those submissions may be freed. */
+NISQA_API int  nisqa_drain(nisqa_engine* e);
 
 /* Same computation with the packed PCM already resident in device memory (clips laid back
  * to back, clip i starting at element offset pcm_offsets[i]); scores stay on the device

@@ -186,29 +186,36 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
     DEPTH = 3                         # batches being decoded ahead of the GPU
     FLIGHT = 5                        # submissions kept in flight on the engine (it has 6 staging slots)
     pool = _PinnedPool(FLIGHT + DEPTH + 1)
-    with ThreadPoolExecutor(max_workers=DEPTH) as feeder:
-        pending = []
-        nxt = 0
+    in_flight = []                    # batches whose kernels are running while later ones are decoded
+    try:
+        with ThreadPoolExecutor(max_workers=DEPTH) as feeder:
+            pending = []
+            nxt = 0
 
-        def top_up():
-            nonlocal nxt
-            while nxt < len(batches) and len(pending) < DEPTH:
-                pending.append(feeder.submit(_load_batch, ds, batches[nxt], pool, nxt % len(pool.bufs), n_threads))
-                nxt += 1
+            def top_up():
+                nonlocal nxt
+                while nxt < len(batches) and len(pending) < DEPTH:
+                    pending.append(feeder.submit(_load_batch, ds, batches[nxt], pool, nxt % len(pool.bufs), n_threads))
+                    nxt += 1
 
-        top_up()
-        pos = 0
-        in_flight = []                # batches whose kernels are running while later ones are decoded
-        for b, batch in enumerate(batches):
-            clips, srs = pending.pop(0).result()
-            handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
-            in_flight.append((handle, batch, clips, srs, pos))
-            pos += len(batch)
-            if len(in_flight) >= FLIGHT:
+            top_up()
+            pos = 0
+            for b, batch in enumerate(batches):
+                clips, srs = pending.pop(0).result()
+                handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
+                in_flight.append((handle, batch, clips, srs, pos))
+                pos += len(batch)
+                if len(in_flight) >= FLIGHT:
+                    finish(in_flight.pop(0))
+                top_up()                                        # a pinned slot is recycled only after its batch finished
+            while in_flight:
                 finish(in_flight.pop(0))
-            top_up()                                        # a pinned slot is recycled only after its batch finished
-        while in_flight:
-            finish(in_flight.pop(0))
+    except BaseException:
+        # a bad file (pending.result()) or a too short / too long clip (finish()) unwinds the loop while earlier
+        # submissions still hold raw pointers into `in_flight`'s score arrays and the pinned PCM buffers: make the
+        # engine forget them before those buffers are released (the reference simply raises, lib:2305-2306)
+        engine.drain()
+        raise
     return out
 
 
@@ -226,7 +233,19 @@ def _predict_all(engine, ds, bs, num_workers):
             except OSError:
                 sizes.append(0)
         shards = nb_dist.shard_rows(sizes, world)
-        local = _predict_rows(engine, ds, shards[rank], bs, num_workers)
+        # a per-file ValueError (unreadable / too short / too long) fires on the one rank that owns the row; the
+        # others would block in the score gather.  Exchange (ok, message) first and raise the same error everywhere
+        # (the reference is single-process and simply raises, lib:2258-2263, 2276-2277, 2305-2306).
+        local, failure = None, None
+        try:
+            local = _predict_rows(engine, ds, shards[rank], bs, num_workers)
+        except ValueError as exc:
+            failure = str(exc)
+        reports = [None] * world
+        tdist.all_gather_object(reports, failure)
+        for msg in reports:                 # lowest rank first: every rank raises the same message
+            if msg is not None:
+                raise ValueError(msg)
         return nb_dist.all_gather_scores(local, shards, n, engine=engine)
     return _predict_rows(engine, ds, np.arange(n, dtype=np.int64), bs, num_workers)
 

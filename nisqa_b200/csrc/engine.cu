@@ -39,9 +39,6 @@ size_t split_plane_bytes(int std_mode, int layer, int n_seg);
 void launch_conv_split(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
                        void*, void*, float*, int, int);
 void launch_unsplit(cudaStream_t, int, int, const void*, const void*, float*, int);
-// conv_wide.cu (experimental)
-void launch_conv_wide(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
-                      void*, void*, float*, int);
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
 int sp_timing_read(long long*, int);
@@ -182,7 +179,6 @@ struct nisqa_engine {
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
   int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
-  int conv_wide = 0;       // EXPERIMENTAL: bit l (3..6) set: layer l runs conv_wide.cu (N = 256 MMAs) instead of conv_split.cu
   int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
   bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
@@ -755,11 +751,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
         snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
         Scope s(e, nm);
-        if (split && ((e->conv_wide >> l) & 1) && l >= 3)
-          launch_conv_wide(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
-                           l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
-                           l == 6 ? LN.feats.as<float>() : nullptr, n_seg);
-        else if (split)
+        if (split)
           launch_conv_split(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
                             l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
                             l == 6 ? LN.feats.as<float>() : nullptr, n_seg, e->tc_timing_layer == l ? 2 : 0);
@@ -1021,6 +1013,18 @@ int nisqa_wait(nisqa_engine* e, int64_t ticket) {
   return 0;
 }
 
+int nisqa_drain(nisqa_engine* e) {
+  if (!e || !e->stream) return NISQA_ERR_INVALID;
+  cudaSetDevice(e->device);
+  // abandon every submission in flight: wait for the device, deliver nothing (the caller's score / PCM buffers
+  // may already be gone - that is what this call is for)
+  cudaError_t err = cudaDeviceSynchronize();
+  for (auto& tk : e->tickets) { tk.active = false; tk.user_scores = nullptr; }
+  for (auto& g : e->stages) g.busy = false;
+  if (err != cudaSuccess) return fail(e, NISQA_ERR_CUDA, std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(err));
+  return 0;
+}
+
 int nisqa_predict_pcm_device(nisqa_engine* e, int n_clips, const void* pcm_dev, const int64_t* pcm_offsets,
                              const int64_t* n_samples, const int32_t* sample_rate, int sample_fmt,
                              float* scores_dev, int32_t* n_segments_out, int32_t* status_out, int sync) {
@@ -1140,7 +1144,6 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
-  if (strcmp(name, "conv_wide") == 0) { e->conv_wide = value & 0x78; return 0; }
   if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }

@@ -410,11 +410,12 @@ void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDe
     return;
   }
   const int smem = frontend_smem_bytes(Q);
-  static int configured_q = 0;
-  if (Q > configured_q) {
-    cudaFuncSetAttribute(frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured_q = Q;
+  // the opt-in is per device (several engines - one per GPU - may live in one process): ask once per device
+  // for the largest window this kernel supports (Q = 4: win up to n_fft)
+  static unsigned long long configured = 0;
+  if (first_launch_on_device(configured)) {
+    cudaFuncSetAttribute(frontend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, frontend_smem_bytes(4));
+    cudaFuncSetAttribute(frontend_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, frontend_smem_bytes(4));
   }
   const dim3 grid(max_pairs, n_clips);
   if (fmt_f32) {

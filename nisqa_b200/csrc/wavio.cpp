@@ -21,6 +21,8 @@
 
 namespace {
 
+constexpr int kMaxChannels = 256;     // libsndfile's own limit is 1024; no speech corpus comes close
+
 struct WavInfo {
   int tag = 0, channels = 0, bits = 0;
   int32_t sample_rate = 0;
@@ -44,7 +46,11 @@ bool parse_header(FILE* f, WavInfo* w) {
       w->channels = b[2] | (b[3] << 8);
       w->sample_rate = (int32_t)((uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24));
       w->bits = b[14] | (b[15] << 8);
+      const int block_align = b[12] | (b[13] << 8);
       if (w->tag == 0xFFFE && sz >= 26) w->tag = b[24] | (b[25] << 8);   // WAVE_FORMAT_EXTENSIBLE
+      // implausible / inconsistent headers are "Could not load file", not a multi-GB decode buffer
+      if (w->channels < 1 || w->channels > kMaxChannels || w->sample_rate < 1) return false;
+      if (w->bits < 8 || w->bits > 64 || (w->bits & 7) || block_align != w->channels * (w->bits / 8)) return false;
       have_fmt = true;
     } else if (memcmp(ck, "data", 4) == 0) {
       if (!have_fmt || w->channels < 1) return false;
@@ -134,7 +140,7 @@ int nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t* sample_rate, 
 // probe reported S16; NISQA_FMT_F32 is always legal (PCM16 is then scaled by 1/32768).
 // ms_channel < 0: mono mix = float32 mean over the channels (librosa.to_mono); else that channel
 // (ignored for mono files, lib:2301).  Returns the number of frames written, or a negative status.
-int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
+static int64_t wav_decode_impl(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
   if (!path || !dst) return NISQA_ERR_INVALID;
   FILE* f = fopen(path, "rb");
   if (!f) return NISQA_ERR_INVALID;
@@ -190,6 +196,15 @@ int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, 
   } else { fclose(f); return NISQA_ERR_INVALID; }
   fclose(f);
   return done == w.n_frames ? done : (int64_t)NISQA_ERR_INVALID;
+}
+
+// no exception crosses the ABI (and none may escape a std::thread of run_parallel: that is std::terminate)
+int64_t nisqa_wav_decode(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
+  try {
+    return wav_decode_impl(path, ms_channel, out_fmt, dst, cap_frames);
+  } catch (...) {
+    return NISQA_ERR_INVALID;
+  }
 }
 
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "nisqa_predict_pcm", "nisqa_predict_pcm_device", "nisqa_stage_dump", "nisqa_segment_counts",
     "nisqa_mel_filterbank", "nisqa_gather_nccl", "nisqa_nccl_unique_id", "nisqa_nccl_init",
     "nisqa_kernel_launches", "nisqa_stream", "nisqa_set_profiling", "nisqa_group_ms", "nisqa_set_option",
-    "nisqa_submit_pcm", "nisqa_wait", "nisqa_join", "nisqa_set_gather_target",
+    "nisqa_submit_pcm", "nisqa_wait", "nisqa_drain", "nisqa_join", "nisqa_set_gather_target",
     "nisqa_wav_probe", "nisqa_wav_decode", "nisqa_wav_probe_batch", "nisqa_wav_decode_batch",
     "nisqa_resample_set_filter", "nisqa_resample_out_len", "nisqa_resample_f32",
 ]
@@ -98,6 +98,8 @@ def load_library(path=None):
     lib.nisqa_join.restype = C.c_int
     lib.nisqa_wait.argtypes = [vp, C.c_int64]
     lib.nisqa_wait.restype = C.c_int
+    lib.nisqa_drain.argtypes = [vp]
+    lib.nisqa_drain.restype = C.c_int
     lib.nisqa_predict_pcm_device.argtypes = [vp, C.c_int, vp, i64p, i64p, i32p, C.c_int, vp, i32p, i32p, C.c_int]
     lib.nisqa_predict_pcm_device.restype = C.c_int
     lib.nisqa_stage_dump.argtypes = [vp, C.c_int, f32p, C.c_int64]
@@ -203,8 +205,14 @@ class Engine(object):
         if rc != 0:
             raise EngineError("%s failed (%d): %s" % (what, rc, self._err()))
 
+    def drain(self):
+        """Abandon the submissions in flight (their buffers may be freed afterwards)."""
+        if getattr(self, "h", None):
+            self.lib.nisqa_drain(self.h)
+
     def close(self):
         if getattr(self, "h", None):
+            self.lib.nisqa_drain(self.h)
             self.lib.nisqa_destroy(self.h)
             self.h = C.c_void_p()
 

@@ -6,6 +6,7 @@ side like the wav decode); this module builds the interpolation table once and w
 None of the shipped checkpoints sets ``ms_sr``; the path exists for user-trained models.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -14,6 +15,7 @@ NUM_ZEROS, PRECISION = 64, 9
 ROLLOFF, BETA = 0.9475937167399596, 14.769656459379492
 
 _ready = False
+_ready_lock = threading.Lock()       # _load_batch runs on several feeder threads: the table is set exactly once
 
 
 def kaiser_best_half_window():
@@ -30,11 +32,13 @@ def _lib():
     from . import engine as _e
     lib = _e.load_library()
     if not _ready:
-        win, num_table = kaiser_best_half_window()
-        rc = lib.nisqa_resample_set_filter(win.ctypes.data_as(C.POINTER(C.c_double)), win.shape[0], num_table)
-        if rc != 0:
-            raise RuntimeError("nisqa_resample_set_filter failed (%d)" % rc)
-        _ready = True
+        with _ready_lock:
+            if not _ready:
+                win, num_table = kaiser_best_half_window()
+                rc = lib.nisqa_resample_set_filter(win.ctypes.data_as(C.POINTER(C.c_double)), win.shape[0], num_table)
+                if rc != 0:
+                    raise RuntimeError("nisqa_resample_set_filter failed (%d)" % rc)
+                _ready = True
     return lib
 
 

@@ -48,9 +48,12 @@ def _parse(buf):
         start = pos + 8
         end = min(start + csz, n)
         if cid == b"fmt ":
-            tag, ch, sr, _, _, bits = struct.unpack_from("<HHIIHH", buf, start)
+            tag, ch, sr, _, block_align, bits = struct.unpack_from("<HHIIHH", buf, start)
             if tag == 0xFFFE and end - start >= 26:
                 (tag,) = struct.unpack_from("<H", buf, start + 24)
+            # same plausibility rules as the native reader (csrc/wavio.cpp parse_header)
+            if not (1 <= ch <= 256) or sr < 1 or bits < 8 or bits > 64 or bits % 8 or block_align != ch * (bits // 8):
+                raise ValueError("implausible fmt chunk")
             fmt = (tag, ch, sr, bits)
         elif cid == b"data":
             payload = (start, end)

@@ -26,12 +26,13 @@ _OPTIONS = {
     "ms_channel": (int, None, "channel to use for multi-channel files (default: mono mix)"),
 }
 _REQUIRED = {"mode", "pretrained_model"}
-# what each mode cannot run without, with the complaint raised when it is missing
+# what each mode cannot run without; the messages are the reference's own (reference run_predict.py:22-37) so that
+# scripts matching on them keep working
 _NEEDS = {
-    "predict_file": [("deg", "predict_file needs --deg <wav file>")],
-    "predict_dir": [("data_dir", "predict_dir needs --data_dir <folder of wav files>")],
-    "predict_csv": [("csv_file", "predict_csv needs --csv_file <table>"),
-                    ("csv_deg", "predict_csv needs --csv_deg <column holding the file names>")],
+    "predict_file": [("deg", "--deg argument with path to input file needed")],
+    "predict_dir": [("data_dir", "--data_dir argument with folder with input files needed")],
+    "predict_csv": [("csv_file", "--csv_file argument with csv file name needed"),
+                    ("csv_deg", "--csv_deg argument with csv column name of the filenames needed")],
 }
 
 
@@ -42,7 +43,7 @@ def parse_args(argv=None):
     args = vars(parser.parse_args(argv))
 
     if args["mode"] not in _NEEDS:
-        raise NotImplementedError("unknown --mode %r" % args["mode"])
+        raise NotImplementedError("--mode given not available")
     for key, complaint in _NEEDS[args["mode"]]:
         if args[key] is None:
             raise ValueError(complaint)

@@ -180,6 +180,69 @@ def test_full_size_properties_config2(engines):
     assert np.all(np.isfinite(s1)) and s1.min() > 0.0 and s1.max() < 6.0
 
 
+
+def _sliced_clips(durations, sr, seed):
+    """Distinct clips of the given durations cut out of a few 30-s synthetic bases (synthesis cost stays bounded)."""
+    bases = [synth.synth_speech_pcm16(900 + i, 30.0, sr) for i in range(8)]
+    rng = np.random.default_rng(seed)
+    clips = []
+    for i, d in enumerate(durations):
+        n = int(round(float(d) * sr))
+        st = int(rng.integers(0, len(bases[0]) - n + 1))
+        clips.append(bases[i % 8][st:st + n])
+    return clips
+
+
+def _check_full_size(eng, args, sd, clips, sr, sample_idx):
+    cfg = E.config_from_args(args)
+    srs = [sr] * len(clips)
+    scores, nseg, status = eng.predict_pcm(clips, srs)
+    assert np.all(status == E.CLIP_OK) and np.all(np.isfinite(scores))
+    want = np.array([E.segment_counts(cfg, len(c), sr)[1] for c in clips], np.int32)
+    np.testing.assert_array_equal(nseg, want)                          # every segment count, exactly
+    worst = 0.0
+    for i in sample_idx:
+        ref, ns, st = O.predict_pcm(args, sd, _f32(clips[i]), sr)
+        assert st == O.STATUS_OK and ns == nseg[i]
+        worst = max(worst, float(np.abs(scores[i] - ref).max()))
+        assert worst <= SCORE_TOL, (i, worst)
+    return scores, nseg, worst
+
+
+def test_config3_full_size_ragged_bs512(engines):
+    """BASELINE configs[2] at FULL size: 512 clips of U(2,30) s at 48 kHz in ONE call = 7 internal passes of
+    <= 32768 segments, the last one smaller than the others (the shape that exposed the lo-plane offset bug of
+    round 1).  Eight sampled clips against the oracle (<= 1e-4), all 512 segment counts exact, and the
+    pass-splitting properties bit-exact: a clip alone == inside the batch, and the reversed batch (different
+    pass boundaries, different plane rows) == the same rows."""
+    eng, args, sd = engines["nisqa.tar"]
+    durs = synth.ragged_durations(512, 2.0, 30.0, seed=11)
+    clips = _sliced_clips(durs, 48000, seed=5)
+    order = np.argsort(durs)
+    sample = [int(order[0]), int(order[3]), int(order[-1]), 0, 100, 255, 400, 511]     # shortest, longest, spread over the passes
+    scores, nseg, worst = _check_full_size(eng, args, sd, clips, 48000, sample)
+    assert int(nseg.sum()) > 6 * 32768                                  # really a multi-pass call
+    for i in (sample[0], sample[2], 511):
+        alone, _, _ = eng.predict_pcm([clips[i]], [48000])
+        np.testing.assert_array_equal(alone[0], scores[i])
+    rev, nrev, _ = eng.predict_pcm(clips[::-1], [48000] * 512)
+    np.testing.assert_array_equal(rev[::-1], scores)
+    print("configs[2] full size: max |d| vs oracle over %d sampled clips = %.2e, %d segments" % (len(sample), worst, int(nseg.sum())))
+
+
+def test_config4_full_size_tts_bs256(engines):
+    """BASELINE configs[3] at FULL size: nisqa_tts.tar, 256 clips of 10 s at 16 kHz (987 segments each) in one
+    call = 8 passes.  Eight sampled clips against the oracle, all segment counts exact, alone == in-batch."""
+    eng, args, sd = engines["nisqa_tts.tar"]
+    clips = _sliced_clips([10.0] * 256, 16000, seed=6)
+    sample = [0, 33, 66, 99, 132, 200, 254, 255]
+    scores, nseg, worst = _check_full_size(eng, args, sd, clips, 16000, sample)
+    assert np.all(nseg == 987) and int(nseg.sum()) > 7 * 32768
+    for i in (0, 132, 255):
+        alone, _, _ = eng.predict_pcm([clips[i]], [16000])
+        np.testing.assert_array_equal(alone[0], scores[i])
+    print("configs[3] full size: max |d| vs oracle over %d sampled clips = %.2e" % (len(sample), worst))
+
 @pytest.mark.parametrize("ckpt,clips", [
     ("nisqa.tar", [(31, 10.0, 48000), (32, 2.3, 48000), (33, 4.0, 16000), (34, 0.1875, 8000)]),
     ("nisqa_tts.tar", [(35, 3.0, 16000), (36, 1.1, 48000)]),
@@ -214,30 +277,6 @@ def test_conv_paths_agree(engines, ckpt, clips):
         np.testing.assert_array_equal(s_again[::-1], out["planes"][0])
     finally:
         eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
-
-
-@pytest.mark.skipif(os.environ.get("NISQA_EXPERIMENTAL") != "1",
-                    reason="round-2 candidate kernel (csrc/conv_wide.cu), never run on a GPU yet: NISQA_EXPERIMENTAL=1 enables it")
-@pytest.mark.parametrize("ckpt,clips", [
-    ("nisqa.tar", [(41, 10.0, 48000), (42, 2.3, 48000), (43, 0.1875, 8000)]),
-    ("nisqa_tts.tar", [(44, 3.0, 16000)]),
-])
-def test_conv_wide_candidate(engines, ckpt, clips):
-    """conv3..6 with one N = 256 MMA per tile (weights as the M operand) against the default plane pipeline:
-    same values up to the extra w_lo * x_lo term (2^-22 relative)."""
-    eng, args, sd = engines[ckpt]
-    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
-    srs = [c[2] for c in clips]
-    try:
-        ref, _, _ = eng.predict_pcm(pcm, srs)
-        ref_feat = eng.stage_dump(E.STAGE_CNN_FEAT)
-        for mask in (0x78, 0x10, 0x08, 0x20, 0x40):
-            eng.set_option("conv_wide", mask)
-            got, _, _ = eng.predict_pcm(pcm, srs)
-            assert np.abs(got - ref).max() <= SCORE_TOL / 10, hex(mask)
-            assert np.abs(eng.stage_dump(E.STAGE_CNN_FEAT) - ref_feat).max() <= ACT_TOL / 4, hex(mask)
-    finally:
-        eng.set_option("conv_wide", 0)
 
 
 def test_device_resident_entry_point_equals_host_entry_point(engines):
@@ -333,9 +372,6 @@ def test_stereo_channel_pick_and_float_wav(wav_dir, built_lib):
             assert np.abs(got - ref).max() <= SCORE_TOL, (ch, row["deg"])
 
 
-@pytest.mark.skipif(os.environ.get("NISQA_EXPERIMENTAL") != "1",
-                    reason="ms_sr ingest path (SURVEY 8f.2): host side verified on the CPU (tests/test_resample.py), the "
-                           "end-to-end run has not been on a GPU yet: NISQA_EXPERIMENTAL=1 enables it")
 def test_ms_sr_checkpoint_resamples_on_ingest(wav_dir, built_lib):
     """A checkpoint whose args carry ms_sr (here: forced through the caller's dict, model:941-942): every file
     is converted to that rate before the engine sees it, like lb.load(path, sr=ms_sr) at lib:2300-2304."""

@@ -227,7 +227,15 @@ def test_bench_rooflines_replay_recorded_line():
     traffic = {k: v["traffic"] for k, v in rec["roofline_kernels"].items()}
     roofs, dom = bench.build_rooflines(rec["kernel_ms_per_step"], peaks, rec["clocks"]["sm_max_mhz"], traffic, 480000)
     assert dom["kernel"] == rec["roofline"]["kernel"] == "frontend"
+    fe_got, fe_want = roofs["frontend"], rec["roofline_kernels"]["frontend"]
+    # round 2: the front-end is reported against the fp32 issue peak (`frac` = the recorded frac_fp32); the HBM view
+    # the r01e line carried as `achieved` / `frac` is kept as hbm_gbs / hbm_frac
+    assert fe_got["bound"] == "fp32-issue" and fe_got["unit"] == "TFLOP/s"
+    assert abs(fe_got["achieved"] - fe_want["fft_tflops"]) <= 1e-9 and abs(fe_got["frac"] - fe_want["fft_tflops"] / fe_got["peak"]) <= 1e-12
+    assert abs(fe_got["hbm_gbs"] - fe_want["achieved"]) <= 1e-6 and abs(fe_got["hbm_frac"] - fe_want["frac"]) <= 1e-12
     for k, want in rec["roofline_kernels"].items():
+        if k == "frontend":
+            continue
         got = roofs[k]
         for field in ("bound", "unit", "traffic"):
             assert got[field] == want[field], (k, field)

@@ -1,14 +1,13 @@
 """Executable specification of the fp16 plane layout that carries activations between the tcgen05 conv layers
-(csrc/conv_split.cu, csrc/conv_wide.cu) - a NumPy emulation of the index arithmetic of those kernels, checked
+(csrc/conv_split.cu) - a NumPy emulation of the index arithmetic of those kernels, checked
 against torch's conv2d on the CPU:
 
   * plane row / swizzle addressing, hi/lo split and its round trip (what conv1 / the epilogues write and
     launch_unsplit reads back),
   * a CTA's tile = one contiguous byte range of a plane, placed at row offset g0 & 7 of a 1024-byte aligned
     buffer, read back through the absolute-address swizzle the UMMA descriptors apply (measured on B200),
-  * the implicit GEMM over row-shifted tiles (9 taps) == conv2d(padding=1), for both operand orders:
-    positions x channels (conv_split.cu) and [W_hi; W_lo] rows x 256 positions with the transposing epilogue
-    of conv_wide.cu (hi warps store, lo warps add, second pass pools / picks the centre column).
+  * the implicit GEMM over row-shifted tiles (9 taps) == conv2d(padding=1), positions x channels, with the
+    epilogue's row <-> (segment, h, w) map, pooling and the centre-column pick of conv6.
 
 No GPU and no library call: this pins the layout contract the CUDA kernels implement (their numerical parity is
 tests/test_gpu_parity.py's job).
@@ -116,53 +115,6 @@ def implicit_gemm(X, wgt, g):
     return D
 
 
-def wide_epilogue(Dt, g, n_live_seg, bias, pool, pow_, center):
-    """conv_wide.cu: Dt[m][n], m = 0..63 hi weight rows, 64..127 lo weight rows; 8 warps: quarter q = w & 3 owns
-    rows 32q..32q+31, positions [128 (w >> 2), +128); hi quarters store S[n][ch], lo quarters add; second pass
-    over S[position][channel]."""
-    nlive = g.G * g.BLK
-    S = np.full((256, 64), np.nan)
-    for phase in (0, 1):
-        for w in range(8):
-            q, n_base = w & 3, (w >> 2) * 128
-            if (q >= 2) != bool(phase):
-                continue
-            for lane in range(32):
-                ch = (q & 1) * 32 + lane
-                for n in range(n_base, n_base + 128):
-                    if n < nlive:
-                        if phase == 0:
-                            S[n, ch] = Dt[q * 32 + lane, n]
-                        else:
-                            S[n, ch] += Dt[q * 32 + lane, n]
-    aff = lambda v: np.maximum(v + bias, 0.0)
-    outs = []
-    for s in range(n_live_seg):
-        if pool:
-            HO = g.H // 2
-            o = np.zeros((HO, pow_, 64))
-            for ph in range(HO):
-                for pw in range(pow_):
-                    if pool == "adapt":
-                        x0, x1 = (pw * g.W) // pow_, ((pw + 1) * g.W + pow_ - 1) // pow_
-                    else:
-                        x0, x1 = 2 * pw, 2 * pw + 2
-                    m = np.full(64, -np.inf)
-                    for hy in (2 * ph, 2 * ph + 1):
-                        for x in range(x0, x1):
-                            m = np.maximum(m, S[s * g.BLK + (hy + 1) * g.P + (x + 1)])
-                    o[ph, pw] = aff(m)
-        else:
-            wout = 1 if center else g.W
-            o = np.zeros((g.H, wout, 64))
-            for h in range(g.H):
-                for w in range(wout):
-                    ww = 2 if center else w + 1
-                    o[h, w] = aff(S[s * g.BLK + (h + 1) * g.P + ww])
-        outs.append(o)
-    return np.stack(outs)
-
-
 @pytest.mark.parametrize("H,W,C", [(24, 7, 16), (12, 5, 32), (12, 5, 64), (6, 3, 64), (24, 8, 16), (6, 2, 64)])
 def test_planes_round_trip_and_zero_padding(H, W, C):
     g = Geom(H, W, C)
@@ -234,13 +186,7 @@ def test_implicit_gemm_over_shifted_tiles_is_conv2d(name, H, W, C, pool, pow_, c
         X = tile_matrix(hi_p, lo_p, g, seg0)
         # conv_split.cu order: positions x channels
         D = implicit_gemm(X, w_sum, g)
-        # conv_wide.cu order: rows = [W_hi ; W_lo], columns = positions; identical sums by linearity
-        Dt = np.concatenate([implicit_gemm(X, w_hi.astype(np.float64), g).T, implicit_gemm(X, w_lo.astype(np.float64), g).T])
-        assert Dt.shape == (128, 256)
-        np.testing.assert_allclose(Dt[:64] + Dt[64:], D.T, rtol=0, atol=1e-9)
-        got = wide_epilogue(Dt, g, live, bias.astype(np.float64), pool, pow_, center)
         tol = 2e-5          # weights enter as w_hi + w_lo (2^-22 of |w|), accumulation in float64 here
-        np.testing.assert_allclose(got, ref[seg0:seg0 + live], rtol=0, atol=tol)
         # conv_split.cu's epilogue: thread <-> tile row r = s*BLK + hh*P + ww (interior rows only)
         for s in range(live):
             for h in range(H):
@@ -251,3 +197,12 @@ def test_implicit_gemm_over_shifted_tiles_is_conv2d(name, H, W, C, pool, pow_, c
                     v = np.maximum(D[r] + bias, 0.0)
                     if not pool:
                         np.testing.assert_allclose(v, ref[seg0 + s, h, 0 if center else w], rtol=0, atol=tol)
+            if pool:
+                # epilogue part 2 of conv_split.cu: max over the staged interior rows of each pooling window
+                # (adaptive windows [floor(pw*W/POW), ceil((pw+1)*W/POW)) or 2x2)
+                for ph in range(H // 2):
+                    for pw in range(pow_):
+                        x0, x1 = ((pw * W) // pow_, -(-(pw + 1) * W // pow_)) if pool == "adapt" else (2 * pw, 2 * pw + 2)
+                        rows = [s * g.BLK + (hy + 1) * g.P + (x + 1) for hy in (2 * ph, 2 * ph + 1) for x in range(x0, x1)]
+                        v = np.maximum(D[rows] + bias, 0.0).max(axis=0)
+                        np.testing.assert_allclose(v, ref[seg0 + s, ph, pw], rtol=0, atol=tol)

@@ -92,6 +92,9 @@ def main():
     csv.writer(open(dst, "w")).writerows(out)
     traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, "
                         "bench.py 64 x 10 s clips (profiles/%s_ncu_full_one_step.csv)" % tag)
+    sys.path.insert(0, ROOT)
+    from nisqa_b200 import build as nb_build
+    traffic["_source_digest"] = nb_build._digest()      # bench.py refuses the table on any other kernel sources
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
     print("wrote", dst)
     for r in out[2:]:

@@ -1,7 +1,7 @@
 """GPU-box A/B of the tcgen05 conv variants (one process per variant so that a faulting variant cannot
 take the others down):
 
-    python tools/tc_ab.py [--lib path.so] [--split 0|1] [--wide MASK] [--timing] [--skip-check] [--tag name]
+    python tools/tc_ab.py [--lib path.so] [--split 0|1] [--timing] [--skip-check] [--tag name]
 
 Prints (1) max |variant - fp32 FFMA path| per CNN stage and the worst |score - oracle| on a few clips,
 (2) per-layer kernel times (CUDA events on the engine stream) and the device-resident throughput of
@@ -13,7 +13,6 @@ sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--lib", default=None)
 ap.add_argument("--split", type=int, default=1, help="1: fp16 plane pipeline (conv_split.cu), 0: legacy fp32-activation tcgen05 kernels")
-ap.add_argument("--wide", type=lambda x: int(x, 0), default=0, help="layer mask for csrc/conv_wide.cu (experimental)")
 ap.add_argument("--timing", action="store_true")
 ap.add_argument("--tag", default="")
 ap.add_argument("--skip-check", action="store_true")
@@ -24,12 +23,11 @@ if a.lib:
     E._lib = E.load_library(os.path.join(ROOT, a.lib))
 import torch
 from oracle import nisqa_oracle as O
-tag = a.tag or ("split=%d wide=%#x lib=%s" % (a.split, a.wide, a.lib or "default"))
+tag = a.tag or ("split=%d lib=%s" % (a.split, a.lib or "default"))
 
 
 def opts(eng):
     eng.set_option("conv_split", a.split)
-    eng.set_option("conv_wide", a.wide)
 
 
 if not a.skip_check:
