@@ -214,10 +214,10 @@ _CPU = {}
 
 
 def host_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    """Cores the CPU arm may really use: affinity mask capped by the cgroup CPU quota (tools/reference_gpu.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import reference_gpu
+    return reference_gpu.effective_cores()
 
 
 def _cpu_worker_init():

@@ -217,7 +217,13 @@ NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
  *   "conv_split" 1 (default): with all of conv2..6 on tcgen05, activations travel between the layers as
  *                fp16 hi/lo plane pairs (csrc/conv_split.cu); 0: fp32 channels-last activations and the
  *                register-staged kernels of csrc/conv_tc.cu.  Results are bit-identical.
- *   "fe_ppc"     frame pairs per front-end CTA (0 = kernel default). */
+ *   "fe_ppc"     frame pairs per front-end CTA (0 = kernel default).
+ *   "td_tiled"   1 (default): time-dependency block + pooling logits as register-tiled GEMM kernels
+ *                (csrc/td_tiled.cu); 0: the one-thread-per-row kernels of csrc/td.cu.
+ *   "lstm_batched" 1 (default): BiLSTM advances up to four clips per CTA in lock step; 0: one CTA per
+ *                (clip, direction).
+ *   "keep_td_out" standard architecture: 1 = also store the per-step BiLSTM outputs so that
+ *                NISQA_STAGE_TD_OUT can be dumped (default 0: only the final states are needed, lib:1107-1115). */
 NISQA_API int    nisqa_set_option(nisqa_engine* e, const char* name, int value);
 NISQA_API double nisqa_group_ms(const nisqa_engine* e, const char* group);
 

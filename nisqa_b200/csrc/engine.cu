@@ -57,6 +57,13 @@ void launch_sa_layer(cudaStream_t, const float*, const float*, const ClipDesc*, 
                      const SaLayerParams&, float*);
 void launch_pool_att(cudaStream_t, const float*, const ClipDesc*, int, int, const PoolHeadParams&, int, float*, float*);
 void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmParams&, float*, float*, float, float*);
+void launch_lstm_batched(cudaStream_t, const float*, const ClipDesc*, const int*, int, const LstmParams&, float*, float*, float, float*);
+void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
+// td_tiled.cu
+void launch_td_in(cudaStream_t, const float*, const float*, const float*, const float*, const float*,
+                  const float*, const float*, float*, float*, int);
+void launch_td_sa(cudaStream_t, const float*, const float*, const ClipDesc*, int, const int*, int, const SaLayerParams&,
+                  float*, const float*, const float*, float*, const PoolHeadParams&, int, float*);
 }  // namespace nisqa
 
 using namespace nisqa;
@@ -132,13 +139,13 @@ constexpr int kLanes = 3;
 constexpr int kStages = 6;     // staging slots / submissions in flight (uploads run ahead of the lanes)
 struct Lane {
   cudaStream_t stream = nullptr;
-  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, logits, feats20, tdout, partial;
+  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, qkv2, logits, feats20, tdout, partial;
   DevBuf planes[7];        // planes[l]: fp16 hi | lo plane pair feeding conv layer l (2..6), conv_split.cu
   size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // offset of the lo plane inside planes[l] (half of the allocation)
   void release() {
     for (auto& b : planes) b.release();
     DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
-                     &feats, &xa, &xb, &qkv, &logits, &feats20, &tdout, &partial};
+                     &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout, &partial};
     for (auto* b : all) b->release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -181,6 +188,9 @@ struct nisqa_engine {
   int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
   int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
   bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
+  int lstm_batched = 1;    // BiLSTM: NB clips per CTA in lock step (td.cu lstm_batched_kernel); 0: one CTA per (clip, direction)
+  int keep_td_out = 0;     // standard arch: also write the per-step LSTM outputs [n_seg][256] (only the stage dump reads them)
+  int td_tiled = 1;        // time-dependency block as register-tiled GEMM kernels (td_tiled.cu); 0: the row-thread kernels of td.cu
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
@@ -612,9 +622,9 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   // ---- tables
   std::vector<ClipDesc>& cl = e->last_clips;
   cl.assign(n, ClipDesc());
-  std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0);
+  std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0), qt64_prefix(n + 1, 0), by_len(n + 1, 0);
   long long pcm_elems = 0;
-  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, Q = 1, max_pairs = 0, max_span = 0;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, n_qt64 = 0, Q = 1, max_pairs = 0, max_span = 0;
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
@@ -628,14 +638,17 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     d.frame_off = n_frames; d.seg_off = n_seg; d.pair_off = n_pairs;
     if (in.host_pcm) { d.pcm_off = pcm_elems; pcm_elems += ((long long)in.n_samples[i] + 15) / 16 * 16; }
     else d.pcm_off = in.dev_off[i];
-    pair_prefix[i] = n_pairs; seg_prefix[i] = n_seg; qt_prefix[i] = n_qt;
+    pair_prefix[i] = n_pairs; seg_prefix[i] = n_seg; qt_prefix[i] = n_qt; qt64_prefix[i] = n_qt64;
     n_frames += d.n_frames; n_seg += d.n_seg;
     n_pairs += (d.n_frames + 1) / 2;
     max_pairs = std::max(max_pairs, (d.n_frames + 1) / 2);
     n_qt += (d.n_seg + 127) / 128;
+    n_qt64 += (d.n_seg + 63) / 64;
     if (ok) { Q = std::max(Q, (p.win + 1023) / 1024); max_span = std::max(max_span, p.hop + p.win); }
   }
-  pair_prefix[n] = n_pairs; seg_prefix[n] = n_seg; qt_prefix[n] = n_qt;
+  pair_prefix[n] = n_pairs; seg_prefix[n] = n_seg; qt_prefix[n] = n_qt; qt64_prefix[n] = n_qt64;
+  for (int i = 0; i < n; ++i) by_len[i] = i;          // clips by decreasing length (batched BiLSTM groups)
+  std::stable_sort(by_len.begin(), by_len.begin() + n, [&](int a, int b) { return cl[a].n_seg > cl[b].n_seg; });
   e->last_n_seg = n_seg; e->last_n_frames = n_frames;
   const int n_out = c.n_out;
 
@@ -649,20 +662,22 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   if (SG.busy) { CK(cudaEventSynchronize(SG.ev_done)); SG.busy = false; }
   SG.lane = in.slot;
 
-  // ---- upload tables (one pinned block: ClipDesc[n] | 3 prefix arrays)
+  // ---- upload tables (one pinned block: ClipDesc[n] | 4 prefix arrays | clips by length)
   const size_t tb_clips = (size_t)n * sizeof(ClipDesc);
   const size_t tb_pref = (size_t)(n + 1) * 4;
-  CK(SG.h_tables.reserve(tb_clips + 3 * tb_pref));
+  CK(SG.h_tables.reserve(tb_clips + 5 * tb_pref));
   char* ht = SG.h_tables.as<char>();
   memcpy(ht, cl.data(), tb_clips);
   memcpy(ht + tb_clips, pair_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + tb_pref, seg_prefix.data(), tb_pref);
   memcpy(ht + tb_clips + 2 * tb_pref, qt_prefix.data(), tb_pref);
+  memcpy(ht + tb_clips + 3 * tb_pref, qt64_prefix.data(), tb_pref);
+  memcpy(ht + tb_clips + 4 * tb_pref, by_len.data(), tb_pref);
   CK(SG.clips.reserve(tb_clips));
-  CK(SG.prefixes.reserve(3 * tb_pref));
+  CK(SG.prefixes.reserve(5 * tb_pref));
   CK(SG.clipmax.reserve((size_t)n * 4));
   CK(cudaMemcpyAsync(SG.clips.p, ht, tb_clips, cudaMemcpyHostToDevice, cs));
-  CK(cudaMemcpyAsync(SG.prefixes.p, ht + tb_clips, 3 * tb_pref, cudaMemcpyHostToDevice, cs));
+  CK(cudaMemcpyAsync(SG.prefixes.p, ht + tb_clips, 5 * tb_pref, cudaMemcpyHostToDevice, cs));
   CK(cudaMemsetAsync(SG.clipmax.p, 0, (size_t)n * 4, cs));
   const ClipDesc* d_clips = SG.clips.as<ClipDesc>();
   unsigned* d_clipmax = SG.clipmax.as<unsigned>();
@@ -672,6 +687,8 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   e->last_stage = in.stage;
   const int* d_seg = d_pair + (n + 1);
   const int* d_qt = d_pair + 2 * (n + 1);
+  const int* d_qt64 = d_pair + 3 * (n + 1);
+  const int* d_by_len = d_pair + 4 * (n + 1);
 
   if (n_seg == 0) {   // nothing valid in this pass: NaN scores
     CK(cudaEventRecord(SG.ev_copied, cs));
@@ -768,27 +785,52 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       CK(LN.qkv.reserve((size_t)n_seg * 192 * 4));
       CK(LN.logits.reserve((size_t)n_seg * n_out * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 64 * 4));
-      { Scope s(e, "lin_ln");
-        launch_lin_ln(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), LN.tdout.as<float>(), n_seg); }
-      e->last_td_in = LN.tdout.as<float>();
-      const float* cur = LN.tdout.as<float>();
-      float* pp[2] = {LN.xa.as<float>(), LN.xb.as<float>()};
-      for (int l = 0; l < c.sa_layers; ++l) {
+      auto sa_params = [&](int l) {
         char k[32];
         auto K = [&](const char* s2) { snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
-        { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, K("qkvT")), W(e, K("qkvb")), LN.qkv.as<float>(), n_seg); }
         SaLayerParams P;
         P.WoT = W(e, K("woT")); P.bo = W(e, K("bo")); P.W1T = W(e, K("w1T")); P.b1 = W(e, K("b1"));
         P.W2T = W(e, K("w2T")); P.b2 = W(e, K("b2")); P.ln1_g = W(e, K("ln1g")); P.ln1_b = W(e, K("ln1b"));
         P.ln2_g = W(e, K("ln2g")); P.ln2_b = W(e, K("ln2b"));
-        { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, LN.qkv.as<float>(), d_clips, n, d_qt, n_qt, P, pp[l & 1]); }
-        cur = pp[l & 1];
-      }
-      e->last_td_out = cur;
+        return P;
+      };
+      auto sa_key = [&](int l, const char* s2) { char k[32]; snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
       PoolHeadParams H;
       H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
       H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
-      { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, LN.logits.as<float>(), scores); }
+      e->last_td_in = LN.tdout.as<float>();
+      const float* cur = LN.tdout.as<float>();
+      float* pp[2] = {LN.xa.as<float>(), LN.xb.as<float>()};
+      if (e->td_tiled) {
+        // tiled path: Linear+LN (+QKV of layer 0) | per layer: attention + out_proj + FFN + LNs (+ next QKV, or the
+        // pooling logits behind the last layer) | per-clip softmax pooling.  qkv ping-pongs between two buffers: a
+        // layer's CTAs read keys / values of rows whose next-layer projection other CTAs are already writing.
+        CK(LN.qkv2.reserve((size_t)n_seg * 192 * 4));
+        float* qk[2] = {LN.qkv.as<float>(), LN.qkv2.as<float>()};
+        { Scope s(e, "lin_ln");
+          launch_td_in(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"),
+                       W(e, sa_key(0, "qkvT")), W(e, sa_key(0, "qkvb")), LN.tdout.as<float>(), qk[0], n_seg); }
+        for (int l = 0; l < c.sa_layers; ++l) {
+          const bool last = l + 1 == c.sa_layers;
+          Scope s(e, "sa_layer");
+          launch_td_sa(st, cur, qk[l & 1], d_clips, n, d_qt64, n_qt64, sa_params(l), pp[l & 1],
+                       last ? nullptr : W(e, sa_key(l + 1, "qkvT")), last ? nullptr : W(e, sa_key(l + 1, "qkvb")),
+                       qk[(l + 1) & 1], H, n_out, LN.logits.as<float>());
+          cur = pp[l & 1];
+        }
+        e->last_td_out = cur;
+        { Scope s(e, "pool"); launch_pool_final(st, cur, LN.logits.as<float>(), d_clips, n, H, n_out, scores); }
+      } else {
+        { Scope s(e, "lin_ln");
+          launch_lin_ln(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), LN.tdout.as<float>(), n_seg); }
+        for (int l = 0; l < c.sa_layers; ++l) {
+          { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, sa_key(l, "qkvT")), W(e, sa_key(l, "qkvb")), LN.qkv.as<float>(), n_seg); }
+          { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, LN.qkv.as<float>(), d_clips, n, d_qt, n_qt, sa_params(l), pp[l & 1]); }
+          cur = pp[l & 1];
+        }
+        e->last_td_out = cur;
+        { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, LN.logits.as<float>(), scores); }
+      }
     } else {
       CK(LN.feats20.reserve((size_t)n_seg * 20 * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 256 * 4));
@@ -797,9 +839,13 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       LstmParams L;
       L.w_ih = W(e, "lstm.wih"); L.w_hh = W(e, "lstm.whh"); L.b = W(e, "lstm.b"); L.w_pool = W(e, "lastbi.w");
       { Scope s(e, "lstm", 2);
-        launch_lstm(st, LN.feats20.as<float>(), d_clips, n, L, LN.tdout.as<float>(), LN.partial.as<float>(), e->pool_bias_std, scores); }
+        if (e->lstm_batched)
+          launch_lstm_batched(st, LN.feats20.as<float>(), d_clips, d_by_len, n, L, e->keep_td_out ? LN.tdout.as<float>() : nullptr,
+                              LN.partial.as<float>(), e->pool_bias_std, scores);
+        else
+          launch_lstm(st, LN.feats20.as<float>(), d_clips, n, L, LN.tdout.as<float>(), LN.partial.as<float>(), e->pool_bias_std, scores); }
       e->last_td_in = nullptr;
-      e->last_td_out = LN.tdout.as<float>();
+      e->last_td_out = (e->lstm_batched && !e->keep_td_out) ? nullptr : LN.tdout.as<float>();
     }
   }
   CK(cudaGetLastError());
@@ -1060,7 +1106,9 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
     case NISQA_STAGE_TD_IN:
       if (std_mode || !e->last_td_in) return fail(e, NISQA_ERR_INVALID, "stage not available for this architecture");
       src = e->last_td_in; count = ns * 64; break;
-    case NISQA_STAGE_TD_OUT: src = e->last_td_out; count = ns * (std_mode ? 256 : 64); break;
+    case NISQA_STAGE_TD_OUT:
+      if (!e->last_td_out) return fail(e, NISQA_ERR_STATE, "the per-step BiLSTM outputs were not kept: nisqa_set_option(\"keep_td_out\", 1) before the predict call");
+      src = e->last_td_out; count = ns * (std_mode ? 256 : 64); break;
     default: return fail(e, NISQA_ERR_INVALID, "unknown stage");
   }
   if (ch > 0) count = ns * hw * ch;
@@ -1143,6 +1191,9 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (!e || !name) return NISQA_ERR_INVALID;
   if (strcmp(name, "conv_tc") == 0) { e->conv_tc = (value == 1) ? 0x7c : (value & 0x7c); return 0; }
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
+  if (strcmp(name, "lstm_batched") == 0) { e->lstm_batched = value != 0; return 0; }
+  if (strcmp(name, "keep_td_out") == 0) { e->keep_td_out = value != 0; return 0; }
+  if (strcmp(name, "td_tiled") == 0) { e->td_tiled = value != 0; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
   if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);

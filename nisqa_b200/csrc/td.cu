@@ -433,6 +433,160 @@ lstm_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipDesc* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Batched BiLSTM (round 2): one CTA advances NB clips of one direction in lock step, so that the recurrent weights
+// (512 x 128 fp32 = 256 KB: half in registers, half in shared memory) are fetched once per step for NB sequences
+// instead of once per sequence - the step is FMA bound (2 x 148 x NB FMAs per thread) instead of LDS / barrier bound,
+// and 256 clips x 2 directions fit on the chip in ONE wave (the one-sequence kernel above needed 3.5 waves of
+// 987 serial steps).  256 threads: thread t owns hidden unit u = t >> 1 and the gate pair gp = t & 1 ((i, f) or
+// (g, o), PyTorch row order i, f, g, o), i.e. two rows of W_hh / W_ih; the pair of lanes of a unit exchanges its four
+// gate values with two shuffles per sequence and both update the (replicated) cell state.  Sequences of a group may
+// have different lengths (clips are sorted by length on the host): a finished sequence keeps its state.
+// `order` lists the clips of the pass by decreasing n_seg; group g = clips order[NB g .. NB g + NB).
+template <int NB>
+__global__ void __launch_bounds__(256, 1)
+lstm_batched_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipDesc* __restrict__ clips,
+                    const int* __restrict__ order, int n_clips, LstmParams P,
+                    float* __restrict__ td_out /*[n_seg][256] or nullptr*/, float* __restrict__ partial /*[n_clips][2]*/) {
+  extern __shared__ __align__(16) float sm[];
+  float2* whs = reinterpret_cast<float2*>(sm);       // [64 k][256 t]: taps 64..127 of this thread's two rows
+  float* hbuf = sm + 2 * 64 * 256;                   // [2][NB][128]
+  float* xbuf = hbuf + 2 * NB * 128;                 // [2][NB][32]   (20 used)
+  float* red = xbuf + 2 * NB * 32;                   // [NB][128]
+  const int t = threadIdx.x, u = t >> 1, gp = t & 1;
+  const int dir = blockIdx.x & 1, g0 = (blockIdx.x >> 1) * NB;
+  int S[NB], clip[NB];
+  const float* fb[NB];
+  size_t seg_off[NB];
+  int maxS = 0;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    clip[b] = (g0 + b < n_clips) ? __ldg(order + g0 + b) : -1;
+    S[b] = 0; fb[b] = feats; seg_off[b] = 0;
+    if (clip[b] >= 0) {
+      const ClipDesc cd = clips[clip[b]];
+      S[b] = cd.n_seg; seg_off[b] = (size_t)cd.seg_off; fb[b] = feats + (size_t)cd.seg_off * 20;
+    }
+    maxS = max(maxS, S[b]);
+  }
+  const int rowA = (2 * gp) * 128 + u, rowB = rowA + 128;
+  float wrA[64], wrB[64], wiA[20], wiB[20];
+  {
+    const float* ra = P.w_hh + ((size_t)dir * 512 + rowA) * 128;
+    const float* rb = P.w_hh + ((size_t)dir * 512 + rowB) * 128;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) { wrA[k] = __ldg(ra + k); wrB[k] = __ldg(rb + k); }
+    for (int k = 0; k < 64; ++k) whs[k * 256 + t] = make_float2(__ldg(ra + 64 + k), __ldg(rb + 64 + k));
+    const float* ia = P.w_ih + ((size_t)dir * 512 + rowA) * 20;
+    const float* ib = P.w_ih + ((size_t)dir * 512 + rowB) * 20;
+#pragma unroll
+    for (int k = 0; k < 20; ++k) { wiA[k] = __ldg(ia + k); wiB[k] = __ldg(ib + k); }
+  }
+  const float biasA = __ldg(P.b + dir * 512 + rowA), biasB = __ldg(P.b + dir * 512 + rowB);
+  for (int i = t; i < 2 * NB * 128; i += 256) hbuf[i] = 0.f;
+  for (int i = t; i < 2 * NB * 32; i += 256) xbuf[i] = 0.f;
+  float cst[NB], hl[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { cst[b] = 0.f; hl[b] = 0.f; }
+  __syncthreads();
+  // x of step 0: thread t < NB * 32 loads element (b = t >> 5, k = t & 31)
+  const int xb_ = t >> 5, xk_ = t & 31;
+  if (t < NB * 32 && xk_ < 20) {
+    int Sb = 0; const float* f = feats;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) if (b == xb_) { Sb = S[b]; f = fb[b]; }
+    if (Sb > 0) xbuf[xb_ * 32 + xk_] = __ldg(f + (size_t)(dir ? Sb - 1 : 0) * 20 + xk_);
+  }
+  __syncthreads();
+
+  for (int step = 0; step < maxS; ++step) {
+    const float* h = hbuf + (step & 1) * NB * 128;
+    const float* xt = xbuf + (step & 1) * NB * 32;
+    float xnext = 0.f;
+    bool xload = false;
+    if (t < NB * 32 && xk_ < 20) {
+      int Sb = 0; const float* f = feats;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) if (b == xb_) { Sb = S[b]; f = fb[b]; }
+      if (step + 1 < Sb) { xnext = __ldg(f + (size_t)(dir ? Sb - 2 - step : step + 1) * 20 + xk_); xload = true; }
+    }
+    float aA[NB], aB[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { aA[b] = biasA; aB[b] = biasB; }
+#pragma unroll
+    for (int k = 0; k < 20; k += 4) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 xv = *reinterpret_cast<const float4*>(xt + b * 32 + k);
+        aA[b] = fmaf(wiA[k], xv.x, aA[b]); aA[b] = fmaf(wiA[k + 1], xv.y, aA[b]);
+        aA[b] = fmaf(wiA[k + 2], xv.z, aA[b]); aA[b] = fmaf(wiA[k + 3], xv.w, aA[b]);
+        aB[b] = fmaf(wiB[k], xv.x, aB[b]); aB[b] = fmaf(wiB[k + 1], xv.y, aB[b]);
+        aB[b] = fmaf(wiB[k + 2], xv.z, aB[b]); aB[b] = fmaf(wiB[k + 3], xv.w, aB[b]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(h + b * 128 + k);
+        aA[b] = fmaf(wrA[k], hv.x, aA[b]); aA[b] = fmaf(wrA[k + 1], hv.y, aA[b]);
+        aA[b] = fmaf(wrA[k + 2], hv.z, aA[b]); aA[b] = fmaf(wrA[k + 3], hv.w, aA[b]);
+        aB[b] = fmaf(wrB[k], hv.x, aB[b]); aB[b] = fmaf(wrB[k + 1], hv.y, aB[b]);
+        aB[b] = fmaf(wrB[k + 2], hv.z, aB[b]); aB[b] = fmaf(wrB[k + 3], hv.w, aB[b]);
+      }
+    }
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) {
+      const float2 w0 = whs[(k) * 256 + t], w1 = whs[(k + 1) * 256 + t], w2 = whs[(k + 2) * 256 + t], w3 = whs[(k + 3) * 256 + t];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(h + b * 128 + 64 + k);
+        aA[b] = fmaf(w0.x, hv.x, aA[b]); aA[b] = fmaf(w1.x, hv.y, aA[b]);
+        aA[b] = fmaf(w2.x, hv.z, aA[b]); aA[b] = fmaf(w3.x, hv.w, aA[b]);
+        aB[b] = fmaf(w0.y, hv.x, aB[b]); aB[b] = fmaf(w1.y, hv.y, aB[b]);
+        aB[b] = fmaf(w2.y, hv.z, aB[b]); aB[b] = fmaf(w3.y, hv.w, aB[b]);
+      }
+    }
+    float* hn = hbuf + ((step + 1) & 1) * NB * 128;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      // gp == 0: (aA, aB) = pre-activations of (i, f); gp == 1: of (g, o)
+      const float actA = gp ? tanhf(aA[b]) : 1.0f / (1.0f + expf(-aA[b]));
+      const float actB = 1.0f / (1.0f + expf(-aB[b]));
+      const float pA = __shfl_xor_sync(0xffffffffu, actA, 1), pB = __shfl_xor_sync(0xffffffffu, actB, 1);
+      const float ig = gp ? pA : actA, fg = gp ? pB : actB, gg = gp ? actA : pA, og = gp ? actB : pB;
+      if (step < S[b]) {                       // warp-uniform: S[b] is the same for every thread
+        cst[b] = fmaf(fg, cst[b], ig * gg);
+        hl[b] = og * tanhf(cst[b]);
+        if (gp == 0) {
+          hn[b * 128 + u] = hl[b];
+          if (td_out) td_out[(seg_off[b] + (size_t)(dir ? S[b] - 1 - step : step)) * 256 + dir * 128 + u] = hl[b];
+        }
+      } else if (gp == 0) {
+        hn[b * 128 + u] = hl[b];               // finished sequence: state carried along unchanged
+      }
+    }
+    if (xload) xbuf[((step + 1) & 1) * NB * 32 + xb_ * 32 + xk_] = xnext;
+    __syncthreads();
+  }
+  // PoolLastStepBi: this direction's final hidden state . w_pool half (lib:1107-1115)
+  if (gp == 0) {
+    const float w = __ldg(P.w_pool + dir * 128 + u);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) red[b * 128 + u] = hl[b] * w;
+  }
+  __syncthreads();
+  if (t < 32 * NB) {
+    const int b = t >> 5, lane = t & 31;
+    float v = red[b * 128 + lane] + red[b * 128 + lane + 32] + red[b * 128 + lane + 64] + red[b * 128 + lane + 96];
+    v = warp_sum(v);
+    int cb = -1;
+#pragma unroll
+    for (int bb = 0; bb < NB; ++bb) if (bb == b) cb = clip[bb];
+    if (lane == 0 && cb >= 0) partial[cb * 2 + dir] = v;      // clips without segments: 0 (lastbi_final writes NaN for them)
+  }
+}
+
 __global__ void lastbi_final_kernel(const float* __restrict__ partial, const ClipDesc* __restrict__ clips,
                                     float bias, float* __restrict__ scores, int n_clips) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,12 +629,38 @@ void launch_pool_att(cudaStream_t st, const float* x, const ClipDesc* clips, int
   pool_logits_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem128, st>>>(x, P, n_heads, logits, n_rows);
   pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
 }
+void launch_pool_final(cudaStream_t st, const float* x, const float* logits, const ClipDesc* clips, int n_clips,
+                       const PoolHeadParams& P, int n_heads, float* scores) {
+  pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
+}
 void launch_lstm(cudaStream_t st, const float* feats20, const ClipDesc* clips, int n_clips,
                  const LstmParams& P, float* td_out, float* partial, float pool_bias, float* scores) {
   static unsigned long long cfg = 0;
   const int smem = kLstmSmemFloats * 4;
   if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   lstm_kernel<<<2 * n_clips, 512, smem, st>>>(feats20, clips, P, td_out, partial);
+  lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
+}
+
+template <int NB> constexpr int lstm_batched_smem() { return (2 * 64 * 256 + 2 * NB * 128 + 2 * NB * 32 + NB * 128) * 4; }
+
+// `order`: device array of the pass's clip indices sorted by decreasing n_seg (host-built, run_pass); the batch
+// width follows the number of sequences per SM: 148 SMs x NB sequences per direction pair of CTAs in one wave
+void launch_lstm_batched(cudaStream_t st, const float* feats20, const ClipDesc* clips, const int* order, int n_clips,
+                         const LstmParams& P, float* td_out, float* partial, float pool_bias, float* scores) {
+  static unsigned long long cfg = 0;
+  if (first_launch_on_device(cfg)) {
+    cudaFuncSetAttribute(lstm_batched_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_batched_smem<1>());
+    cudaFuncSetAttribute(lstm_batched_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_batched_smem<2>());
+    cudaFuncSetAttribute(lstm_batched_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_batched_smem<4>());
+  }
+  const int seqs = 2 * n_clips;
+  if (seqs <= 148)
+    lstm_batched_kernel<1><<<2 * n_clips, 256, lstm_batched_smem<1>(), st>>>(feats20, clips, order, n_clips, P, td_out, partial);
+  else if (seqs <= 2 * 148)
+    lstm_batched_kernel<2><<<2 * ((n_clips + 1) / 2), 256, lstm_batched_smem<2>(), st>>>(feats20, clips, order, n_clips, P, td_out, partial);
+  else
+    lstm_batched_kernel<4><<<2 * ((n_clips + 3) / 4), 256, lstm_batched_smem<4>(), st>>>(feats20, clips, order, n_clips, P, td_out, partial);
   lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
 }
 

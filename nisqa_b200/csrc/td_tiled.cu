@@ -1,0 +1,453 @@
+// td_tiled.cu - time-dependency block + attention-pool logits of the adapt architecture as register-tiled fp32
+// GEMMs (round 2; replaces the one-thread-per-row kernels of td.cu, which ran at 6 % occupancy):
+//
+//   td_in_kernel   : Linear 384->64 + LayerNorm (reference nisqa/NISQA_lib.py:989-991) and, fused behind it, the
+//                    QKV projection of encoder layer 0 (in_proj of nn.MultiheadAttention, lib:1032)
+//   td_sa_kernel   : one encoder layer for 64 queries of one clip (lib:1025-1040): softmax(q k^T) v over the clip's
+//                    own keys (flash-style, keys in blocks of 64, online max / sum), out_proj, +x, LN1, FFN(ReLU),
+//                    +, LN2 - and, fused behind it, either the NEXT layer's QKV projection or (last layer) the
+//                    PoolAttFF logits of all heads  w2_h . relu(W1_h x + b1_h) + b2_h  (lib:1173)
+//
+// Every matrix product is a 64 x 64 x 64 tile product on the FFMA pipe: 256 threads = 16 (ty) x 16 (tx), a thread
+// owns rows 4ty..4ty+3 and four columns, operands sit in shared memory, the A operand always row-major
+// [row][k] with a padded leading dimension of 68 floats and read as float4 along k:
+//   gemm_nn : B k-major [k][n]  (weights as packed by the engine, V), columns 4tx..4tx+3, LDS.128 along n
+//   gemm_nt : B row-major [n][k] (K of q k^T), columns tx, tx+16, tx+32, tx+48 - consecutive lanes read consecutive
+//             rows of pitch 68 floats = 4 banks apart: conflict-free LDS.128 along k
+// A row's 64 columns live in the 16 lanes of one half-warp, so softmax / LayerNorm reductions are four xor-shuffles,
+// and P (the softmax numerators) is written and re-read by the same half-warp: no block barrier inside a key block.
+// Weights stream through two shared-memory buffers with cp.async (16 KB chunks, L2 resident), the next chunk in
+// flight while the current one is multiplied.  fp32 throughout (parity: +-1e-4 on the scores).
+#include "common.cuh"
+
+namespace nisqa {
+
+struct SaLayerParams {
+  const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
+  const float* b2; const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+};
+struct PoolHeadParams { const float* W1T; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3; };
+
+namespace {
+
+constexpr int kT = 64;            // tile edge (rows, columns, k chunk)
+constexpr int kLd = 68;           // leading dimension of row-major tiles (floats): 16-byte aligned rows, 4 banks apart
+constexpr int kTileF = kT * kLd;  // floats of a padded tile
+constexpr int kNT = 256;
+
+__device__ __forceinline__ void cp16(float* dst_smem, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? 16 : 0;                       // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 64 rows x 64 floats, global (row pitch src_ld floats) -> shared (row pitch dst_ld floats); rows >= rows_valid are
+// zero-filled.  All 256 threads, 4 x 16 bytes each.
+__device__ __forceinline__ void tile_load_async(float* dst, int dst_ld, const float* src, long long src_ld, int rows_valid, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * kNT;
+    const int r = idx >> 4, c4 = idx & 15;
+    const bool ok = r < rows_valid;
+    cp16(dst + r * dst_ld + c4 * 4, src + (ok ? (long long)r * src_ld + c4 * 4 : 0), ok);
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// acc[i][j] += sum_k A[4ty+i][k] * B[k][4tx+j]
+__device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float* __restrict__ A, const float* __restrict__ B,
+                                        int ldb, int ty, int tx) {
+  const float* a0 = A + (4 * ty) * kLd;
+  const float* b0 = B + 4 * tx;
+#pragma unroll 2
+  for (int k = 0; k < kT; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * kLd + k);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(b0 + (k + kk) * ldb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]);
+        acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
+        acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]);
+        acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+      }
+    }
+  }
+}
+
+// acc[i][j] += sum_k A[4ty+i][k] * B[tx+16j][k]
+__device__ __forceinline__ void gemm_nt(float (&acc)[4][4], const float* __restrict__ A, const float* __restrict__ B,
+                                        int ty, int tx) {
+  const float* a0 = A + (4 * ty) * kLd;
+  const float* b0 = B + tx * kLd;
+#pragma unroll 2
+  for (int k = 0; k < kT; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * kLd + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(b0 + (16 * j) * kLd + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = acc[i][j];
+        s = fmaf(a[i].x, b[j].x, s); s = fmaf(a[i].y, b[j].y, s);
+        s = fmaf(a[i].z, b[j].z, s); s = fmaf(a[i].w, b[j].w, s);
+        acc[i][j] = s;
+      }
+  }
+}
+
+// reductions over the 16 lanes (tx) that share a row
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float row_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// nn.LayerNorm(64) (biased variance, eps 1e-5) of the rows held as v[i][0..3] = columns 4tx..4tx+3
+__device__ __forceinline__ void layernorm_rows(float (&v)[4][4], const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int tx) {
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + tx), be = __ldg(reinterpret_cast<const float4*>(beta) + tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mean = row_sum((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) * (1.0f / 64.0f);
+    const float d0 = v[i][0] - mean, d1 = v[i][1] - mean, d2 = v[i][2] - mean, d3 = v[i][3] - mean;
+    const float var = row_sum(fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3)) * (1.0f / 64.0f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    v[i][0] = d0 * rstd * g.x + be.x; v[i][1] = d1 * rstd * g.y + be.y;
+    v[i][2] = d2 * rstd * g.z + be.z; v[i][3] = d3 * rstd * g.w + be.w;
+  }
+}
+
+__device__ __forceinline__ void store_rows_smem(float* X, const float (&v)[4][4], int ty, int tx) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(X + (4 * ty + i) * kLd + 4 * tx) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+}
+
+// QKV projection of a 64-row tile X (shared, row-major) -> qkv[row0 + r][192]; Wbuf: two [64][64] buffers, the
+// first chunk (part 0) must already be in flight into Wbuf[0] as the most recent cp.async group.
+__device__ __forceinline__ void qkv_tail(const float* X, float* Wbuf, const float* __restrict__ WT3,
+                                         const float* __restrict__ b3, float* __restrict__ qkv, long long row0,
+                                         int rows_valid, int tid, int ty, int tx) {
+#pragma unroll 1
+  for (int part = 0; part < 3; ++part) {
+    if (part + 1 < 3) tile_load_async(Wbuf + ((part + 1) & 1) * 4096, 64, WT3 + (part + 1) * 4096, 64, 64, tid);
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    float acc[4][4];
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b3 + part * 64) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+    gemm_nn(acc, X, Wbuf + (part & 1) * 4096, 64, ty, tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * ty + i < rows_valid)
+        *reinterpret_cast<float4*>(qkv + (row0 + 4 * ty + i) * 192 + part * 64 + 4 * tx) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();                        // buffer (part & 1) is refilled by the next iteration's prefetch
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kInSmemFloats = 2 * kTileF + 2 * 4096 + kTileF;
+
+__global__ void __launch_bounds__(kNT, 2)
+td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restrict__ WT /*[384][64]*/,
+             const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+             const float* __restrict__ qkvT /*[3][64][64]*/, const float* __restrict__ qkvb /*[192]*/,
+             float* __restrict__ x0 /*[n][64]*/, float* __restrict__ qkv /*[n][192]*/, int n_rows) {
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                       // [2][64][68]
+  float* Ws = sm + 2 * kTileF;          // [2][64][64]
+  float* Xs = Ws + 2 * 4096;            // [64][68]
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const long long row0 = (long long)blockIdx.x * kT;
+  const int rows_valid = (int)min((long long)kT, (long long)n_rows - row0);
+  const float* src = feats + row0 * 384;
+
+  tile_load_async(As, kLd, src, 384, rows_valid, tid);
+  tile_load_async(Ws, 64, WT, 64, 64, tid);
+  cp_commit();
+  float acc[4][4];
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+  }
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c) {
+    if (c + 1 < 6) {
+      tile_load_async(As + ((c + 1) & 1) * kTileF, kLd, src + (c + 1) * 64, 384, rows_valid, tid);
+      tile_load_async(Ws + ((c + 1) & 1) * 4096, 64, WT + (size_t)(c + 1) * 4096, 64, 64, tid);
+    } else {
+      tile_load_async(Ws + ((c + 1) & 1) * 4096, 64, qkvT, 64, 64, tid);       // first QKV chunk rides behind the last k chunk
+    }
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    gemm_nn(acc, As + (c & 1) * kTileF, Ws + (c & 1) * 4096, 64, ty, tx);
+    __syncthreads();
+  }
+  layernorm_rows(acc, gamma, beta, tx);
+  store_rows_smem(Xs, acc, ty, tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * ty + i < rows_valid)
+      *reinterpret_cast<float4*>(x0 + (row0 + 4 * ty + i) * 64 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  // QKV of layer 0: its first weight chunk is in flight into Ws[0] (6 & 1 == 0); qkv_tail syncs before reading Xs
+  qkv_tail(Xs, Ws, qkvT, qkvb, qkv, row0, rows_valid, tid, ty, tx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared memory: Qs | Ps | Kb[2] | Vb[2]  (Kb/Vb double as weight buffers after the attention loop)
+constexpr int kSaSmemFloats = 2 * kTileF + 2 * kTileF + 2 * 4096;
+
+__global__ void __launch_bounds__(kNT, 2)
+td_sa_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv, const ClipDesc* __restrict__ clips,
+             int n_clips, const int* __restrict__ qtile_prefix /*64-row tiles*/, SaLayerParams P,
+             float* __restrict__ x_out,
+             const float* __restrict__ next_qkvT, const float* __restrict__ next_qkvb, float* __restrict__ qkv_next,
+             PoolHeadParams H, int n_heads, float* __restrict__ logits) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                          // [64][68]  queries, later the row tile fed to the linears
+  float* Ps = sm + kTileF;                 // [64][68]  softmax numerators, later scratch row tile
+  float* Kb = Ps + kTileF;                 // [2][64][68]
+  float* Vb = Kb + 2 * kTileF;             // [2][64][64]
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int c = upper_slot(qtile_prefix, n_clips, blockIdx.x);
+  const ClipDesc cd = clips[c];
+  const int S = cd.n_seg;
+  const int q0 = (blockIdx.x - __ldg(qtile_prefix + c)) * kT;
+  const int rows_valid = min(kT, S - q0);
+  const long long row0 = (long long)cd.seg_off + q0;
+  const float* kv_base = qkv + (long long)cd.seg_off * 192;
+
+  // ---- attention: Q tile, then key blocks of 64 (K row-major [key][d], V k-major [key][d])
+  tile_load_async(Qs, kLd, qkv + row0 * 192, 192, rows_valid, tid);
+  tile_load_async(Kb, kLd, kv_base + 64, 192, min(kT, S), tid);
+  tile_load_async(Vb, 64, kv_base + 128, 192, min(kT, S), tid);
+  cp_commit();
+  float o[4][4];
+  zero_acc(o);
+  float m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; }
+  const int n_kb = (S + kT - 1) / kT;
+#pragma unroll 1
+  for (int kb = 0; kb < n_kb; ++kb) {
+    const int j0 = kb * kT;
+    if (kb + 1 < n_kb) {
+      const int nv = min(kT, S - (j0 + kT));
+      tile_load_async(Kb + ((kb + 1) & 1) * kTileF, kLd, kv_base + (long long)(j0 + kT) * 192 + 64, 192, nv, tid);
+      tile_load_async(Vb + ((kb + 1) & 1) * 4096, 64, kv_base + (long long)(j0 + kT) * 192 + 128, 192, nv, tid);
+    }
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();                               // K/V block kb (and Q) landed for every thread
+    float s[4][4];
+    zero_acc(s);
+    gemm_nt(s, Qs, Kb + (kb & 1) * kTileF, ty, tx);           // s[i][j]: query 4ty+i, key j0 + tx + 16j
+    const int nk = S - j0;                                     // keys >= nk of this block do not exist
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float bm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { if (tx + 16 * j >= nk) s[i][j] = -INFINITY; bm = fmaxf(bm, s[i][j]); }
+      bm = row_max(bm);                                        // every block holds >= 1 real key: bm is finite
+      const float mn = fmaxf(m[i], bm);
+      const float sc = expf(m[i] - mn);                        // first block: expf(-inf) = 0
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = expf(s[i][j] - mn);                    // masked keys: expf(-inf) = 0
+        ps += p;
+        Ps[(4 * ty + i) * kLd + tx + 16 * j] = p;
+      }
+      l[i] = l[i] * sc + row_sum(ps);
+      m[i] = mn;
+      o[i][0] *= sc; o[i][1] *= sc; o[i][2] *= sc; o[i][3] *= sc;
+    }
+    __syncwarp();                                  // P rows 4ty..4ty+3 are written and read by this half-warp only
+    gemm_nn(o, Ps, Vb + (kb & 1) * 4096, 64, ty, tx);         // o[i][j]: query 4ty+i, d = 4tx + j
+    __syncthreads();                               // block kb consumed: its buffers are the prefetch target of kb + 2
+  }
+  // ---- out_proj + residual + LN1, FFN + residual + LN2; weights stream through Kb (as [64][64] chunks)
+  float* Wb = Kb;                                  // two [64][64] weight buffers inside the K region (2 x 4096 <= 2 x kTileF)
+  tile_load_async(Wb, 64, P.WoT, 64, 64, tid);
+  cp_commit();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float inv = 1.0f / l[i];
+    o[i][0] *= inv; o[i][1] *= inv; o[i][2] *= inv; o[i][3] *= inv;
+  }
+  store_rows_smem(Qs, o, ty, tx);                  // attention output tile (Q is no longer needed)
+  tile_load_async(Wb + 4096, 64, P.W1T, 64, 64, tid);
+  cp_commit();
+  cp_wait<1>();
+  __syncthreads();
+  float v[4][4];
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bo) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i][0] = bb.x; v[i][1] = bb.y; v[i][2] = bb.z; v[i][3] = bb.w; }
+  }
+  gemm_nn(v, Qs, Wb, 64, ty, tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = min(4 * ty + i, rows_valid - 1);                             // rows beyond the clip: any valid row
+    const float4 xr = __ldg(reinterpret_cast<const float4*>(x_in + (row0 + r) * 64) + tx);
+    v[i][0] += xr.x; v[i][1] += xr.y; v[i][2] += xr.z; v[i][3] += xr.w;
+  }
+  layernorm_rows(v, P.ln1_g, P.ln1_b, tx);
+  store_rows_smem(Ps, v, ty, tx);                  // LN1 output: FFN input (and residual, kept in v)
+  __syncthreads();                                 // Wb[0] (Wo) consumed, Ps complete
+  tile_load_async(Wb, 64, P.W2T, 64, 64, tid);
+  cp_commit();
+  cp_wait<1>();                                    // W1 landed
+  __syncthreads();
+  float h[4][4];
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(P.b1) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i][0] = bb.x; h[i][1] = bb.y; h[i][2] = bb.z; h[i][3] = bb.w; }
+  }
+  gemm_nn(h, Ps, Wb + 4096, 64, ty, tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[i][j] = fmaxf(h[i][j], 0.f);
+  store_rows_smem(Qs, h, ty, tx);                  // FFN hidden tile
+  __syncthreads();                                 // Wb[1] (W1) consumed, Qs complete
+  const bool last = next_qkvT == nullptr;
+  // first chunk of the fused tail rides behind W2
+  if (!last) tile_load_async(Wb + 4096, 64, next_qkvT, 64, 64, tid);
+  else tile_load_async(Wb + 4096, 64, H.W1T, 128, 64, tid);
+  cp_commit();
+  cp_wait<1>();                                    // W2 landed
+  __syncthreads();
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(P.b2) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i][0] = bb.x; h[i][1] = bb.y; h[i][2] = bb.z; h[i][3] = bb.w; }
+  }
+  gemm_nn(h, Qs, Wb, 64, ty, tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] += h[i][j];
+  layernorm_rows(v, P.ln2_g, P.ln2_b, tx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * ty + i < rows_valid)
+      *reinterpret_cast<float4*>(x_out + (row0 + 4 * ty + i) * 64 + 4 * tx) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+  store_rows_smem(Ps, v, ty, tx);                  // layer output tile: input of the fused tail
+  __syncthreads();                                 // Wb[0] (W2) consumed, Ps complete
+
+  if (!last) {
+    // ---- next layer's QKV projection (its part 0 is in flight into Wb[1])
+#pragma unroll 1
+    for (int part = 0; part < 3; ++part) {
+      const int cur = (part + 1) & 1;
+      if (part + 1 < 3) tile_load_async(Wb + (cur ^ 1) * 4096, 64, next_qkvT + (part + 1) * 4096, 64, 64, tid);
+      cp_commit();
+      cp_wait<1>();
+      __syncthreads();
+      float acc[4][4];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(next_qkvb + part * 64) + tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+      gemm_nn(acc, Ps, Wb + cur * 4096, 64, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (4 * ty + i < rows_valid)
+          *reinterpret_cast<float4*>(qkv_next + (row0 + 4 * ty + i) * 192 + part * 64 + 4 * tx) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+    }
+  } else {
+    // ---- PoolAttFF logits of every head: chunk q = (head, half) of W1T [head][64 k][128 j]; chunk 0 is in flight
+    const int n_chunks = 2 * n_heads;
+    float part_logit[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int q = 0; q < n_chunks; ++q) {
+      const int cur = (q + 1) & 1;
+      if (q + 1 < n_chunks) {
+        const int hn = (q + 1) >> 1, halfn = (q + 1) & 1;
+        tile_load_async(Wb + (cur ^ 1) * 4096, 64, H.W1T + (size_t)hn * 64 * 128 + halfn * 64, 128, 64, tid);
+      }
+      cp_commit();
+      cp_wait<1>();
+      __syncthreads();
+      const int hd = q >> 1, half = q & 1;
+      float acc[4][4];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(H.b1 + hd * 128 + half * 64) + tx);
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(H.w2 + hd * 128 + half * 64) + tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+      gemm_nn(acc, Ps, Wb + cur * 4096, 64, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float t = part_logit[i];
+        t = fmaf(w2.x, fmaxf(acc[i][0], 0.f), t); t = fmaf(w2.y, fmaxf(acc[i][1], 0.f), t);
+        t = fmaf(w2.z, fmaxf(acc[i][2], 0.f), t); t = fmaf(w2.w, fmaxf(acc[i][3], 0.f), t);
+        part_logit[i] = t;
+      }
+      if (half == 1) {
+        const float b2 = __ldg(H.b2 + hd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float tot = row_sum(part_logit[i]);
+          if (tx == 0 && 4 * ty + i < rows_valid) logits[(row0 + 4 * ty + i) * n_heads + hd] = tot + b2;
+          part_logit[i] = 0.f;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+void launch_td_in(cudaStream_t st, const float* feats, const float* WT, const float* b, const float* g, const float* be,
+                  const float* qkvT, const float* qkvb, float* x0, float* qkv, int n_rows) {
+  static unsigned long long cfg = 0;
+  const int smem = kInSmemFloats * 4;
+  if (first_launch_on_device(cfg)) cudaFuncSetAttribute(td_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  td_in_kernel<<<(n_rows + kT - 1) / kT, kNT, smem, st>>>(feats, WT, b, g, be, qkvT, qkvb, x0, qkv, n_rows);
+}
+
+void launch_td_sa(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips, int n_clips,
+                  const int* qtile64_prefix, int n_qtiles, const SaLayerParams& P, float* x_out,
+                  const float* next_qkvT, const float* next_qkvb, float* qkv_next,
+                  const PoolHeadParams& H, int n_heads, float* logits) {
+  static unsigned long long cfg = 0;
+  const int smem = kSaSmemFloats * 4;
+  if (first_launch_on_device(cfg)) cudaFuncSetAttribute(td_sa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  td_sa_kernel<<<n_qtiles, kNT, smem, st>>>(x_in, qkv, clips, n_clips, qtile64_prefix, P, x_out,
+                                            next_qkvT, next_qkvb, qkv_next, H, n_heads, logits);
+}
+
+}  // namespace nisqa

@@ -55,7 +55,11 @@ def test_every_stage_matches_oracle(engines, ckpt, clips):
     eng, args, sd = engines[ckpt]
     pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
     srs = [c[2] for c in clips]
-    scores, nseg, status = eng.predict_pcm(pcm, srs)
+    eng.set_option("keep_td_out", 1)              # BiLSTM: per-step outputs are only stored for the dump
+    try:
+        scores, nseg, status = eng.predict_pcm(pcm, srs)
+    finally:
+        eng.set_option("keep_td_out", 0)
     assert np.all(status == E.CLIP_OK)
     dumps = {name: eng.stage_dump(st) for name, st, _ in STAGES}
     off = {name: 0 for name, _, _ in STAGES}
@@ -277,6 +281,56 @@ def test_conv_paths_agree(engines, ckpt, clips):
         np.testing.assert_array_equal(s_again[::-1], out["planes"][0])
     finally:
         eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
+
+
+def test_td_paths_agree(engines):
+    """The register-tiled time-dependency kernels (td_tiled.cu, default) against the row-thread kernels of td.cu:
+    the same fp32 arithmetic in a different summation order - scores and the block's output within fp32 noise,
+    for short clips (one partial query tile), clips spanning several key blocks and the 1297-segment maximum."""
+    eng, args, sd = engines["nisqa.tar"]
+    clips = [(51, 10.0, 48000), (52, 0.1875, 8000), (53, 2.56, 48000), (54, 2.6, 48000), (55, 52.0, 16000), (56, 5.2, 44100)]
+    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
+    srs = [c[2] for c in clips]
+    try:
+        eng.set_option("td_tiled", 0)
+        s0, n0, _ = eng.predict_pcm(pcm, srs)
+        t0 = eng.stage_dump(E.STAGE_TD_OUT); i0 = eng.stage_dump(E.STAGE_TD_IN)
+        eng.set_option("td_tiled", 1)
+        s1, n1, _ = eng.predict_pcm(pcm, srs)
+        t1 = eng.stage_dump(E.STAGE_TD_OUT); i1 = eng.stage_dump(E.STAGE_TD_IN)
+    finally:
+        eng.set_option("td_tiled", 1)
+    np.testing.assert_array_equal(n0, n1)
+    assert np.abs(i0 - i1).max() <= 2e-5 and np.abs(t0 - t1).max() <= 1e-4, (float(np.abs(i0 - i1).max()), float(np.abs(t0 - t1).max()))
+    assert np.abs(s0 - s1).max() <= SCORE_TOL / 10, float(np.abs(s0 - s1).max())
+
+
+def test_lstm_paths_agree(engines):
+    """Batched BiLSTM (NB clips of one direction per CTA, sorted by length) against the one-sequence kernel: the same
+    fp32 dot products in a different summation order -> scores within fp32 noise; ragged lengths inside a group, a
+    too-short clip (no segments) and batch sizes that select the NB = 1, 2 and 4 variants."""
+    eng, args, sd = engines["nisqa_tts.tar"]
+    spec = [(61, 10.0, 16000), (62, 0.5, 16000), (63, 3.3, 48000), (64, 0.01, 16000), (65, 6.1, 22050), (66, 2.0, 16000), (67, 1.1, 8000)]
+    base = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in spec]
+    for reps in (1, 25, 50):                      # 7, 175, 350 clips -> 14, 350, 700 sequences: NB = 1, 4 (> 296) / 2
+        pcm = base * reps
+        srs = [c[2] for c in spec] * reps
+        try:
+            eng.set_option("lstm_batched", 0)
+            s0, n0, st0 = eng.predict_pcm(pcm, srs)
+            eng.set_option("lstm_batched", 1)
+            s1, n1, st1 = eng.predict_pcm(pcm, srs)
+        finally:
+            eng.set_option("lstm_batched", 1)
+        np.testing.assert_array_equal(st0, st1)
+        np.testing.assert_array_equal(np.isnan(s0), np.isnan(s1))
+        ok = st1 == E.CLIP_OK
+        assert np.abs(s0[ok] - s1[ok]).max() <= 2e-5, float(np.abs(s0[ok] - s1[ok]).max())
+        assert st1[3] == E.CLIP_TOO_SHORT and np.isnan(s1[3, 0])
+        np.testing.assert_array_equal(s1[:7], s1[7 * (reps - 1):])     # the same clip scores the same in any group
+    pcm = base[:5] * 30                              # 150 clips -> 300 sequences: NB = 4
+    s, _, _ = eng.predict_pcm(pcm, [c[2] for c in spec][:5] * 30)
+    np.testing.assert_array_equal(s[:5], s[145:])
 
 
 def test_device_resident_entry_point_equals_host_entry_point(engines):

@@ -91,6 +91,21 @@ def host_info():
     return info
 
 
+def effective_cores():
+    """Host cores this process can really use: the affinity mask, cut down to the cgroup CPU quota (the GPU boxes show
+    128 cores but run under `cpu.max = 1600000 100000`, i.e. 16 CPUs - the reason the same CPU baseline printed 87 and
+    420-460 clips/s on two "128 core" boxes in round 1)."""
+    info = host_info()
+    cores = info.get("affinity") or info.get("nproc") or 1
+    try:
+        quota, period = info.get("cpu_max", "max").split()[:2]
+        if quota != "max" and int(quota) > 0:
+            cores = max(1, min(cores, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return cores
+
+
 def measure(n_clips=64, bs=64, seconds=10.0, sr=48000, workers=None, ckpt=None, model_iters=10, ours=None,
             allow_cpu=False):
     """-> dict (see module docstring).  ``ours``: optional callable(list of wav paths) -> [n, 5] scores of the
@@ -105,9 +120,9 @@ def measure(n_clips=64, bs=64, seconds=10.0, sr=48000, workers=None, ckpt=None, 
     from nisqa_b200 import synth, wav
     nisqaModel, NL = _import_reference()
     ckpt = ckpt or os.path.join(ROOT, "weights", "nisqa.tar")
-    cores = host_info().get("affinity") or os.cpu_count() or 1
+    cores = effective_cores()
     if workers is None:
-        workers = max(1, min(cores // 2, 32))
+        workers = max(1, min(cores, 32))
     out = {"impl": "unmodified reference nisqa/ package, PyTorch %s eager, device cuda" % torch.__version__,
            "front_end": "oracle/librosa_compat.py (NumPy restatement of librosa 0.8.1; real librosa is not installable offline)",
            "clips": n_clips, "bs": bs, "num_workers": workers, "host": host_info()}
@@ -159,10 +174,38 @@ def measure(n_clips=64, bs=64, seconds=10.0, sr=48000, workers=None, ckpt=None, 
             sync()
         ms = (e0.elapsed_time(e1) if cuda else (time.perf_counter() - t0) * 1e3) / model_iters
         out["model_only"] = {"clips_per_s": xb.shape[0] / (ms / 1e3), "ms_per_batch": ms, "batch": int(xb.shape[0]),
-                             "input": "resident padded segments %s fp32 (%.0f MB)" % (list(xb.shape), xb.numel() * 4 / 1e6)}
+                             "input": "resident padded segments %s fp32 (%.0f MB)" % (list(xb.shape), xb.numel() * 4 / 1e6),
+                             "tf32": "PyTorch defaults: cuDNN convolutions may use TF32 (torch.backends.cudnn.allow_tf32 = %s)"
+                                     % torch.backends.cudnn.allow_tf32}
+        # the same forward with TF32 switched off: the reference's fp32 arithmetic on this GPU (what its CPU path and
+        # the 1e-4 parity target mean); scores of the first batch against the default (TF32) run
+        if cuda:
+            with torch.no_grad():
+                y_tf32 = m.model(xb, n_wins).float().cpu().numpy()
+                old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+                torch.backends.cudnn.allow_tf32 = False
+                torch.backends.cuda.matmul.allow_tf32 = False
+                try:
+                    for _ in range(3):
+                        y_fp32 = m.model(xb, n_wins)
+                    sync()
+                    e0.record()
+                    for _ in range(model_iters):
+                        m.model(xb, n_wins)
+                    e1.record()
+                    sync()
+                finally:
+                    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+            ms32 = e0.elapsed_time(e1) / model_iters
+            y_fp32 = y_fp32.float().cpu().numpy()
+            out["model_only_fp32"] = {"clips_per_s": xb.shape[0] / (ms32 / 1e3), "ms_per_batch": ms32,
+                                      "max_abs_diff_vs_default_tf32_run": float(np.abs(y_fp32 - y_tf32).max())}
         if ours is not None:
             got = np.asarray(ours([os.path.join(td, f) for f in names]), dtype=np.float64)
             out["max_abs_diff_engine_vs_reference_gpu"] = float(np.abs(got - ref_scores).max())
+            if cuda:
+                first = [names.index(df["deg"].iloc[int(i)]) for i in idx.numpy()] if hasattr(idx, "numpy") else list(range(xb.shape[0]))
+                out["max_abs_diff_engine_vs_reference_gpu_fp32"] = float(np.abs(got[first] - y_fp32.astype(np.float64)).max())
     finally:
         shutil.rmtree(td, ignore_errors=True)
     return out
