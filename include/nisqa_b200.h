@@ -217,6 +217,8 @@ NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
  *   "conv_split" 1 (default): with all of conv2..6 on tcgen05, activations travel between the layers as
  *                fp16 hi/lo plane pairs (csrc/conv_split.cu); 0: fp32 channels-last activations and the
  *                register-staged kernels of csrc/conv_tc.cu.  Results are bit-identical.
+ *   "conv_pipe"  bit mask of the conv layers (2..6) whose plane kernel runs as persistent warp-specialised CTAs
+ *                (default / 1 = all); a cleared bit selects the one-tile-per-CTA kernel.  Bit-identical results.
  *   "fe_ppc"     frame pairs per front-end CTA (0 = kernel default).
  *   "td_tiled"   1 (default): time-dependency block + pooling logits as register-tiled GEMM kernels
  *                (csrc/td_tiled.cu); 0: the one-thread-per-row kernels of csrc/td.cu.

@@ -192,7 +192,7 @@ conv_tc_kernel(const float* __restrict__ in /*[seg][H][W][CIN] fp32*/,
             const uint64_t dal = make_desc(a_lo + aoff, AROWS * 16, 128);
             const uint64_t db = make_desc(bst + (uint32_t)(2 * ks) * (2 * COUT * 16), 2 * COUT * 16, 128);
             umma_f16(d, dah, db, C::IDESC_2N, (t | ks) != 0);     // [0,C) += hi*hi ; [C,2C) += hi*lo
-            umma_f16(d, dal, db, C::IDESC_1N, 1);                 // [0,C) += lo*hi
+            umma_f16(d + COUT, dal, db, C::IDESC_1N, 1);          // [C,2C) += lo*hi (the small accumulator, see conv_split.cu)
           }
         }
         umma_commit(bar_empty + 8 * s);          // stage s may be refilled once these MMAs retire

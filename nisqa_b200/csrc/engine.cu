@@ -42,6 +42,7 @@ void launch_unsplit(cudaStream_t, int, int, const void*, const void*, float*, in
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
 int sp_timing_read(long long*, int);
+int pipe_timing_read(long long*, int, int);
 #endif
 // td.cu
 struct SaLayerParams {
@@ -185,6 +186,7 @@ struct nisqa_engine {
   bool weights_loaded = false;
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
+  int conv_pipe = 0x78;    // bit l (conv2's small tiles are faster one per CTA, four CTAs per SM): conv2..6 plane kernels as persistent warp-specialised CTAs (conv_pipe_kernel); 0: one tile per CTA
   int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
   int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
   bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
@@ -771,7 +773,8 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         if (split)
           launch_conv_split(st, std_mode, l, plane_hi(l), plane_lo(l), W(e, kt), W(e, kb), e->tc_scale[l],
                             l < 6 ? plane_hi(l + 1) : nullptr, l < 6 ? plane_lo(l + 1) : nullptr,
-                            l == 6 ? LN.feats.as<float>() : nullptr, n_seg, e->tc_timing_layer == l ? 2 : 0);
+                            l == 6 ? LN.feats.as<float>() : nullptr, n_seg,
+                            (e->tc_timing_layer == l ? 2 : 0) | (((e->conv_pipe >> l) & 1) ? 4 : 0));
         else if (e->conv_tc & (1 << l))
           launch_conv_tc(st, std_mode, l, cin_[l], W(e, kt), W(e, kb), e->tc_scale[l], cout_[l], n_seg);
         else
@@ -876,7 +879,9 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     if (n_seg_out) n_seg_out[i] = plan[i].n_seg;
     if (status_out) status_out[i] = plan[i].status;
   }
-  const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 32768;
+  // segments per internal pass: 131072 segments keep ~8 GB of activation planes per compute lane (sized for the
+  // 180 GB of a B200) and give the BiLSTM >= 128 clips per launch at configs[3]; one 64-clip batch is 15 808
+  const int max_seg = e->cfg.max_chunk_segments > 0 ? e->cfg.max_chunk_segments : 131072;
   float* scores_all = scores_dev;
   if (!scores_all) {
     DevBuf& sb = ticket_out ? e->tickets[e->next_ticket % kStages].scores : e->scores;
@@ -890,7 +895,7 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
     int i1 = i0; long long segs = 0;
     while (i1 < n_clips) {
       const long long s = plan[i1].status == NISQA_CLIP_OK ? plan[i1].n_seg : 0;
-      if (i1 > i0 && segs + s > max_seg) break;
+      if (i1 > i0 && (segs + s > max_seg || i1 - i0 >= 32768)) break;      // (clips ride in grid.y of the front-end: < 65536)
       segs += s; ++i1;
     }
     PassInput in;
@@ -1195,6 +1200,7 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (strcmp(name, "keep_td_out") == 0) { e->keep_td_out = value != 0; return 0; }
   if (strcmp(name, "td_tiled") == 0) { e->td_tiled = value != 0; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
+  if (strcmp(name, "conv_pipe") == 0) { e->conv_pipe = (value == 1) ? 0x78 : (value & 0x7c); return 0; }
   if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }
   return fail(e, NISQA_ERR_INVALID, std::string("unknown option ") + name);
 }
@@ -1329,5 +1335,8 @@ extern "C" __attribute__((visibility("default"))) int nisqa_debug_tc_timing(long
 }
 extern "C" __attribute__((visibility("default"))) int nisqa_debug_sp_timing(long long* host, int n) {
   return nisqa::sp_timing_read(host, n);
+}
+extern "C" __attribute__((visibility("default"))) int nisqa_debug_pipe_timing(long long* host, int n, int reset) {
+  return nisqa::pipe_timing_read(host, n, reset);
 }
 #endif

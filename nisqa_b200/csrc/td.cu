@@ -510,18 +510,24 @@ lstm_batched_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipD
       for (int b = 0; b < NB; ++b) if (b == xb_) { Sb = S[b]; f = fb[b]; }
       if (step + 1 < Sb) { xnext = __ldg(f + (size_t)(dir ? Sb - 2 - step : step + 1) * 20 + xk_); xload = true; }
     }
-    float aA[NB], aB[NB];
+    // every row keeps two partial sums (even / odd taps), whatever NB is: a clip's result must not depend on how many
+    // clips share its CTA (alone == in a batch, bit for bit), and one 148-long dependent FMA chain per row would
+    // leave the NB = 1 variant latency bound
+    constexpr int PART = 2;
+    float pA[NB][PART], pB[NB][PART];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { aA[b] = biasA; aB[b] = biasB; }
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int q = 0; q < PART; ++q) { pA[b][q] = q ? 0.f : biasA; pB[b][q] = q ? 0.f : biasB; }
 #pragma unroll
     for (int k = 0; k < 20; k += 4) {
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 xv = *reinterpret_cast<const float4*>(xt + b * 32 + k);
-        aA[b] = fmaf(wiA[k], xv.x, aA[b]); aA[b] = fmaf(wiA[k + 1], xv.y, aA[b]);
-        aA[b] = fmaf(wiA[k + 2], xv.z, aA[b]); aA[b] = fmaf(wiA[k + 3], xv.w, aA[b]);
-        aB[b] = fmaf(wiB[k], xv.x, aB[b]); aB[b] = fmaf(wiB[k + 1], xv.y, aB[b]);
-        aB[b] = fmaf(wiB[k + 2], xv.z, aB[b]); aB[b] = fmaf(wiB[k + 3], xv.w, aB[b]);
+        pA[b][0] = fmaf(wiA[k], xv.x, pA[b][0]); pA[b][1 % PART] = fmaf(wiA[k + 1], xv.y, pA[b][1 % PART]);
+        pA[b][2 % PART] = fmaf(wiA[k + 2], xv.z, pA[b][2 % PART]); pA[b][3 % PART] = fmaf(wiA[k + 3], xv.w, pA[b][3 % PART]);
+        pB[b][0] = fmaf(wiB[k], xv.x, pB[b][0]); pB[b][1 % PART] = fmaf(wiB[k + 1], xv.y, pB[b][1 % PART]);
+        pB[b][2 % PART] = fmaf(wiB[k + 2], xv.z, pB[b][2 % PART]); pB[b][3 % PART] = fmaf(wiB[k + 3], xv.w, pB[b][3 % PART]);
       }
     }
 #pragma unroll
@@ -529,10 +535,10 @@ lstm_batched_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipD
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 hv = *reinterpret_cast<const float4*>(h + b * 128 + k);
-        aA[b] = fmaf(wrA[k], hv.x, aA[b]); aA[b] = fmaf(wrA[k + 1], hv.y, aA[b]);
-        aA[b] = fmaf(wrA[k + 2], hv.z, aA[b]); aA[b] = fmaf(wrA[k + 3], hv.w, aA[b]);
-        aB[b] = fmaf(wrB[k], hv.x, aB[b]); aB[b] = fmaf(wrB[k + 1], hv.y, aB[b]);
-        aB[b] = fmaf(wrB[k + 2], hv.z, aB[b]); aB[b] = fmaf(wrB[k + 3], hv.w, aB[b]);
+        pA[b][0] = fmaf(wrA[k], hv.x, pA[b][0]); pA[b][1 % PART] = fmaf(wrA[k + 1], hv.y, pA[b][1 % PART]);
+        pA[b][2 % PART] = fmaf(wrA[k + 2], hv.z, pA[b][2 % PART]); pA[b][3 % PART] = fmaf(wrA[k + 3], hv.w, pA[b][3 % PART]);
+        pB[b][0] = fmaf(wrB[k], hv.x, pB[b][0]); pB[b][1 % PART] = fmaf(wrB[k + 1], hv.y, pB[b][1 % PART]);
+        pB[b][2 % PART] = fmaf(wrB[k + 2], hv.z, pB[b][2 % PART]); pB[b][3 % PART] = fmaf(wrB[k + 3], hv.w, pB[b][3 % PART]);
       }
     }
 #pragma unroll 4
@@ -541,11 +547,18 @@ lstm_batched_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipD
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 hv = *reinterpret_cast<const float4*>(h + b * 128 + 64 + k);
-        aA[b] = fmaf(w0.x, hv.x, aA[b]); aA[b] = fmaf(w1.x, hv.y, aA[b]);
-        aA[b] = fmaf(w2.x, hv.z, aA[b]); aA[b] = fmaf(w3.x, hv.w, aA[b]);
-        aB[b] = fmaf(w0.y, hv.x, aB[b]); aB[b] = fmaf(w1.y, hv.y, aB[b]);
-        aB[b] = fmaf(w2.y, hv.z, aB[b]); aB[b] = fmaf(w3.y, hv.w, aB[b]);
+        pA[b][0] = fmaf(w0.x, hv.x, pA[b][0]); pA[b][1 % PART] = fmaf(w1.x, hv.y, pA[b][1 % PART]);
+        pA[b][2 % PART] = fmaf(w2.x, hv.z, pA[b][2 % PART]); pA[b][3 % PART] = fmaf(w3.x, hv.w, pA[b][3 % PART]);
+        pB[b][0] = fmaf(w0.y, hv.x, pB[b][0]); pB[b][1 % PART] = fmaf(w1.y, hv.y, pB[b][1 % PART]);
+        pB[b][2 % PART] = fmaf(w2.y, hv.z, pB[b][2 % PART]); pB[b][3 % PART] = fmaf(w3.y, hv.w, pB[b][3 % PART]);
       }
+    }
+    float aA[NB], aB[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (PART == 4) { aA[b] = (pA[b][0] + pA[b][1 % PART]) + (pA[b][2 % PART] + pA[b][3 % PART]); aB[b] = (pB[b][0] + pB[b][1 % PART]) + (pB[b][2 % PART] + pB[b][3 % PART]); }
+      else if (PART == 2) { aA[b] = pA[b][0] + pA[b][1 % PART]; aB[b] = pB[b][0] + pB[b][1 % PART]; }
+      else { aA[b] = pA[b][0]; aB[b] = pB[b][0]; }
     }
     float* hn = hbuf + ((step + 1) & 1) * NB * 128;
 #pragma unroll

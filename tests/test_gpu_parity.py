@@ -219,7 +219,9 @@ def test_config3_full_size_ragged_bs512(engines):
     round 1).  Eight sampled clips against the oracle (<= 1e-4), all 512 segment counts exact, and the
     pass-splitting properties bit-exact: a clip alone == inside the batch, and the reversed batch (different
     pass boundaries, different plane rows) == the same rows."""
-    eng, args, sd = engines["nisqa.tar"]
+    _, args, sd = engines["nisqa.tar"]
+    eng = E.Engine(E.config_from_args(args, max_chunk_segments=32768), 0)      # 7 passes (the default pass is 131072 segments)
+    eng.load_state_dict(sd)
     durs = synth.ragged_durations(512, 2.0, 30.0, seed=11)
     clips = _sliced_clips(durs, 48000, seed=5)
     order = np.argsort(durs)
@@ -231,13 +233,18 @@ def test_config3_full_size_ragged_bs512(engines):
         np.testing.assert_array_equal(alone[0], scores[i])
     rev, nrev, _ = eng.predict_pcm(clips[::-1], [48000] * 512)
     np.testing.assert_array_equal(rev[::-1], scores)
+    eng.close()
+    big, nbig, _ = engines["nisqa.tar"][0].predict_pcm(clips, [48000] * 512)     # default pass size: 2 passes
+    np.testing.assert_array_equal(big, scores)
     print("configs[2] full size: max |d| vs oracle over %d sampled clips = %.2e, %d segments" % (len(sample), worst, int(nseg.sum())))
 
 
 def test_config4_full_size_tts_bs256(engines):
     """BASELINE configs[3] at FULL size: nisqa_tts.tar, 256 clips of 10 s at 16 kHz (987 segments each) in one
     call = 8 passes.  Eight sampled clips against the oracle, all segment counts exact, alone == in-batch."""
-    eng, args, sd = engines["nisqa_tts.tar"]
+    _, args, sd = engines["nisqa_tts.tar"]
+    eng = E.Engine(E.config_from_args(args, max_chunk_segments=32768), 0)      # 8 passes of 33 clips (the last one: 25)
+    eng.load_state_dict(sd)
     clips = _sliced_clips([10.0] * 256, 16000, seed=6)
     sample = [0, 33, 66, 99, 132, 200, 254, 255]
     scores, nseg, worst = _check_full_size(eng, args, sd, clips, 16000, sample)
@@ -245,6 +252,9 @@ def test_config4_full_size_tts_bs256(engines):
     for i in (0, 132, 255):
         alone, _, _ = eng.predict_pcm([clips[i]], [16000])
         np.testing.assert_array_equal(alone[0], scores[i])
+    eng.close()
+    big, _, _ = engines["nisqa_tts.tar"][0].predict_pcm(clips, [16000] * 256)     # default pass size: 2 passes of 128 clips
+    np.testing.assert_array_equal(big, scores)
     print("configs[3] full size: max |d| vs oracle over %d sampled clips = %.2e" % (len(sample), worst))
 
 @pytest.mark.parametrize("ckpt,clips", [
@@ -252,8 +262,9 @@ def test_config4_full_size_tts_bs256(engines):
     ("nisqa_tts.tar", [(35, 3.0, 16000), (36, 1.1, 48000)]),
 ])
 def test_conv_paths_agree(engines, ckpt, clips):
-    """The three conv2..conv6 implementations behind nisqa_set_option: fp16-plane tcgen05 pipeline
-    (default, conv_split.cu), fp32-activation tcgen05 kernels (conv_tc.cu) and fp32 FFMA (cnn.cu).
+    """The conv2..conv6 implementations behind nisqa_set_option: fp16-plane tcgen05 pipeline as persistent
+    warp-specialised CTAs (default) and as one tile per CTA (conv_split.cu), fp32-activation tcgen05 kernels
+    (conv_tc.cu) and fp32 FFMA (cnn.cu).
     Both tcgen05 paths do the same split and issue the same MMAs in the same order, so their scores and
     features are BIT-identical; the FFMA path agrees to fp32 rounding noise; growing / shrinking batches
     reuse the zero-padded planes (stale rows of earlier, larger passes must not leak)."""
@@ -262,13 +273,16 @@ def test_conv_paths_agree(engines, ckpt, clips):
     srs = [c[2] for c in clips]
     out = {}
     try:
-        for name, opts in (("planes", dict(conv_tc=1, conv_split=1)), ("tc_f32", dict(conv_tc=1, conv_split=0)),
-                           ("ffma", dict(conv_tc=0, conv_split=0))):
+        for name, opts in (("planes", dict(conv_tc=1, conv_split=1, conv_pipe=1)), ("planes_1tile", dict(conv_tc=1, conv_split=1, conv_pipe=0)),
+                           ("tc_f32", dict(conv_tc=1, conv_split=0)), ("ffma", dict(conv_tc=0, conv_split=0))):
             for k, v in opts.items():
                 eng.set_option(k, v)
             sc, nseg, st = eng.predict_pcm(pcm, srs)
             out[name] = (sc.copy(), eng.stage_dump(E.STAGE_CNN_FEAT), eng.stage_dump(E.STAGE_POOL3))
-        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1)
+        np.testing.assert_array_equal(out["planes"][0], out["planes_1tile"][0])     # persistent CTAs == one tile per CTA
+        np.testing.assert_array_equal(out["planes"][1], out["planes_1tile"][1])
+        np.testing.assert_array_equal(out["planes"][2], out["planes_1tile"][2])
         np.testing.assert_array_equal(out["planes"][0], out["tc_f32"][0])
         np.testing.assert_array_equal(out["planes"][1], out["tc_f32"][1])
         assert np.abs(out["planes"][2] - out["tc_f32"][2]).max() <= 1e-5      # planes dump = hi + lo (2^-22 relative)
@@ -280,7 +294,7 @@ def test_conv_paths_agree(engines, ckpt, clips):
         s_again, _, _ = eng.predict_pcm(pcm[::-1], srs[::-1])
         np.testing.assert_array_equal(s_again[::-1], out["planes"][0])
     finally:
-        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1)
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1)
 
 
 def test_td_paths_agree(engines):
