@@ -32,6 +32,9 @@ struct FbTables {
   const int*   band_start; // [49] prefix offsets into weights
   const int*   band_k0;    // [48] first FFT bin of each band
   const float* weights;    // concatenated non-zero runs, band-major
+  const float2* wtab;      // [4][1024] window[n] * W_4096^(r n) (0 for n >= win): window and residue twiddle in one load
+  int n_mag;               // bins 0 .. n_mag-1 carry a non-zero filterbank weight (magnitudes are formed for these only)
+  int pad_;
 };
 
 // Kernel attributes (the dynamic shared-memory opt-in) are per device and several engines - one per GPU - may live

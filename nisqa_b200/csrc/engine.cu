@@ -114,7 +114,8 @@ struct HostBuf {  // pinned
 struct FbEntry {
   int sr = 0, hop = 0, win = 0;
   std::vector<float> dense;      // [n_mels][n_bins] host copy (nisqa_mel_filterbank)
-  DevBuf window, band_start, band_k0, weights;
+  DevBuf window, band_start, band_k0, weights, wtab;
+  int n_mag = 0;
 };
 
 struct ClipPlan {
@@ -233,7 +234,7 @@ struct nisqa_engine {
   int gather_rows = 0;              // ncclAllGather of its [gather_rows, n_out] scores on its own lane
 
   ~nisqa_engine() {
-    for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); delete f; }
+    for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); f->wtab.release(); delete f; }
     DevBuf* all[] = {&warena, &fb_table, &tw4096, &scores, &dump};
     for (auto* b : all) b->release();
     h_scores.release();
@@ -363,6 +364,22 @@ int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
   std::vector<float> window((size_t)(win + 1023) / 1024 * 1024, 0.f);   // zero-padded to the FFT sub-length
   for (int n = 0; n < win; ++n) window[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)win));
   if (win == 1) window[0] = 1.f;
+  // fused window x residue twiddle table of the pipelined front-end: wt[r][n] = hann[n] * e^{-2 pi i r n / 4096}
+  std::vector<float2> wtab(4 * 1024, make_float2(0.f, 0.f));
+  for (int r = 0; r < 4; ++r)
+    for (int nn = 0; nn < win && nn < 1024; ++nn) {
+      const double wv = (win == 1) ? 1.0 : 0.5 - 0.5 * cos(2.0 * M_PI * (double)nn / (double)win);
+      const float wf = (float)wv;                                   // the float32 window the reference multiplies with
+      const double a = -2.0 * M_PI * (double)(((long)r * nn) & 4095) / 4096.0;
+      wtab[r * 1024 + nn] = make_float2((float)((double)wf * cos(a)), (float)((double)wf * sin(a)));
+    }
+  int n_mag = 0;
+  for (int i = 0; i < n_mels; ++i)
+    for (int k = 0; k < n_bins; ++k)
+      if (fb->dense[(size_t)i * n_bins + k] != 0.f) n_mag = std::max(n_mag, k + 1);
+  fb->n_mag = n_mag;
+  CK(fb->wtab.reserve(wtab.size() * sizeof(float2)));
+  CK(cudaMemcpy(fb->wtab.p, wtab.data(), wtab.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CK(fb->window.reserve(window.size() * 4));
   CK(fb->band_start.reserve(band_start.size() * 4));
   CK(fb->band_k0.reserve(band_k0.size() * 4));
@@ -379,6 +396,9 @@ int build_fb(nisqa_engine* e, int sr, int hop, int win, int* id_out) {
     tab[i].band_start = e->fbs[i]->band_start.as<int>();
     tab[i].band_k0 = e->fbs[i]->band_k0.as<int>();
     tab[i].weights = e->fbs[i]->weights.as<float>();
+    tab[i].wtab = e->fbs[i]->wtab.as<float2>();
+    tab[i].n_mag = e->fbs[i]->n_mag;
+    tab[i].pad_ = 0;
   }
   CK(cudaDeviceSynchronize());      // the table may be in use by passes in flight on any lane
   CK(e->fb_table.reserve(tab.size() * sizeof(FbTables) + 64 * sizeof(FbTables)));

@@ -175,6 +175,76 @@ __device__ __forceinline__ float mel_bands(const float2* scratch, const int* ban
   return out;
 }
 
+// ---- two-stage variant used by the pipelined kernel (round 2) ---------------------------------------------------
+// Stage A (whole CTA): |X_a[k]|, |X_b[k]| of the two packed real frames for the bins that carry a filterbank weight
+// (k < n_mag), each formed ONCE and written over Z[k] in its plane (Z[k] is read by the owner of bin k and, as a mirror,
+// by the owner of bin 4096 - k >= 2048 > n_mag - 1 only: in place is race free; k = 2048 mirrors itself).
+__device__ __forceinline__ void mag_stage(float2* scratch, int n_mag, int tid) {
+  // k = tid + 128 it: plane (k & 3) = tid & 3 and slot (k >> 2) = (tid >> 2) + 32 it
+  float2* pk = scratch + (tid & 3) * kScratchPerWarp + (tid >> 2);
+  const int kk0 = (kNfft - tid) & (kNfft - 1);
+  const float2* pn = scratch + (kk0 & 3) * kScratchPerWarp + (kk0 >> 2);
+  for (int k = tid; k < n_mag; k += kFeThreads) {
+    const float2 zk = *pk, zn = *pn;
+    const float ar = zk.x + zn.x, ai = zk.y - zn.y;        // 2 * X_a[k]
+    const float br = zk.y + zn.y, bi = zk.x - zn.x;        // 2 * X_b[k] (up to a unit factor)
+    float ma, mb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
+    *pk = make_float2(ma, mb);
+    pk += 32; pn -= 32;                                     // (tid = 0, it = 0: k = kk = 0 reads the same slot twice)
+    if (k == 0) pn += 1024;                                 // 4096 - 0 wraps to bin 0; from k = 128 on the mirror is 3968 - ...
+  }
+}
+
+// Stage B: the 12 bands of this warp as weighted sums of the staged magnitudes, then the same multi-value butterfly
+// reduction and dB as mel_bands.  `pscale` = 2^-30 for PCM16 input fed as raw integers (|X| scales by 2^15 exactly).
+__device__ __forceinline__ float mel_bands_staged(const float2* scratch, const int* band_meta,
+                                                  const float* __restrict__ weights, int warp, int lane,
+                                                  bool validB, float pscale, float* __restrict__ mel_row0) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int slot = 0; slot < kMels / 4; ++slot) {
+    const int b = warp + slot * 4;
+    const int beg = band_meta[b], iters = (band_meta[b + 1] - beg) >> 5;
+    const int k = band_meta[kMels + 1 + b] + lane;
+    const float2* pk = scratch + (k & 3) * kScratchPerWarp + (k >> 2);
+    const float* wt = weights + beg + lane;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+      const float w = __ldg(wt);
+      const float2 m = *pk;                    // padded bins (weight 0) may hold raw spectrum values: finite, times 0
+      wt += 32; pk += 8;
+      s0 = fmaf(w, m.x, s0);
+      s1 = fmaf(w, m.y, s1);
+    }
+    v[2 * slot] = s0;
+    v[2 * slot + 1] = s1;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = up ? v[i + o] : v[i];
+      const float send = up ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float out = -INFINITY;
+  const int my_slot = lane >> 1, f = lane & 1;
+  if (lane < 2 * (kMels / 4) && (f == 0 || validB)) {
+    const float sv = 0.5f * v[0];
+    const float p = (sv * sv) * pscale;
+    out = 10.0f * log10f(fmaxf(p, 1e-8f));
+    mel_row0[(size_t)f * kMels + warp + my_slot * 4] = out;
+  }
+  return out;
+}
+
 // ---- generic kernel: one CTA per frame pair, any window length (win <= 1024*Q <= n_fft) ------
 template <typename T>
 __global__ void __launch_bounds__(kFeThreads, 5)
@@ -324,35 +394,38 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
     const bool interior = a >= 0 && a + span <= cd.n_samples;
     const int shift = interior ? (int)((reinterpret_cast<uintptr_t>(y + a) & 15) / sizeof(T)) : 0;
     const T* src = reinterpret_cast<const T*>(smem_raw + s * pp_slot_bytes<T>()) + shift;
-    // input stage, branch-free so that the loads of 4 elements are in flight together: the window
-    // table is zero-padded to 1024 and the sample index is clamped into the slot for n >= win
+    // input stage: ONE table load per element (window x residue twiddle, zero beyond the window), samples as raw
+    // integers (PCM16: the 2^-15 of libsndfile's conversion is exact and is applied to the band power at the end),
+    // loads of 4 elements in flight together; the sample index is clamped into the slot for n >= win
     float2 x[32];
     const int hopB = validB ? cd.hop : 0;
+    const float2* wtab = fb.wtab + r * 1024 + lane;
     constexpr int CH = 4;
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += CH) {
-      float w[CH], sa[CH], sb[CH];
-      float2 t[CH];
+      float2 wt[CH];
+      float sa[CH], sb[CH];
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int n = lane + 32 * (j0 + u);
         const int ni = min(n, cd.win - 1);
-        w[u] = __ldg(fb.window + n);
-        if (r != 0) t[u] = __ldg(tw1 + ((r - 1) * 32 + j0 + u) * 32 + lane);
-        sa[u] = sample_to_float<T>(src[ni]);
-        sb[u] = sample_to_float<T>(src[ni + hopB]);
+        wt[u] = __ldg(wtab + 32 * (j0 + u));
+        sa[u] = (float)src[ni];
+        sb[u] = (float)src[ni + hopB];
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
-        float2 v = make_float2(w[u] * sa[u], validB ? w[u] * sb[u] : 0.f);
-        if (r != 0) v = cmul(v, t[u]);
-        x[j0 + u] = v;
+        const float sbv = validB ? sb[u] : 0.f;
+        x[j0 + u] = make_float2(fmaf(sa[u], wt[u].x, -(sbv * wt[u].y)), fmaf(sa[u], wt[u].y, sbv * wt[u].x));
       }
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
     __syncthreads();                    // all four planes written
-    wmax = fmaxf(wmax, mel_bands(scratch, band_meta, fb.weights, warp, lane, validB,
-                                 mel + (size_t)(cd.frame_off + 2 * p) * kMels));
+    mag_stage(scratch, fb.n_mag, tid);
+    __syncthreads();                    // magnitudes staged
+    wmax = fmaxf(wmax, mel_bands_staged(scratch, band_meta, fb.weights, warp, lane, validB,
+                                        sizeof(T) == 2 ? 9.313225746154785e-10f : 1.0f,
+                                        mel + (size_t)(cd.frame_off + 2 * p) * kMels));
   }
   wmax = warp_max(wmax);
   if (lane == 0 && wmax > -INFINITY) atomicMax(clipmax + c, f2key(wmax));
