@@ -348,6 +348,55 @@ def run_reference(a, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def sharded_predict_csv_check(eng, rank, world, local):
+    """BASELINE configs[4] in miniature on the real ranks: `nisqaModel(mode=predict_csv).predict()` (the product
+    surface: _loadDatasetsCSVpredict -> predict_dim -> rows sharded over the ranks -> ONE ncclAllGather through the
+    engine) over 16 clips per rank, compared on rank 0 with the same rows computed by ONE engine in one process (must
+    be bit-identical: clips are independent) and with the oracle on two of them."""
+    import shutil
+    import tempfile
+    import torch.distributed as dist
+    import pandas as pd
+    from nisqa_b200 import synth, wav
+    from nisqa_b200.NISQA_model import nisqaModel
+    n = 16 * world
+    box = [tempfile.mkdtemp(prefix="nisqa_cfg5_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    td = box[0]
+    specs = [(3000 + i, 1.0 + 0.25 * (i % 9), (48000, 16000, 44100)[i % 3]) for i in range(n)]
+    try:
+        if rank == 0:
+            for seed, sec, sr in specs:
+                wav.write_wav_pcm16(os.path.join(td, "c%04d.wav" % seed), synth.synth_speech_pcm16(seed, sec, sr), sr)
+            pd.DataFrame({"deg": ["c%04d.wav" % s for s, _, _ in specs]}).to_csv(os.path.join(td, "files.csv"), index=False)
+        dist.barrier()
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = nisqaModel({"mode": "predict_csv", "pretrained_model": CKPT, "data_dir": td, "csv_file": "files.csv",
+                            "csv_deg": "deg", "output_dir": None, "tr_bs_val": 8, "tr_num_workers": 2, "ms_channel": None})
+            df = m.predict()
+        m.model.close()
+        dist.barrier()
+        if rank != 0:
+            return None
+        cols = ["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]
+        got = df[cols].to_numpy(dtype=np.float32)
+        pcm = [wav.read_wav(os.path.join(td, "c%04d.wav" % s))[0] for s, _, _ in specs]
+        single = eng.predict_pcm(pcm, [sr for _, _, sr in specs])[0]
+        from oracle import nisqa_oracle as O
+        args, sd = O.load_checkpoint(CKPT)
+        worst = 0.0
+        for i in (0, n - 1):
+            ref = O.predict_pcm(args, sd, pcm[i].astype(np.float32) / 32768.0, specs[i][2])[0]
+            worst = max(worst, float(np.abs(got[i] - ref).max()))
+        return {"rows": n, "ranks": world, "api": "nisqaModel(mode='predict_csv').predict() under torchrun, rows sharded, one ncclAllGather",
+                "bit_identical_to_single_process": bool(np.array_equal(got, single)), "max_abs_vs_oracle": worst}
+    finally:
+        if rank == 0:
+            shutil.rmtree(td, ignore_errors=True)
+
+
 def run_ours(a, rank, world, local):
     import torch
     from nisqa_b200 import engine as E
@@ -493,6 +542,13 @@ def run_ours(a, rank, world, local):
                 acc[k] += v
     eng.set_profiling(False)
     kernel_ms = dict((k, v / prof_steps) for k, v in acc.items())
+    sharded = None
+    if world > 1:
+        try:
+            eng.set_gather_target(0, 0)
+            sharded = sharded_predict_csv_check(eng, rank, world, local)
+        except Exception as exc:                 # never takes the bench line down; reported instead
+            sharded = {"error": repr(exc)}
 
     if rank != 0:
         return
@@ -533,7 +589,7 @@ def run_ours(a, rank, world, local):
             "kernel_ms_per_step": kernel_ms, "cnn_ms_per_step": cnn_ms,
             "achieved_tflops_whole_step": FLOP_PER_CLIP * BS / (ms_dev / a.steps / 1e3) / 1e12,
             "parity_max_abs_vs_oracle": parity,
-            "cpu_baseline": cpu_base, "reference_gpu": ref_gpu}
+            "cpu_baseline": cpu_base, "reference_gpu": ref_gpu, "sharded_predict_csv": sharded}
     print(json.dumps(line), flush=True)
 
 

@@ -364,10 +364,10 @@ struct PipeCfg {
   static constexpr int BUF_RAW = (2 * C::A_BYTES > STG_BYTES) ? 2 * C::A_BYTES : STG_BYTES;
   static constexpr int BUF_BYTES = (BUF_RAW + 1023) & ~1023;
   static constexpr bool RESIDENT = 2 * BUF_BYTES + 9 * C::B_STAGE <= 196 * 1024;      // all nine taps stay in shared memory
-  static constexpr int NSW = RESIDENT ? 9 : 3;
+  static constexpr int NSW = RESIDENT ? 9 : ((2 * BUF_BYTES + 4 * C::B_STAGE <= 216 * 1024) ? 4 : 3);
   static constexpr int OFF_B = 2 * BUF_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSW * C::B_STAGE;
-  static constexpr int N_BAR = 2 + 2 + 2 * NSW + 2 + 2;
+  static constexpr int N_BAR = 2 + 2 + 2 * NSW + 2 + 2 + 2;
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * N_BAR + 32 + 1024;
   static constexpr int COLS_TILE = 4 * C::COUT;                        // 2 M-tiles x [hi*hi+lo*hi | hi*lo]
   static constexpr int TMEM_ALLOC = 2 * COLS_TILE;                     // 512 (C_out 64) / 256 (C_out 32): powers of two
@@ -391,7 +391,7 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
   const uint32_t b_base = sbase + Pc::OFF_B;
   const uint32_t bar0 = sbase + Pc::OFF_BAR;
   const uint32_t bar_a_full = bar0, bar_a_free = bar0 + 16, bar_b_full = bar0 + 32, bar_b_empty = bar_b_full + 8 * NSW;
-  const uint32_t bar_acc_full = bar_b_empty + 8 * NSW, bar_acc_free = bar_acc_full + 16;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * NSW, bar_acc_free = bar_acc_full + 16, bar_stage_ready = bar_acc_free + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Pc::OFF_BAR + 8 * Pc::N_BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -401,6 +401,7 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
       mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_free + 8 * i, 1);
       mbar_init(bar_acc_full + 8 * i, 2);          // both MMA issuers commit
       mbar_init(bar_acc_free + 8 * i, 8);          // one arrival per epilogue warp
+      mbar_init(bar_stage_ready + 8 * i, 8);       // un-pooled layers: the staged output image is complete
     }
     for (int i = 0; i < NSW; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 2); }
     fence_barrier_init();
@@ -411,14 +412,35 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    // ===== producer A: activation tile of every tile this CTA owns, two buffers ahead of the epilogue =====
+    // ===== producer A: activation tile of every tile this CTA owns, two buffers ahead of the epilogue.  For the
+    // un-pooled layers it also ships the staged output image of tile it-2 (bulk stores) out of the buffer it is
+    // about to refill - the epilogue warps never wait for a store =====
     if (lane == 0) {
       constexpr uint32_t A_COPY = (uint32_t)C::AROWS * ROWB;
+      auto store_tile = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(bar_stage_ready + 8 * b, (j >> 1) & 1);          // all eight epilogue warps have staged tile j
+        const int seg0 = (blockIdx.x + j * (int)gridDim.x) * G;
+        const int nvalid = min(G, n_seg - seg0);
+        const uint32_t sb = sbase + b * Pc::BUF_BYTES;
+        if constexpr (C::OUT_SPLIT) {
+          const size_t img0 = (size_t)(kSplitLead + seg0 * BLK) * C::OROWB;
+          const uint32_t bytes = (uint32_t)nvalid * C::OBLK * C::OROWB;
+          bulk_s2g(out_hi + img0, sb, bytes);
+          bulk_s2g(out_lo + img0, sb + C::IMG_BYTES, bytes);
+        } else {
+          const uint32_t per_seg = C::HO * C::WO * COUT * 4;
+          bulk_s2g(out_f32 + (size_t)seg0 * (per_seg / 4), sb, (uint32_t)nvalid * per_seg);
+        }
+        bulk_commit();
+        bulk_wait_read0();                                         // the stores have read the buffer
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1, ph = (it >> 1) & 1;
         const long long tw = PIPE_NOW();
-        mbar_wait(bar_a_free + 8 * buf, ph ^ 1);           // the epilogue of tile it-2 has left the buffer
+        if constexpr (C::POOL == SP_POOL_NONE) { if (it >= 2) store_tile(it - 2); }
+        else mbar_wait(bar_a_free + 8 * buf, ph ^ 1);              // the pooling epilogue of tile it-2 has left the buffer
         PIPE_ADD(9, tw);
         const int g0 = kSplitLead + tile * G * BLK - HALO;
         const uint32_t sh = (uint32_t)(g0 & 7);
@@ -427,6 +449,8 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
         bulk_g2s(a_hi + sh * ROWB, in_hi + (size_t)g0 * ROWB, A_COPY, bar_a_full + 8 * buf);
         bulk_g2s(a_lo + sh * ROWB, in_lo + (size_t)g0 * ROWB, A_COPY, bar_a_full + 8 * buf);
       }
+      if constexpr (C::POOL == SP_POOL_NONE)
+        for (int j = (it >= 2 ? it - 2 : 0); j < it; ++j) store_tile(j);
     }
   } else if (warp == 9) {
     // ===== producer W: the nine weight taps per tile through the ring (once, when they all stay resident) =====
@@ -466,9 +490,11 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
         for (int t = 0; t < 9; ++t, ++cnt) {
           const int s = Pc::RESIDENT ? t : cnt % NSW;
           tw = PIPE_NOW();
-          mbar_wait(bar_b_full + 8 * s, Pc::RESIDENT ? 0 : (cnt / NSW) & 1);
+          if (!Pc::RESIDENT || it == 0) {                  // (an already completed barrier still costs ~150 cycles to ask)
+            mbar_wait(bar_b_full + 8 * s, Pc::RESIDENT ? 0 : (cnt / NSW) & 1);
+            tc_fence_after();
+          }
           if (mt == 0) PIPE_ADD(2, tw);
-          tc_fence_after();
           const int tapoff = (t / 3 - 1) * P + (t % 3 - 1);
           const uint32_t bst = b_base + s * C::B_STAGE;
           const uint32_t row = sh + (uint32_t)(HALO + mt * 128 + tapoff);
@@ -557,29 +583,15 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_free + 8 * buf);          // this warp's share of the accumulators is in shared memory
-      if constexpr (C::POOL == SP_POOL_NONE) fence_proxy_async();  // staged image -> visible to the bulk store
-      if (tid == 0) PIPE_ADD(6, tw);
-      tw = PIPE_NOW();
-      named_bar_sync(1, EPI_THREADS);                              // staging tile complete (epilogue warps only)
       if constexpr (C::POOL == SP_POOL_NONE) {
-        if (tid == 0) {
-          const int nvalid = min(G, n_seg - seg0);
-          const uint32_t sb = sbase + buf * Pc::BUF_BYTES;
-          if constexpr (C::OUT_SPLIT) {
-            const size_t img0 = (size_t)(kSplitLead + seg0 * BLK) * C::OROWB;
-            const uint32_t bytes = (uint32_t)nvalid * C::OBLK * C::OROWB;
-            bulk_s2g(out_hi + img0, sb, bytes);
-            bulk_s2g(out_lo + img0, sb + C::IMG_BYTES, bytes);
-          } else {
-            const uint32_t per_seg = C::HO * C::WO * COUT * 4;
-            bulk_s2g(out_f32 + (size_t)seg0 * (per_seg / 4), sb, (uint32_t)nvalid * per_seg);
-          }
-          bulk_commit();
-          bulk_wait_read0();                                       // the stores have read the buffer
-          mbar_arrive(bar_a_free + 8 * buf);
-          PIPE_ADD(7, tw);
-        }
+        fence_proxy_async();                                       // staged image -> visible to the producer's bulk stores
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_stage_ready + 8 * buf);
+        if (tid == 0) PIPE_ADD(6, tw);
       } else {
+        if (tid == 0) PIPE_ADD(6, tw);
+        tw = PIPE_NOW();
+        named_bar_sync(1, EPI_THREADS);                            // staging tile complete (epilogue warps only)
         constexpr int POW = C::POW, HO = H / 2, C8 = COUT / 8;
         for (int i2 = tid; i2 < G * HO * POW * C8; i2 += EPI_THREADS) {
           const int c8 = i2 % C8;

@@ -150,6 +150,41 @@ def test_two_rank_gloo_exchange(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def test_two_rank_error_is_raised_on_every_rank(tmp_path):
+    """A per-file ValueError fires on the one rank that owns the row; the N>1 path exchanges (ok, message) before the
+    score gather so that EVERY rank raises the reference's error instead of blocking in the collective."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, numpy as np, pandas as pd\n"
+        "sys.path.insert(0, %r)\n"
+        "from nisqa_b200 import dist as D, NISQA_lib as NL\n"
+        "rank, world, _ = D.init_process_group(backend='gloo')\n"
+        "def fake_rows(engine, ds, rows, bs, nw):\n"
+        "    if 5 in [int(r) for r in rows]:\n"
+        "        raise ValueError('Could not load file c5.wav')\n"
+        "    return np.zeros((len(rows), 1), np.float32)\n"
+        "NL._predict_rows = fake_rows\n"
+        "class Eng: n_out = 1\n"
+        "class Ds:\n"
+        "    df = pd.DataFrame({'deg': ['c%%d.wav' %% i for i in range(9)]})\n"
+        "    def __len__(self): return 9\n"
+        "    def file_path(self, i): return '/nonexistent/c%%d.wav' %% i\n"
+        "try:\n"
+        "    NL._predict_all(Eng(), Ds(), 4, 0)\n"
+        "    msg = 'no error'\n"
+        "except ValueError as e:\n"
+        "    msg = str(e)\n"
+        "open(os.path.join(%r, 'msg%%d' %% rank), 'w').write(msg)\n"
+        "import torch.distributed as dist\n"
+        "dist.barrier(); dist.destroy_process_group()\n" % (ROOT, str(tmp_path)))
+    port = 31500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "msg0").read_text() == (tmp_path / "msg1").read_text() == "Could not load file c5.wav"
+
+
 @pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16", "alaw", "ulaw_stereo"])
 def test_native_wav_reader_matches_oracle_loader(tmp_path, kind, built_lib):
     """csrc/wavio.cpp (nisqa_wav_probe / nisqa_wav_decode, host-only entry points of the C-ABI)."""
