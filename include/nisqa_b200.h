@@ -217,6 +217,8 @@ NISQA_API int    nisqa_set_profiling(nisqa_engine* e, int on);
  *   "conv_split" 1 (default): with all of conv2..6 on tcgen05, activations travel between the layers as
  *                fp16 hi/lo plane pairs (csrc/conv_split.cu); 0: fp32 channels-last activations and the
  *                register-staged kernels of csrc/conv_tc.cu.  Results are bit-identical.
+ *   "conv12"     1 (default): conv1 + pool1 + conv2 + pool2 run as ONE persistent kernel (csrc/conv12.cu), the pool1
+ *                activations never reach HBM (NISQA_STAGE_POOL1 is then not dumpable); 0: separate kernels.
  *   "conv_pipe"  bit mask of the conv layers (2..6) whose plane kernel runs as persistent warp-specialised CTAs
  *                (default / 1 = all); a cleared bit selects the one-tile-per-CTA kernel.  Bit-identical results.
  *   "fe_ppc"     frame pairs per front-end CTA (0 = kernel default).

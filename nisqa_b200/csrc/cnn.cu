@@ -14,6 +14,7 @@
 // fp32 FFMA is a parity decision: TF32 operands alone move MOS by 2e-3.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "conv1_cell.cuh"
 
 namespace nisqa {
 
@@ -31,8 +32,6 @@ conv1_pool1_kernel(const float* __restrict__ mel, const int* __restrict__ seg_fr
                    const float* __restrict__ b1 /*[16]*/, float* __restrict__ out,
                    unsigned char* __restrict__ out_hi, unsigned char* __restrict__ out_lo, int n_seg) {
   constexpr int PW = (MODE == 0) ? 7 : 8;
-  constexpr int NWC = (MODE == 0) ? 3 : 2;       // window columns
-  constexpr int PC = NWC + 2;                    // patch columns
   __shared__ __align__(16) float ws[9 * 16 + 16];
   for (int i = threadIdx.x; i < 9 * 16 + 16; i += blockDim.x)
     ws[i] = (i < 144) ? __ldg(w1 + i) : __ldg(b1 + i - 144);
@@ -45,59 +44,9 @@ conv1_pool1_kernel(const float* __restrict__ mel, const int* __restrict__ seg_fr
   const int ph = cell % 24, pw = cell / 24;      // lanes run along mel rows: coalesced reads
   const int f0 = __ldg(seg_frame0 + seg);
   const float thr = __ldg(seg_thr + seg);
-  const int r0 = 2 * ph - 1;                     // first patch row (mel index)
-  const int c0 = (MODE == 0) ? 2 * pw - 1 : 2 * pw - 2;   // first patch col (frame in segment)
-
-  float patch[4][PC];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < PC; ++j) {
-      const int r = r0 + i, t = c0 + j;
-      float v = 0.f;                             // zero padding of the segment's own border
-      if (r >= 0 && r < kMels && t >= 0 && t < kSegLen)
-        v = fmaxf(__ldg(mel + (size_t)(f0 + t) * kMels + r), thr);
-      patch[i][j] = v;
-    }
 
   float res[16];
-#pragma unroll
-  for (int cq = 0; cq < 4; ++cq) {
-    float acc[2][NWC][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < NWC; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const float4 w = *reinterpret_cast<const float4*>(ws + tap * 16 + cq * 4);
-      const int ky = tap / 3, kx = tap % 3;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < NWC; ++j) {
-          const float a = patch[i + ky][j + kx];
-          acc[i][j][0] = fmaf(a, w.x, acc[i][j][0]);
-          acc[i][j][1] = fmaf(a, w.y, acc[i][j][1]);
-          acc[i][j][2] = fmaf(a, w.z, acc[i][j][2]);
-          acc[i][j][3] = fmaf(a, w.w, acc[i][j][3]);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float m = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < NWC; ++j) {
-          const int col = c0 + 1 + j;            // conv output column of this window slot
-          if (MODE == 0 || (col >= 0 && col < kSegLen)) m = fmaxf(m, acc[i][j][c]);
-        }
-      res[cq * 4 + c] = fmaxf(m + ws[144 + cq * 4 + c], 0.f);   // bias + ReLU commute with max
-    }
-  }
+  conv1_cell<MODE>(mel, f0, thr, ws, ph, pw, res);
   if constexpr (SPLIT) {
     const int g = kSplitLead + seg * (25 * (PW + 1)) + (ph + 1) * (PW + 1) + (pw + 1);
 #pragma unroll

@@ -39,6 +39,9 @@ size_t split_plane_bytes(int std_mode, int layer, int n_seg);
 void launch_conv_split(cudaStream_t, int, int, const void*, const void*, const void*, const float*, float,
                        void*, void*, float*, int, int);
 void launch_unsplit(cudaStream_t, int, int, const void*, const void*, float*, int);
+// conv12.cu
+void launch_conv12(cudaStream_t, int, const float*, const int*, const float*, const float*, const float*, const void*,
+                   const float*, float, void*, void*, int);
 #ifdef NISQA_TC_TIMING
 int tc_timing_read(long long*, int);
 int sp_timing_read(long long*, int);
@@ -187,6 +190,8 @@ struct nisqa_engine {
   bool weights_loaded = false;
   bool profiling = false;
   int fe_ppc = 0;          // frame pairs per front-end CTA (0: kernel default)
+  int conv12 = 1;          // conv1 + pool1 + conv2 + pool2 in one persistent kernel (conv12.cu): pool1 never reaches HBM
+  bool last_conv12 = false;
   int conv_pipe = 0x78;    // bit l (conv2's small tiles are faster one per CTA, four CTAs per SM): conv2..6 plane kernels as persistent warp-specialised CTAs (conv_pipe_kernel); 0: one tile per CTA
   int conv_split = 1;      // conv2..6 exchange activations as fp16 hi/lo plane pairs (conv_split.cu); needs conv_tc == 0x7c
   int tc_timing_layer = 0; // NISQA_TC_TIMING builds: the layer whose CTAs record their phase stamps
@@ -749,7 +754,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     const bool split = e->conv_split && e->conv_tc == 0x7c;
     e->last_split = split;
     if (split) {
-      for (int l = 2; l <= 6; ++l) {
+      for (int l = (e->conv12 ? 3 : 2); l <= 6; ++l) {
         // the lo plane sits at a fixed offset of the ALLOCATION (not of this pass's n_seg): the zero rows /
         // columns of both planes must stay where they were when the buffer was cleared
         CK(LN.planes[l].reserve_zeroed(2 * split_plane_bytes(std_mode, l, n_seg), st));
@@ -776,16 +781,24 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
                        seg_frame0, seg_thr, seg_clip); }
     auto plane_hi = [&](int l) { return LN.planes[l].as<char>(); };
     auto plane_lo = [&](int l) { return LN.planes[l].as<char>() + LN.plane_bytes[l]; };
-    { Scope s(e, "conv1");
+    const bool fused12 = split && e->conv12;
+    e->last_conv12 = fused12;
+    if (fused12) {
+      Scope s(e, "conv12");
+      launch_conv12(st, std_mode, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"), W(e, "conv1.b"),
+                    W(e, "conv2.wtc"), W(e, "conv2.b"), e->tc_scale[2], plane_hi(3), plane_lo(3), n_seg);
+    } else {
+      Scope s(e, "conv1");
       launch_conv1(st, std_mode, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"),
                    W(e, "conv1.b"), split ? nullptr : LN.act1.as<float>(), n_seg,
-                   split ? plane_hi(2) : nullptr, split ? plane_lo(2) : nullptr); }
+                   split ? plane_hi(2) : nullptr, split ? plane_lo(2) : nullptr);
+    }
     {
       const float* cin_[7] = {nullptr, nullptr, LN.act1.as<float>(), LN.act2.as<float>(), LN.act3.as<float>(),
                               LN.act4.as<float>(), LN.act5.as<float>()};
       float* cout_[7] = {nullptr, nullptr, LN.act2.as<float>(), LN.act3.as<float>(), LN.act4.as<float>(),
                          LN.act5.as<float>(), LN.feats.as<float>()};
-      for (int l = 2; l <= 6; ++l) {
+      for (int l = fused12 ? 3 : 2; l <= 6; ++l) {
         char nm[16], kw[24], kt[24], kb[24];
         snprintf(nm, sizeof nm, "conv%d", l); snprintf(kw, sizeof kw, "conv%d.w", l);
         snprintf(kt, sizeof kt, "conv%d.wtc", l); snprintf(kb, sizeof kb, "conv%d.b", l);
@@ -1140,6 +1153,8 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   if (!out) return count;
   int plane_layer = 0;          // stage lives in the plane pair feeding this conv layer
   if (e->last_split) {
+    if (stage == NISQA_STAGE_POOL1 && e->last_conv12)
+      return fail(e, NISQA_ERR_STATE, "pool1 lives only in shared memory on the fused conv1+conv2 path: nisqa_set_option(\"conv12\", 0) before the predict call");
     switch (stage) {
       case NISQA_STAGE_POOL1: plane_layer = 2; break;
       case NISQA_STAGE_POOL2: plane_layer = 3; break;
@@ -1219,6 +1234,7 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (strcmp(name, "lstm_batched") == 0) { e->lstm_batched = value != 0; return 0; }
   if (strcmp(name, "keep_td_out") == 0) { e->keep_td_out = value != 0; return 0; }
   if (strcmp(name, "td_tiled") == 0) { e->td_tiled = value != 0; return 0; }
+  if (strcmp(name, "conv12") == 0) { e->conv12 = value != 0; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
   if (strcmp(name, "conv_pipe") == 0) { e->conv_pipe = (value == 1) ? 0x78 : (value & 0x7c); return 0; }
   if (strcmp(name, "tc_timing_layer") == 0) { e->tc_timing_layer = value; return 0; }

@@ -166,7 +166,8 @@ def config_from_args(args, max_chunk_segments=0):
     cfg.hop_s, cfg.win_s = float(args["ms_hop_length"]), float(args["ms_win_length"])
     cfg.fmax = float(args["ms_fmax"])
     cfg.sa_layers = int(args["td_sa_num_layers"]) if arch == ARCH_ADAPT_SA_ATTFF else 0
-    cfg.max_chunk_segments = int(max_chunk_segments)
+    # NISQA_MAX_CHUNK: experiment knob (segments per internal pass) for A/B runs of the pass size
+    cfg.max_chunk_segments = int(max_chunk_segments) or int(os.environ.get("NISQA_MAX_CHUNK", "0"))
     return cfg
 
 

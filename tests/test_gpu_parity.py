@@ -56,10 +56,12 @@ def test_every_stage_matches_oracle(engines, ckpt, clips):
     pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
     srs = [c[2] for c in clips]
     eng.set_option("keep_td_out", 1)              # BiLSTM: per-step outputs are only stored for the dump
+    eng.set_option("conv12", 0)                   # pool1 only exists in HBM when conv1 / conv2 run as separate kernels
     try:
         scores, nseg, status = eng.predict_pcm(pcm, srs)
     finally:
         eng.set_option("keep_td_out", 0)
+        eng.set_option("conv12", 1)
     assert np.all(status == E.CLIP_OK)
     dumps = {name: eng.stage_dump(st) for name, st, _ in STAGES}
     off = {name: 0 for name, _, _ in STAGES}
@@ -273,13 +275,17 @@ def test_conv_paths_agree(engines, ckpt, clips):
     srs = [c[2] for c in clips]
     out = {}
     try:
-        for name, opts in (("planes", dict(conv_tc=1, conv_split=1, conv_pipe=1)), ("planes_1tile", dict(conv_tc=1, conv_split=1, conv_pipe=0)),
+        for name, opts in (("planes", dict(conv_tc=1, conv_split=1, conv_pipe=1, conv12=1)),
+                           ("planes_sep12", dict(conv_tc=1, conv_split=1, conv_pipe=1, conv12=0)),
+                           ("planes_1tile", dict(conv_tc=1, conv_split=1, conv_pipe=0, conv12=0)),
                            ("tc_f32", dict(conv_tc=1, conv_split=0)), ("ffma", dict(conv_tc=0, conv_split=0))):
             for k, v in opts.items():
                 eng.set_option(k, v)
             sc, nseg, st = eng.predict_pcm(pcm, srs)
-            out[name] = (sc.copy(), eng.stage_dump(E.STAGE_CNN_FEAT), eng.stage_dump(E.STAGE_POOL3))
-        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1)
+            out[name] = (sc.copy(), eng.stage_dump(E.STAGE_CNN_FEAT), eng.stage_dump(E.STAGE_POOL3), eng.stage_dump(E.STAGE_POOL2))
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1); eng.set_option("conv12", 1)
+        for i in range(4):                                                          # fused conv1+conv2 == separate kernels
+            np.testing.assert_array_equal(out["planes"][i], out["planes_sep12"][i])
         np.testing.assert_array_equal(out["planes"][0], out["planes_1tile"][0])     # persistent CTAs == one tile per CTA
         np.testing.assert_array_equal(out["planes"][1], out["planes_1tile"][1])
         np.testing.assert_array_equal(out["planes"][2], out["planes_1tile"][2])
@@ -294,7 +300,7 @@ def test_conv_paths_agree(engines, ckpt, clips):
         s_again, _, _ = eng.predict_pcm(pcm[::-1], srs[::-1])
         np.testing.assert_array_equal(s_again[::-1], out["planes"][0])
     finally:
-        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1)
+        eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1); eng.set_option("conv12", 1)
 
 
 def test_td_paths_agree(engines):

@@ -9,7 +9,7 @@ from oracle import nisqa_oracle as O
 import test_gpu_parity as T
 args, sd = O.load_checkpoint(os.path.join(ROOT, "weights", "nisqa_tts.tar"))
 eng = E.Engine(E.config_from_args(args), 0); eng.load_state_dict(sd)
-eng.set_option("keep_td_out", 1)
+eng.set_option("keep_td_out", 1); eng.set_option("conv12", 0)
 clips = T._sliced_clips([10.0] * 256, 16000, seed=6)
 stages = [("mel_db", E.STAGE_MEL_DB), ("pool1", E.STAGE_POOL1), ("pool2", E.STAGE_POOL2), ("conv3", E.STAGE_CONV3),
           ("pool3", E.STAGE_POOL3), ("conv5", E.STAGE_CONV5), ("cnn_feat", E.STAGE_CNN_FEAT), ("td_out", E.STAGE_TD_OUT)]

@@ -28,6 +28,7 @@ tag = a.tag or ("split=%d lib=%s" % (a.split, a.lib or "default"))
 
 def opts(eng):
     eng.set_option("conv_split", a.split)
+    eng.set_option("conv12", 0)          # the per-stage comparison dumps pool1
 
 
 if not a.skip_check:
