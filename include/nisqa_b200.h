@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NISQA_B200_ABI_VERSION 1
+#define NISQA_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NISQA_API __attribute__((visibility("default")))
@@ -38,6 +38,17 @@ typedef struct nisqa_engine nisqa_engine;
 enum nisqa_arch {
   NISQA_ARCH_ADAPT_SA_ATTFF  = 0, /* nisqa.tar, nisqa_mos_only.tar: AdaptCNN + SelfAttention + PoolAttFF */
   NISQA_ARCH_STD_LSTM_LASTBI = 1  /* nisqa_tts.tar: StandardCNN + BiLSTM + PoolLastStepBi            */
+};
+
+/* pooling over time (reference lib:1066-1225).  The shipped checkpoints use ATT_FF (nisqa*.tar) and LAST_STEP_BI
+ * (nisqa_tts.tar); the others are reachable through user-trained checkpoints. */
+enum nisqa_pool {
+  NISQA_POOL_ATT_FF       = 0, /* PoolAttFF, h = 128 (lib:1156-1183)                  */
+  NISQA_POOL_ATT          = 1, /* PoolAtt (lib:1131-1154)                             */
+  NISQA_POOL_AVG          = 2, /* PoolAvg (lib:1185-1204)                             */
+  NISQA_POOL_MAX          = 3, /* PoolMax (lib:1206-1225)                             */
+  NISQA_POOL_LAST_STEP    = 4, /* PoolLastStep (lib:1117-1129)                        */
+  NISQA_POOL_LAST_STEP_BI = 5  /* PoolLastStepBi (lib:1099-1115), BiLSTM only         */
 };
 
 enum nisqa_sample_fmt { NISQA_FMT_S16 = 0, NISQA_FMT_F32 = 1 };
@@ -83,6 +94,8 @@ typedef struct nisqa_config {
   double  fmax;          /* ms_fmax Hz */
   int32_t sa_layers;     /* td_sa_num_layers (adapt arch), else 0 */
   int32_t max_chunk_segments; /* 0 = default; upper bound on segments processed per internal pass */
+  int32_t pool;          /* enum nisqa_pool */
+  int32_t pos_enc;       /* td_sa_pos_enc: add the checkpoint's positional-encoding buffer after the input LayerNorm (lib:1042-1062) */
 } nisqa_config;
 
 /* One state_dict entry, passed straight through: name as in the checkpoint

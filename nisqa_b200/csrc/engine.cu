@@ -54,18 +54,15 @@ struct SaLayerParams {
 };
 struct PoolHeadParams { const float* W1T; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3; };
 struct LstmParams { const float* w_ih; const float* w_hh; const float* b; const float* w_pool; };
-void launch_lin_ln(cudaStream_t, const float*, const float*, const float*, const float*, const float*, float*, int);
 void launch_fc20(cudaStream_t, const float*, const float*, const float*, float*, int);
-void launch_qkv(cudaStream_t, const float*, const float*, const float*, float*, int);
-void launch_sa_layer(cudaStream_t, const float*, const float*, const ClipDesc*, int, const int*, int,
-                     const SaLayerParams&, float*);
-void launch_pool_att(cudaStream_t, const float*, const ClipDesc*, int, int, const PoolHeadParams&, int, float*, float*);
 void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmParams&, float*, float*, float, float*);
 void launch_lstm_batched(cudaStream_t, const float*, const ClipDesc*, const int*, int, const LstmParams&, float*, float*, float, float*);
 void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
 // td_tiled.cu
 void launch_td_in(cudaStream_t, const float*, const float*, const float*, const float*, const float*,
-                  const float*, const float*, float*, float*, int);
+                  const float*, const float*, const float*, const int*, const ClipDesc*, float*, float*, int);
+struct PoolSimpleParams { const float* a1; const float* a1b; const float* w3; const float* b3; };
+void launch_pool_simple(cudaStream_t, const float*, int, const ClipDesc*, int, int, const PoolSimpleParams&, int, int, float*);
 void launch_td_sa(cudaStream_t, const float*, const float*, const ClipDesc*, int, const int*, int, const SaLayerParams&,
                   float*, const float*, const float*, float*, const PoolHeadParams&, int, float*);
 }  // namespace nisqa
@@ -198,7 +195,6 @@ struct nisqa_engine {
   bool last_split = false; // the last pass ran the plane pipeline (stage dumps convert back to fp32)
   int lstm_batched = 1;    // BiLSTM: NB clips per CTA in lock step (td.cu lstm_batched_kernel); 0: one CTA per (clip, direction)
   int keep_td_out = 0;     // standard arch: also write the per-step LSTM outputs [n_seg][256] (only the stage dump reads them)
-  int td_tiled = 1;        // time-dependency block as register-tiled GEMM kernels (td_tiled.cu); 0: the row-thread kernels of td.cu
   int conv_tc = 0x7c;      // bit l set: conv layer l (2..6) runs on tcgen05 (fp16 two-term split); else fp32 FFMA
   std::vector<TimerSlot> timers;
 
@@ -563,14 +559,27 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       o = P.alloc(K("ln2b"), 64); memcpy(&P.arena[o], e2->d, 256);
     }
     const int nh = e->cfg.n_out;
+    auto head_prefix = [&](int h) {
+      char pf[64];
+      if (nh == 1) snprintf(pf, sizeof pf, "pool.model.");
+      else snprintf(pf, sizeof pf, "pool_layers.%d.model.", h);   // head order mos,noi,dis,col,loud (lib:1461-1465)
+      return std::string(pf);
+    };
+    if (e->cfg.pos_enc) {
+      auto it = P.t.find(td + "pos_encoder.pe");                  // registered buffer [max_len, 1, 64] (lib:1051-1058)
+      if (it == P.t.end() || it->second.nd != 3 || it->second.dims[1] != 1 || it->second.dims[2] != 64)
+        return fail(e, NISQA_ERR_WEIGHTS, "missing tensor " + td + "pos_encoder.pe");
+      if (e->cfg.max_segments > 0 && it->second.dims[0] < e->cfg.max_segments)
+        return fail(e, NISQA_ERR_WEIGHTS, "positional encoding shorter than ms_max_segments");
+      const size_t o2 = P.alloc("pe", (size_t)it->second.numel);
+      memcpy(&P.arena[o2], it->second.d, (size_t)it->second.numel * 4);
+    }
+    if (e->cfg.pool == NISQA_POOL_ATT_FF) {
     const size_t oW1 = P.alloc("pool.w1T", (size_t)nh * 64 * 128), ob1 = P.alloc("pool.b1", nh * 128),
                  ow2 = P.alloc("pool.w2", nh * 128), ob2 = P.alloc("pool.b2", nh),
                  ow3 = P.alloc("pool.w3", nh * 64), ob3 = P.alloc("pool.b3", nh);
     for (int h = 0; h < nh; ++h) {
-      char pf[64];
-      if (nh == 1) snprintf(pf, sizeof pf, "pool.model.");
-      else snprintf(pf, sizeof pf, "pool_layers.%d.model.", h);   // head order mos,noi,dis,col,loud (lib:1461-1465)
-      const std::string p(pf);
+      const std::string p = head_prefix(h);
       const TensorView* w1 = P.get(p + "linear1.weight", {128, 64});
       const TensorView* b1 = P.get(p + "linear1.bias", {128});
       const TensorView* w2 = P.get(p + "linear2.weight", {1, 128});
@@ -584,6 +593,23 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       P.arena[ob2 + h] = b2->d[0];
       memcpy(&P.arena[ow3 + h * 64], w3->d, 256);
       P.arena[ob3 + h] = b3->d[0];
+    }
+    } else {
+      // PoolAtt: linear1 (64 -> 1 attention logit) + linear2 (64 -> 1); PoolAvg / PoolMax / PoolLastStep: linear (64 -> 1)
+      const bool att = e->cfg.pool == NISQA_POOL_ATT;
+      const size_t oa1 = P.alloc("pool.a1", nh * 64), oa1b = P.alloc("pool.a1b", nh),
+                   ow3 = P.alloc("pool.w3", nh * 64), ob3 = P.alloc("pool.b3", nh);
+      for (int h = 0; h < nh; ++h) {
+        const std::string p = head_prefix(h);
+        const TensorView* a1 = att ? P.get(p + "linear1.weight", {1, 64}) : nullptr;
+        const TensorView* a1b = att ? P.get(p + "linear1.bias", {1}) : nullptr;
+        const TensorView* w3 = P.get(p + (att ? "linear2.weight" : "linear.weight"), {1, 64});
+        const TensorView* b3 = P.get(p + (att ? "linear2.bias" : "linear.bias"), {1});
+        if ((att && (!a1 || !a1b)) || !w3 || !b3) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+        if (att) { memcpy(&P.arena[oa1 + h * 64], a1->d, 256); P.arena[oa1b + h] = a1b->d[0]; }
+        memcpy(&P.arena[ow3 + h * 64], w3->d, 256);
+        P.arena[ob3 + h] = b3->d[0];
+      }
     }
   } else {
     const TensorView* fw = P.get("cnn.model.fc_out.weight", {20, 768});
@@ -609,11 +635,14 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       memcpy(&P.arena[owh + (size_t)d * 512 * 128], wh->d, 512 * 128 * 4);
       for (int g = 0; g < 512; ++g) P.arena[obb + d * 512 + g] = bi->d[g] + bh->d[g];
     }
-    const TensorView* pw = P.get("pool.model.linear.weight", {1, 256});
+    const TensorView* pw = P.get("pool.model.linear.weight", {1, 256});      // every pooling module of this arch: Linear(256 -> 1)
     const TensorView* pb = P.get("pool.model.linear.bias", {1});
     if (!pw || !pb) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
     o = P.alloc("lastbi.w", 256); memcpy(&P.arena[o], pw->d, 1024);
     e->pool_bias_std = pb->d[0];
+    o = P.alloc("pool.w3", 256); memcpy(&P.arena[o], pw->d, 1024);
+    o = P.alloc("pool.b3", 1); P.arena[o] = pb->d[0];
+    P.alloc("pool.a1", 1); P.alloc("pool.a1b", 1);
   }
   // conv1 is stored as [tap][16]: same as the generic [ci=1][tap][cout] packing.
   CK(e->warena.reserve(P.arena.size() * 4));
@@ -651,7 +680,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   cl.assign(n, ClipDesc());
   std::vector<int> pair_prefix(n + 1, 0), seg_prefix(n + 1, 0), qt_prefix(n + 1, 0), qt64_prefix(n + 1, 0), by_len(n + 1, 0);
   long long pcm_elems = 0;
-  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, n_qt64 = 0, Q = 1, max_pairs = 0, max_span = 0;
+  int n_frames = 0, n_seg = 0, n_pairs = 0, n_qt = 0, n_qt64 = 0, Q = 1, max_pairs = 0, max_span = 0, max_n_seg = 0;
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
@@ -671,6 +700,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     max_pairs = std::max(max_pairs, (d.n_frames + 1) / 2);
     n_qt += (d.n_seg + 127) / 128;
     n_qt64 += (d.n_seg + 63) / 64;
+    max_n_seg = std::max(max_n_seg, d.n_seg);
     if (ok) { Q = std::max(Q, (p.win + 1023) / 1024); max_span = std::max(max_span, p.hop + p.win); }
   }
   pair_prefix[n] = n_pairs; seg_prefix[n] = n_seg; qt_prefix[n] = n_qt; qt64_prefix[n] = n_qt64;
@@ -821,52 +851,47 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       CK(LN.qkv.reserve((size_t)n_seg * 192 * 4));
       CK(LN.logits.reserve((size_t)n_seg * n_out * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 64 * 4));
+      auto sa_key = [&](int l, const char* s2) { char k[32]; snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
       auto sa_params = [&](int l) {
-        char k[32];
-        auto K = [&](const char* s2) { snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
         SaLayerParams P;
-        P.WoT = W(e, K("woT")); P.bo = W(e, K("bo")); P.W1T = W(e, K("w1T")); P.b1 = W(e, K("b1"));
-        P.W2T = W(e, K("w2T")); P.b2 = W(e, K("b2")); P.ln1_g = W(e, K("ln1g")); P.ln1_b = W(e, K("ln1b"));
-        P.ln2_g = W(e, K("ln2g")); P.ln2_b = W(e, K("ln2b"));
+        P.WoT = W(e, sa_key(l, "woT")); P.bo = W(e, sa_key(l, "bo")); P.W1T = W(e, sa_key(l, "w1T")); P.b1 = W(e, sa_key(l, "b1"));
+        P.W2T = W(e, sa_key(l, "w2T")); P.b2 = W(e, sa_key(l, "b2")); P.ln1_g = W(e, sa_key(l, "ln1g")); P.ln1_b = W(e, sa_key(l, "ln1b"));
+        P.ln2_g = W(e, sa_key(l, "ln2g")); P.ln2_b = W(e, sa_key(l, "ln2b"));
         return P;
       };
-      auto sa_key = [&](int l, const char* s2) { char k[32]; snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
-      PoolHeadParams H;
-      H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
+      const bool attff = c.pool == NISQA_POOL_ATT_FF;
+      PoolHeadParams H = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (attff) {
+        H.W1T = W(e, "pool.w1T"); H.b1 = W(e, "pool.b1"); H.w2 = W(e, "pool.w2"); H.b2 = W(e, "pool.b2");
+      }
       H.w3 = W(e, "pool.w3"); H.b3 = W(e, "pool.b3");
       e->last_td_in = LN.tdout.as<float>();
       const float* cur = LN.tdout.as<float>();
       float* pp[2] = {LN.xa.as<float>(), LN.xb.as<float>()};
-      if (e->td_tiled) {
-        // tiled path: Linear+LN (+QKV of layer 0) | per layer: attention + out_proj + FFN + LNs (+ next QKV, or the
-        // pooling logits behind the last layer) | per-clip softmax pooling.  qkv ping-pongs between two buffers: a
-        // layer's CTAs read keys / values of rows whose next-layer projection other CTAs are already writing.
-        CK(LN.qkv2.reserve((size_t)n_seg * 192 * 4));
-        float* qk[2] = {LN.qkv.as<float>(), LN.qkv2.as<float>()};
-        { Scope s(e, "lin_ln");
-          launch_td_in(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"),
-                       W(e, sa_key(0, "qkvT")), W(e, sa_key(0, "qkvb")), LN.tdout.as<float>(), qk[0], n_seg); }
-        for (int l = 0; l < c.sa_layers; ++l) {
-          const bool last = l + 1 == c.sa_layers;
-          Scope s(e, "sa_layer");
-          launch_td_sa(st, cur, qk[l & 1], d_clips, n, d_qt64, n_qt64, sa_params(l), pp[l & 1],
-                       last ? nullptr : W(e, sa_key(l + 1, "qkvT")), last ? nullptr : W(e, sa_key(l + 1, "qkvb")),
-                       qk[(l + 1) & 1], H, n_out, LN.logits.as<float>());
-          cur = pp[l & 1];
-        }
-        e->last_td_out = cur;
-        { Scope s(e, "pool"); launch_pool_final(st, cur, LN.logits.as<float>(), d_clips, n, H, n_out, scores); }
-      } else {
-        { Scope s(e, "lin_ln");
-          launch_lin_ln(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"), LN.tdout.as<float>(), n_seg); }
-        for (int l = 0; l < c.sa_layers; ++l) {
-          { Scope s(e, "qkv"); launch_qkv(st, cur, W(e, sa_key(l, "qkvT")), W(e, sa_key(l, "qkvb")), LN.qkv.as<float>(), n_seg); }
-          { Scope s(e, "sa_layer"); launch_sa_layer(st, cur, LN.qkv.as<float>(), d_clips, n, d_qt, n_qt, sa_params(l), pp[l & 1]); }
-          cur = pp[l & 1];
-        }
-        e->last_td_out = cur;
-        { Scope s(e, "pool", 2); launch_pool_att(st, cur, d_clips, n, n_seg, H, n_out, LN.logits.as<float>(), scores); }
+      // Linear+LN (+positional encoding, +QKV of layer 0) | per layer: attention + out_proj + FFN + LNs (+ next QKV, or
+      // the PoolAttFF logits behind the last layer) | per-clip pooling.  qkv ping-pongs between two buffers: a layer's
+      // CTAs read keys / values of rows whose next-layer projection other CTAs are already writing.
+      CK(LN.qkv2.reserve((size_t)n_seg * 192 * 4));
+      float* qk[2] = {LN.qkv.as<float>(), LN.qkv2.as<float>()};
+      { Scope s(e, "lin_ln");
+        launch_td_in(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"),
+                     W(e, sa_key(0, "qkvT")), W(e, sa_key(0, "qkvb")), c.pos_enc ? W(e, "pe") : nullptr, seg_clip, d_clips,
+                     LN.tdout.as<float>(), qk[0], n_seg); }
+      for (int l = 0; l < c.sa_layers; ++l) {
+        const bool last = l + 1 == c.sa_layers;
+        Scope s(e, "sa_layer");
+        launch_td_sa(st, cur, qk[l & 1], d_clips, n, d_qt64, n_qt64, sa_params(l), pp[l & 1],
+                     last ? nullptr : W(e, sa_key(l + 1, "qkvT")), last ? nullptr : W(e, sa_key(l + 1, "qkvb")),
+                     qk[(l + 1) & 1], H, attff ? n_out : 0, LN.logits.as<float>());
+        cur = pp[l & 1];
       }
+      e->last_td_out = cur;
+      { Scope s(e, "pool");
+        if (attff) launch_pool_final(st, cur, LN.logits.as<float>(), d_clips, n, H, n_out, scores);
+        else {
+          PoolSimpleParams Q = {W(e, "pool.a1"), W(e, "pool.a1b"), W(e, "pool.w3"), W(e, "pool.b3")};
+          launch_pool_simple(st, cur, 64, d_clips, n, c.pool, Q, n_out, max_n_seg, scores);
+        } }
     } else {
       CK(LN.feats20.reserve((size_t)n_seg * 20 * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 256 * 4));
@@ -874,14 +899,22 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       { Scope s(e, "fc_out"); launch_fc20(st, LN.feats.as<float>(), W(e, "fc.wT"), W(e, "fc.b"), LN.feats20.as<float>(), n_seg); }
       LstmParams L;
       L.w_ih = W(e, "lstm.wih"); L.w_hh = W(e, "lstm.whh"); L.b = W(e, "lstm.b"); L.w_pool = W(e, "lastbi.w");
+      const bool lastbi = c.pool == NISQA_POOL_LAST_STEP_BI;
+      const bool keep = e->keep_td_out || !lastbi;        // the other pooling modules read every step's output
       { Scope s(e, "lstm", 2);
         if (e->lstm_batched)
-          launch_lstm_batched(st, LN.feats20.as<float>(), d_clips, d_by_len, n, L, e->keep_td_out ? LN.tdout.as<float>() : nullptr,
-                              LN.partial.as<float>(), e->pool_bias_std, scores);
+          launch_lstm_batched(st, LN.feats20.as<float>(), d_clips, d_by_len, n, L, keep ? LN.tdout.as<float>() : nullptr,
+                              LN.partial.as<float>(), e->pool_bias_std, lastbi ? scores : nullptr);
         else
-          launch_lstm(st, LN.feats20.as<float>(), d_clips, n, L, LN.tdout.as<float>(), LN.partial.as<float>(), e->pool_bias_std, scores); }
+          launch_lstm(st, LN.feats20.as<float>(), d_clips, n, L, LN.tdout.as<float>(), LN.partial.as<float>(), e->pool_bias_std,
+                      lastbi ? scores : nullptr); }
+      if (!lastbi) {
+        Scope s(e, "pool");
+        PoolSimpleParams Q = {W(e, "pool.a1"), W(e, "pool.a1b"), W(e, "pool.w3"), W(e, "pool.b3")};
+        launch_pool_simple(st, LN.tdout.as<float>(), 256, d_clips, n, c.pool, Q, 1, max_n_seg, scores);
+      }
       e->last_td_in = nullptr;
-      e->last_td_out = (e->lstm_batched && !e->keep_td_out) ? nullptr : LN.tdout.as<float>();
+      e->last_td_out = (e->lstm_batched && !keep) ? nullptr : LN.tdout.as<float>();
     }
   }
   CK(cudaGetLastError());
@@ -1013,6 +1046,11 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
     return fail(e, NISQA_ERR_INVALID, "bad front-end parameters");
   if (cfg->arch == NISQA_ARCH_ADAPT_SA_ATTFF && (cfg->sa_layers < 1 || cfg->sa_layers > 8))
     return fail(e, NISQA_ERR_INVALID, "sa_layers");
+  if (cfg->pool < NISQA_POOL_ATT_FF || cfg->pool > NISQA_POOL_LAST_STEP_BI ||
+      (cfg->arch == NISQA_ARCH_ADAPT_SA_ATTFF && cfg->pool == NISQA_POOL_LAST_STEP_BI) ||
+      (cfg->arch == NISQA_ARCH_STD_LSTM_LASTBI && (cfg->pool == NISQA_POOL_ATT_FF || cfg->pool == NISQA_POOL_ATT)))
+    return fail(e, NISQA_ERR_INVALID, "pooling module not available for this architecture");
+  if (cfg->pos_enc && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) return fail(e, NISQA_ERR_INVALID, "pos_enc needs the self-attention architecture");
   int count = 0;
   CK(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return fail(e, NISQA_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");
@@ -1233,7 +1271,6 @@ int nisqa_set_option(nisqa_engine* e, const char* name, int value) {
   if (strcmp(name, "fe_ppc") == 0) { e->fe_ppc = value; return 0; }
   if (strcmp(name, "lstm_batched") == 0) { e->lstm_batched = value != 0; return 0; }
   if (strcmp(name, "keep_td_out") == 0) { e->keep_td_out = value != 0; return 0; }
-  if (strcmp(name, "td_tiled") == 0) { e->td_tiled = value != 0; return 0; }
   if (strcmp(name, "conv12") == 0) { e->conv12 = value != 0; return 0; }
   if (strcmp(name, "conv_split") == 0) { e->conv_split = value != 0; return 0; }
   if (strcmp(name, "conv_pipe") == 0) { e->conv_pipe = (value == 1) ? 0x78 : (value & 0x7c); return 0; }

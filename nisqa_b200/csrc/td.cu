@@ -91,163 +91,11 @@ linear_rows_kernel(const float* __restrict__ in, int K, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// qkv[row] = [ (Wq x + bq)/8 | Wk x + bk | Wv x + bv ]   (1/sqrt(64) folded into Wq,bq on the host)
-__global__ void __launch_bounds__(kRows)
-qkv_kernel(const float* __restrict__ x, const float* __restrict__ WT3 /*[3][64][64]*/,
-           const float* __restrict__ b3 /*[192]*/, float* __restrict__ qkv, int n_rows) {
-  extern __shared__ __align__(16) float sm[];
-  float* xs = sm;
-  float* ws = sm + kRows * kXS;         // [64][64]
-  const int row0 = blockIdx.x * kRows, tid = threadIdx.x;
-  for (int i = tid; i < kRows * 64; i += kRows) {
-    const int r = i >> 6, k = i & 63;
-    xs[r * kXS + k] = (row0 + r < n_rows) ? __ldg(x + (size_t)(row0 + r) * 64 + k) : 0.f;
-  }
-  for (int part = 0; part < 3; ++part) {
-    __syncthreads();
-    stage_f4(ws, WT3 + part * 4096, 4096);
-    __syncthreads();
-    float acc[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = __ldg(b3 + part * 64 + j);
-    rowgemm<64>(acc, xs + tid * kXS, ws, 64);
-    if (row0 + tid < n_rows) {
-      float4* o = reinterpret_cast<float4*>(qkv + (size_t)(row0 + tid) * 192 + part * 64);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) o[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// One encoder layer minus the QKV projection, for 128 queries of one clip per CTA:
-//   flash-style softmax(q k^T) v over the clip's own keys (online max/sum, keys in blocks of 8)
-//   -> out_proj -> +x -> LN1 -> FFN(ReLU) -> + -> LN2          (reference lib:1032-1038)
 struct SaLayerParams {
-  const float* WoT; const float* bo;         // [64][64] k-major, [64]
-  const float* W1T; const float* b1;
-  const float* W2T; const float* b2;
-  const float* ln1_g; const float* ln1_b;
-  const float* ln2_g; const float* ln2_b;
+  const float* WoT; const float* bo; const float* W1T; const float* b1; const float* W2T;
+  const float* b2; const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
 };
-
-constexpr int kKeyTile = 64;
-constexpr int kSaSmemFloats = 3 * 4096 + 2 * kKeyTile * 64 + kRows * kXS;
-
-__global__ void __launch_bounds__(kRows, 2)
-sa_layer_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv,
-                const ClipDesc* __restrict__ clips, int n_clips, const int* __restrict__ qtile_prefix,
-                SaLayerParams P, float* __restrict__ x_out) {
-  extern __shared__ __align__(16) float sm[];
-  float* wo = sm; float* w1 = sm + 4096; float* w2 = sm + 8192;
-  float* ks = sm + 12288;                      // [64 keys][64]
-  float* vs = ks + kKeyTile * 64;
-  float* xs = vs + kKeyTile * 64;              // per-thread rows, stride 65
-  const int tid = threadIdx.x;
-  const int c = upper_slot(qtile_prefix, n_clips, blockIdx.x);
-  const ClipDesc cd = clips[c];
-  const int S = cd.n_seg;
-  const int q0 = (blockIdx.x - __ldg(qtile_prefix + c)) * kRows;
-  const int qi = q0 + tid;
-  const bool active = qi < S;
-  const size_t rowg = (size_t)cd.seg_off + (active ? qi : 0);
-
-  stage_f4(wo, P.WoT, 4096); stage_f4(w1, P.W1T, 4096); stage_f4(w2, P.W2T, 4096);
-
-  float q[64], o[64];
-  {
-    const float4* qp = reinterpret_cast<const float4*>(qkv + rowg * 192);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { const float4 t = __ldg(qp + i); q[4*i] = t.x; q[4*i+1] = t.y; q[4*i+2] = t.z; q[4*i+3] = t.w; }
-  }
-#pragma unroll
-  for (int j = 0; j < 64; ++j) o[j] = 0.f;
-  float m = -INFINITY, l = 0.f;
-
-  for (int j0 = 0; j0 < S; j0 += kKeyTile) {
-    __syncthreads();
-    for (int i = tid; i < kKeyTile * 16; i += kRows) {       // float4 granules of k and v rows
-      const int kr = i >> 4, g = i & 15;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (j0 + kr < S) {
-        const float4* src = reinterpret_cast<const float4*>(qkv + ((size_t)cd.seg_off + j0 + kr) * 192);
-        kv = __ldg(src + 16 + g); vv = __ldg(src + 32 + g);
-      }
-      reinterpret_cast<float4*>(ks)[i] = kv; reinterpret_cast<float4*>(vs)[i] = vv;
-    }
-    __syncthreads();
-    const int nk = min(kKeyTile, S - j0);
-    for (int jb = 0; jb < nk; jb += 8) {
-      float s[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4* kr = reinterpret_cast<const float4*>(ks + (jb + u) * 64);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const float4 kk = kr[g];
-          a0 = fmaf(q[4*g], kk.x, a0); a1 = fmaf(q[4*g+1], kk.y, a1);
-          a2 = fmaf(q[4*g+2], kk.z, a2); a3 = fmaf(q[4*g+3], kk.w, a3);
-        }
-        s[u] = (jb + u < nk) ? (a0 + a1) + (a2 + a3) : -INFINITY;
-      }
-      float bm = s[0];
-#pragma unroll
-      for (int u = 1; u < 8; ++u) bm = fmaxf(bm, s[u]);
-      const float mn = fmaxf(m, bm);
-      const float sc = expf(m - mn);          // m == -inf on the first block: expf(-inf) = 0
-      l *= sc;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) o[j] *= sc;
-      m = mn;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float p = expf(s[u] - mn);      // masked tail: expf(-inf) = 0
-        l += p;
-        const float4* vr = reinterpret_cast<const float4*>(vs + (jb + u) * 64);
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const float4 vv = vr[g];
-          o[4*g] = fmaf(p, vv.x, o[4*g]); o[4*g+1] = fmaf(p, vv.y, o[4*g+1]);
-          o[4*g+2] = fmaf(p, vv.z, o[4*g+2]); o[4*g+3] = fmaf(p, vv.w, o[4*g+3]);
-        }
-      }
-    }
-  }
-  const float inv = 1.0f / l;
-  float* xrow = xs + tid * kXS;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) xrow[j] = o[j] * inv;
-
-  // out_proj + residual + LN1   (q[] reused as the accumulator, o[] as the residual stream)
-#pragma unroll
-  for (int j = 0; j < 64; ++j) q[j] = __ldg(P.bo + j);
-  rowgemm<64>(q, xrow, wo, 64);
-  {
-    const float4* xp = reinterpret_cast<const float4*>(x_in + rowg * 64);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { const float4 t = __ldg(xp + i); o[4*i] = t.x + q[4*i]; o[4*i+1] = t.y + q[4*i+1]; o[4*i+2] = t.z + q[4*i+2]; o[4*i+3] = t.w + q[4*i+3]; }
-  }
-  layernorm64(o, P.ln1_g, P.ln1_b);
-  // FFN
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { xrow[j] = o[j]; q[j] = __ldg(P.b1 + j); }
-  rowgemm<64>(q, xrow, w1, 64);
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { xrow[j] = fmaxf(q[j], 0.f); q[j] = __ldg(P.b2 + j); }
-  rowgemm<64>(q, xrow, w2, 64);
-#pragma unroll
-  for (int j = 0; j < 64; ++j) o[j] += q[j];
-  layernorm64(o, P.ln2_g, P.ln2_b);
-  if (active) {
-    float4* op = reinterpret_cast<float4*>(x_out + rowg * 64);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) op[i] = make_float4(o[4*i], o[4*i+1], o[4*i+2], o[4*i+3]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// PoolAttFF logits: logit[row][h] = w2_h . relu(W1_h x + b1_h) + b2_h      (lib:1173)
+// PoolAttFF (lib:1156-1183): the logits w2_h . relu(W1_h x + b1_h) + b2_h come out of td_sa_kernel's fused tail
 struct PoolHeadParams {      // device pointers, heads concatenated
   const float* W1T;   // [n_heads][64 k][128 j]
   const float* b1;    // [n_heads][128]
@@ -256,47 +104,6 @@ struct PoolHeadParams {      // device pointers, heads concatenated
   const float* w3;    // [n_heads][64]
   const float* b3;    // [n_heads]
 };
-
-__global__ void __launch_bounds__(kRows)
-pool_logits_kernel(const float* __restrict__ x, PoolHeadParams P, int n_heads,
-                   float* __restrict__ logits, int n_rows) {
-  extern __shared__ __align__(16) float sm[];
-  float* xs = sm;
-  float* ws = sm + kRows * kXS;         // [64][128]
-  const int row0 = blockIdx.x * kRows, tid = threadIdx.x;
-  for (int i = tid; i < kRows * 64; i += kRows) {
-    const int r = i >> 6, k = i & 63;
-    xs[r * kXS + k] = (row0 + r < n_rows) ? __ldg(x + (size_t)(row0 + r) * 64 + k) : 0.f;
-  }
-  for (int h = 0; h < n_heads; ++h) {
-    __syncthreads();
-    stage_f4(ws, P.W1T + (size_t)h * 64 * 128, 64 * 128);
-    __syncthreads();
-    float logit = __ldg(P.b2 + h);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      float acc[64];
-#pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = __ldg(P.b1 + h * 128 + half * 64 + j);
-      // columns [half*64, half*64+64) of the [64][128] tile: row stride 128
-      const float* xrow = xs + tid * kXS;
-#pragma unroll 4
-      for (int k = 0; k < 64; ++k) {
-        const float xv = xrow[k];
-        const float4* w4 = reinterpret_cast<const float4*>(ws + k * 128 + half * 64);
-#pragma unroll
-        for (int qd = 0; qd < 16; ++qd) {
-          const float4 w = w4[qd];
-          acc[qd*4] = fmaf(xv, w.x, acc[qd*4]); acc[qd*4+1] = fmaf(xv, w.y, acc[qd*4+1]);
-          acc[qd*4+2] = fmaf(xv, w.z, acc[qd*4+2]); acc[qd*4+3] = fmaf(xv, w.w, acc[qd*4+3]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 64; ++j) logit = fmaf(__ldg(P.w2 + h * 128 + half * 64 + j), fmaxf(acc[j], 0.f), logit);
-    }
-    if (row0 + tid < n_rows) logits[(size_t)(row0 + tid) * n_heads + h] = logit;
-  }
-}
 
 // softmax over the clip's time steps, weighted sum of x, Linear 64->1   (lib:1177-1181)
 // grid = n_clips, block = 64 * n_heads; thread (h, d)
@@ -331,6 +138,84 @@ __global__ void pool_final_kernel(const float* __restrict__ x, const float* __re
   __syncthreads();
   for (int o = 32; o > 0; o >>= 1) { if (d < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
   if (d == 0) scores[blockIdx.x * n_heads + h] = red[h * 64] + __ldg(P.b3 + h);
+}
+
+// ---------------------------------------------------------------------------------------
+// The other pooling modules of the reference (user-trained checkpoints), one CTA per clip, D threads
+// (thread d owns feature d; D = 64 after self-attention, 256 after the BiLSTM):
+//   mode 1 PoolAtt       (lib:1131-1154): att_t = a1 . x_t + a1b, softmax over the clip's steps, sum_t att_t x_t, Linear
+//   mode 2 PoolAvg       (lib:1185-1204): mean over the clip's steps, Linear
+//   mode 3 PoolMax       (lib:1206-1225): max over the clip's steps, Linear
+//   mode 4 PoolLastStep  (lib:1117-1129): x at the last valid step, Linear
+// One Linear(D -> 1) per head (NISQA_DIM: five heads with their own weights, lib:260-268).
+struct PoolSimpleParams { const float* a1; const float* a1b; const float* w3; const float* b3; };
+
+template <int D>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < D / 32; ++w) t += red[w];
+  return t;
+}
+template <int D>
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < D / 32; ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+
+template <int D>
+__global__ void __launch_bounds__(D)
+pool_simple_kernel(const float* __restrict__ x /*[n_seg][D]*/, const ClipDesc* __restrict__ clips, int mode,
+                   PoolSimpleParams P, int n_heads, float* __restrict__ scores) {
+  extern __shared__ __align__(16) float slog[];          // mode 1: softmax numerators of the clip's steps
+  __shared__ float red[D / 32];
+  const ClipDesc cd = clips[blockIdx.x];
+  const int S = cd.n_seg, d = threadIdx.x, lane = d & 31, warp = d >> 5;
+  if (S <= 0) { if (d < n_heads) scores[blockIdx.x * n_heads + d] = __int_as_float(0x7fc00000); return; }
+  const float* xb = x + (size_t)cd.seg_off * D;
+  float pooled = 0.f;
+  if (mode == 2) {
+    for (int t = 0; t < S; ++t) pooled += __ldg(xb + (size_t)t * D + d);
+    pooled = pooled / (float)S;
+  } else if (mode == 3) {
+    pooled = -INFINITY;
+    for (int t = 0; t < S; ++t) pooled = fmaxf(pooled, __ldg(xb + (size_t)t * D + d));
+  } else if (mode == 4) {
+    pooled = __ldg(xb + (size_t)(S - 1) * D + d);
+  }
+  for (int h = 0; h < n_heads; ++h) {
+    if (mode == 1) {
+      __syncthreads();                                    // slog of the previous head consumed
+      for (int t = warp; t < S; t += D / 32) {
+        float a = 0.f;
+        for (int k = lane; k < D; k += 32) a = fmaf(__ldg(xb + (size_t)t * D + k), __ldg(P.a1 + h * D + k), a);
+        a = warp_sum(a);
+        if (lane == 0) slog[t] = a + __ldg(P.a1b + h);
+      }
+      __syncthreads();
+      float mx = -INFINITY;
+      for (int t = d; t < S; t += D) mx = fmaxf(mx, slog[t]);
+      mx = block_max<D>(mx, red);
+      float sum = 0.f;
+      for (int t = d; t < S; t += D) { const float e = expf(slog[t] - mx); slog[t] = e; sum += e; }
+      sum = block_sum<D>(sum, red);                       // (its barriers also publish the numerators)
+      float acc = 0.f;
+      for (int t = 0; t < S; ++t) acc = fmaf(slog[t], __ldg(xb + (size_t)t * D + d), acc);
+      pooled = acc / sum;
+    }
+    const float tot = block_sum<D>(pooled * __ldg(P.w3 + h * D + d), red);
+    if (d == 0) scores[blockIdx.x * n_heads + h] = tot + __ldg(P.b3 + h);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -584,7 +469,7 @@ lstm_batched_kernel(const float* __restrict__ feats /*[n_seg][20]*/, const ClipD
   }
   // PoolLastStepBi: this direction's final hidden state . w_pool half (lib:1107-1115)
   if (gp == 0) {
-    const float w = __ldg(P.w_pool + dir * 128 + u);
+    const float w = P.w_pool ? __ldg(P.w_pool + dir * 128 + u) : 0.f;      // (other pooling modes read td_out instead)
 #pragma unroll
     for (int b = 0; b < NB; ++b) red[b * 128 + u] = hl[b] * w;
   }
@@ -609,38 +494,10 @@ __global__ void lastbi_final_kernel(const float* __restrict__ partial, const Cli
 }
 
 // ------------------------------------------------------------------ host launchers
-constexpr int kRowSmem64 = (kRows * kXS + 64 * 64) * 4;
 constexpr int kRowSmem20 = (kRows * kXS + 64 * 20) * 4;
-constexpr int kRowSmem128 = (kRows * kXS + 64 * 128) * 4;
 
-void launch_lin_ln(cudaStream_t st, const float* feats, const float* WT, const float* b,
-                   const float* g, const float* be, float* out, int n_rows) {
-  static unsigned long long cfg = 0;
-  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(linear_rows_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); }
-  linear_rows_kernel<64, true><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(feats, 384, WT, b, g, be, out, n_rows);
-}
 void launch_fc20(cudaStream_t st, const float* feats, const float* WT, const float* b, float* out, int n_rows) {
   linear_rows_kernel<20, false><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem20, st>>>(feats, 768, WT, b, nullptr, nullptr, out, n_rows);
-}
-void launch_qkv(cudaStream_t st, const float* x, const float* WT3, const float* b3, float* qkv, int n_rows) {
-  static unsigned long long cfg = 0;
-  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem64); }
-  qkv_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem64, st>>>(x, WT3, b3, qkv, n_rows);
-}
-void launch_sa_layer(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips,
-                     int n_clips, const int* qtile_prefix, int n_qtiles, const SaLayerParams& P,
-                     float* x_out) {
-  static unsigned long long cfg = 0;
-  const int smem = kSaSmemFloats * 4;
-  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
-  sa_layer_kernel<<<n_qtiles, kRows, smem, st>>>(x_in, qkv, clips, n_clips, qtile_prefix, P, x_out);
-}
-void launch_pool_att(cudaStream_t st, const float* x, const ClipDesc* clips, int n_clips, int n_rows,
-                     const PoolHeadParams& P, int n_heads, float* logits, float* scores) {
-  static unsigned long long cfg = 0;
-  if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(pool_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem128); }
-  pool_logits_kernel<<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem128, st>>>(x, P, n_heads, logits, n_rows);
-  pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
 }
 void launch_pool_final(cudaStream_t st, const float* x, const float* logits, const ClipDesc* clips, int n_clips,
                        const PoolHeadParams& P, int n_heads, float* scores) {
@@ -652,7 +509,19 @@ void launch_lstm(cudaStream_t st, const float* feats20, const ClipDesc* clips, i
   const int smem = kLstmSmemFloats * 4;
   if (first_launch_on_device(cfg)) { cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }
   lstm_kernel<<<2 * n_clips, 512, smem, st>>>(feats20, clips, P, td_out, partial);
-  lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
+  if (scores) lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
+}
+
+void launch_pool_simple(cudaStream_t st, const float* x, int D, const ClipDesc* clips, int n_clips, int mode,
+                        const PoolSimpleParams& P, int n_heads, int max_seg, float* scores) {
+  const int smem = (mode == 1 ? max_seg : 0) * 4 + 16;
+  if (D == 64) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pool_simple_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pool_simple_kernel<64><<<n_clips, 64, smem, st>>>(x, clips, mode, P, n_heads, scores);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pool_simple_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pool_simple_kernel<256><<<n_clips, 256, smem, st>>>(x, clips, mode, P, n_heads, scores);
+  }
 }
 
 template <int NB> constexpr int lstm_batched_smem() { return (2 * 64 * 256 + 2 * NB * 128 + 2 * NB * 32 + NB * 128) * 4; }
@@ -674,7 +543,7 @@ void launch_lstm_batched(cudaStream_t st, const float* feats20, const ClipDesc* 
     lstm_batched_kernel<2><<<2 * ((n_clips + 1) / 2), 256, lstm_batched_smem<2>(), st>>>(feats20, clips, order, n_clips, P, td_out, partial);
   else
     lstm_batched_kernel<4><<<2 * ((n_clips + 3) / 4), 256, lstm_batched_smem<4>(), st>>>(feats20, clips, order, n_clips, P, td_out, partial);
-  lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
+  if (scores) lastbi_final_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(partial, clips, pool_bias, scores, n_clips);
 }
 
 }  // namespace nisqa

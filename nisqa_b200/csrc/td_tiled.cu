@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(kNT, 2)
 td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restrict__ WT /*[384][64]*/,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const float* __restrict__ qkvT /*[3][64][64]*/, const float* __restrict__ qkvb /*[192]*/,
+             const float* __restrict__ pe /*[max_len][64] positional encoding or nullptr*/,
+             const int* __restrict__ seg_clip, const ClipDesc* __restrict__ clips,
              float* __restrict__ x0 /*[n][64]*/, float* __restrict__ qkv /*[n][192]*/, int n_rows) {
   extern __shared__ __align__(16) float sm[];
   float* As = sm;                       // [2][64][68]
@@ -213,6 +215,16 @@ td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restri
     __syncthreads();
   }
   layernorm_rows(acc, gamma, beta, tx);
+  if (pe != nullptr) {
+    // PositionalEncoding (lib:1042-1062): x[t] += pe[t], t = position of the segment inside its clip
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long row = row0 + min(4 * ty + i, rows_valid - 1);
+      const int t = (int)(row - clips[__ldg(seg_clip + row)].seg_off);
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(pe + (size_t)t * 64) + tx);
+      acc[i][0] += pv.x; acc[i][1] += pv.y; acc[i][2] += pv.z; acc[i][3] += pv.w;
+    }
+  }
   store_rows_smem(Xs, acc, ty, tx);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -345,7 +357,7 @@ td_sa_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv, cons
   const bool last = next_qkvT == nullptr;
   // first chunk of the fused tail rides behind W2
   if (!last) tile_load_async(Wb + 4096, 64, next_qkvT, 64, 64, tid);
-  else tile_load_async(Wb + 4096, 64, H.W1T, 128, 64, tid);
+  else if (n_heads > 0) tile_load_async(Wb + 4096, 64, H.W1T, 128, 64, tid);      // (n_heads == 0: another pooling module follows)
   cp_commit();
   cp_wait<1>();                                    // W2 landed
   __syncthreads();
@@ -432,11 +444,12 @@ td_sa_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv, cons
 
 // ------------------------------------------------------------------ host launchers
 void launch_td_in(cudaStream_t st, const float* feats, const float* WT, const float* b, const float* g, const float* be,
-                  const float* qkvT, const float* qkvb, float* x0, float* qkv, int n_rows) {
+                  const float* qkvT, const float* qkvb, const float* pe, const int* seg_clip, const ClipDesc* clips,
+                  float* x0, float* qkv, int n_rows) {
   static unsigned long long cfg = 0;
   const int smem = kInSmemFloats * 4;
   if (first_launch_on_device(cfg)) cudaFuncSetAttribute(td_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  td_in_kernel<<<(n_rows + kT - 1) / kT, kNT, smem, st>>>(feats, WT, b, g, be, qkvT, qkvb, x0, qkv, n_rows);
+  td_in_kernel<<<(n_rows + kT - 1) / kT, kNT, smem, st>>>(feats, WT, b, g, be, qkvT, qkvb, pe, seg_clip, clips, x0, qkv, n_rows);
 }
 
 void launch_td_sa(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips, int n_clips,

@@ -13,11 +13,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnisqa_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_IN_FLIGHT = 6          # staging slots of the engine (nisqa_submit_pcm)
 ARCH_ADAPT_SA_ATTFF, ARCH_STD_LSTM_LASTBI = 0, 1
 FMT_S16, FMT_F32 = 0, 1
 CLIP_OK, CLIP_TOO_SHORT, CLIP_TOO_LONG = 0, 1, 2
+POOL_ATT_FF, POOL_ATT, POOL_AVG, POOL_MAX, POOL_LAST_STEP, POOL_LAST_STEP_BI = range(6)
 (STAGE_MEL_DB, STAGE_POOL1, STAGE_POOL2, STAGE_CONV3, STAGE_POOL3, STAGE_CONV5, STAGE_CNN_FEAT,
  STAGE_TD_IN, STAGE_TD_OUT) = range(9)
 
@@ -38,7 +39,7 @@ class NisqaConfig(C.Structure):
                 ("n_fft", C.c_int32), ("n_mels", C.c_int32), ("seg_len", C.c_int32),
                 ("seg_hop", C.c_int32), ("max_segments", C.c_int32), ("hop_s", C.c_double),
                 ("win_s", C.c_double), ("fmax", C.c_double), ("sa_layers", C.c_int32),
-                ("max_chunk_segments", C.c_int32)]
+                ("max_chunk_segments", C.c_int32), ("pool", C.c_int32), ("pos_enc", C.c_int32)]
 
 
 class NisqaTensor(C.Structure):
@@ -135,13 +136,22 @@ def config_from_args(args, max_chunk_segments=0):
     cnn, td, pool = args.get("cnn_model"), args.get("td"), args.get("pool")
     if args.get("model") not in ("NISQA", "NISQA_DIM"):
         raise NotImplementedError("Model not available in the B200 engine: %r" % args.get("model"))
-    if (cnn, td, pool) == ("adapt", "self_att", "att"):
+    pool_mode = {"avg": POOL_AVG, "max": POOL_MAX, "last_step": POOL_LAST_STEP, "last_step_bi": POOL_LAST_STEP_BI}.get(pool)
+    if pool == "att":
+        if args.get("pool_att_h") == 128:
+            pool_mode = POOL_ATT_FF
+        elif args.get("pool_att_h") in (None, 0):
+            pool_mode = POOL_ATT
+        else:
+            raise NotImplementedError("pool_att_h=%r is not implemented by the B200 engine (128 or None)" % args.get("pool_att_h"))
+    if pool_mode is None:
+        raise NotImplementedError("Pool option not available in the B200 engine: %r" % pool)
+    if (cnn, td) == ("adapt", "self_att") and pool_mode != POOL_LAST_STEP_BI:
         arch = ARCH_ADAPT_SA_ATTFF
         ok = (list(args["cnn_pool_1"]) == [24, 7] and list(args["cnn_pool_2"]) == [12, 5]
               and list(args["cnn_pool_3"]) == [6, 3] and args.get("cnn_fc_out_h") in (None, 0)
-              and args["td_sa_d_model"] == 64 and args["td_sa_nhead"] == 1 and args["td_sa_h"] == 64
-              and not args.get("td_sa_pos_enc") and args.get("pool_att_h") == 128)
-    elif (cnn, td, pool) == ("standard", "lstm", "last_step_bi"):
+              and args["td_sa_d_model"] == 64 and args["td_sa_nhead"] == 1 and args["td_sa_h"] == 64)
+    elif (cnn, td) == ("standard", "lstm") and pool_mode in (POOL_LAST_STEP_BI, POOL_AVG, POOL_MAX, POOL_LAST_STEP):
         arch = ARCH_STD_LSTM_LASTBI
         ok = (args.get("cnn_fc_out_h") == 20 and args["td_lstm_h"] == 128
               and args["td_lstm_num_layers"] == 1 and bool(args["td_lstm_bidirectional"])
@@ -168,6 +178,8 @@ def config_from_args(args, max_chunk_segments=0):
     cfg.sa_layers = int(args["td_sa_num_layers"]) if arch == ARCH_ADAPT_SA_ATTFF else 0
     # NISQA_MAX_CHUNK: experiment knob (segments per internal pass) for A/B runs of the pass size
     cfg.max_chunk_segments = int(max_chunk_segments) or int(os.environ.get("NISQA_MAX_CHUNK", "0"))
+    cfg.pool = pool_mode
+    cfg.pos_enc = 1 if (arch == ARCH_ADAPT_SA_ATTFF and args.get("td_sa_pos_enc")) else 0
     return cfg
 
 

@@ -134,7 +134,7 @@ def standard_cnn(sd, x, args, taps=None):
 
 
 # --------------------------------------------------------- time dependency (a11/a12/a16)
-def self_attention(sd, feats, taps=None):
+def self_attention(sd, feats, taps=None, pos_enc=False):
     """lib:988-996 + lib:1025-1040 for ONE clip (so no key-padding mask is needed).
 
     nn.MultiheadAttention with one head: q,k,v = in_proj; q *= 1/sqrt(64); softmax(q k^T) v;
@@ -143,6 +143,9 @@ def self_attention(sd, feats, taps=None):
     x = F.linear(feats, sd[p + "linear.weight"], sd[p + "linear.bias"])
     x = F.layer_norm(x, (x.shape[-1],), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
     if taps is not None: taps["sa_in"] = x
+    if pos_enc:
+        # PositionalEncoding (lib:1042-1062): x + pe[:S] with the registered buffer [max_len, 1, d] (eval: no dropout)
+        x = x + sd[p + "pos_encoder.pe"][:x.shape[0], 0, :]
     n_layers = len({k.split(".")[3] for k in sd if k.startswith(p + "layers.")})
     for l in range(n_layers):
         q = p + "layers.%d." % l
@@ -194,6 +197,28 @@ def pool_attff(sd, prefix, x):
     return F.linear(pooled, sd[prefix + "linear3.weight"], sd[prefix + "linear3.bias"]).reshape(-1)
 
 
+def pool_att(sd, prefix, x):
+    """PoolAtt (lib:1131-1154) for one clip: att = linear1(x); softmax over time; weighted sum; linear2."""
+    a = torch.softmax(F.linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]).t(), dim=1)     # [1,S]
+    return F.linear(a @ x, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"]).reshape(-1)
+
+
+def pool_avg(sd, prefix, x):
+    """PoolAvg (lib:1185-1204): sum over the valid steps / n_wins, Linear."""
+    v = torch.div(x.sum(0, keepdim=True), float(x.shape[0]))
+    return F.linear(v, sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]).reshape(-1)
+
+
+def pool_max(sd, prefix, x):
+    """PoolMax (lib:1206-1225): max over the valid steps, Linear."""
+    return F.linear(x.max(0, keepdim=True)[0], sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]).reshape(-1)
+
+
+def pool_last_step(sd, prefix, x):
+    """PoolLastStep (lib:1117-1129): the last valid step, Linear."""
+    return F.linear(x[-1:, :], sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]).reshape(-1)
+
+
 def pool_last_step_bi(sd, prefix, x):
     """lib:1107-1115: forward hidden at the last valid step || backward hidden at step 0."""
     H = x.shape[1] // 2
@@ -215,7 +240,7 @@ def forward_from_mel(args, sd, spec, taps=None):
             raise NotImplementedError(args["cnn_model"])
         if taps is not None: taps["cnn_feat"] = feats
         if args["td"] == "self_att":
-            td = self_attention(sd, feats, taps)
+            td = self_attention(sd, feats, taps, pos_enc=bool(args.get("td_sa_pos_enc")))
         elif args["td"] == "lstm":
             td = bilstm(sd, feats)
         else:
@@ -228,9 +253,11 @@ def forward_from_mel(args, sd, spec, taps=None):
         outs = []
         for pf in prefixes:
             if args["pool"] == "att":
-                outs.append(pool_attff(sd, pf, td))
+                outs.append(pool_attff(sd, pf, td) if args.get("pool_att_h") else pool_att(sd, pf, td))
             elif args["pool"] == "last_step_bi":
                 outs.append(pool_last_step_bi(sd, pf, td))
+            elif args["pool"] in ("avg", "max", "last_step"):
+                outs.append({"avg": pool_avg, "max": pool_max, "last_step": pool_last_step}[args["pool"]](sd, pf, td))
             else:
                 raise NotImplementedError(args["pool"])
     return torch.cat(outs).numpy()

@@ -66,12 +66,16 @@ def test_segment_counts_bit_exact_vs_oracle(built_lib, ckpt):
 
 def test_config_refuses_unknown_architectures():
     args, _ = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa.tar"))
-    for k, v in (("pool", "avg"), ("td", "lstm"), ("cnn_model", "dff"), ("model", "NISQA_DE")):
+    for k, v in (("pool", "last_step_bi"), ("pool_att_h", 64), ("td", "lstm"), ("cnn_model", "dff"), ("model", "NISQA_DE"),
+                 ("td_sa_nhead", 4)):
         bad = dict(args); bad[k] = v
         with pytest.raises(NotImplementedError):
             E.config_from_args(bad)
     # ms_sr is an ingest parameter (clips are converted to that rate before the engine sees them, 8f.2)
     assert E.config_from_args(dict(args, ms_sr=16000)).n_out == 5
+    # the other pooling modules and the positional encoding are implemented
+    assert E.config_from_args(dict(args, pool="avg")).pool == E.POOL_AVG
+    assert E.config_from_args(dict(args, pool="att", pool_att_h=None, td_sa_pos_enc=True)).pos_enc == 1
 
 
 def test_no_cpu_fallback(built_lib):

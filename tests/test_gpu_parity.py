@@ -303,28 +303,6 @@ def test_conv_paths_agree(engines, ckpt, clips):
         eng.set_option("conv_tc", 1); eng.set_option("conv_split", 1); eng.set_option("conv_pipe", 1); eng.set_option("conv12", 1)
 
 
-def test_td_paths_agree(engines):
-    """The register-tiled time-dependency kernels (td_tiled.cu, default) against the row-thread kernels of td.cu:
-    the same fp32 arithmetic in a different summation order - scores and the block's output within fp32 noise,
-    for short clips (one partial query tile), clips spanning several key blocks and the 1297-segment maximum."""
-    eng, args, sd = engines["nisqa.tar"]
-    clips = [(51, 10.0, 48000), (52, 0.1875, 8000), (53, 2.56, 48000), (54, 2.6, 48000), (55, 52.0, 16000), (56, 5.2, 44100)]
-    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in clips]
-    srs = [c[2] for c in clips]
-    try:
-        eng.set_option("td_tiled", 0)
-        s0, n0, _ = eng.predict_pcm(pcm, srs)
-        t0 = eng.stage_dump(E.STAGE_TD_OUT); i0 = eng.stage_dump(E.STAGE_TD_IN)
-        eng.set_option("td_tiled", 1)
-        s1, n1, _ = eng.predict_pcm(pcm, srs)
-        t1 = eng.stage_dump(E.STAGE_TD_OUT); i1 = eng.stage_dump(E.STAGE_TD_IN)
-    finally:
-        eng.set_option("td_tiled", 1)
-    np.testing.assert_array_equal(n0, n1)
-    assert np.abs(i0 - i1).max() <= 2e-5 and np.abs(t0 - t1).max() <= 1e-4, (float(np.abs(i0 - i1).max()), float(np.abs(t0 - t1).max()))
-    assert np.abs(s0 - s1).max() <= SCORE_TOL / 10, float(np.abs(s0 - s1).max())
-
-
 def test_lstm_paths_agree(engines):
     """Batched BiLSTM (NB clips of one direction per CTA, sorted by length) against the one-sequence kernel: the same
     fp32 dot products in a different summation order -> scores within fp32 noise; ragged lengths inside a group, a
@@ -351,6 +329,30 @@ def test_lstm_paths_agree(engines):
     pcm = base[:5] * 30                              # 150 clips -> 300 sequences: NB = 4
     s, _, _ = eng.predict_pcm(pcm, [c[2] for c in spec][:5] * 30)
     np.testing.assert_array_equal(s[:5], s[145:])
+
+
+def test_architecture_variants(built_lib):
+    """PoolAtt / PoolAvg / PoolMax / PoolLastStep after self-attention and after the BiLSTM, and the
+    positional encoding - against the oracle AND against the scores of the unmodified reference modules
+    (tests/golden/variants.npz), in one batch and alone."""
+    from oracle import variants as V
+    g = np.load(os.path.join(GOLDEN, "variants.npz"))
+    pcm = [synth.synth_speech_pcm16(s, sec, sr) for s, sec, sr in V.CLIPS]
+    srs = [c[2] for c in V.CLIPS]
+    for name, (base, _) in V.VARIANTS.items():
+        bargs, bsd = O.load_checkpoint(os.path.join(WEIGHTS, base))
+        args, sd = V.variant_checkpoint(name, bargs, bsd)
+        eng = E.Engine(E.config_from_args(args), 0)
+        eng.load_state_dict(sd)
+        scores, nseg, status = eng.predict_pcm(pcm, srs)
+        assert np.all(status == E.CLIP_OK), name
+        assert np.abs(scores - g[name]).max() <= SCORE_TOL, (name, float(np.abs(scores - g[name]).max()))
+        for i, (p, sr) in enumerate(zip(pcm, srs)):
+            ref, ns, st = O.predict_pcm(args, sd, _f32(p), sr)
+            assert ns == nseg[i] and np.abs(scores[i] - ref).max() <= SCORE_TOL, (name, i)
+        alone, _, _ = eng.predict_pcm(pcm[1:2], srs[1:2])
+        np.testing.assert_array_equal(alone[0], scores[1])
+        eng.close()
 
 
 def test_device_resident_entry_point_equals_host_entry_point(engines):

@@ -32,6 +32,28 @@ def test_oracle_matches_reference_modules(name, ckpt):
             np.testing.assert_array_equal(taps["mel_db"], g["mel_%d" % i])
 
 
+def _variant(name):
+    from oracle import variants as V
+    args, sd = O.load_checkpoint(os.path.join(WEIGHTS, V.VARIANTS[name][0]))
+    return V.variant_checkpoint(name, args, sd)
+
+
+def test_oracle_matches_reference_modules_on_the_variants():
+    """the other pooling modules and the positional encoding.  tests/golden/variants.npz holds the
+    scores of the UNMODIFIED reference modules built with each variant's options and loaded (strict) with the seeded
+    variant weights of oracle/variants.py (oracle/make_variant_golden.py)."""
+    from oracle import variants as V
+    g = np.load(os.path.join(GOLDEN, "variants.npz"))
+    assert sorted(g.files) == sorted(V.VARIANTS)
+    for name in V.VARIANTS:
+        args, sd = _variant(name)
+        for i, (seed, sec, sr) in enumerate(V.CLIPS):
+            pcm = synth.synth_speech_pcm16(seed, sec, sr)
+            sc, nseg, st = O.predict_pcm(args, sd, pcm.astype(np.float32) / 32768.0, sr)
+            assert st == O.STATUS_OK
+            np.testing.assert_allclose(sc, g[name][i], rtol=0, atol=5e-6, err_msg=name)
+
+
 def test_reference_results_do_not_depend_on_batch_composition():
     """the per-clip (unpadded) oracle is equivalent to the padded batches."""
     g = np.load(os.path.join(GOLDEN, "nisqa_mixed.npz"))
