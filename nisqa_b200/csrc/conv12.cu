@@ -10,7 +10,9 @@
 //
 //   warps 0..7    epilogue: TMEM -> bias / ReLU -> staging -> max-pool -> fp16 hi / lo planes of pool2 (conv3's input)
 //   warps 8..13   producers: one thread per pooled cell (24 x 7 or 24 x 8), all 16 channels (conv1_cell.cuh, FFMA)
-//   warp  14      loads conv2's weights (all nine taps stay resident: 18 KB)
+//   warp  14      loads conv2's weights (all nine taps stay resident: 18 KB) and stages every segment's 15 mel rows
+//                 (2880 contiguous bytes) into a four-slot shared-memory ring with bulk copies, several tiles ahead:
+//                 the producers never wait for global memory
 //   warps 15,16   MMA issuers, one per M-tile (two issuers reach the tensor pipe's rate, one does not)
 //
 // One tile = one segment (its padded 25 x 8 / 25 x 9 map is 200 / 225 of the 256 GEMM rows).  Three A buffers, two
@@ -40,8 +42,12 @@ struct C12Cfg {
   static constexpr int OFF_B = OFF_STG + STG_BYTES;
   static constexpr int B_BYTES = 9 * C::B_STAGE;
   static constexpr int OFF_W1 = OFF_B + B_BYTES;        // conv1: [9][16] weights + 16 biases (fp32)
-  static constexpr int OFF_BAR = OFF_W1 + 1024;
-  static constexpr int N_BAR = 2 * NA + 2 + 2 + 1;
+  static constexpr int NM = 4;                          // mel slots (one segment = kSegLen x kMels fp32 = 2880 bytes)
+  static constexpr int MEL_BYTES = kSegLen * kMels * 4;
+  static constexpr int MEL_SLOT = (MEL_BYTES + 127) & ~127;
+  static constexpr int OFF_MEL = OFF_W1 + 1024;
+  static constexpr int OFF_BAR = OFF_MEL + NM * MEL_SLOT;
+  static constexpr int N_BAR = 2 * NA + 2 + 2 + 1 + 2 * NM;
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * N_BAR + 32 + 1024;
   static constexpr int COLS_TILE = 4 * C::COUT;         // 128
   static constexpr int TMEM_ALLOC = 2 * COLS_TILE;      // 256
@@ -69,6 +75,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
   const uint32_t bar0 = sbase + K::OFF_BAR;
   const uint32_t bar_a_full = bar0, bar_a_free = bar0 + 8 * NA;
   const uint32_t bar_acc_full = bar_a_free + 8 * NA, bar_acc_free = bar_acc_full + 16, bar_w = bar_acc_free + 16;
+  const uint32_t bar_mel_full = bar_w + 8, bar_mel_free = bar_mel_full + 8 * K::NM;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + K::OFF_BAR + 8 * K::N_BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = n_seg;
@@ -84,6 +91,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 2); mbar_init(bar_acc_free + 8 * i, 8); }
     mbar_init(bar_w, 1);
+    for (int i = 0; i < K::NM; ++i) { mbar_init(bar_mel_full + 8 * i, 1); mbar_init(bar_mel_free + 8 * i, K::N_PROD_WARPS); }
     fence_barrier_init();
   }
   fence_proxy_async();                 // the zero fill above is read by the tensor core (async proxy)
@@ -100,9 +108,14 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
     const uint32_t row = (uint32_t)(HALO + (ph + 1) * P + (pw + 1));   // plane row q of the cell sits at tile row HALO + q
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int buf = it % NA, use = it / NA;
+      const int buf = it % NA, use = it / NA, ms = it % K::NM;
+      const float thr = __ldg(seg_thr + tile);
       float res[16];
-      if (has_cell) conv1_cell<MODE>(mel, __ldg(seg_frame0 + tile), __ldg(seg_thr + tile), ws, ph, pw, res);
+      mbar_wait(bar_mel_full + 8 * ms, (it / K::NM) & 1);     // the segment's 15 mel rows are in the ring
+      if (has_cell)
+        conv1_cell<MODE, false>(reinterpret_cast<const float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT), 0, thr, ws, ph, pw, res);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mel_free + 8 * ms);      // (the patch sits in registers: the slot may be refilled)
       mbar_wait(bar_a_free + 8 * buf, (use & 1) ^ 1);         // the MMAs of tile it - NA have read the buffer
       if (has_cell) {
         unsigned char* a_hi = smem + buf * K::BUF_BYTES;
@@ -127,6 +140,14 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       mbar_expect_tx(bar_w, K::B_BYTES);
       for (int t = 0; t < 9; ++t)
         bulk_g2s(b_base + t * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_w);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ms = it % K::NM;
+        const int f0 = __ldg(seg_frame0 + tile);
+        mbar_wait(bar_mel_free + 8 * ms, ((it / K::NM) & 1) ^ 1);
+        mbar_expect_tx(bar_mel_full + 8 * ms, K::MEL_BYTES);
+        bulk_g2s(sbase + K::OFF_MEL + ms * K::MEL_SLOT, mel + (size_t)f0 * kMels, K::MEL_BYTES, bar_mel_full + 8 * ms);
+      }
     }
   } else if (warp >= K::W_MMA0) {
     // ===== MMA issuers =====

@@ -7,8 +7,9 @@
 
 namespace nisqa {
 
-// ws: [9][16] folded conv1 weights followed by the 16 biases (shared memory)
-template <int MODE>
+// ws: [9][16] folded conv1 weights followed by the 16 biases (shared memory).  LDG: `mel` is global memory read through
+// the read-only path; false: a shared-memory copy of the segment's 15 mel rows (f0 = 0).
+template <int MODE, bool LDG = true>
 __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0, float thr, const float* ws,
                                            int ph, int pw, float (&res)[16]) {
   constexpr int NWC = (MODE == 0) ? 3 : 2;       // window columns
@@ -23,7 +24,7 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
       const int r = r0 + i, t = c0 + j;
       float v = 0.f;                             // zero padding of the segment's own border
       if (r >= 0 && r < kMels && t >= 0 && t < kSegLen)
-        v = fmaxf(__ldg(mel + (size_t)(f0 + t) * kMels + r), thr);
+        v = fmaxf(LDG ? __ldg(mel + (size_t)(f0 + t) * kMels + r) : mel[(f0 + t) * kMels + r], thr);
       patch[i][j] = v;
     }
 
