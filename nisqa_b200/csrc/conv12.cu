@@ -26,6 +26,17 @@
 
 namespace nisqa {
 
+#ifdef NISQA_TC_TIMING
+__device__ long long g_c12_timing[256 * 16];        // per CTA: cycles accumulated per role / wait (tools/pipe_timing.py)
+#define C12_NOW() clock64()
+#define C12_ADD(slot, t0) do { if (blockIdx.x < 256) g_c12_timing[blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
+#define C12_COUNT(slot, n) do { if (blockIdx.x < 256) g_c12_timing[blockIdx.x * 16 + (slot)] += (n); } while (0)
+#else
+#define C12_NOW() 0ll
+#define C12_ADD(slot, t0) do { (void)(t0); } while (0)
+#define C12_COUNT(slot, n) do { } while (0)
+#endif
+
 template <int MODE>
 struct C12Cfg {
   using C = typename std::conditional<MODE == 0, SpConv2A, SpConv2S>::type;
@@ -111,12 +122,19 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       const int buf = it % NA, use = it / NA, ms = it % K::NM;
       const float thr = __ldg(seg_thr + tile);
       float res[16];
+      long long tw = C12_NOW();
       mbar_wait(bar_mel_full + 8 * ms, (it / K::NM) & 1);     // the segment's 15 mel rows are in the ring
+      if (cell == 0) C12_ADD(0, tw);
+      tw = C12_NOW();
       if (has_cell)
         conv1_cell<MODE, false>(reinterpret_cast<const float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT), 0, thr, ws, ph, pw, res);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mel_free + 8 * ms);      // (the patch sits in registers: the slot may be refilled)
+      if (cell == 0) C12_ADD(1, tw);
+      tw = C12_NOW();
       mbar_wait(bar_a_free + 8 * buf, (use & 1) ^ 1);         // the MMAs of tile it - NA have read the buffer
+      if (cell == 0) C12_ADD(2, tw);
+      tw = C12_NOW();
       if (has_cell) {
         unsigned char* a_hi = smem + buf * K::BUF_BYTES;
         unsigned char* a_lo = a_hi + C::A_BYTES;
@@ -134,6 +152,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       fence_proxy_async();                                    // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
+      if (cell == 0) { C12_ADD(3, tw); C12_COUNT(15, 1); }
     }
   } else if (warp == K::W_LOAD) {
     if (lane == 0) {
@@ -157,8 +176,13 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it % NA, use = it / NA, ab = it & 1, aph = (it >> 1) & 1;
+        long long tw = C12_NOW();
         mbar_wait(bar_acc_free + 8 * ab, aph ^ 1);            // accumulators of tile it-2 drained
+        if (mt == 0) C12_ADD(4, tw);
+        tw = C12_NOW();
         mbar_wait(bar_a_full + 8 * buf, use & 1);
+        if (mt == 0) C12_ADD(5, tw);
+        tw = C12_NOW();
         tc_fence_after();
         const uint32_t a_hi = sbase + buf * K::BUF_BYTES, a_lo = a_hi + C::A_BYTES;
         const uint32_t d = tmem + ab * K::COLS_TILE + mt * (2 * COUT);
@@ -177,6 +201,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
         }
         umma_commit(bar_a_free + 8 * buf);
         umma_commit(bar_acc_full + 8 * ab);
+        if (mt == 0) C12_ADD(6, tw);
       }
     }
   } else {
@@ -186,7 +211,10 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1, aph = (it >> 1) & 1;
+      long long tw = C12_NOW();
       mbar_wait(bar_acc_full + 8 * ab, aph);
+      if (tid == 0) C12_ADD(7, tw);
+      tw = C12_NOW();
       tc_fence_after();
       {
         const int r = mt * 128 + quarter * 32 + lane;         // tile row == plane row q of the segment
@@ -217,6 +245,8 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_free + 8 * ab);
+      if (tid == 0) C12_ADD(8, tw);
+      tw = C12_NOW();
       named_bar_sync(1, EPI_THREADS);                         // staging tile complete
       constexpr int POW = C::POW, HO = H / 2, C8 = COUT / 8;
       for (int i2 = tid; i2 < HO * POW * C8; i2 += EPI_THREADS) {
@@ -243,6 +273,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
         *reinterpret_cast<uint4*>(out_lo + o) = lo;
       }
       named_bar_sync(2, EPI_THREADS);                         // staging tile consumed: the next tile may overwrite it
+      if (tid == 0) C12_ADD(9, tw);
     }
   }
   tc_fence_before();
@@ -266,6 +297,14 @@ static void launch_c12(cudaStream_t st, const float* mel, const int* seg_frame0,
   const int grid = std::min(n_seg, n_sm > 0 ? n_sm : 148);
   conv12_kernel<MODE><<<grid, K::NT, K::SMEM_BYTES, st>>>(mel, seg_frame0, seg_thr, w1, b1, wtc, bias, scale, out_hi, out_lo, n_seg);
 }
+
+#ifdef NISQA_TC_TIMING
+int c12_timing_read(long long* host, int n, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(host, g_c12_timing, sizeof(long long) * n);
+  if (reset) { static long long zero[256 * 16]; cudaMemcpyToSymbol(g_c12_timing, zero, sizeof zero); }
+  return rc;
+}
+#endif
 
 // conv1 + pool1 + conv2 + pool2: mel segments -> the plane pair feeding conv3
 void launch_conv12(cudaStream_t st, int std_mode, const float* mel, const int* seg_frame0, const float* seg_thr,

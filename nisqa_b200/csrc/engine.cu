@@ -46,6 +46,7 @@ void launch_conv12(cudaStream_t, int, const float*, const int*, const float*, co
 int tc_timing_read(long long*, int);
 int sp_timing_read(long long*, int);
 int pipe_timing_read(long long*, int, int);
+int c12_timing_read(long long*, int, int);
 #endif
 // td.cu
 struct SaLayerParams {
@@ -1411,5 +1412,8 @@ extern "C" __attribute__((visibility("default"))) int nisqa_debug_sp_timing(long
 }
 extern "C" __attribute__((visibility("default"))) int nisqa_debug_pipe_timing(long long* host, int n, int reset) {
   return nisqa::pipe_timing_read(host, n, reset);
+}
+extern "C" __attribute__((visibility("default"))) int nisqa_debug_c12_timing(long long* host, int n, int reset) {
+  return nisqa::c12_timing_read(host, n, reset);
 }
 #endif

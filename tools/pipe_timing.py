@@ -26,4 +26,16 @@ for layer in (2, 3, 4, 5, 6):
     tiles = t[:, 15].mean()
     print("conv%d  tiles/CTA %.1f  per tile (cycles, mean over CTAs): " % (layer, tiles) +
           "  ".join("%s %.0f" % (names[i], t[:, i].mean() / max(tiles, 1)) for i in (0, 1, 2, 4, 5, 6, 7, 9, 11)), flush=True)
+lib.nisqa_debug_c12_timing.argtypes = [C.POINTER(C.c_longlong), C.c_int, C.c_int]
+eng.set_option("conv_pipe", 1)
+buf = (C.c_longlong * (256 * 16))()
+eng.predict_pcm(clips, [48000] * 64)
+lib.nisqa_debug_c12_timing(buf, 256 * 16, 1)
+eng.predict_pcm(clips, [48000] * 64)
+lib.nisqa_debug_c12_timing(buf, 256 * 16, 1)
+t = np.array(buf[:], dtype=np.float64).reshape(256, 16)[:148]
+tiles = t[:, 15].mean()
+n12 = ["prod:wait_mel", "prod:conv1_cell", "prod:wait_a_free", "prod:split+store", "iss:wait_acc_free", "iss:wait_a_full",
+       "iss:issue", "epi:wait_acc_full", "epi:tmem->stage", "epi:pool+store"]
+print("conv12  tiles/CTA %.1f  per tile (cycles): " % tiles + "  ".join("%s %.0f" % (n12[i], t[:, i].mean() / max(tiles, 1)) for i in range(10)), flush=True)
 eng.close()
