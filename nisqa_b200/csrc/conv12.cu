@@ -9,14 +9,17 @@
 // i-1.  Reference: nisqa/NISQA_lib.py:688-695 (AdaptCNN) / 811-818 (StandardCNN).
 //
 //   warps 0..7    epilogue: TMEM -> bias / ReLU -> staging -> max-pool -> fp16 hi / lo planes of pool2 (conv3's input)
-//   warps 8..13   producers: one thread per pooled cell (24 x 7 or 24 x 8), all 16 channels (conv1_cell.cuh, FFMA)
-//   warp  14      loads conv2's weights (all nine taps stay resident: 18 KB) and stages every segment's 15 mel rows
-//                 (2880 contiguous bytes) into a four-slot shared-memory ring with bulk copies, several tiles ahead:
-//                 the producers never wait for global memory
-//   warps 15,16   MMA issuers, one per M-tile (two issuers reach the tensor pipe's rate, one does not)
+//   warps 8..15   producers: one thread per pooled cell (24 x 7 or 24 x 8; a warp owns three pooled rows), all 16 channels
+//                 (conv1_cell.cuh, packed FFMA2).  Lanes run along the pooled columns: consecutive plane rows, so that
+//                 the 16-byte stores into the swizzled A image are bank-conflict free
+//   warp  16      loads conv2's weights (all nine taps stay resident: 18 KB) and stages every segment's 15 mel rows
+//                 (192 bytes each, padded to a pitch of 52 floats: the producers' patch reads spread over the banks)
+//                 into a four-slot shared-memory ring with bulk copies, several tiles ahead: the producers never wait
+//                 for global memory
+//   warps 17,18   MMA issuers, one per M-tile (two issuers reach the tensor pipe's rate, one does not)
 //
 // One tile = one segment (its padded 25 x 8 / 25 x 9 map is 200 / 225 of the 256 GEMM rows).  Three A buffers, two
-// accumulator sets, one staging tile.  Arithmetic identical to conv1_pool1_kernel + conv_split_kernel<Conv2>: the
+// accumulator sets, two staging tiles.  Arithmetic identical to conv1_pool1_kernel + conv_split_kernel<Conv2>: the
 // same fp32 conv1, the same split, the same MMAs in the same order per accumulator - bit-identical results.
 #include <algorithm>
 #include <type_traits>
@@ -42,20 +45,23 @@ struct C12Cfg {
   using C = typename std::conditional<MODE == 0, SpConv2A, SpConv2S>::type;
   static constexpr int PW = C::W;                       // pooled width of conv1's output = conv2's input width
   static constexpr int NCELL = 24 * PW;                 // producer threads with work
-  static constexpr int N_PROD_WARPS = 6;
-  static_assert(NCELL <= N_PROD_WARPS * 32, "one thread per pooled cell");
+  static constexpr int N_PROD_WARPS = 8;
+  static constexpr int CPW = 3 * PW;                    // cells per producer warp: three pooled rows
+  static_assert(CPW <= 32 && N_PROD_WARPS * CPW == NCELL, "a warp owns three pooled rows");
   static constexpr int NT = (8 + N_PROD_WARPS + 1 + 2) * 32;
   static constexpr int W_PROD0 = 8, W_LOAD = 8 + N_PROD_WARPS, W_MMA0 = W_LOAD + 1;
   static constexpr int NA = 3;                          // A buffers (hi + lo tile each)
   static constexpr int BUF_BYTES = 2 * C::A_BYTES;
   static constexpr int STG_BYTES = (C::G * C::H * C::W * C::STG_STRIDE * 4 + 1023) & ~1023;
   static constexpr int OFF_STG = NA * BUF_BYTES;
-  static constexpr int OFF_B = OFF_STG + STG_BYTES;
+  static constexpr int NSTG = 2;                        // staging tiles: a warp starts draining tile i+1 while others still pool tile i
+  static constexpr int OFF_B = OFF_STG + NSTG * STG_BYTES;
   static constexpr int B_BYTES = 9 * C::B_STAGE;
   static constexpr int OFF_W1 = OFF_B + B_BYTES;        // conv1: [9][16] weights + 16 biases (fp32)
   static constexpr int NM = 4;                          // mel slots (one segment = kSegLen x kMels fp32 = 2880 bytes)
   static constexpr int MEL_BYTES = kSegLen * kMels * 4;
-  static constexpr int MEL_SLOT = (MEL_BYTES + 127) & ~127;
+  static constexpr int MEL_PITCH = 52;                  // floats per staged mel row: 16-byte aligned rows, 2 * 52 = 8 banks (mod 32) per pooled column
+  static constexpr int MEL_SLOT = (kSegLen * MEL_PITCH * 4 + 127) & ~127;
   static constexpr int OFF_MEL = OFF_W1 + 1024;
   static constexpr int OFF_BAR = OFF_MEL + NM * MEL_SLOT;
   static constexpr int N_BAR = 2 * NA + 2 + 2 + 1 + 2 * NM;
@@ -113,27 +119,27 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
 
   if (warp >= K::W_PROD0 && warp < K::W_LOAD) {
     // ===== producers: conv1 + pool1 of tile `it` into A buffer it % NA =====
-    const int cell = tid - K::W_PROD0 * 32;
-    const bool has_cell = cell < K::NCELL;
-    const int ph = cell % 24, pw = cell / 24;                 // lanes run along mel rows: coalesced reads
+    const int cell = (warp - K::W_PROD0) * K::CPW + lane;
+    const bool has_cell = lane < K::CPW;
+    const int ph = cell / K::PW, pw = cell - ph * K::PW;      // lanes run along the pooled columns: consecutive plane rows
     const uint32_t row = (uint32_t)(HALO + (ph + 1) * P + (pw + 1));   // plane row q of the cell sits at tile row HALO + q
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it % NA, use = it / NA, ms = it % K::NM;
-      const float thr = __ldg(seg_thr + tile);
       float res[16];
       long long tw = C12_NOW();
       mbar_wait(bar_mel_full + 8 * ms, (it / K::NM) & 1);     // the segment's 15 mel rows are in the ring
-      if (cell == 0) C12_ADD(0, tw);
+      if (tid == K::W_PROD0 * 32) C12_ADD(0, tw);
       tw = C12_NOW();
-      if (has_cell)
-        conv1_cell<MODE, false>(reinterpret_cast<const float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT), 0, thr, ws, ph, pw, res);
+      const float* mslot = reinterpret_cast<const float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT);
+      const float thr = mslot[kMels];                         // the clip's top_db floor, left in row 0's padding by the load warp
+      if (has_cell) conv1_cell<MODE, false, K::MEL_PITCH>(mslot, 0, thr, ws, ph, pw, res);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mel_free + 8 * ms);      // (the patch sits in registers: the slot may be refilled)
-      if (cell == 0) C12_ADD(1, tw);
+      if (tid == K::W_PROD0 * 32) C12_ADD(1, tw);
       tw = C12_NOW();
       mbar_wait(bar_a_free + 8 * buf, (use & 1) ^ 1);         // the MMAs of tile it - NA have read the buffer
-      if (cell == 0) C12_ADD(2, tw);
+      if (tid == K::W_PROD0 * 32) C12_ADD(2, tw);
       tw = C12_NOW();
       if (has_cell) {
         unsigned char* a_hi = smem + buf * K::BUF_BYTES;
@@ -152,21 +158,28 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       fence_proxy_async();                                    // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
-      if (cell == 0) { C12_ADD(3, tw); C12_COUNT(15, 1); }
+      if (tid == K::W_PROD0 * 32) { C12_ADD(3, tw); C12_COUNT(15, 1); }
     }
   } else if (warp == K::W_LOAD) {
     if (lane == 0) {
       mbar_expect_tx(bar_w, K::B_BYTES);
       for (int t = 0; t < 9; ++t)
         bulk_g2s(b_base + t * C::B_STAGE, wtc + (size_t)t * (C::B_STAGE / 2), C::B_STAGE, bar_w);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int ms = it % K::NM;
-        const int f0 = __ldg(seg_frame0 + tile);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int ms = it % K::NM;
+      const int f0 = __ldg(seg_frame0 + tile);
+      if (lane == 0) {
+        const float thr = __ldg(seg_thr + tile);               // (a global-load latency the producers must not see)
         mbar_wait(bar_mel_free + 8 * ms, ((it / K::NM) & 1) ^ 1);
+        *reinterpret_cast<float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT + kMels * 4) = thr;   // released by the arrive below
         mbar_expect_tx(bar_mel_full + 8 * ms, K::MEL_BYTES);
-        bulk_g2s(sbase + K::OFF_MEL + ms * K::MEL_SLOT, mel + (size_t)f0 * kMels, K::MEL_BYTES, bar_mel_full + 8 * ms);
       }
+      __syncwarp();                                            // slot free and the transaction count armed
+      if (lane < kSegLen)                                      // lane t: mel row t of the segment (192 contiguous bytes)
+        bulk_g2s(sbase + K::OFF_MEL + ms * K::MEL_SLOT + lane * (K::MEL_PITCH * 4), mel + (size_t)(f0 + lane) * kMels,
+                 kMels * 4, bar_mel_full + 8 * ms);
     }
   } else if (warp >= K::W_MMA0) {
     // ===== MMA issuers =====
@@ -207,10 +220,10 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
   } else {
     // ===== epilogue (conv2: bias, ReLU, max-pool, split, store) =====
     const int quarter = warp & 3, mt = warp >> 2;
-    float* stg = reinterpret_cast<float*>(smem + K::OFF_STG);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1, aph = (it >> 1) & 1;
+      float* stg = reinterpret_cast<float*>(smem + K::OFF_STG + (it & 1) * K::STG_BYTES);
       long long tw = C12_NOW();
       mbar_wait(bar_acc_full + 8 * ab, aph);
       if (tid == 0) C12_ADD(7, tw);
@@ -272,7 +285,8 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
         *reinterpret_cast<uint4*>(out_hi + o) = hi;
         *reinterpret_cast<uint4*>(out_lo + o) = lo;
       }
-      named_bar_sync(2, EPI_THREADS);                         // staging tile consumed: the next tile may overwrite it
+      // (no second barrier: tile it+1 is staged in the other tile, and the barrier of tile it+1 - passed by every
+      // warp only after it finished pooling tile it - orders the reuse of this one for tile it+2)
       if (tid == 0) C12_ADD(9, tw);
     }
   }

@@ -4,12 +4,17 @@
 //   MODE 1 (standard, lib:813-814): MaxPool2d(2, stride 2, padding (0,1)) -> 24x8 : cols {2j-1,2j}
 #pragma once
 #include "common.cuh"
+#include "f32x2.cuh"
+
+#ifndef NISQA_C1_PK
+#define NISQA_C1_PK 1        // conv1 FMAs as packed FFMA2 (bit-identical to the scalar form)
+#endif
 
 namespace nisqa {
 
 // ws: [9][16] folded conv1 weights followed by the 16 biases (shared memory).  LDG: `mel` is global memory read through
-// the read-only path; false: a shared-memory copy of the segment's 15 mel rows (f0 = 0).
-template <int MODE, bool LDG = true>
+// the read-only path; false: a shared-memory copy of the segment's 15 mel rows (f0 = 0), rows PITCH floats apart.
+template <int MODE, bool LDG = true, int PITCH = kMels>
 __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0, float thr, const float* ws,
                                            int ph, int pw, float (&res)[16]) {
   constexpr int NWC = (MODE == 0) ? 3 : 2;       // window columns
@@ -24,10 +29,53 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
       const int r = r0 + i, t = c0 + j;
       float v = 0.f;                             // zero padding of the segment's own border
       if (r >= 0 && r < kMels && t >= 0 && t < kSegLen)
-        v = fmaxf(LDG ? __ldg(mel + (size_t)(f0 + t) * kMels + r) : mel[(f0 + t) * kMels + r], thr);
+        v = fmaxf(LDG ? __ldg(mel + (size_t)(f0 + t) * PITCH + r) : mel[(f0 + t) * PITCH + r], thr);
       patch[i][j] = v;
     }
 
+#if NISQA_C1_PK
+  // 16 channels as 8 packed pairs (FFMA2: the same fp32 FMA per element and tap order as the scalar form, half the
+  // instructions - the producer warps of conv12 are issue bound)
+#pragma unroll
+  for (int cq = 0; cq < 4; ++cq) {
+    f2 acc[2][NWC][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NWC; ++j) { acc[i][j][0] = 0ull; acc[i][j][1] = 0ull; }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4 w = *reinterpret_cast<const float4*>(ws + tap * 16 + cq * 4);
+      const f2 w01 = pk(w.x, w.y), w23 = pk(w.z, w.w);
+      const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NWC; ++j) {
+          const f2 a = bc(patch[i + ky][j + kx]);
+          acc[i][j][0] = fma2(a, w01, acc[i][j][0]);
+          acc[i][j][1] = fma2(a, w23, acc[i][j][1]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NWC; ++j) {
+          const int col = c0 + 1 + j;            // conv output column of this window slot
+          if (MODE == 0 || (col >= 0 && col < kSegLen)) {
+            const float2 v = upk(acc[i][j][h]);
+            m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
+          }
+        }
+      res[cq * 4 + 2 * h] = fmaxf(m0 + ws[144 + cq * 4 + 2 * h], 0.f);           // bias + ReLU commute with max
+      res[cq * 4 + 2 * h + 1] = fmaxf(m1 + ws[144 + cq * 4 + 2 * h + 1], 0.f);
+    }
+  }
+}
+#else
 #pragma unroll
   for (int cq = 0; cq < 4; ++cq) {
     float acc[2][NWC][4];
@@ -66,5 +114,6 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
     }
   }
 }
+#endif
 
 }  // namespace nisqa

@@ -12,6 +12,19 @@
 // clamp, which is applied by the consumers (conv1 / stage dump) as max(dB, clipmax - 80).
 // Grid: x = frame pair, y = clip.
 #include "common.cuh"
+#include "f32x2.cuh"
+
+// experiment switches (tools/tc_ab_build.sh builds variant libraries); defaults = the measured winners, profiles/r02q_ab_kernels.txt:
+// packing the FFT butterflies made the kernel 5 % slower (it is latency bound at five warps per scheduler, not issue bound)
+#ifndef NISQA_FE_PK_FFT
+#define NISQA_FE_PK_FFT 0      // butterflies / twiddle products as packed FADD2 / FMUL2 / FFMA2
+#endif
+#ifndef NISQA_FE_PK_MAG
+#define NISQA_FE_PK_MAG 0      // magnitude stage with packed adds
+#endif
+#ifndef NISQA_FE_MEL
+#define NISQA_FE_MEL 2         // 0: scalar band loop unrolled by 4, 1: rolled packed loop, 2: packed loop unrolled by 4
+#endif
 
 namespace nisqa {
 
@@ -45,8 +58,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// In-register 32-point forward DFT, decimation in frequency: X[rev5(i)] ends up in x[i].
-__device__ __forceinline__ void fft32(float2 (&x)[32]) {
+// In-register 32-point forward DFT, decimation in frequency: X[rev5(i)] ends up in x[i].  Complex values are packed
+// (re, im) register pairs (f32x2.cuh): a butterfly's sum / difference is one FADD2 each, a twiddle product FMUL2 + FFMA2;
+// the -i products are formed from the scalar halves (two FADDs, no multiply).
+__device__ __forceinline__ void fft32(f2 (&x)[32]) {
 #pragma unroll
   for (int half = 16; half >= 1; half >>= 1) {
 #pragma unroll
@@ -54,12 +69,26 @@ __device__ __forceinline__ void fft32(float2 (&x)[32]) {
 #pragma unroll
       for (int j = 0; j < half; ++j) {
         const int k = j * (16 / half);
-        const float2 a = x[base + j], b = x[base + j + half];
-        x[base + j] = make_float2(a.x + b.x, a.y + b.y);
+#if NISQA_FE_PK_FFT
+        const f2 a = x[base + j], b = x[base + j + half];
+        x[base + j] = add2(a, b);
+        if (k == 0) {
+          x[base + j + half] = sub2(a, b);
+        } else if (k == 8) {                       // (a - b) * (-i) = (d.y, -d.x)
+          const float2 af = upk(a), bf = upk(b);
+          x[base + j + half] = pk(af.y - bf.y, bf.x - af.x);
+        } else {
+          const float2 w = w32(k);
+          x[base + j + half] = cmul2(sub2(a, b), pk(w.x, w.y), pk(-w.y, w.x));
+        }
+#else
+        const float2 a = upk(x[base + j]), b = upk(x[base + j + half]);
+        x[base + j] = pk(a.x + b.x, a.y + b.y);
         const float2 d = make_float2(a.x - b.x, a.y - b.y);
-        if (k == 0) x[base + j + half] = d;
-        else if (k == 8) x[base + j + half] = make_float2(d.y, -d.x);
-        else x[base + j + half] = cmul(d, w32(k));
+        if (k == 0) x[base + j + half] = pk(d);
+        else if (k == 8) x[base + j + half] = pk(d.y, -d.x);
+        else x[base + j + half] = pk(cmul(d, w32(k)));
+#endif
       }
     }
   }
@@ -91,14 +120,24 @@ int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWar
 
 // ---- shared pieces of the two front-end kernels ---------------------------------------------
 // 1024-point FFT of one residue plane: x[j] = input n = lane + 32 j (already twiddled by
-// W_4096^(r n)); result Z_r[m] is left in tile[m] (m = 0..1023).
-__device__ __forceinline__ void fft1024_plane(float2 (&x)[32], float2* tile, int lane,
-                                              const float2* __restrict__ tw2) {
+// W_4096^(r n)); result Z_r[m] is left in tile[m] (m = 0..1023).  tw2x[q][lane] = (t.x, t.y, -t.y, t.x), t = W_1024^(lane q):
+// both operand forms of the packed complex product in one 16-byte load.
+__device__ __forceinline__ void fft1024_plane(f2 (&x)[32], float2* tile_, int lane,
+                                              const float4* __restrict__ tw2x) {
+  f2* tile = reinterpret_cast<f2*>(tile_);
   fft32(x);                                      // A_l[q] at x[rev5(q)]
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    float2 v = x[rev5(q)];
-    if (q != 0) v = cmul(v, __ldg(tw2 + q * 32 + lane));                   // W_1024^(l q), coalesced
+    f2 v = x[rev5(q)];
+    if (q != 0) {
+#if NISQA_FE_PK_FFT
+      const float4 t = __ldg(tw2x + q * 32 + lane);                        // W_1024^(l q), coalesced
+      v = cmul2(v, pk(t.x, t.y), pk(t.z, t.w));
+#else
+      const float2 t = __ldg(reinterpret_cast<const float2*>(tw2x) - 1024 + q * 32 + lane);   // the float2 table sits in front
+      v = pk(cmul(upk(v), t));
+#endif
+    }
     tile[lane * 33 + q] = v;
   }
   __syncwarp();
@@ -181,18 +220,29 @@ __device__ __forceinline__ float mel_bands(const float2* scratch, const int* ban
 // by the owner of bin 4096 - k >= 2048 > n_mag - 1 only: in place is race free; k = 2048 mirrors itself).
 __device__ __forceinline__ void mag_stage(float2* scratch, int n_mag, int tid) {
   // k = tid + 128 it: plane (k & 3) = tid & 3 and slot (k >> 2) = (tid >> 2) + 32 it
-  float2* pk = scratch + (tid & 3) * kScratchPerWarp + (tid >> 2);
+  f2* pk_ = reinterpret_cast<f2*>(scratch + (tid & 3) * kScratchPerWarp + (tid >> 2));
   const int kk0 = (kNfft - tid) & (kNfft - 1);
-  const float2* pn = scratch + (kk0 & 3) * kScratchPerWarp + (kk0 >> 2);
+  const f2* pn = reinterpret_cast<const f2*>(scratch + (kk0 & 3) * kScratchPerWarp + (kk0 >> 2));
   for (int k = tid; k < n_mag; k += kFeThreads) {
-    const float2 zk = *pk, zn = *pn;
-    const float ar = zk.x + zn.x, ai = zk.y - zn.y;        // 2 * X_a[k]
-    const float br = zk.y + zn.y, bi = zk.x - zn.x;        // 2 * X_b[k] (up to a unit factor)
+    const f2 zk = *pk_, zn = *pn;
     float ma, mb;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
-    *pk = make_float2(ma, mb);
-    pk += 32; pn -= 32;                                     // (tid = 0, it = 0: k = kk = 0 reads the same slot twice)
+#if NISQA_FE_PK_MAG
+    const f2 sm = add2(zk, zn);                            // (2 Re X_a[k], 2 Re X_b[k])
+    const float2 df = upk(sub2(zk, zn));                   // (-+2 Im X_b[k], 2 Im X_a[k])
+    const float2 pw = upk(mul2(sm, sm));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(df.y, df.y, pw.x)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(df.x, df.x, pw.y)));
+#else
+    {
+      const float2 k_ = upk(zk), n_ = upk(zn);
+      const float ar = k_.x + n_.x, ai = k_.y - n_.y;      // 2 * X_a[k]
+      const float br = k_.y + n_.y, bi = k_.x - n_.x;      // 2 * X_b[k] (up to a unit factor)
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ma) : "f"(fmaf(ar, ar, ai * ai)));
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mb) : "f"(fmaf(br, br, bi * bi)));
+    }
+#endif
+    *pk_ = pk(ma, mb);
+    pk_ += 32; pn -= 32;                                    // (tid = 0, it = 0: k = kk = 0 reads the same slot twice)
     if (k == 0) pn += 1024;                                 // 4096 - 0 wraps to bin 0; from k = 128 on the mirror is 3968 - ...
   }
 }
@@ -202,42 +252,59 @@ __device__ __forceinline__ void mag_stage(float2* scratch, int n_mag, int tid) {
 __device__ __forceinline__ float mel_bands_staged(const float2* scratch, const int* band_meta,
                                                   const float* __restrict__ weights, int warp, int lane,
                                                   bool validB, float pscale, float* __restrict__ mel_row0) {
-  float v[32];
+  // v[i]: packed (frame A, frame B) partial sums of slot i in this lane.  The band loop is kept rolled: one weight load,
+  // one magnitude pair, one FFMA2 per 32 bins and lane; trip counts (1 .. ~10 rows per band) are warp uniform.
+  f2 v[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  for (int i = 0; i < 16; ++i) v[i] = 0ull;
 #pragma unroll
   for (int slot = 0; slot < kMels / 4; ++slot) {
     const int b = warp + slot * 4;
-    const int beg = band_meta[b], iters = (band_meta[b + 1] - beg) >> 5;
+    const int beg = band_meta[b], end = band_meta[b + 1];
     const int k = band_meta[kMels + 1 + b] + lane;
-    const float2* pk = scratch + (k & 3) * kScratchPerWarp + (k >> 2);
+    const f2* pm = reinterpret_cast<const f2*>(scratch + (k & 3) * kScratchPerWarp + (k >> 2));
     const float* wt = weights + beg + lane;
+    // padded bins (weight 0) may hold raw spectrum values: finite, times 0
+#if NISQA_FE_MEL == 0
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
-    for (int it = 0; it < iters; ++it) {
+    for (int it = (end - beg) >> 5; it > 0; --it, wt += 32, pm += 8) {
       const float w = __ldg(wt);
-      const float2 m = *pk;                    // padded bins (weight 0) may hold raw spectrum values: finite, times 0
-      wt += 32; pk += 8;
+      const float2 m = upk(*pm);
       s0 = fmaf(w, m.x, s0);
       s1 = fmaf(w, m.y, s1);
     }
-    v[2 * slot] = s0;
-    v[2 * slot + 1] = s1;
+    v[slot] = pk(s0, s1);
+#elif NISQA_FE_MEL == 1
+    f2 acc = 0ull;
+#pragma unroll 1
+    for (int it = (end - beg) >> 5; it > 0; --it, wt += 32, pm += 8) acc = fma2(bc(__ldg(wt)), *pm, acc);
+    v[slot] = acc;
+#else
+    f2 acc = 0ull;
+#pragma unroll 4
+    for (int it = (end - beg) >> 5; it > 0; --it, wt += 32, pm += 8) acc = fma2(bc(__ldg(wt)), *pm, acc);
+    v[slot] = acc;
+#endif
   }
+  // multi-value butterfly over the 12 (padded to 16) packed values: after the steps with lane offsets 16, 8, 4, 2 lane L
+  // holds the value of slot (L >> 1) & ... summed over 16 lanes; the last step adds the partner lane (L ^ 1)
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & (2 * o)) != 0;
 #pragma unroll
     for (int i = 0; i < o; ++i) {
-      const float keep = up ? v[i + o] : v[i];
-      const float send = up ? v[i] : v[i + o];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      const f2 keep = up ? v[i + o] : v[i];
+      const f2 send = up ? v[i] : v[i + o];
+      v[i] = add2(keep, __shfl_xor_sync(0xffffffffu, send, 2 * o));
     }
   }
+  const float2 tot = upk(add2(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1)));
+  // lane L now holds slot s(L) = bit-reversal free index: bits 4..1 of L select the slot (offset 16 -> +8, 8 -> +4, ...)
   float out = -INFINITY;
   const int my_slot = lane >> 1, f = lane & 1;
-  if (lane < 2 * (kMels / 4) && (f == 0 || validB)) {
-    const float sv = 0.5f * v[0];
+  if (my_slot < kMels / 4 && (f == 0 || validB)) {
+    const float sv = 0.5f * (f == 0 ? tot.x : tot.y);
     const float p = (sv * sv) * pscale;
     out = 10.0f * log10f(fmaxf(p, 1e-8f));
     mel_row0[(size_t)f * kMels + warp + my_slot * 4] = out;
@@ -251,7 +318,7 @@ __global__ void __launch_bounds__(kFeThreads, 5)
 frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, int n_clips,
                 const FbTables* __restrict__ fbs,
                 const float2* __restrict__ tw1 /*[3][32][32]: W4096^(r*(lane+32j))*/,
-                const float2* __restrict__ tw2 /*[32][32]: W1024^(lane*q)*/, float* __restrict__ mel,
+                const float4* __restrict__ tw2 /*[32][32]: W1024^(lane*q) as (x, y, -y, x)*/, float* __restrict__ mel,
                 unsigned* __restrict__ clipmax, int Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* zin = reinterpret_cast<float2*>(smem_raw);                     // [1024*Q] packed input
@@ -296,7 +363,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
   // ---- b. warp r: 1024-point FFT of the residue-r subsequence
   {
     const int r = warp;
-    float2 x[32];
+    f2 x[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = lane + 32 * j;
@@ -311,7 +378,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
         }
       }
       if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));   // coalesced per-lane table
-      x[j] = v;
+      x[j] = pk(v);
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
   }
@@ -360,7 +427,7 @@ template <typename T>
 __global__ void __launch_bounds__(kFeThreads, 5)
 frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips,
                    const FbTables* __restrict__ fbs, const float2* __restrict__ tw1,
-                   const float2* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax,
+                   const float4* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax,
                    int ppc /*frame pairs per CTA*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* scratch = reinterpret_cast<float2*>(smem_raw + 2 * pp_slot_bytes<T>());
@@ -397,9 +464,13 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
     // input stage: ONE table load per element (window x residue twiddle, zero beyond the window), samples as raw
     // integers (PCM16: the 2^-15 of libsndfile's conversion is exact and is applied to the band power at the end),
     // loads of 4 elements in flight together; the sample index is clamped into the slot for n >= win
-    float2 x[32];
+    // (an odd clip's last pair has no frame B: hopB = 0 transforms frame A twice, the copy is neither stored nor counted)
+    f2 x[32];
     const int hopB = validB ? cd.hop : 0;
     const float2* wtab = fb.wtab + r * 1024 + lane;
+    // PCM16: 1023 + hop + shift < the slot's 1544 elements (hop <= 512 whenever win <= 1024), unfilled elements are
+    // finite integers under a zero window weight; float input could hold non-finite garbage there: clamped
+    const int nmax = sizeof(T) == 2 ? 4096 : cd.win - 1;
     constexpr int CH = 4;
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += CH) {
@@ -408,16 +479,14 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
 #pragma unroll
       for (int u = 0; u < CH; ++u) {
         const int n = lane + 32 * (j0 + u);
-        const int ni = min(n, cd.win - 1);
+        const int ni = sizeof(T) == 2 ? n : min(n, nmax);
         wt[u] = __ldg(wtab + 32 * (j0 + u));
         sa[u] = (float)src[ni];
         sb[u] = (float)src[ni + hopB];
       }
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const float sbv = validB ? sb[u] : 0.f;
-        x[j0 + u] = make_float2(fmaf(sa[u], wt[u].x, -(sbv * wt[u].y)), fmaf(sa[u], wt[u].y, sbv * wt[u].x));
-      }
+      for (int u = 0; u < CH; ++u)
+        x[j0 + u] = pk(fmaf(sa[u], wt[u].x, -(sb[u] * wt[u].y)), fmaf(sa[u], wt[u].y, sb[u] * wt[u].x));
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
     __syncthreads();                    // all four planes written
@@ -467,7 +536,7 @@ void launch_frontend(cudaStream_t st, const void* pcm, int fmt_f32, const ClipDe
                      int n_clips, int max_pairs, const FbTables* fbs,
                      const float2* tw, float* mel, unsigned* clipmax, int Q, int max_span, int ppc) {
   const float2* tw1 = tw;               // [3][32][32]
-  const float2* tw2 = tw + 3 * 1024;    // [32][32]
+  const float4* tw2 = reinterpret_cast<const float4*>(tw + 4 * 1024);    // [32][32] (x, y, -y, x)
   if (Q == 1 && max_span <= kSpanMax) { // the pipelined multi-pair kernel
     static unsigned long long configured = 0;
     if (first_launch_on_device(configured)) {
