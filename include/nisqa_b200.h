@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NISQA_B200_ABI_VERSION 2
+#define NISQA_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NISQA_API __attribute__((visibility("default")))
@@ -50,6 +50,14 @@ enum nisqa_pool {
   NISQA_POOL_LAST_STEP    = 4, /* PoolLastStep (lib:1117-1129)                        */
   NISQA_POOL_LAST_STEP_BI = 5  /* PoolLastStepBi (lib:1099-1115), BiLSTM only         */
 };
+
+/* double-ended model NISQA_DE (reference lib:272-424; train_nisqa_double_ended.yaml): time alignment of the reference
+ * clip's features to the degraded clip's (Alignment, lib:1228-1285), how the alignment is applied, and the fusion of the
+ * two feature streams (Fusion, lib:1380-1417).  The attention modules with learned weights (AttBahdanau, AttLuong) and
+ * de_align 'none' are refused. */
+enum nisqa_de_align { NISQA_DE_ALIGN_DOT = 1, NISQA_DE_ALIGN_COSINE = 2, NISQA_DE_ALIGN_DISTANCE = 3 };
+enum nisqa_de_apply { NISQA_DE_APPLY_HARD = 0, NISQA_DE_APPLY_SOFT = 1 };
+enum nisqa_de_fuse  { NISQA_DE_FUSE_XY_MINUS = 0 /* 'x/y/-' */, NISQA_DE_FUSE_PLUS_MINUS = 1 /* '+/-' */, NISQA_DE_FUSE_XY = 2 /* 'x/y' */ };
 
 enum nisqa_sample_fmt { NISQA_FMT_S16 = 0, NISQA_FMT_F32 = 1 };
 
@@ -96,6 +104,15 @@ typedef struct nisqa_config {
   int32_t max_chunk_segments; /* 0 = default; upper bound on segments processed per internal pass */
   int32_t pool;          /* enum nisqa_pool */
   int32_t pos_enc;       /* td_sa_pos_enc: add the checkpoint's positional-encoding buffer after the input LayerNorm (lib:1042-1062) */
+  /* NISQA_DE (arch NISQA_ARCH_ADAPT_SA_ATTFF, n_out 1).  A double-ended engine takes its clips in PAIRS: clip 2p is the
+   * degraded signal, clip 2p + 1 its reference (csv_deg / csv_ref of one dataset row, lib:2132-2156); n_clips must be
+   * even; scores_out row 2p holds the pair's score, row 2p + 1 is NaN; a pair with a skipped clip scores NaN. */
+  int32_t double_ended;  /* 1: NISQA_DE */
+  int32_t de_align;      /* enum nisqa_de_align */
+  int32_t de_align_apply;/* enum nisqa_de_apply */
+  int32_t de_fuse;       /* enum nisqa_de_fuse (de_fuse_dim must be None) */
+  int32_t td2_layers;    /* td_2 = 'self_att' (d_model 64, one head, h 64): number of layers, >= 1 */
+  int32_t td2_pos_enc;   /* td_2_sa_pos_enc */
 } nisqa_config;
 
 /* One state_dict entry, passed straight through: name as in the checkpoint

@@ -39,8 +39,9 @@ class SpeechQualityDataset(object):
                  to_memory_workers=0, transform=None, seg_hop_length=1, ms_n_fft=1024,
                  ms_hop_length=80, ms_win_length=170, ms_n_mels=32, ms_sr=48e3, ms_fmax=16e3,
                  ms_channel=None, double_ended=False, filename_column_ref=None, dim=False):
-        if double_ended:
-            raise NotImplementedError("double-ended models are outside the B200 predict path")
+        if double_ended and filename_column_ref is None:
+            # the reference indexes df[None] here (lib:2133) - predict_file / predict_dir have no reference column
+            raise KeyError(filename_column_ref)
         if mos_column != "predict_only":
             raise NotImplementedError("only predict_only datasets are on the B200 path")
         if transform is not None or to_memory:
@@ -56,6 +57,8 @@ class SpeechQualityDataset(object):
         self.ms_n_fft, self.ms_hop_length, self.ms_win_length = ms_n_fft, ms_hop_length, ms_win_length
         self.ms_n_mels, self.ms_sr, self.ms_fmax = ms_n_mels, ms_sr, ms_fmax
         self.ms_channel = ms_channel
+        self.double_ended = bool(double_ended)
+        self.filename_column_ref = filename_column_ref
         self.dim = dim
 
     def __len__(self):
@@ -63,6 +66,10 @@ class SpeechQualityDataset(object):
 
     def file_path(self, index):
         return os.path.join(self.data_dir, self.df[self.filename_column].iloc[index])
+
+    def file_path_ref(self, index):
+        """Reference signal of a double-ended row (lib:2132-2134)."""
+        return os.path.join(self.data_dir, self.df[self.filename_column_ref].iloc[index])
 
     def target_sr(self):
         """``ms_sr`` of the checkpoint as an int, or None (= every file at its native rate, lib:2300)."""
@@ -165,6 +172,27 @@ def _load_batch_resampled(ds, paths, sr, nf, target, pool, slot, n_threads):
     return clips, [target] * len(paths)
 
 
+def _load_batch_de(ds, batch):
+    """Double-ended rows (lib:2132-2156): clip 2j = degraded file (``ms_channel`` applies), clip 2j + 1 = its reference
+    (always the mono mix: the reference call passes no ``ms_channel``, lib:2146-2154); the engine takes the pairs in
+    this order.  Mixed sample formats / ``ms_sr`` go through float32."""
+    clips, srs = [], []
+    target = ds.target_sr()
+    for i in batch:
+        for path, ch in ((ds.file_path(int(i)), ds.ms_channel), (ds.file_path_ref(int(i)), None)):
+            y, sr = read_wav(path, ch)
+            if target is not None and sr != target:
+                try:
+                    y, sr = nb_resample.resample(y, sr, target), target
+                except Exception:
+                    raise ValueError("Could not load file {}".format(path))
+            clips.append(np.ascontiguousarray(y))
+            srs.append(int(sr))
+    if any(c.dtype != clips[0].dtype for c in clips):
+        clips = [c if c.dtype == np.float32 else c.astype(np.float32) / np.float32(32768.0) for c in clips]
+    return clips, srs
+
+
 def _predict_rows(engine, ds, rows, bs, num_workers):
     """Scores for the given dataset rows (in that order) through the C-ABI, bs clips per call.
     Pipeline: decode batch b+1 (thread pool, native reader -> pinned memory) while the engine has up
@@ -175,13 +203,16 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
     batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
     n_threads = max(1, int(num_workers) if num_workers else 1)     # native decode threads per batch
 
+    de = getattr(ds, "double_ended", False)
+    per_row = 2 if de else 1          # a double-ended row is a (degraded, reference) pair of clips
+
     def finish(job):
         handle, batch, clips, srs, pos = job
         scores, nseg, status = engine.wait(handle)
         for j, st in enumerate(status):
-            if st != nb_engine.CLIP_OK:
-                _raise_for_status(ds, engine, int(batch[j]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
-        out[pos:pos + len(batch)] = scores
+            if st != nb_engine.CLIP_OK:      # (the reference names the degraded file for either signal, lib:2187-2192)
+                _raise_for_status(ds, engine, int(batch[j // per_row]), clips[j].shape[0], srs[j], int(nseg[j]), int(st))
+        out[pos:pos + len(batch)] = scores[::per_row]
 
     DEPTH = 3                         # batches being decoded ahead of the GPU
     FLIGHT = 5                        # submissions kept in flight on the engine (it has 6 staging slots)
@@ -195,7 +226,10 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
             def top_up():
                 nonlocal nxt
                 while nxt < len(batches) and len(pending) < DEPTH:
-                    pending.append(feeder.submit(_load_batch, ds, batches[nxt], pool, nxt % len(pool.bufs), n_threads))
+                    if de:
+                        pending.append(feeder.submit(_load_batch_de, ds, batches[nxt]))
+                    else:
+                        pending.append(feeder.submit(_load_batch, ds, batches[nxt], pool, nxt % len(pool.bufs), n_threads))
                     nxt += 1
 
             top_up()

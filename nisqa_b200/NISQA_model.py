@@ -6,7 +6,8 @@ same precedence of checkpoint args vs. CLI args, but with the torch modules repl
 
 ``evaluate()`` (reference model:48-52, 572-715) prints the reference's per-database statistics of the last
 ``predict()`` from :mod:`nisqa_b200.evaluate`.  Out of scope here:
-``train()``, ``mode == 'main'`` and double-ended models raise ``NotImplementedError``.  There is no CPU device: ``tr_device='cpu'``
+``train()`` and ``mode == 'main'`` raise ``NotImplementedError``.  Double-ended checkpoints (NISQA_DE) run in
+``predict_csv`` mode with ``args['csv_ref']`` naming the reference column, as in the reference (model:846, 951-955).  There is no CPU device: ``tr_device='cpu'``
 or a machine without CUDA raises.
 """
 import datetime
@@ -114,7 +115,7 @@ class nisqaModel(object):
         else:
             raise NotImplementedError("mode not available")
 
-    def _dataset(self, df, data_dir, filename_column, df_con=None):
+    def _dataset(self, df, data_dir, filename_column, df_con=None, filename_column_ref=None):
         a = self.args
         return NL.SpeechQualityDataset(
             df, df_con=df_con, data_dir=data_dir, filename_column=filename_column,
@@ -123,7 +124,7 @@ class nisqaModel(object):
             transform=None, ms_n_fft=a["ms_n_fft"], ms_hop_length=a["ms_hop_length"],
             ms_win_length=a["ms_win_length"], ms_n_mels=a["ms_n_mels"], ms_sr=a["ms_sr"],
             ms_fmax=a["ms_fmax"], ms_channel=a["ms_channel"], double_ended=a["double_ended"],
-            dim=a["dim"], filename_column_ref=None)
+            dim=a["dim"], filename_column_ref=filename_column_ref)
 
     def _loadDatasetsFolder(self):
         # unsorted glob of lower-case *.wav, basenames in column 'deg' (model:746-748)
@@ -151,7 +152,9 @@ class nisqaModel(object):
             dcon = pd.read_csv(os.path.join(self.args["data_dir"], self.args["csv_con"]))
         else:
             dcon = None
-        self.ds_val = self._dataset(dfile, self.args["data_dir"], self.args["csv_deg"], df_con=dcon)
+        # double-ended checkpoints read the reference signal's column from args['csv_ref'] (model:846)
+        self.ds_val = self._dataset(dfile, self.args["data_dir"], self.args["csv_deg"], df_con=dcon,
+                                    filename_column_ref=self.args["csv_ref"])
 
     # ------------------------------------------------------------------ model (model:928-1030)
     def _loadModel(self):
@@ -172,10 +175,11 @@ class nisqaModel(object):
             self.args["csv_mos_val"] = None
         else:
             self.args["dim"] = False
-        if self.args["model"] == "NISQA_DE":
-            raise NotImplementedError("NISQA_DE (double-ended) is outside the B200 predict path")
-        self.args["double_ended"] = False
-        self.args["csv_ref"] = None
+        if self.args["model"] == "NISQA_DE":      # model:951-955
+            self.args["double_ended"] = True
+        else:
+            self.args["double_ended"] = False
+            self.args["csv_ref"] = None
         for k, v in (("output_dir", None), ("ms_channel", None), ("tr_bs_val", 1), ("tr_num_workers", 0)):
             self.args.setdefault(k, v)
 

@@ -60,7 +60,9 @@ void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmPar
 void launch_lstm_batched(cudaStream_t, const float*, const ClipDesc*, const int*, int, const LstmParams&, float*, float*, float, float*);
 void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
 // td_tiled.cu
-void launch_td_in(cudaStream_t, const float*, const float*, const float*, const float*, const float*,
+void launch_de_align(cudaStream_t, const float*, const ClipDesc*, int, const int*, int, int, int, int, float*, int, float*);
+void launch_de_finalize(cudaStream_t, const ClipDesc*, int, int, float*);
+void launch_td_in(cudaStream_t, const float*, const float*, int, const float*, const float*, const float*,
                   const float*, const float*, const float*, const int*, const ClipDesc*, float*, float*, int);
 struct PoolSimpleParams { const float* a1; const float* a1b; const float* w3; const float* b3; };
 void launch_pool_simple(cudaStream_t, const float*, int, const ClipDesc*, int, int, const PoolSimpleParams&, int, int, float*);
@@ -121,6 +123,7 @@ struct FbEntry {
 
 struct ClipPlan {
   int hop, win, n_frames, n_seg, status, fb_id;
+  int run;     // processed by the pass: status OK and, in a double-ended engine, its partner's status OK too
 };
 
 struct Ticket {          // one asynchronous nisqa_submit_pcm call
@@ -142,13 +145,13 @@ constexpr int kLanes = 3;
 constexpr int kStages = 6;     // staging slots / submissions in flight (uploads run ahead of the lanes)
 struct Lane {
   cudaStream_t stream = nullptr;
-  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, qkv2, logits, feats20, tdout, partial;
+  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, qkv2, logits, feats20, tdout, partial, fused, td2in;
   DevBuf planes[7];        // planes[l]: fp16 hi | lo plane pair feeding conv layer l (2..6), conv_split.cu
   size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // offset of the lo plane inside planes[l] (half of the allocation)
   void release() {
     for (auto& b : planes) b.release();
     DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
-                     &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout, &partial};
+                     &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout, &partial, &fused, &td2in};
     for (auto* b : all) b->release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -507,57 +510,82 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
 
   if (e->cfg.arch == NISQA_ARCH_ADAPT_SA_ATTFF) {
     const std::string td = "time_dependency.model.";
-    const TensorView* lw = P.get(td + "linear.weight", {64, 384});
-    const TensorView* lb = P.get(td + "linear.bias", {64});
-    const TensorView* ng = P.get(td + "norm1.weight", {64});
-    const TensorView* nb = P.get(td + "norm1.bias", {64});
-    if (!lw || !lb || !ng || !nb) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-    size_t o = P.alloc("lin.wT", 384 * 64);
-    // engine feature order k' = h*64 + c  <->  reference view(-1, 64*6) order c*6 + h (lib:706)
-    for (int h = 0; h < 6; ++h)
-      for (int c = 0; c < 64; ++c)
-        for (int j = 0; j < 64; ++j) P.arena[o + ((size_t)h * 64 + c) * 64 + j] = lw->d[(size_t)j * 384 + c * 6 + h];
-    o = P.alloc("lin.b", 64); memcpy(&P.arena[o], lb->d, 256);
-    o = P.alloc("ln0.g", 64); memcpy(&P.arena[o], ng->d, 256);
-    o = P.alloc("ln0.b", 64); memcpy(&P.arena[o], nb->d, 256);
-    for (int l = 0; l < e->cfg.sa_layers; ++l) {
-      char pf[96]; snprintf(pf, sizeof pf, "time_dependency.model.layers.%d.", l);
-      char key[64];
-      const std::string p(pf);
-      const TensorView* iw = P.get(p + "self_attn.in_proj_weight", {192, 64});
-      const TensorView* ib = P.get(p + "self_attn.in_proj_bias", {192});
-      const TensorView* ow = P.get(p + "self_attn.out_proj.weight", {64, 64});
-      const TensorView* ob = P.get(p + "self_attn.out_proj.bias", {64});
-      const TensorView* w1 = P.get(p + "linear1.weight", {64, 64});
-      const TensorView* b1 = P.get(p + "linear1.bias", {64});
-      const TensorView* w2 = P.get(p + "linear2.weight", {64, 64});
-      const TensorView* b2 = P.get(p + "linear2.bias", {64});
-      const TensorView* g1 = P.get(p + "norm1.weight", {64});
-      const TensorView* e1 = P.get(p + "norm1.bias", {64});
-      const TensorView* g2 = P.get(p + "norm2.weight", {64});
-      const TensorView* e2 = P.get(p + "norm2.bias", {64});
-      if (!iw || !ib || !ow || !ob || !w1 || !b1 || !w2 || !b2 || !g1 || !e1 || !g2 || !e2)
-        return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-      auto K = [&](const char* s) { snprintf(key, sizeof key, "sa%d.%s", l, s); return std::string(key); };
-      o = P.alloc(K("qkvT"), 3 * 4096);
-      for (int part = 0; part < 3; ++part) {
-        const float sc = part == 0 ? 0.125f : 1.f;      // q * 1/sqrt(64): exact power of two
-        for (int k = 0; k < 64; ++k)
-          for (int j = 0; j < 64; ++j)
-            P.arena[o + part * 4096 + k * 64 + j] = iw->d[(size_t)(part * 64 + j) * 64 + k] * sc;
+    // one SelfAttention stack (lib:945-1040): Linear(in -> 64) + LayerNorm + `layers` encoder layers.  `kp` prefixes the
+    // arena keys ("" = time_dependency, "2" = time_dependency_2 of the double-ended model)
+    auto pack_sa_stack = [&](const std::string& ck, const std::string& kp, int in_dim, int layers, bool cnn_order) -> bool {
+      const TensorView* lw = P.get(ck + "linear.weight", {64, in_dim});
+      const TensorView* lb = P.get(ck + "linear.bias", {64});
+      const TensorView* ng = P.get(ck + "norm1.weight", {64});
+      const TensorView* nb = P.get(ck + "norm1.bias", {64});
+      if (!lw || !lb || !ng || !nb) return false;
+      size_t o = P.alloc("lin" + kp + ".wT", (size_t)in_dim * 64);
+      if (cnn_order) {
+        // engine feature order k' = h*64 + c  <->  reference view(-1, 64*6) order c*6 + h (lib:706)
+        for (int h = 0; h < 6; ++h)
+          for (int c = 0; c < 64; ++c)
+            for (int j = 0; j < 64; ++j) P.arena[o + ((size_t)h * 64 + c) * 64 + j] = lw->d[(size_t)j * 384 + c * 6 + h];
+      } else {
+        pack_linear_T(P, o, lw, 64, in_dim);
       }
-      o = P.alloc(K("qkvb"), 192);
-      for (int j = 0; j < 192; ++j) P.arena[o + j] = ib->d[j] * (j < 64 ? 0.125f : 1.f);
-      o = P.alloc(K("woT"), 4096); pack_linear_T(P, o, ow, 64, 64);
-      o = P.alloc(K("bo"), 64); memcpy(&P.arena[o], ob->d, 256);
-      o = P.alloc(K("w1T"), 4096); pack_linear_T(P, o, w1, 64, 64);
-      o = P.alloc(K("b1"), 64); memcpy(&P.arena[o], b1->d, 256);
-      o = P.alloc(K("w2T"), 4096); pack_linear_T(P, o, w2, 64, 64);
-      o = P.alloc(K("b2"), 64); memcpy(&P.arena[o], b2->d, 256);
-      o = P.alloc(K("ln1g"), 64); memcpy(&P.arena[o], g1->d, 256);
-      o = P.alloc(K("ln1b"), 64); memcpy(&P.arena[o], e1->d, 256);
-      o = P.alloc(K("ln2g"), 64); memcpy(&P.arena[o], g2->d, 256);
-      o = P.alloc(K("ln2b"), 64); memcpy(&P.arena[o], e2->d, 256);
+      o = P.alloc("lin" + kp + ".b", 64); memcpy(&P.arena[o], lb->d, 256);
+      o = P.alloc("ln" + kp + "0.g", 64); memcpy(&P.arena[o], ng->d, 256);
+      o = P.alloc("ln" + kp + "0.b", 64); memcpy(&P.arena[o], nb->d, 256);
+      for (int l = 0; l < layers; ++l) {
+        char pf[96]; snprintf(pf, sizeof pf, "layers.%d.", l);
+        char key[64];
+        const std::string p = ck + pf;
+        const TensorView* iw = P.get(p + "self_attn.in_proj_weight", {192, 64});
+        const TensorView* ib = P.get(p + "self_attn.in_proj_bias", {192});
+        const TensorView* ow = P.get(p + "self_attn.out_proj.weight", {64, 64});
+        const TensorView* ob = P.get(p + "self_attn.out_proj.bias", {64});
+        const TensorView* w1 = P.get(p + "linear1.weight", {64, 64});
+        const TensorView* b1 = P.get(p + "linear1.bias", {64});
+        const TensorView* w2 = P.get(p + "linear2.weight", {64, 64});
+        const TensorView* b2 = P.get(p + "linear2.bias", {64});
+        const TensorView* g1 = P.get(p + "norm1.weight", {64});
+        const TensorView* e1 = P.get(p + "norm1.bias", {64});
+        const TensorView* g2 = P.get(p + "norm2.weight", {64});
+        const TensorView* e2 = P.get(p + "norm2.bias", {64});
+        if (!iw || !ib || !ow || !ob || !w1 || !b1 || !w2 || !b2 || !g1 || !e1 || !g2 || !e2) return false;
+        auto K = [&](const char* s2) { snprintf(key, sizeof key, "sa%s%d.%s", kp.c_str(), l, s2); return std::string(key); };
+        o = P.alloc(K("qkvT"), 3 * 4096);
+        for (int part = 0; part < 3; ++part) {
+          const float sc = part == 0 ? 0.125f : 1.f;      // q * 1/sqrt(64): exact power of two
+          for (int k = 0; k < 64; ++k)
+            for (int j = 0; j < 64; ++j)
+              P.arena[o + part * 4096 + k * 64 + j] = iw->d[(size_t)(part * 64 + j) * 64 + k] * sc;
+        }
+        o = P.alloc(K("qkvb"), 192);
+        for (int j = 0; j < 192; ++j) P.arena[o + j] = ib->d[j] * (j < 64 ? 0.125f : 1.f);
+        o = P.alloc(K("woT"), 4096); pack_linear_T(P, o, ow, 64, 64);
+        o = P.alloc(K("bo"), 64); memcpy(&P.arena[o], ob->d, 256);
+        o = P.alloc(K("w1T"), 4096); pack_linear_T(P, o, w1, 64, 64);
+        o = P.alloc(K("b1"), 64); memcpy(&P.arena[o], b1->d, 256);
+        o = P.alloc(K("w2T"), 4096); pack_linear_T(P, o, w2, 64, 64);
+        o = P.alloc(K("b2"), 64); memcpy(&P.arena[o], b2->d, 256);
+        o = P.alloc(K("ln1g"), 64); memcpy(&P.arena[o], g1->d, 256);
+        o = P.alloc(K("ln1b"), 64); memcpy(&P.arena[o], e1->d, 256);
+        o = P.alloc(K("ln2g"), 64); memcpy(&P.arena[o], g2->d, 256);
+        o = P.alloc(K("ln2b"), 64); memcpy(&P.arena[o], e2->d, 256);
+      }
+      return true;
+    };
+    auto pack_pos_enc = [&](const std::string& ck, const std::string& key) -> int {
+      auto it = P.t.find(ck + "pos_encoder.pe");                  // registered buffer [max_len, 1, 64] (lib:1051-1058)
+      if (it == P.t.end() || it->second.nd != 3 || it->second.dims[1] != 1 || it->second.dims[2] != 64)
+        return fail(e, NISQA_ERR_WEIGHTS, "missing tensor " + ck + "pos_encoder.pe");
+      if (e->cfg.max_segments > 0 && it->second.dims[0] < e->cfg.max_segments)
+        return fail(e, NISQA_ERR_WEIGHTS, "positional encoding shorter than ms_max_segments");
+      const size_t o2 = P.alloc(key, (size_t)it->second.numel);
+      memcpy(&P.arena[o2], it->second.d, (size_t)it->second.numel * 4);
+      return 0;
+    };
+    if (!pack_sa_stack(td, "", 384, e->cfg.sa_layers, true)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    if (e->cfg.double_ended) {
+      const std::string td2 = "time_dependency_2.model.";
+      const int fdim = e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128;
+      if (!pack_sa_stack(td2, "2", fdim, e->cfg.td2_layers, false)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+      if (e->cfg.td2_pos_enc) { int rc = pack_pos_enc(td2, "pe2"); if (rc) return rc; }
     }
     const int nh = e->cfg.n_out;
     auto head_prefix = [&](int h) {
@@ -566,15 +594,7 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       else snprintf(pf, sizeof pf, "pool_layers.%d.model.", h);   // head order mos,noi,dis,col,loud (lib:1461-1465)
       return std::string(pf);
     };
-    if (e->cfg.pos_enc) {
-      auto it = P.t.find(td + "pos_encoder.pe");                  // registered buffer [max_len, 1, 64] (lib:1051-1058)
-      if (it == P.t.end() || it->second.nd != 3 || it->second.dims[1] != 1 || it->second.dims[2] != 64)
-        return fail(e, NISQA_ERR_WEIGHTS, "missing tensor " + td + "pos_encoder.pe");
-      if (e->cfg.max_segments > 0 && it->second.dims[0] < e->cfg.max_segments)
-        return fail(e, NISQA_ERR_WEIGHTS, "positional encoding shorter than ms_max_segments");
-      const size_t o2 = P.alloc("pe", (size_t)it->second.numel);
-      memcpy(&P.arena[o2], it->second.d, (size_t)it->second.numel * 4);
-    }
+    if (e->cfg.pos_enc) { int rc = pack_pos_enc(td, "pe"); if (rc) return rc; }
     if (e->cfg.pool == NISQA_POOL_ATT_FF) {
     const size_t oW1 = P.alloc("pool.w1T", (size_t)nh * 64 * 128), ob1 = P.alloc("pool.b1", nh * 128),
                  ow2 = P.alloc("pool.w2", nh * 128), ob2 = P.alloc("pool.b2", nh),
@@ -685,7 +705,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
   for (int i = 0; i < n; ++i) {
     const ClipPlan& p = in.plan[i];
     ClipDesc& d = cl[i];
-    const bool ok = p.status == NISQA_CLIP_OK;
+    const bool ok = p.run != 0;
     d.n_samples = (int)in.n_samples[i];
     d.fb_id = ok ? p.fb_id : 0;
     d.hop = p.hop; d.win = p.win;
@@ -852,14 +872,6 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       CK(LN.qkv.reserve((size_t)n_seg * 192 * 4));
       CK(LN.logits.reserve((size_t)n_seg * n_out * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 64 * 4));
-      auto sa_key = [&](int l, const char* s2) { char k[32]; snprintf(k, sizeof k, "sa%d.%s", l, s2); return std::string(k); };
-      auto sa_params = [&](int l) {
-        SaLayerParams P;
-        P.WoT = W(e, sa_key(l, "woT")); P.bo = W(e, sa_key(l, "bo")); P.W1T = W(e, sa_key(l, "w1T")); P.b1 = W(e, sa_key(l, "b1"));
-        P.W2T = W(e, sa_key(l, "w2T")); P.b2 = W(e, sa_key(l, "b2")); P.ln1_g = W(e, sa_key(l, "ln1g")); P.ln1_b = W(e, sa_key(l, "ln1b"));
-        P.ln2_g = W(e, sa_key(l, "ln2g")); P.ln2_b = W(e, sa_key(l, "ln2b"));
-        return P;
-      };
       const bool attff = c.pool == NISQA_POOL_ATT_FF;
       PoolHeadParams H = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
       if (attff) {
@@ -874,17 +886,45 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       // CTAs read keys / values of rows whose next-layer projection other CTAs are already writing.
       CK(LN.qkv2.reserve((size_t)n_seg * 192 * 4));
       float* qk[2] = {LN.qkv.as<float>(), LN.qkv2.as<float>()};
-      { Scope s(e, "lin_ln");
-        launch_td_in(st, LN.feats.as<float>(), W(e, "lin.wT"), W(e, "lin.b"), W(e, "ln0.g"), W(e, "ln0.b"),
-                     W(e, sa_key(0, "qkvT")), W(e, sa_key(0, "qkvb")), c.pos_enc ? W(e, "pe") : nullptr, seg_clip, d_clips,
-                     LN.tdout.as<float>(), qk[0], n_seg); }
-      for (int l = 0; l < c.sa_layers; ++l) {
-        const bool last = l + 1 == c.sa_layers;
-        Scope s(e, "sa_layer");
-        launch_td_sa(st, cur, qk[l & 1], d_clips, n, d_qt64, n_qt64, sa_params(l), pp[l & 1],
-                     last ? nullptr : W(e, sa_key(l + 1, "qkvT")), last ? nullptr : W(e, sa_key(l + 1, "qkvb")),
-                     qk[(l + 1) & 1], H, attff ? n_out : 0, LN.logits.as<float>());
-        cur = pp[l & 1];
+      const bool de = c.double_ended != 0;
+      // one SelfAttention stack; `kp` = "" (time_dependency) or "2" (time_dependency_2); the stack that feeds the pooling
+      // module computes the PoolAttFF logits behind its last layer
+      auto sa_stack = [&](const std::string& kp, const float* in_rows, int nk, int layers, bool pos_enc, bool feeds_pool,
+                          float* x0) -> const float* {
+        auto key = [&](int l, const char* s2) { char k[40]; snprintf(k, sizeof k, "sa%s%d.%s", kp.c_str(), l, s2); return std::string(k); };
+        auto params = [&](int l) {
+          SaLayerParams P;
+          P.WoT = W(e, key(l, "woT")); P.bo = W(e, key(l, "bo")); P.W1T = W(e, key(l, "w1T")); P.b1 = W(e, key(l, "b1"));
+          P.W2T = W(e, key(l, "w2T")); P.b2 = W(e, key(l, "b2")); P.ln1_g = W(e, key(l, "ln1g")); P.ln1_b = W(e, key(l, "ln1b"));
+          P.ln2_g = W(e, key(l, "ln2g")); P.ln2_b = W(e, key(l, "ln2b"));
+          return P;
+        };
+        { Scope s(e, "lin_ln");
+          launch_td_in(st, in_rows, W(e, "lin" + kp + ".wT"), nk, W(e, "lin" + kp + ".b"), W(e, "ln" + kp + "0.g"), W(e, "ln" + kp + "0.b"),
+                       W(e, key(0, "qkvT")), W(e, key(0, "qkvb")), pos_enc ? W(e, kp.empty() ? "pe" : "pe2") : nullptr, seg_clip, d_clips,
+                       x0, qk[0], n_seg); }
+        const float* cur2 = x0;
+        for (int l = 0; l < layers; ++l) {
+          const bool last = l + 1 == layers;
+          Scope s(e, "sa_layer");
+          launch_td_sa(st, cur2, qk[l & 1], d_clips, n, d_qt64, n_qt64, params(l), pp[l & 1],
+                       last ? nullptr : W(e, key(l + 1, "qkvT")), last ? nullptr : W(e, key(l + 1, "qkvb")),
+                       qk[(l + 1) & 1], H, (feeds_pool && attff) ? n_out : 0, LN.logits.as<float>());
+          cur2 = pp[l & 1];
+        }
+        return cur2;
+      };
+      cur = sa_stack("", LN.feats.as<float>(), 6, c.sa_layers, c.pos_enc != 0, !de, LN.tdout.as<float>());
+      if (de) {
+        // NISQA_DE (lib:404-424): align the reference clip's rows to the degraded clip's, fuse, second time-dependency stack
+        const int nf = c.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 3 : 2;
+        CK(LN.fused.reserve((size_t)n_seg * 64 * nf * 4));
+        CK(LN.td2in.reserve((size_t)n_seg * 64 * 4));
+        CK(cudaMemsetAsync(LN.fused.p, 0, (size_t)n_seg * 64 * nf * 4, st));      // rows of the reference clips stay zero
+        { Scope s(e, "de_align");
+          launch_de_align(st, cur, d_clips, n, d_qt64, n_qt64, c.de_align, c.de_align_apply == NISQA_DE_APPLY_SOFT, c.de_fuse,
+                          LN.fused.as<float>(), n_out, nullptr); }
+        cur = sa_stack("2", LN.fused.as<float>(), nf, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
       }
       e->last_td_out = cur;
       { Scope s(e, "pool");
@@ -892,7 +932,8 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         else {
           PoolSimpleParams Q = {W(e, "pool.a1"), W(e, "pool.a1b"), W(e, "pool.w3"), W(e, "pool.b3")};
           launch_pool_simple(st, cur, 64, d_clips, n, c.pool, Q, n_out, max_n_seg, scores);
-        } }
+        }
+        if (de) launch_de_finalize(st, d_clips, n, n_out, scores); }
     } else {
       CK(LN.feats20.reserve((size_t)n_seg * 20 * 4));
       CK(LN.tdout.reserve((size_t)n_seg * 256 * 4));
@@ -943,8 +984,15 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
       int rc = build_fb(e, sample_rate[i], plan[i].hop, plan[i].win, &plan[i].fb_id);
       if (rc) return rc;
     }
+    plan[i].run = plan[i].status == NISQA_CLIP_OK;
     if (n_seg_out) n_seg_out[i] = plan[i].n_seg;
     if (status_out) status_out[i] = plan[i].status;
+  }
+  const int unit = e->cfg.double_ended ? 2 : 1;      // clips travel in (degraded, reference) pairs through a double-ended engine
+  if (e->cfg.double_ended) {
+    if (n_clips & 1) return fail(e, NISQA_ERR_INVALID, "a double-ended engine takes clips in (degraded, reference) pairs: n_clips must be even");
+    for (int i = 0; i < n_clips; i += 2)
+      if (!plan[i].run || !plan[i + 1].run) plan[i].run = plan[i + 1].run = 0;      // the pair scores NaN
   }
   // segments per internal pass: 131072 segments keep ~8 GB of activation planes per compute lane (sized for the
   // 180 GB of a B200) and give the BiLSTM >= 128 clips per launch at configs[3]; one 64-clip batch is 15 808
@@ -961,9 +1009,10 @@ int predict_common(nisqa_engine* e, int n_clips, const void* const* host_pcm, co
   while (i0 < n_clips) {
     int i1 = i0; long long segs = 0;
     while (i1 < n_clips) {
-      const long long s = plan[i1].status == NISQA_CLIP_OK ? plan[i1].n_seg : 0;
+      long long s = 0;
+      for (int u = 0; u < unit; ++u) s += plan[i1 + u].run ? plan[i1 + u].n_seg : 0;
       if (i1 > i0 && (segs + s > max_seg || i1 - i0 >= 32768)) break;      // (clips ride in grid.y of the front-end: < 65536)
-      segs += s; ++i1;
+      segs += s; i1 += unit;
     }
     PassInput in;
     in.n_clips = i1 - i0; in.plan = plan.data() + i0; in.n_samples = n_samples + i0;
@@ -1052,6 +1101,16 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
       (cfg->arch == NISQA_ARCH_STD_LSTM_LASTBI && (cfg->pool == NISQA_POOL_ATT_FF || cfg->pool == NISQA_POOL_ATT)))
     return fail(e, NISQA_ERR_INVALID, "pooling module not available for this architecture");
   if (cfg->pos_enc && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) return fail(e, NISQA_ERR_INVALID, "pos_enc needs the self-attention architecture");
+  if (cfg->double_ended) {
+    if (cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF || cfg->n_out != 1)
+      return fail(e, NISQA_ERR_INVALID, "NISQA_DE: AdaptCNN + self-attention, one output");
+    if (cfg->de_align < NISQA_DE_ALIGN_DOT || cfg->de_align > NISQA_DE_ALIGN_DISTANCE)
+      return fail(e, NISQA_ERR_INVALID, "de_align: dot, cosine or distance");
+    if (cfg->de_align_apply != NISQA_DE_APPLY_HARD && cfg->de_align_apply != NISQA_DE_APPLY_SOFT)
+      return fail(e, NISQA_ERR_INVALID, "de_align_apply");
+    if (cfg->de_fuse < NISQA_DE_FUSE_XY_MINUS || cfg->de_fuse > NISQA_DE_FUSE_XY) return fail(e, NISQA_ERR_INVALID, "de_fuse");
+    if (cfg->td2_layers < 1 || cfg->td2_layers > 8) return fail(e, NISQA_ERR_INVALID, "td_2 must be a self-attention stack (td2_layers 1..8)");
+  }
   int count = 0;
   CK(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return fail(e, NISQA_ERR_CUDA, "no such CUDA device (there is no CPU fallback)");

@@ -219,13 +219,14 @@ __device__ __forceinline__ void store_rows_smem(float* X, const float (&v)[4][4]
 }
 
 // QKV projection of a 64-row tile X (shared, row-major) -> qkv[row0 + r][192]; Wbuf: two [64][64] buffers, the
-// first chunk (part 0) must already be in flight into Wbuf[0] as the most recent cp.async group.
+// first chunk (part 0) must already be in flight into Wbuf[b0] as the most recent cp.async group.
 __device__ __forceinline__ void qkv_tail(const float* X, float* Wbuf, const float* __restrict__ WT3,
                                          const float* __restrict__ b3, float* __restrict__ qkv, long long row0,
-                                         int rows_valid, int tid, int ty, int tx) {
+                                         int rows_valid, int tid, int ty, int tx, int b0 = 0) {
 #pragma unroll 1
-  for (int part = 0; part < 3; ++part) {
-    if (part + 1 < 3) tile_load_async(Wbuf + ((part + 1) & 1) * 4096, 64, WT3 + (part + 1) * 4096, 64, 64, tid);
+  for (int part_ = 0; part_ < 3; ++part_) {
+    const int part = part_;
+    if (part + 1 < 3) tile_load_async(Wbuf + ((part + 1 + b0) & 1) * 4096, 64, WT3 + (part + 1) * 4096, 64, 64, tid);
     cp_commit();
     cp_wait<1>();
     __syncthreads();
@@ -233,7 +234,7 @@ __device__ __forceinline__ void qkv_tail(const float* X, float* Wbuf, const floa
     const float4 bb = __ldg(reinterpret_cast<const float4*>(b3 + part * 64) + tx);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
-    gemm_nn(acc, X, Wbuf + (part & 1) * 4096, 64, ty, tx);
+    gemm_nn(acc, X, Wbuf + ((part + b0) & 1) * 4096, 64, ty, tx);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (4 * ty + i < rows_valid)
@@ -249,7 +250,7 @@ __device__ __forceinline__ void qkv_tail(const float* X, float* Wbuf, const floa
 constexpr int kInSmemFloats = 2 * kTileF + 2 * 4096 + kTileF;
 
 __global__ void __launch_bounds__(kNT, 2)
-td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restrict__ WT /*[384][64]*/,
+td_in_kernel(const float* __restrict__ feats /*[n][64 nk]*/, const float* __restrict__ WT /*[64 nk][64]*/, int nk,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const float* __restrict__ qkvT /*[3][64][64]*/, const float* __restrict__ qkvb /*[192]*/,
              const float* __restrict__ pe /*[max_len][64] positional encoding or nullptr*/,
@@ -262,9 +263,10 @@ td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restri
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const long long row0 = (long long)blockIdx.x * kT;
   const int rows_valid = (int)min((long long)kT, (long long)n_rows - row0);
-  const float* src = feats + row0 * 384;
+  const int ld = 64 * nk;                 // 384 CNN features, or the 192 / 128 fused features of the double-ended model
+  const float* src = feats + row0 * ld;
 
-  tile_load_async(As, kLd, src, 384, rows_valid, tid);
+  tile_load_async(As, kLd, src, ld, rows_valid, tid);
   tile_load_async(Ws, 64, WT, 64, 64, tid);
   cp_commit();
   float acc[4][4];
@@ -274,9 +276,9 @@ td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restri
     for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
   }
 #pragma unroll 1
-  for (int c = 0; c < 6; ++c) {
-    if (c + 1 < 6) {
-      tile_load_async(As + ((c + 1) & 1) * kTileF, kLd, src + (c + 1) * 64, 384, rows_valid, tid);
+  for (int c = 0; c < nk; ++c) {
+    if (c + 1 < nk) {
+      tile_load_async(As + ((c + 1) & 1) * kTileF, kLd, src + (c + 1) * 64, ld, rows_valid, tid);
       tile_load_async(Ws + ((c + 1) & 1) * 4096, 64, WT + (size_t)(c + 1) * 4096, 64, 64, tid);
     } else {
       tile_load_async(Ws + ((c + 1) & 1) * 4096, 64, qkvT, 64, 64, tid);       // first QKV chunk rides behind the last k chunk
@@ -303,8 +305,8 @@ td_in_kernel(const float* __restrict__ feats /*[n][384]*/, const float* __restri
   for (int i = 0; i < 4; ++i)
     if (4 * ty + i < rows_valid)
       *reinterpret_cast<float4*>(x0 + (row0 + 4 * ty + i) * 64 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  // QKV of layer 0: its first weight chunk is in flight into Ws[0] (6 & 1 == 0); qkv_tail syncs before reading Xs
-  qkv_tail(Xs, Ws, qkvT, qkvb, qkv, row0, rows_valid, tid, ty, tx);
+  // QKV of layer 0: its first weight chunk is in flight into Ws[nk & 1]; qkv_tail syncs before reading Xs
+  qkv_tail(Xs, Ws, qkvT, qkvb, qkv, row0, rows_valid, tid, ty, tx, nk & 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -515,14 +517,220 @@ td_sa_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Double-ended model (NISQA_DE, reference lib:272-424): time alignment of the reference clip's features to the degraded
+// clip's (Alignment, lib:1228-1285) and feature fusion (Fusion, lib:1380-1417), for 64 degraded steps of one pair.
+//   x = time_dependency output of the degraded clip (clip 2p), y = of the reference clip (clip 2p + 1)
+//   score[i][j] : dot  x_i . y_j (AttDot, lib:1287-1296) | cosine similarity (AttCosine, lib:1298-1308, eps 1e-8) |
+//                 -mean_d |x_id - y_jd| (AttDistance with its default norms, lib:1310-1323); keys j >= n_wins_y masked
+//   hard        : y_al[i] = y[argmax_j softmax(score[i])] = y[first maximal score] (ApplyHardAttention, lib:1359-1368)
+//   soft        : y_al[i] = softmax_j(score[i]) . y (ApplySoftAttention, lib:1370-1378), online max / sum over key blocks
+//   fuse        : [x, y_al, x - y_al] | [x + y_al, x - y_al] | [x, y_al]  ->  fused[row][64 * nf]
+// Same 64 x 64 register tiling as td_sa_kernel; the y block serves as K (row-major, pitch 68) and as V.
+enum { DE_ALIGN_DOT = 1, DE_ALIGN_COSINE = 2, DE_ALIGN_DISTANCE = 3 };      // = enum nisqa_de_align (the learned / 'none' modules are refused)
+enum { DE_FUSE_XY_MINUS = 0, DE_FUSE_PLUS_MINUS = 1, DE_FUSE_XY = 2 };
+
+// s[i][j] -= sum_k |A[4ty+i][k] - B[tx+16j][k]|
+__device__ __forceinline__ void absdiff_nt(float (&s)[4][4], const float* __restrict__ A, const float* __restrict__ B, int ty, int tx) {
+  const float* a0 = A + (4 * ty) * kLd;
+  const float* b0 = B + tx * kLd;
+#pragma unroll 2
+  for (int k = 0; k < kT; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * kLd + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(b0 + (16 * j) * kLd + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        s[i][j] -= (fabsf(a[i].x - b[j].x) + fabsf(a[i].y - b[j].y)) + (fabsf(a[i].z - b[j].z) + fabsf(a[i].w - b[j].w));
+  }
+}
+
+constexpr int kDeSmemFloats = 2 * kTileF + 2 * kTileF + 2 * kT;      // Qs | Ps | Yb[2] | 1 / |y| of the two blocks
+
+__global__ void __launch_bounds__(kNT, 2)
+de_align_kernel(const float* __restrict__ x_td /*[n_seg][64]*/, const ClipDesc* __restrict__ clips, int n_clips,
+                const int* __restrict__ qtile_prefix /*64-row tiles*/, int align, int soft, int fuse,
+                float* __restrict__ fused /*[n_seg][64 nf]*/) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                          // [64][68] degraded rows x
+  float* Ps = sm + kTileF;                 // [64][68] softmax numerators (soft attention)
+  float* Yb = Ps + kTileF;                 // [2][64][68] reference rows y
+  float* Yn = Yb + 2 * kTileF;             // [2][64] 1 / max(|y_j|, eps)
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int c = upper_slot(qtile_prefix, n_clips, blockIdx.x);
+  if (c & 1) return;                       // reference clips are keys only
+  const ClipDesc cd = clips[c], cr = clips[c + 1];
+  const int Sx = cd.n_seg, Sy = cr.n_seg;
+  if (Sx <= 0 || Sy <= 0) return;
+  const int q0 = (blockIdx.x - __ldg(qtile_prefix + c)) * kT;
+  const int rows_valid = min(kT, Sx - q0);
+  const long long row0 = (long long)cd.seg_off + q0;
+  const float* y_base = x_td + (long long)cr.seg_off * 64;
+  const int nf = fuse == DE_FUSE_XY_MINUS ? 3 : 2;
+
+  tile_load_async(Qs, kLd, x_td + row0 * 64, 64, rows_valid, tid);
+  tile_load_async(Yb, kLd, y_base, 64, min(kT, Sy), tid);
+  cp_commit();
+  float o[4][4];
+  zero_acc(o);
+  {
+    float m[4], l[4], rq[4];
+    int best[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; best[i] = 0; rq[i] = 1.f; }
+    const int n_kb = (Sy + kT - 1) / kT;
+#pragma unroll 1
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int j0 = kb * kT;
+      if (kb + 1 < n_kb) tile_load_async(Yb + ((kb + 1) & 1) * kTileF, kLd, y_base + (long long)(j0 + kT) * 64, 64, min(kT, Sy - (j0 + kT)), tid);
+      cp_commit();
+      cp_wait<1>();
+      __syncthreads();
+      const float* Y = Yb + (kb & 1) * kTileF;
+      if (align == DE_ALIGN_COSINE) {
+        // nn.CosineSimilarity: x . y / (max(|x|, eps) max(|y|, eps)); four threads per key row, 16 features each
+        const int r = tid >> 2, qd = tid & 3;
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(Y + r * kLd + qd * 16 + k);
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        if (qd == 0) Yn[(kb & 1) * kT + r] = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
+        if (kb == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float qs = 0.f;
+            const float4 v = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * kLd + 4 * tx);
+            qs = fmaf(v.x, v.x, qs); qs = fmaf(v.y, v.y, qs); qs = fmaf(v.z, v.z, qs); qs = fmaf(v.w, v.w, qs);
+            rq[i] = 1.0f / fmaxf(sqrtf(row_sum(qs)), 1e-8f);
+          }
+        }
+        __syncthreads();
+      }
+      float s[4][4];
+      zero_acc(s);
+      if (align == DE_ALIGN_DISTANCE) {
+        absdiff_nt(s, Qs, Y, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[i][j] *= (1.0f / 64.0f);
+      } else {
+        gemm_nt(s, Qs, Y, ty, tx);
+        if (align == DE_ALIGN_COSINE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ry = Yn[(kb & 1) * kT + tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i][j] = s[i][j] * rq[i] * ry;
+          }
+        }
+      }
+      const int nkeys = Sy - j0;
+      if (!soft) {
+        // first maximal score of the row: columns of a thread ascend with j and with the block; ties between threads
+        // are resolved towards the smaller key index
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (tx + 16 * j < nkeys && s[i][j] > bv) { bv = s[i][j]; bi = j0 + tx + 16 * j; }
+#pragma unroll
+          for (int of = 8; of > 0; of >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, of);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, of);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (bv > m[i]) { m[i] = bv; best[i] = bi; }       // (strictly greater: an earlier block keeps a tie)
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float bm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { if (tx + 16 * j >= nkeys) s[i][j] = -INFINITY; bm = fmaxf(bm, s[i][j]); }
+          bm = row_max(bm);
+          const float mn = fmaxf(m[i], bm);
+          const float sc = expf(m[i] - mn);
+          float ps = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float p = expf(s[i][j] - mn);
+            ps += p;
+            Ps[(4 * ty + i) * kLd + tx + 16 * j] = p;
+          }
+          l[i] = l[i] * sc + row_sum(ps);
+          m[i] = mn;
+          o[i][0] *= sc; o[i][1] *= sc; o[i][2] *= sc; o[i][3] *= sc;
+        }
+        __syncwarp();
+        gemm_nn(o, Ps, Y, kLd, ty, tx);                      // o[i][d] += sum_j p[i][j] y[j][d]
+      }
+      __syncthreads();                                       // block kb consumed
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!soft) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y_base + (long long)best[i] * 64) + tx);
+        o[i][0] = v.x; o[i][1] = v.y; o[i][2] = v.z; o[i][3] = v.w;
+      } else {
+        const float inv = 1.0f / l[i];
+        o[i][0] *= inv; o[i][1] *= inv; o[i][2] *= inv; o[i][3] *= inv;
+      }
+    }
+  }
+  // ---- fusion (lib:1402-1417)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (4 * ty + i >= rows_valid) continue;
+    const float4 xv = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * kLd + 4 * tx);
+    const float4 yv = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+    const float4 df = make_float4(xv.x - yv.x, xv.y - yv.y, xv.z - yv.z, xv.w - yv.w);
+    float4* dst = reinterpret_cast<float4*>(fused + (row0 + 4 * ty + i) * (64 * nf)) + tx;
+    if (fuse == DE_FUSE_XY_MINUS) { dst[0] = xv; dst[16] = yv; dst[32] = df; }
+    else if (fuse == DE_FUSE_PLUS_MINUS) { dst[0] = make_float4(xv.x + yv.x, xv.y + yv.y, xv.z + yv.z, xv.w + yv.w); dst[16] = df; }
+    else { dst[0] = xv; dst[16] = yv; }
+  }
+}
+
+// scores of a double-ended pass: row 2p = the pair's score (NaN when either clip was skipped), row 2p + 1 = NaN
+__global__ void de_finalize_kernel(const ClipDesc* __restrict__ clips, int n_clips, int n_out, float* __restrict__ scores) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clips) return;
+  const bool bad = (c & 1) || clips[c].n_seg <= 0 || clips[c + 1].n_seg <= 0;
+  if (bad) for (int h = 0; h < n_out; ++h) scores[c * n_out + h] = __int_as_float(0x7fc00000);
+}
+
 // ------------------------------------------------------------------ host launchers
-void launch_td_in(cudaStream_t st, const float* feats, const float* WT, const float* b, const float* g, const float* be,
+void launch_td_in(cudaStream_t st, const float* feats, const float* WT, int nk, const float* b, const float* g, const float* be,
                   const float* qkvT, const float* qkvb, const float* pe, const int* seg_clip, const ClipDesc* clips,
                   float* x0, float* qkv, int n_rows) {
   static unsigned long long cfg = 0;
   const int smem = kInSmemFloats * 4;
   if (first_launch_on_device(cfg)) cudaFuncSetAttribute(td_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  td_in_kernel<<<(n_rows + kT - 1) / kT, kNT, smem, st>>>(feats, WT, b, g, be, qkvT, qkvb, pe, seg_clip, clips, x0, qkv, n_rows);
+  td_in_kernel<<<(n_rows + kT - 1) / kT, kNT, smem, st>>>(feats, WT, nk, b, g, be, qkvT, qkvb, pe, seg_clip, clips, x0, qkv, n_rows);
+}
+
+void launch_de_align(cudaStream_t st, const float* x_td, const ClipDesc* clips, int n_clips, const int* qtile64_prefix,
+                     int n_qtiles, int align, int soft, int fuse, float* fused, int n_out, float* scores_unused) {
+  (void)n_out; (void)scores_unused;
+  static unsigned long long cfg = 0;
+  const int smem = kDeSmemFloats * 4;
+  if (first_launch_on_device(cfg)) cudaFuncSetAttribute(de_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  de_align_kernel<<<n_qtiles, kNT, smem, st>>>(x_td, clips, n_clips, qtile64_prefix, align, soft, fuse, fused);
+}
+
+void launch_de_finalize(cudaStream_t st, const ClipDesc* clips, int n_clips, int n_out, float* scores) {
+  de_finalize_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clips, n_clips, n_out, scores);
 }
 
 void launch_td_sa(cudaStream_t st, const float* x_in, const float* qkv, const ClipDesc* clips, int n_clips,

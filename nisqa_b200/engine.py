@@ -13,12 +13,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnisqa_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_IN_FLIGHT = 6          # staging slots of the engine (nisqa_submit_pcm)
 ARCH_ADAPT_SA_ATTFF, ARCH_STD_LSTM_LASTBI = 0, 1
 FMT_S16, FMT_F32 = 0, 1
 CLIP_OK, CLIP_TOO_SHORT, CLIP_TOO_LONG = 0, 1, 2
 POOL_ATT_FF, POOL_ATT, POOL_AVG, POOL_MAX, POOL_LAST_STEP, POOL_LAST_STEP_BI = range(6)
+# NISQA_DE options (enum nisqa_de_align / nisqa_de_apply / nisqa_de_fuse)
+DE_ALIGN = {"dot": 1, "cosine": 2, "distance": 3}
+DE_APPLY = {"hard": 0, "soft": 1}
+DE_FUSE = {"x/y/-": 0, "+/-": 1, "x/y": 2}
 (STAGE_MEL_DB, STAGE_POOL1, STAGE_POOL2, STAGE_CONV3, STAGE_POOL3, STAGE_CONV5, STAGE_CNN_FEAT,
  STAGE_TD_IN, STAGE_TD_OUT) = range(9)
 
@@ -39,7 +43,9 @@ class NisqaConfig(C.Structure):
                 ("n_fft", C.c_int32), ("n_mels", C.c_int32), ("seg_len", C.c_int32),
                 ("seg_hop", C.c_int32), ("max_segments", C.c_int32), ("hop_s", C.c_double),
                 ("win_s", C.c_double), ("fmax", C.c_double), ("sa_layers", C.c_int32),
-                ("max_chunk_segments", C.c_int32), ("pool", C.c_int32), ("pos_enc", C.c_int32)]
+                ("max_chunk_segments", C.c_int32), ("pool", C.c_int32), ("pos_enc", C.c_int32),
+                ("double_ended", C.c_int32), ("de_align", C.c_int32), ("de_align_apply", C.c_int32),
+                ("de_fuse", C.c_int32), ("td2_layers", C.c_int32), ("td2_pos_enc", C.c_int32)]
 
 
 class NisqaTensor(C.Structure):
@@ -134,8 +140,9 @@ def config_from_args(args, max_chunk_segments=0):
     """Checkpoint ``args`` (reference model:941-942) -> nisqa_config.  Refuses anything the
     kernels do not implement (no fallback)."""
     cnn, td, pool = args.get("cnn_model"), args.get("td"), args.get("pool")
-    if args.get("model") not in ("NISQA", "NISQA_DIM"):
+    if args.get("model") not in ("NISQA", "NISQA_DIM", "NISQA_DE"):
         raise NotImplementedError("Model not available in the B200 engine: %r" % args.get("model"))
+    de = args.get("model") == "NISQA_DE"
     pool_mode = {"avg": POOL_AVG, "max": POOL_MAX, "last_step": POOL_LAST_STEP, "last_step_bi": POOL_LAST_STEP_BI}.get(pool)
     if pool == "att":
         if args.get("pool_att_h") == 128:
@@ -160,7 +167,22 @@ def config_from_args(args, max_chunk_segments=0):
         raise NotImplementedError(
             "architecture cnn=%r td=%r pool=%r is not implemented by the B200 engine" % (cnn, td, pool))
     ks = args.get("cnn_kernel_size")
-    ok = ok and (ks == 3 or tuple(ks) == (3, 3)) and args.get("td_2") in (None, "skip")
+    ok = ok and (ks == 3 or tuple(ks) == (3, 3))
+    if de:
+        # double-ended model (reference lib:272-424, config/train_nisqa_double_ended.yaml): AdaptCNN + self-attention on
+        # both signals, alignment without learned weights, fusion without the optional Linear, td_2 = self-attention
+        if arch != ARCH_ADAPT_SA_ATTFF:
+            raise NotImplementedError("NISQA_DE is implemented for cnn_model='adapt', td='self_att'")
+        if args.get("de_align") not in DE_ALIGN:
+            raise NotImplementedError("de_align=%r is not implemented by the B200 engine (dot, cosine, distance)" % (args.get("de_align"),))
+        if args.get("de_align_apply") not in DE_APPLY or args.get("de_fuse") not in DE_FUSE:
+            raise NotImplementedError("de_align_apply / de_fuse option not available: %r / %r" % (args.get("de_align_apply"), args.get("de_fuse")))
+        if args.get("de_fuse_dim"):
+            raise NotImplementedError("de_fuse_dim is not implemented by the B200 engine")
+        ok = ok and args.get("td_2") == "self_att" and args.get("td_2_sa_d_model") == 64 and args.get("td_2_sa_nhead") == 1 \
+            and args.get("td_2_sa_h") == 64
+    else:
+        ok = ok and args.get("td_2") in (None, "skip")
     ok = ok and (args["cnn_c_out_1"], args["cnn_c_out_2"], args["cnn_c_out_3"]) == (16, 32, 64)
     ok = ok and args["ms_n_fft"] == 4096 and args["ms_n_mels"] == 48 and args["ms_seg_length"] == 15
     if not ok:
@@ -180,6 +202,11 @@ def config_from_args(args, max_chunk_segments=0):
     cfg.max_chunk_segments = int(max_chunk_segments) or int(os.environ.get("NISQA_MAX_CHUNK", "0"))
     cfg.pool = pool_mode
     cfg.pos_enc = 1 if (arch == ARCH_ADAPT_SA_ATTFF and args.get("td_sa_pos_enc")) else 0
+    if de:
+        cfg.double_ended = 1
+        cfg.de_align, cfg.de_align_apply, cfg.de_fuse = DE_ALIGN[args["de_align"]], DE_APPLY[args["de_align_apply"]], DE_FUSE[args["de_fuse"]]
+        cfg.td2_layers = int(args["td_2_sa_num_layers"])
+        cfg.td2_pos_enc = 1 if args.get("td_2_sa_pos_enc") else 0
     return cfg
 
 

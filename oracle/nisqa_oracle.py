@@ -186,6 +186,79 @@ def bilstm(sd, feats):
     return torch.cat(outs, dim=1)                                   # [S, 2H] fwd || bwd
 
 
+# ------------------------------------------------- double-ended model
+def de_align(args, x, y):
+    """Alignment.forward (lib:1274-1285) for ONE pair: attention scores of every degraded step against the reference
+    clip's own steps (no padding, so no mask), softmax over the reference steps, hard (argmax -> gather, lib:1359-1368)
+    or soft (att @ y, lib:1370-1378) application.  x [Sx, d], y [Sy, d] -> y aligned to x [Sx, d]."""
+    method = args["de_align"]
+    if method == "dot":                                    # AttDot lib:1287-1296
+        att = x @ y.t()
+    elif method == "cosine":                               # AttCosine lib:1298-1308: nn.CosineSimilarity(dim=3), eps 1e-8
+        att = F.cosine_similarity(x[:, None, :], y[None, :, :], dim=2, eps=1e-8)
+    elif method == "distance":                             # AttDistance lib:1310-1323 with dist_norm = weight_norm = 1
+        att = -(x[None, :, :] - y[:, None, :]).abs().pow(1).mean(dim=2).pow(1).t()
+    else:
+        raise NotImplementedError(method)
+    att = torch.softmax(att, dim=1)
+    if args["de_align_apply"] == "hard":
+        return y[att.argmax(1)]
+    if args["de_align_apply"] == "soft":
+        return att @ y
+    raise NotImplementedError(args["de_align_apply"])
+
+
+def de_fuse(args, x, y):
+    """Fusion.forward (lib:1402-1417); de_fuse_dim (the optional Linear) is not restated."""
+    mode = args["de_fuse"]
+    if mode == "x/y/-":
+        return torch.cat((x, y, x - y), 1)
+    if mode == "+/-":
+        return torch.cat((x + y, x - y), 1)
+    if mode == "x/y":
+        return torch.cat((x, y), 1)
+    raise NotImplementedError(mode)
+
+
+def forward_de_from_mel(args, sd, spec, spec_ref, taps=None):
+    """NISQA_DE.forward (lib:404-424) for one (degraded, reference) pair of mel dB spectrograms -> score [1]."""
+    if args["cnn_model"] != "adapt" or args["td"] != "self_att" or args.get("td_2") != "self_att" or args.get("de_fuse_dim"):
+        raise NotImplementedError("oracle: NISQA_DE with AdaptCNN + self-attention + td_2 self-attention")
+    with torch.no_grad():
+        outs = []
+        for sp in (spec, spec_ref):
+            feats = adapt_cnn(sd, segments(sp, args), args)
+            outs.append(self_attention(sd, feats, pos_enc=bool(args.get("td_sa_pos_enc"))))
+        x, y = outs
+        y_al = de_align(args, x, y)
+        if taps is not None: taps["de_x"], taps["de_y"], taps["de_y_aligned"] = x, y, y_al
+        fused = de_fuse(args, x, y_al)
+        sd2 = {k.replace("time_dependency_2.", "time_dependency."): v for k, v in sd.items() if k.startswith("time_dependency_2.")}
+        td2 = self_attention(sd2, fused, pos_enc=bool(args.get("td_2_sa_pos_enc")))
+        if taps is not None: taps["td2_out"] = td2
+        pf = "pool.model."
+        if args["pool"] == "att":
+            out = pool_attff(sd, pf, td2) if args.get("pool_att_h") else pool_att(sd, pf, td2)
+        elif args["pool"] in ("avg", "max", "last_step"):
+            out = {"avg": pool_avg, "max": pool_max, "last_step": pool_last_step}[args["pool"]](sd, pf, td2)
+        else:
+            raise NotImplementedError(args["pool"])
+    return out.numpy()
+
+
+def predict_pcm_de(args, sd, y_deg, sr_deg, y_ref, sr_ref, taps=None):
+    """(degraded, reference) float32 mono samples -> (score [1], (n_seg_deg, n_seg_ref), status) - lib:2132-2214 +
+    lib:1420-1439 for one double-ended row."""
+    y_deg = np.ascontiguousarray(y_deg, dtype=np.float32)
+    y_ref = np.ascontiguousarray(y_ref, dtype=np.float32)
+    _, n1, st1 = segment_counts(y_deg.shape[0], sr_deg, args)
+    _, n2, st2 = segment_counts(y_ref.shape[0], sr_ref, args)
+    if st1 != STATUS_OK or st2 != STATUS_OK:
+        return np.full(1, np.nan, dtype=np.float32), (n1, n2), (st1 if st1 != STATUS_OK else st2)
+    score = forward_de_from_mel(args, sd, mel_db(y_deg, sr_deg, args), mel_db(y_ref, sr_ref, args), taps)
+    return score.astype(np.float32), (n1, n2), STATUS_OK
+
+
 # ---------------------------------------------------------------------- pooling (a13/a17)
 def pool_attff(sd, prefix, x):
     """lib:1171-1183 for one clip: att = W2 relu(W1 x + b1) + b2; softmax over time;

@@ -23,6 +23,67 @@ VARIANTS = {
     "tts_pool_max": ("nisqa_tts.tar", {"pool": "max"}),
     "tts_pool_last_step": ("nisqa_tts.tar", {"pool": "last_step"}),
 }
+# double-ended variants (NISQA_DE, reference lib:272-424): nisqa_mos_only.tar's CNN, first self-attention stack and
+# PoolAttFF head (identical shapes) + seeded weights for time_dependency_2 (input width 192 or 128)
+DE_VARIANTS = {
+    "de_cosine_hard": {"de_align": "cosine", "de_align_apply": "hard", "de_fuse": "x/y/-"},        # config/train_nisqa_double_ended.yaml
+    "de_dot_soft": {"de_align": "dot", "de_align_apply": "soft", "de_fuse": "+/-"},
+    "de_distance_soft_xy": {"de_align": "distance", "de_align_apply": "soft", "de_fuse": "x/y", "td_2_sa_pos_enc": True,
+                            "td_2_sa_num_layers": 1},
+    "de_dot_hard": {"de_align": "dot", "de_align_apply": "hard", "de_fuse": "x/y"},
+}
+# (degraded, reference) pairs: (seed, seconds, sample rate) each; the degraded signal of pair 0 / 1 is derived from its
+# reference (delay + noise + clipping: what a double-ended model is for), pair 2 has unrelated signals of other lengths
+DE_PAIRS = [((81, 2.4, 48000), (81, 2.4, 48000)), ((82, 1.3, 16000), (82, 1.5, 16000)), ((83, 3.1, 44100), (84, 2.0, 48000))]
+
+
+def de_pair_pcm(pair):
+    """-> (deg int16, sr_deg, ref int16, sr_ref) of one DE_PAIRS entry."""
+    from nisqa_b200 import synth
+    (sd_, secd, srd), (sr_, secr, srr) = pair
+    ref = synth.synth_speech_pcm16(sr_, secr, srr)
+    if sd_ == sr_ and srd == srr:
+        rng = np.random.default_rng(1000 + sd_)
+        n = int(secd * srd)
+        x = np.roll(ref.astype(np.float32), int(0.013 * srd))[:n] if n <= len(ref) else np.resize(ref.astype(np.float32), n)
+        x = x * 1.6 + rng.standard_normal(n).astype(np.float32) * 250.0
+        deg = np.clip(x, -9000, 9000).astype(np.int16)
+    else:
+        deg = synth.synth_speech_pcm16(sd_, secd, srd)
+    return deg, srd, ref, srr
+
+
+def de_checkpoint(name, base_args, base_sd):
+    """-> (args, state_dict) of a double-ended variant built on nisqa_mos_only.tar."""
+    over = DE_VARIANTS[name]
+    args = dict(base_args)
+    args.update({"model": "NISQA_DE", "td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_pos_enc": None,
+                 "td_2_sa_num_layers": 2, "td_2_sa_h": 64, "td_2_sa_dropout": 0.1, "td_2_lstm_h": None,
+                 "td_2_lstm_num_layers": None, "td_2_lstm_dropout": None, "td_2_lstm_bidirectional": None,
+                 "de_fuse_dim": None})
+    args.update(over)
+    sd = {k: v for k, v in base_sd.items()}
+    fdim = 192 if args["de_fuse"] == "x/y/-" else 128
+    rng = np.random.default_rng(sum(map(ord, name)))
+
+    def put(key, shape, scale, offset=0.0):
+        sd["time_dependency_2.model." + key] = torch.from_numpy((rng.standard_normal(shape) * scale + offset).astype(np.float32))
+
+    put("linear.weight", (64, fdim), 1.0 / math.sqrt(fdim)); put("linear.bias", (64,), 0.05)
+    put("norm1.weight", (64,), 0.05, 1.0); put("norm1.bias", (64,), 0.05)
+    for l in range(args["td_2_sa_num_layers"]):
+        q = "layers.%d." % l
+        put(q + "self_attn.in_proj_weight", (192, 64), 0.125); put(q + "self_attn.in_proj_bias", (192,), 0.05)
+        put(q + "self_attn.out_proj.weight", (64, 64), 0.125); put(q + "self_attn.out_proj.bias", (64,), 0.05)
+        put(q + "linear1.weight", (64, 64), 0.125); put(q + "linear1.bias", (64,), 0.05)
+        put(q + "linear2.weight", (64, 64), 0.125); put(q + "linear2.bias", (64,), 0.05)
+        put(q + "norm1.weight", (64,), 0.05, 1.0); put(q + "norm1.bias", (64,), 0.05)
+        put(q + "norm2.weight", (64,), 0.05, 1.0); put(q + "norm2.bias", (64,), 0.05)
+    if args.get("td_2_sa_pos_enc"):
+        sd["time_dependency_2.model.pos_encoder.pe"] = positional_encoding()
+    return args, sd
+
+
 # clips every variant is scored on: (seed, seconds, sample rate)
 CLIPS = [(71, 2.0, 48000), (72, 0.9, 16000), (73, 3.7, 44100)]
 

@@ -34,15 +34,17 @@ def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "nisqa_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nisqa_config), offsetof(nisqa_config, hop_s),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nisqa_config), offsetof(nisqa_config, hop_s),'
         ' offsetof(nisqa_config, fmax), offsetof(nisqa_config, max_chunk_segments), sizeof(nisqa_tensor),'
-        ' offsetof(nisqa_tensor, ndim), offsetof(nisqa_tensor, dims));return 0;}\n')
+        ' offsetof(nisqa_tensor, ndim), offsetof(nisqa_tensor, dims), offsetof(nisqa_config, double_ended),'
+        ' offsetof(nisqa_config, td2_pos_enc));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     got = [ctypes.sizeof(E.NisqaConfig), E.NisqaConfig.hop_s.offset, E.NisqaConfig.fmax.offset,
            E.NisqaConfig.max_chunk_segments.offset, ctypes.sizeof(E.NisqaTensor),
-           E.NisqaTensor.ndim.offset, E.NisqaTensor.dims.offset]
+           E.NisqaTensor.ndim.offset, E.NisqaTensor.dims.offset, E.NisqaConfig.double_ended.offset,
+           E.NisqaConfig.td2_pos_enc.offset]
     assert [int(x) for x in out] == got
 
 

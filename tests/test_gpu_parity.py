@@ -355,6 +355,65 @@ def test_architecture_variants(built_lib):
         eng.close()
 
 
+def test_double_ended_model(built_lib, tmp_path):
+    """NISQA_DE through the C-ABI (clips in (degraded, reference) pairs) against the scores of the
+    unmodified reference model (tests/golden/variants_de.npz) and the oracle; pair alone == pair in the batch; a
+    too-short reference makes the pair NaN with the status on the right clip; and the product surface:
+    nisqaModel(mode='predict_csv', csv_ref=...) on a checkpoint file."""
+    import pandas as pd
+    import torch
+    from oracle import variants as V
+    from nisqa_b200 import wav
+    from nisqa_b200.NISQA_model import nisqaModel
+    g = np.load(os.path.join(GOLDEN, "variants_de.npz"))
+    bargs, bsd = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa_mos_only.tar"))
+    pairs = [V.de_pair_pcm(p) for p in V.DE_PAIRS]
+    clips, srs = [], []
+    for deg, srd, ref, srr in pairs:
+        clips += [deg, ref]; srs += [srd, srr]
+    for name in V.DE_VARIANTS:
+        args, sd = V.de_checkpoint(name, bargs, bsd)
+        eng = E.Engine(E.config_from_args(args), 0)
+        eng.load_state_dict(sd)
+        scores, nseg, status = eng.predict_pcm(clips, srs)
+        assert np.all(status == E.CLIP_OK), name
+        assert np.all(np.isnan(scores[1::2])), name                       # reference rows carry no score
+        got = scores[0::2, 0]
+        # hard alignment picks ONE reference step per degraded step: a near-tie decided differently moves the score by
+        # more than rounding, so the hard variants get a looser bound than the soft ones (same budget as everywhere)
+        tol = SCORE_TOL if args["de_align_apply"] == "soft" else 5 * SCORE_TOL
+        assert np.abs(got - g[name][:, 0]).max() <= tol, (name, got, g[name][:, 0])
+        for i, (deg, srd, ref, srr) in enumerate(pairs):
+            sc, ns, st = O.predict_pcm_de(args, sd, _f32(deg), srd, _f32(ref), srr)
+            assert (nseg[2 * i], nseg[2 * i + 1]) == ns and abs(got[i] - sc[0]) <= tol, (name, i)
+        alone, _, _ = eng.predict_pcm(clips[2:4], srs[2:4])
+        np.testing.assert_array_equal(alone[0], scores[2])
+        short = np.zeros(100, np.int16)
+        s2, _, st2 = eng.predict_pcm([clips[0], short, clips[2], clips[3]], [srs[0], 48000, srs[2], srs[3]])
+        assert st2[1] == E.CLIP_TOO_SHORT and st2[0] == E.CLIP_OK and np.isnan(s2[0, 0])
+        np.testing.assert_array_equal(s2[2], scores[2])
+        with pytest.raises(E.EngineError):
+            eng.predict_pcm(clips[:3], srs[:3])                            # odd number of clips
+        eng.close()
+    # product surface
+    name = "de_cosine_hard"
+    args, sd = V.de_checkpoint(name, bargs, bsd)
+    rows = []
+    for i, (deg, srd, ref, srr) in enumerate(pairs):
+        wav.write_wav_pcm16(str(tmp_path / ("deg%d.wav" % i)), deg, srd)
+        wav.write_wav_pcm16(str(tmp_path / ("ref%d.wav" % i)), ref, srr)
+        rows.append(("deg%d.wav" % i, "ref%d.wav" % i))
+    pd.DataFrame(rows, columns=["deg", "ref"]).to_csv(tmp_path / "files.csv", index=False)
+    torch.save({"args": args, "model_state_dict": sd}, tmp_path / "de.tar")
+    m = nisqaModel({"mode": "predict_csv", "pretrained_model": str(tmp_path / "de.tar"), "csv_file": "files.csv",
+                    "csv_deg": "deg", "csv_ref": "ref", "data_dir": str(tmp_path), "output_dir": None, "ms_channel": None,
+                    "tr_bs_val": 2, "tr_num_workers": 0})
+    df = m.predict()
+    assert df["mos_pred"].dtype == np.float64
+    assert np.abs(df["mos_pred"].to_numpy() - g[name][:, 0]).max() <= 5 * SCORE_TOL
+    m.model.close()
+
+
 def test_device_resident_entry_point_equals_host_entry_point(engines):
     import torch
     eng, args, sd = engines["nisqa.tar"]

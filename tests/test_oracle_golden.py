@@ -54,6 +54,24 @@ def test_oracle_matches_reference_modules_on_the_variants():
             np.testing.assert_allclose(sc, g[name][i], rtol=0, atol=5e-6, err_msg=name)
 
 
+def test_oracle_matches_reference_double_ended_model():
+    """NISQA_DE (lib:272-424) - alignment (dot / cosine / distance, hard / soft), fusion (three modes),
+    second self-attention stack (with and without positional encoding).  tests/golden/variants_de.npz holds the scores
+    of the UNMODIFIED reference NISQA_DE run through nisqaModel(mode='predict_csv', csv_ref=...) in padded batches of
+    two pairs (oracle/make_variant_golden.py); the oracle restates one pair at a time."""
+    from oracle import variants as V
+    g = np.load(os.path.join(GOLDEN, "variants_de.npz"))
+    assert sorted(g.files) == sorted(V.DE_VARIANTS)
+    bargs, bsd = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa_mos_only.tar"))
+    for name in V.DE_VARIANTS:
+        args, sd = V.de_checkpoint(name, bargs, bsd)
+        for i, pair in enumerate(V.DE_PAIRS):
+            deg, srd, ref, srr = V.de_pair_pcm(pair)
+            sc, _, st = O.predict_pcm_de(args, sd, deg.astype(np.float32) / 32768.0, srd, ref.astype(np.float32) / 32768.0, srr)
+            assert st == O.STATUS_OK
+            np.testing.assert_allclose(sc, g[name][i], rtol=0, atol=5e-6, err_msg=name)
+
+
 def test_reference_results_do_not_depend_on_batch_composition():
     """the per-clip (unpadded) oracle is equivalent to the padded batches."""
     g = np.load(os.path.join(GOLDEN, "nisqa_mixed.npz"))
