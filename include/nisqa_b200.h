@@ -111,7 +111,8 @@ typedef struct nisqa_config {
   int32_t de_align;      /* enum nisqa_de_align */
   int32_t de_align_apply;/* enum nisqa_de_apply */
   int32_t de_fuse;       /* enum nisqa_de_fuse (de_fuse_dim must be None) */
-  int32_t td2_layers;    /* td_2 = 'self_att' (d_model 64, one head, h 64): number of layers, >= 1 */
+  int32_t td2_layers;    /* td_2 = 'self_att' (d_model 64, one head, h 64): number of layers; 0 = td_2 'skip'.  NISQA_DE needs >= 1;
+                          * NISQA / NISQA_DIM run it as a second stack behind the first (lib:114-141, 236-268) */
   int32_t td2_pos_enc;   /* td_2_sa_pos_enc */
 } nisqa_config;
 
@@ -229,6 +230,20 @@ NISQA_API int     nisqa_resample_set_filter(const double* half_window, int64_t n
 NISQA_API int64_t nisqa_resample_out_len(int64_t n, int32_t sr_orig, int32_t sr_new);
 NISQA_API int64_t nisqa_resample_f32(const float* x, int64_t n, int32_t sr_orig, int32_t sr_new, float* y,
                                      int64_t cap);
+
+/* The same conversion ON THE DEVICE (csrc/resample_gpu.cu; bit-identical to nisqa_resample_f32: float64 weights, the
+ * float32 accumulator rounded after every addition, resampy's sequential time register reproduced per clip).
+ * nisqa_resample_device converts one host clip (S16 samples are scaled by 1/32768 first, like the ingest) and copies the
+ * result back - the parity hook; returns the number of samples written or a negative status.
+ * nisqa_predict_pcm_resampled is nisqa_predict_pcm for checkpoints with ms_sr != None: every clip is converted to
+ * target_sr on the device (clips already at target_sr are only copied) and the predict path runs on the converted PCM
+ * where it lies, in HBM (reference lib:2300-2304 followed by the rest of get_librosa_melspec). */
+NISQA_API int     nisqa_resample_device(nisqa_engine* e, const void* x, int64_t n, int sample_fmt, int32_t sr_orig,
+                                        int32_t sr_new, float* y, int64_t cap);
+NISQA_API int     nisqa_predict_pcm_resampled(nisqa_engine* e, int n_clips, const void* const* pcm,
+                                              const int64_t* n_samples, const int32_t* sample_rate, int sample_fmt,
+                                              int32_t target_sr, float* scores_out, int32_t* n_segments_out,
+                                              int32_t* status_out);
 
 /* bookkeeping for bench.py */
 NISQA_API int64_t nisqa_kernel_launches(const nisqa_engine* e);   /* total kernels launched so far      */

@@ -125,8 +125,8 @@ def _load_batch(ds, batch, pool, slot, n_threads):
     paths = [ds.file_path(int(i)) for i in batch]
     sr, nf, kind, arr = probe_batch(paths, ds.ms_channel, n_threads)
     target = ds.target_sr()
-    if target is not None and bool((sr != target).any()):
-        return _load_batch_resampled(ds, paths, sr, nf, target, pool, slot, n_threads)
+    if target is not None and bool((sr != target).any()) and os.environ.get("NISQA_RESAMPLE", "device") == "host":
+        return _load_batch_resampled(ds, paths, sr, nf, target, pool, slot, n_threads)     # host threads (A/B, tests)
     dtype = np.int16 if not kind.any() else np.float32
     offs = np.zeros(len(paths), np.int64)
     if len(paths) > 1:
@@ -236,7 +236,14 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
             pos = 0
             for b, batch in enumerate(batches):
                 clips, srs = pending.pop(0).result()
-                handle = engine.submit_pcm(clips, srs)          # asynchronous: H2D + kernels enqueued
+                target = ds.target_sr()
+                if target is not None and not de and any(sr != target for sr in srs):
+                    # ms_sr checkpoint (lib:2300-2304): the clips travel at their native rates and are converted on
+                    # the device (csrc/resample_gpu.cu), where the predict path picks them up - one synchronous call
+                    handle = (None,) + tuple(engine.predict_pcm_resampled(clips, srs, target))
+                    srs = [target] * len(srs)
+                else:
+                    handle = engine.submit_pcm(clips, srs)      # asynchronous: H2D + kernels enqueued
                 in_flight.append((handle, batch, clips, srs, pos))
                 pos += len(batch)
                 if len(in_flight) >= FLIGHT:

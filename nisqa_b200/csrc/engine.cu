@@ -60,6 +60,9 @@ void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmPar
 void launch_lstm_batched(cudaStream_t, const float*, const ClipDesc*, const int*, int, const LstmParams&, float*, float*, float, float*);
 void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
 // td_tiled.cu
+struct ResampleClip { long long in_off, out_off, time_off; int n_in, n_out, n_fix, copy; double ratio; };
+void launch_resample(cudaStream_t, const void*, int, const ResampleClip*, int, int, double*, const double*, int, int, float*);
+bool resample_table(std::vector<double>*, int*);
 void launch_de_align(cudaStream_t, const float*, const ClipDesc*, int, const int*, int, int, int, int, float*, int, float*);
 void launch_de_finalize(cudaStream_t, const ClipDesc*, int, int, float*);
 void launch_td_in(cudaStream_t, const float*, const float*, int, const float*, const float*, const float*,
@@ -204,6 +207,9 @@ struct nisqa_engine {
 
   // weights arena (device) + offsets
   DevBuf warena;
+  DevBuf rs_raw, rs_out, rs_clips, rs_times, rs_win;   // device resampler of the ingest (resample_gpu.cu)
+  HostBuf rs_host;
+  int rs_nwin = 0, rs_num_table = 0;
   std::map<std::string, size_t> woff;   // float offsets into warena
   float pool_bias_std = 0.f;
   float tc_scale[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // 2^-S of the fp16 weight pre-scale, per conv layer
@@ -240,7 +246,8 @@ struct nisqa_engine {
 
   ~nisqa_engine() {
     for (auto* f : fbs) { f->window.release(); f->band_start.release(); f->band_k0.release(); f->weights.release(); f->wtab.release(); delete f; }
-    DevBuf* all[] = {&warena, &fb_table, &tw4096, &scores, &dump};
+    DevBuf* all[] = {&warena, &fb_table, &tw4096, &scores, &dump, &rs_raw, &rs_out, &rs_clips, &rs_times, &rs_win};
+    rs_host.release();
     for (auto* b : all) b->release();
     h_scores.release();
     for (auto& tk : tickets) { tk.pinned.release(); tk.scores.release(); if (tk.done) cudaEventDestroy(tk.done); }
@@ -581,9 +588,11 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       return 0;
     };
     if (!pack_sa_stack(td, "", 384, e->cfg.sa_layers, true)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
-    if (e->cfg.double_ended) {
+    if (e->cfg.double_ended || e->cfg.td2_layers > 0) {
+      // time_dependency_2: behind the fusion of the double-ended model (input 192 / 128), or a second stack behind the
+      // first one in NISQA / NISQA_DIM (lib:114-141, 236-268; input 64)
       const std::string td2 = "time_dependency_2.model.";
-      const int fdim = e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128;
+      const int fdim = !e->cfg.double_ended ? 64 : (e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128);
       if (!pack_sa_stack(td2, "2", fdim, e->cfg.td2_layers, false)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
       if (e->cfg.td2_pos_enc) { int rc = pack_pos_enc(td2, "pe2"); if (rc) return rc; }
     }
@@ -914,7 +923,12 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         }
         return cur2;
       };
-      cur = sa_stack("", LN.feats.as<float>(), 6, c.sa_layers, c.pos_enc != 0, !de, LN.tdout.as<float>());
+      const bool td2_single = !de && c.td2_layers > 0;      // NISQA / NISQA_DIM with td_2 = 'self_att'
+      cur = sa_stack("", LN.feats.as<float>(), 6, c.sa_layers, c.pos_enc != 0, !de && !td2_single, LN.tdout.as<float>());
+      if (td2_single) {
+        CK(LN.td2in.reserve((size_t)n_seg * 64 * 4));
+        cur = sa_stack("2", cur, 1, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
+      }
       if (de) {
         // NISQA_DE (lib:404-424): align the reference clip's rows to the degraded clip's, fuse, second time-dependency stack
         const int nf = c.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 3 : 2;
@@ -1101,6 +1115,8 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
       (cfg->arch == NISQA_ARCH_STD_LSTM_LASTBI && (cfg->pool == NISQA_POOL_ATT_FF || cfg->pool == NISQA_POOL_ATT)))
     return fail(e, NISQA_ERR_INVALID, "pooling module not available for this architecture");
   if (cfg->pos_enc && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) return fail(e, NISQA_ERR_INVALID, "pos_enc needs the self-attention architecture");
+  if (cfg->td2_layers < 0 || cfg->td2_layers > 8 || (cfg->td2_layers > 0 && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF))
+    return fail(e, NISQA_ERR_INVALID, "td_2 = 'self_att' needs the self-attention architecture (td2_layers 0..8)");
   if (cfg->double_ended) {
     if (cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF || cfg->n_out != 1)
       return fail(e, NISQA_ERR_INVALID, "NISQA_DE: AdaptCNN + self-attention, one output");
@@ -1219,6 +1235,91 @@ int nisqa_predict_pcm_device(nisqa_engine* e, int n_clips, const void* pcm_dev, 
   if (n_clips > 0 && (!pcm_dev || !pcm_offsets || !scores_dev)) return fail(e, NISQA_ERR_INVALID, "null argument");
   return predict_common(e, n_clips, nullptr, pcm_dev, pcm_offsets, n_samples, sample_rate, sample_fmt,
                         nullptr, scores_dev, n_segments_out, status_out, sync);
+}
+
+
+// ---- device resampler of the ingest: host clips at their own rates -> packed float32 PCM at
+// `target` Hz in e->rs_out (clip i at element offset offs[i], n_fix[i] samples), on lane 0's stream (synchronised).
+static int resample_to_device(nisqa_engine* e, int n_clips, const void* const* pcm, const int64_t* n_samples,
+                              const int32_t* sample_rate, int fmt, int32_t target, std::vector<int64_t>* offs,
+                              std::vector<int64_t>* n_fix) {
+  if (fmt != NISQA_FMT_S16 && fmt != NISQA_FMT_F32) return fail(e, NISQA_ERR_INVALID, "sample_fmt");
+  if (target <= 0) return fail(e, NISQA_ERR_INVALID, "target sample rate");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = e->lanes[0].stream;
+  if (!e->rs_nwin) {
+    std::vector<double> win;
+    int num_table = 0;
+    if (!resample_table(&win, &num_table))
+      return fail(e, NISQA_ERR_STATE, "nisqa_resample_set_filter has not been called (the interpolation table)");
+    CK(e->rs_win.reserve(win.size() * 8));
+    CK(cudaMemcpy(e->rs_win.p, win.data(), win.size() * 8, cudaMemcpyHostToDevice));
+    e->rs_nwin = (int)win.size(); e->rs_num_table = num_table;
+  }
+  const size_t esz = fmt == NISQA_FMT_F32 ? 4 : 2;
+  std::vector<ResampleClip> rc(n_clips);
+  offs->assign(n_clips, 0); n_fix->assign(n_clips, 0);
+  long long in_elems = 0, out_elems = 0, t_entries = 0;
+  int max_fix = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    if (n_samples[i] < 0 || n_samples[i] > (int64_t)INT32_MAX / 4 || sample_rate[i] <= 0)
+      return fail(e, NISQA_ERR_INVALID, "resample: clip length / sample rate");
+    ResampleClip& c = rc[i];
+    c.n_in = (int)n_samples[i];
+    c.copy = sample_rate[i] == target;
+    c.ratio = (double)target / (double)sample_rate[i];
+    c.n_out = c.copy ? c.n_in : (int)((double)c.n_in * c.ratio);                      // resampy: int(shape * ratio)
+    c.n_fix = c.copy ? c.n_in : (int)ceil((double)c.n_in * c.ratio);                  // librosa fix_length
+    if (!c.copy && c.n_out < 1) return fail(e, NISQA_ERR_INVALID, "resample: signal too short for the target rate");
+    c.in_off = in_elems; in_elems += ((long long)c.n_in + 15) / 16 * 16;
+    c.out_off = out_elems; out_elems += ((long long)c.n_fix + 15) / 16 * 16;
+    c.time_off = t_entries; t_entries += (c.n_fix + 255) / 256 + 1;
+    (*offs)[i] = c.out_off; (*n_fix)[i] = c.n_fix;
+    max_fix = std::max(max_fix, c.n_fix);
+  }
+  if (n_clips == 0) return 0;
+  CK(e->rs_raw.reserve((size_t)std::max<long long>(in_elems, 16) * esz));
+  CK(e->rs_out.reserve((size_t)std::max<long long>(out_elems, 16) * 4));
+  CK(e->rs_times.reserve((size_t)t_entries * 8));
+  CK(e->rs_clips.reserve(rc.size() * sizeof(ResampleClip)));
+  CK(e->rs_host.reserve(rc.size() * sizeof(ResampleClip)));
+  memcpy(e->rs_host.p, rc.data(), rc.size() * sizeof(ResampleClip));
+  CK(cudaMemcpyAsync(e->rs_clips.p, e->rs_host.p, rc.size() * sizeof(ResampleClip), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < n_clips; ++i)
+    if (rc[i].n_in > 0)
+      CK(cudaMemcpyAsync(e->rs_raw.as<char>() + (size_t)rc[i].in_off * esz, pcm[i], (size_t)rc[i].n_in * esz, cudaMemcpyHostToDevice, st));
+  e->launches += 2;
+  launch_resample(st, e->rs_raw.p, fmt == NISQA_FMT_F32, e->rs_clips.as<ResampleClip>(), n_clips, max_fix, e->rs_times.as<double>(),
+                  e->rs_win.as<double>(), e->rs_nwin, e->rs_num_table, e->rs_out.as<float>());
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nisqa_resample_device(nisqa_engine* e, const void* x, int64_t n, int sample_fmt, int32_t sr_orig, int32_t sr_new,
+                          float* y, int64_t cap) {
+  if (!e || !x || !y) return NISQA_ERR_INVALID;
+  std::vector<int64_t> offs, n_fix;
+  const void* ptrs[1] = {x};
+  int rc = resample_to_device(e, 1, ptrs, &n, &sr_orig, sample_fmt, sr_new, &offs, &n_fix);
+  if (rc) return rc;
+  if (n_fix[0] > cap) return fail(e, NISQA_ERR_INVALID, "resample: output buffer too small");
+  CK(cudaMemcpy(y, e->rs_out.as<float>() + offs[0], (size_t)n_fix[0] * 4, cudaMemcpyDeviceToHost));
+  return (int)n_fix[0];
+}
+
+int nisqa_predict_pcm_resampled(nisqa_engine* e, int n_clips, const void* const* pcm, const int64_t* n_samples,
+                                const int32_t* sample_rate, int sample_fmt, int32_t target_sr,
+                                float* scores_out, int32_t* n_segments_out, int32_t* status_out) {
+  if (!e) return NISQA_ERR_INVALID;
+  if (n_clips > 0 && (!pcm || !n_samples || !sample_rate || !scores_out)) return fail(e, NISQA_ERR_INVALID, "null argument");
+  std::vector<int64_t> offs, n_fix;
+  int rc = resample_to_device(e, n_clips, pcm, n_samples, sample_rate, sample_fmt, target_sr, &offs, &n_fix);
+  if (rc) return rc;
+  std::vector<int32_t> srs(n_clips, target_sr);
+  // the converted clips are ordinary float32 PCM resident in HBM: the device entry of the predict path takes over
+  return predict_common(e, n_clips, nullptr, e->rs_out.p, offs.data(), n_fix.data(), srs.data(), NISQA_FMT_F32,
+                        scores_out, nullptr, n_segments_out, status_out, 1);
 }
 
 int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {

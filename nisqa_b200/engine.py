@@ -35,6 +35,7 @@ EXPORTS = [
     "nisqa_submit_pcm", "nisqa_wait", "nisqa_drain", "nisqa_join", "nisqa_set_gather_target",
     "nisqa_wav_probe", "nisqa_wav_decode", "nisqa_wav_probe_batch", "nisqa_wav_decode_batch",
     "nisqa_resample_set_filter", "nisqa_resample_out_len", "nisqa_resample_f32",
+    "nisqa_resample_device", "nisqa_predict_pcm_resampled",
 ]
 
 
@@ -99,6 +100,10 @@ def load_library(path=None):
     lib.nisqa_resample_out_len.restype = C.c_int64
     lib.nisqa_resample_f32.argtypes = [f32p, C.c_int64, C.c_int32, C.c_int32, f32p, C.c_int64]
     lib.nisqa_resample_f32.restype = C.c_int64
+    lib.nisqa_resample_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int32, C.c_int32, f32p, C.c_int64]
+    lib.nisqa_resample_device.restype = C.c_int
+    lib.nisqa_predict_pcm_resampled.argtypes = [vp, C.c_int, C.POINTER(vp), i64p, i32p, C.c_int, C.c_int32, f32p, i32p, i32p]
+    lib.nisqa_predict_pcm_resampled.restype = C.c_int
     lib.nisqa_set_gather_target.argtypes = [vp, vp, C.c_int]
     lib.nisqa_set_gather_target.restype = C.c_int
     lib.nisqa_join.argtypes = [vp]
@@ -181,6 +186,10 @@ def config_from_args(args, max_chunk_segments=0):
             raise NotImplementedError("de_fuse_dim is not implemented by the B200 engine")
         ok = ok and args.get("td_2") == "self_att" and args.get("td_2_sa_d_model") == 64 and args.get("td_2_sa_nhead") == 1 \
             and args.get("td_2_sa_h") == 64
+    elif args.get("td_2") == "self_att":
+        # a second self-attention stack behind the first one (lib:114-141, 236-268)
+        ok = ok and arch == ARCH_ADAPT_SA_ATTFF and args.get("td_2_sa_d_model") == 64 and args.get("td_2_sa_nhead") == 1 \
+            and args.get("td_2_sa_h") == 64
     else:
         ok = ok and args.get("td_2") in (None, "skip")
     ok = ok and (args["cnn_c_out_1"], args["cnn_c_out_2"], args["cnn_c_out_3"]) == (16, 32, 64)
@@ -202,11 +211,12 @@ def config_from_args(args, max_chunk_segments=0):
     cfg.max_chunk_segments = int(max_chunk_segments) or int(os.environ.get("NISQA_MAX_CHUNK", "0"))
     cfg.pool = pool_mode
     cfg.pos_enc = 1 if (arch == ARCH_ADAPT_SA_ATTFF and args.get("td_sa_pos_enc")) else 0
+    if args.get("td_2") == "self_att":
+        cfg.td2_layers = int(args["td_2_sa_num_layers"])
+        cfg.td2_pos_enc = 1 if args.get("td_2_sa_pos_enc") else 0
     if de:
         cfg.double_ended = 1
         cfg.de_align, cfg.de_align_apply, cfg.de_fuse = DE_ALIGN[args["de_align"]], DE_APPLY[args["de_align_apply"]], DE_FUSE[args["de_fuse"]]
-        cfg.td2_layers = int(args["td_2_sa_num_layers"])
-        cfg.td2_pos_enc = 1 if args.get("td_2_sa_pos_enc") else 0
     return cfg
 
 
@@ -314,6 +324,49 @@ class Engine(object):
         self._check(rc, "nisqa_predict_pcm")
         return scores, nseg, status
 
+    def resample_device(self, x, sr_orig, sr_new):
+        """One int16 / float32 clip converted on the device (csrc/resample_gpu.cu) -> float32 at sr_new."""
+        from . import resample as _rs
+        n_out = _rs.out_len(x.shape[0], sr_orig, sr_new)              # (also sets the interpolation table once)
+        x = np.ascontiguousarray(x)
+        fmt = FMT_S16 if x.dtype == np.int16 else FMT_F32
+        if fmt == FMT_F32 and x.dtype != np.float32:
+            raise ValueError("clips must be int16 or float32")
+        y = np.empty(max(n_out, 1), dtype=np.float32)
+        got = self.lib.nisqa_resample_device(self.h, x.ctypes.data, x.shape[0], fmt, int(sr_orig), int(sr_new),
+                                             y.ctypes.data_as(C.POINTER(C.c_float)), y.shape[0])
+        if got < 0:
+            self._check(got, "nisqa_resample_device")
+        return y[:got]
+
+    def predict_pcm_resampled(self, clips, sample_rates, target_sr):
+        """predict_pcm for checkpoints with ``ms_sr``: clips at their own rates are converted to ``target_sr`` on the
+        device and scored there.  Synchronous.  Returns (scores, n_segments, status)."""
+        from . import resample as _rs
+        _rs.out_len(1, 1, 1)                                          # the interpolation table is set once
+        n = len(clips)
+        if n == 0:
+            return (np.zeros((0, self.n_out), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int32))
+        dt = clips[0].dtype
+        if any(c.dtype != dt for c in clips):
+            clips = [c if c.dtype == np.float32 else c.astype(np.float32) / np.float32(32768.0) for c in clips]
+            dt = np.dtype(np.float32)
+        if dt not in (np.dtype(np.int16), np.dtype(np.float32)):
+            raise ValueError("clips must be int16 or float32")
+        clips = [np.ascontiguousarray(c) for c in clips]
+        ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in clips])
+        ns = np.array([c.shape[0] for c in clips], dtype=np.int64)
+        sr = np.ascontiguousarray(sample_rates, dtype=np.int32)
+        scores = np.empty((n, self.n_out), dtype=np.float32)
+        nseg = np.empty(n, dtype=np.int32)
+        status = np.empty(n, dtype=np.int32)
+        rc = self.lib.nisqa_predict_pcm_resampled(
+            self.h, n, ptrs, ns.ctypes.data_as(C.POINTER(C.c_int64)), sr.ctypes.data_as(C.POINTER(C.c_int32)),
+            FMT_S16 if dt == np.int16 else FMT_F32, int(target_sr), scores.ctypes.data_as(C.POINTER(C.c_float)),
+            nseg.ctypes.data_as(C.POINTER(C.c_int32)), status.ctypes.data_as(C.POINTER(C.c_int32)))
+        self._check(rc, "nisqa_predict_pcm_resampled")
+        return scores, nseg, status
+
     def submit_pcm(self, clips, sample_rates):
         """Asynchronous predict_pcm: returns a handle; ``wait(handle)`` -> (scores, n_segments, status).
         Up to six submissions are in flight (H2D of the next batch overlaps this batch's kernels)."""
@@ -341,7 +394,8 @@ class Engine(object):
         return (ticket.value, scores, nseg, status, clips, ptrs, ns, sr)      # keeps the buffers alive
 
     def wait(self, handle):
-        self._check(self.lib.nisqa_wait(self.h, handle[0]), "nisqa_wait")
+        if handle[0] is not None:             # (None: a synchronous call's results wrapped as a handle)
+            self._check(self.lib.nisqa_wait(self.h, handle[0]), "nisqa_wait")
         return handle[1], handle[2], handle[3]
 
     def submit_pcm_ptrs(self, ptrs, n_samples, sample_rates, fmt, scores_out, nseg, status):

@@ -318,6 +318,12 @@ def forward_from_mel(args, sd, spec, taps=None):
             td = bilstm(sd, feats)
         else:
             raise NotImplementedError(args["td"])
+        if args.get("td_2") == "self_att":
+            # TimeDependency 2 (lib:114-141, 236-268): a second stack with the first one's output as its input
+            sd2 = {k.replace("time_dependency_2.", "time_dependency."): v for k, v in sd.items() if k.startswith("time_dependency_2.")}
+            td = self_attention(sd2, td, pos_enc=bool(args.get("td_2_sa_pos_enc")))
+        elif args.get("td_2") not in (None, "skip"):
+            raise NotImplementedError(args["td_2"])
         if taps is not None: taps["td_out"] = td
         if args["model"] == "NISQA_DIM":
             prefixes = ["pool_layers.%d.model." % i for i in range(5)]

@@ -22,6 +22,11 @@ VARIANTS = {
     "tts_pool_avg": ("nisqa_tts.tar", {"pool": "avg"}),
     "tts_pool_max": ("nisqa_tts.tar", {"pool": "max"}),
     "tts_pool_last_step": ("nisqa_tts.tar", {"pool": "last_step"}),
+    # td_2 = 'self_att': a second self-attention stack behind the first (lib:114-141, 236-268), seeded weights
+    "dim_td2_sa": ("nisqa.tar", {"td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_h": 64,
+                                 "td_2_sa_num_layers": 2, "td_2_sa_pos_enc": None, "td_2_sa_dropout": 0.1}),
+    "mos_td2_sa_pos_enc": ("nisqa_mos_only.tar", {"td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_h": 64,
+                                                  "td_2_sa_num_layers": 1, "td_2_sa_pos_enc": True, "td_2_sa_dropout": 0.1}),
 }
 # double-ended variants (NISQA_DE, reference lib:272-424): nisqa_mos_only.tar's CNN, first self-attention stack and
 # PoolAttFF head (identical shapes) + seeded weights for time_dependency_2 (input width 192 or 128)
@@ -53,23 +58,12 @@ def de_pair_pcm(pair):
     return deg, srd, ref, srr
 
 
-def de_checkpoint(name, base_args, base_sd):
-    """-> (args, state_dict) of a double-ended variant built on nisqa_mos_only.tar."""
-    over = DE_VARIANTS[name]
-    args = dict(base_args)
-    args.update({"model": "NISQA_DE", "td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_pos_enc": None,
-                 "td_2_sa_num_layers": 2, "td_2_sa_h": 64, "td_2_sa_dropout": 0.1, "td_2_lstm_h": None,
-                 "td_2_lstm_num_layers": None, "td_2_lstm_dropout": None, "td_2_lstm_bidirectional": None,
-                 "de_fuse_dim": None})
-    args.update(over)
-    sd = {k: v for k, v in base_sd.items()}
-    fdim = 192 if args["de_fuse"] == "x/y/-" else 128
-    rng = np.random.default_rng(sum(map(ord, name)))
-
+def td2_weights(sd, args, in_dim, rng):
+    """Seeded weights of a time_dependency_2 self-attention stack (input width in_dim) written into sd."""
     def put(key, shape, scale, offset=0.0):
         sd["time_dependency_2.model." + key] = torch.from_numpy((rng.standard_normal(shape) * scale + offset).astype(np.float32))
 
-    put("linear.weight", (64, fdim), 1.0 / math.sqrt(fdim)); put("linear.bias", (64,), 0.05)
+    put("linear.weight", (64, in_dim), 1.0 / math.sqrt(in_dim)); put("linear.bias", (64,), 0.05)
     put("norm1.weight", (64,), 0.05, 1.0); put("norm1.bias", (64,), 0.05)
     for l in range(args["td_2_sa_num_layers"]):
         q = "layers.%d." % l
@@ -81,6 +75,20 @@ def de_checkpoint(name, base_args, base_sd):
         put(q + "norm2.weight", (64,), 0.05, 1.0); put(q + "norm2.bias", (64,), 0.05)
     if args.get("td_2_sa_pos_enc"):
         sd["time_dependency_2.model.pos_encoder.pe"] = positional_encoding()
+
+
+def de_checkpoint(name, base_args, base_sd):
+    """-> (args, state_dict) of a double-ended variant built on nisqa_mos_only.tar."""
+    over = DE_VARIANTS[name]
+    args = dict(base_args)
+    args.update({"model": "NISQA_DE", "td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_pos_enc": None,
+                 "td_2_sa_num_layers": 2, "td_2_sa_h": 64, "td_2_sa_dropout": 0.1, "td_2_lstm_h": None,
+                 "td_2_lstm_num_layers": None, "td_2_lstm_dropout": None, "td_2_lstm_bidirectional": None,
+                 "de_fuse_dim": None})
+    args.update(over)
+    sd = {k: v for k, v in base_sd.items()}
+    fdim = 192 if args["de_fuse"] == "x/y/-" else 128
+    td2_weights(sd, args, fdim, np.random.default_rng(sum(map(ord, name))))
     return args, sd
 
 
@@ -122,4 +130,6 @@ def variant_checkpoint(name, base_args, base_sd):
                 lin("linear")
     if args.get("td_sa_pos_enc"):
         sd["time_dependency.model.pos_encoder.pe"] = positional_encoding()
+    if args.get("td_2") == "self_att":
+        td2_weights(sd, args, 64, np.random.default_rng(sum(map(ord, name))))
     return args, sd

@@ -521,6 +521,79 @@ def test_ms_sr_checkpoint_resamples_on_ingest(wav_dir, built_lib):
         assert np.abs(got - ref).max() <= SCORE_TOL, row["deg"]
 
 
+def test_device_resampler_is_bit_identical_to_the_host_resampler(engines, wav_dir, monkeypatch):
+    """csrc/resample_gpu.cu against csrc/resample.cpp (itself bit-identical to the oracle's restatement
+    of resampy 'kaiser_best', tests/test_resample.py): up- and down-sampling, rational and awkward ratios, PCM16 and
+    float input, lengths around the 256-sample chunks; then the product surface with the host path selected."""
+    from nisqa_b200 import resample as RS
+    from nisqa_b200.NISQA_model import nisqaModel
+    eng = engines["nisqa.tar"][0]
+    cases = [(48000, 16000, 1.3), (16000, 48000, 0.7), (44100, 48000, 1.0), (48000, 44100, 0.9), (8000, 22050, 0.5),
+             (32000, 32000, 0.4), (48000, 8000, 0.31), (22050, 16000, 0.77)]
+    for sr0, sr1, sec in cases:
+        x = synth.synth_speech_pcm16(900 + sr0 // 1000, sec, sr0)
+        for xin in (x, synth.synth_speech_f32(901 + sr1 // 1000, sec, sr0)[:len(x) - 3]):
+            host = RS.resample(xin, sr0, sr1)
+            dev = eng.resample_device(xin, sr0, sr1)
+            assert dev.shape == host.shape, (sr0, sr1)
+            np.testing.assert_array_equal(dev, host, err_msg="%d -> %d" % (sr0, sr1))
+    a = {"mode": "predict_dir", "pretrained_model": os.path.join(WEIGHTS, "nisqa.tar"), "data_dir": str(wav_dir),
+         "output_dir": None, "tr_bs_val": 3, "tr_num_workers": 2, "ms_sr": 16000}
+    dev = nisqaModel(dict(a)).predict().sort_values("deg")
+    monkeypatch.setenv("NISQA_RESAMPLE", "host")
+    host = nisqaModel(dict(a)).predict().sort_values("deg")
+    cols = ["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]
+    np.testing.assert_array_equal(dev[cols].to_numpy(), host[cols].to_numpy())
+
+
+def test_run_evaluate_end_to_end(tmp_path, built_lib, capsys):
+    """run_evaluate.py's flow (predict_csv on a labelled per-file table + per-condition table, then
+    evaluate()) on the GPU engine: the printed report and the statistics equal nisqa_b200.evaluate applied to the
+    ORACLE's scores of the same files (the statistics themselves are pinned to the reference's functions by
+    tests/golden/eval_golden.json, tests/test_evaluate.py)."""
+    import run_evaluate
+    from nisqa_b200 import evaluate as EV
+    from nisqa_b200.NISQA_model import nisqaModel
+    rng = np.random.default_rng(11)
+    args, sd = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa.tar"))
+    rows = []
+    for i in range(12):
+        seed, sec, sr = 700 + i, 1.0 + 0.2 * (i % 5), (48000, 16000, 32000)[i % 3]
+        pcm = synth.synth_speech_pcm16(seed, sec, sr)
+        if i % 4 == 3:
+            pcm = np.clip(pcm.astype(np.int32) * 6, -32768, 32767).astype(np.int16)      # a distorted condition
+        wav.write_wav_pcm16(str(tmp_path / ("e%02d.wav" % i)), pcm, sr)
+        ref = O.predict_pcm(args, sd, _f32(pcm), sr)[0]
+        rows.append(dict(deg="e%02d.wav" % i, db="db%d" % (i // 6), con=1 + (i % 6) // 2, oracle=ref,
+                         **{k: float(np.clip(v + rng.normal(0, 0.15), 1, 5)) for k, v in zip(("mos", "noi", "dis", "col", "loud"), ref)}))
+    dfile = pd.DataFrame(rows)
+    dcon = dfile.groupby(["db", "con"], as_index=False)[["mos", "noi", "dis", "col", "loud"]].mean()
+    for k in ("mos", "noi", "dis", "col", "loud"):
+        dcon[k + "_ci"] = 0.2
+    dfile.drop(columns=["oracle"]).to_csv(tmp_path / "file.csv", index=False)
+    dcon.to_csv(tmp_path / "con.csv", index=False)
+    a = run_evaluate.parse_args(["--pretrained_model", os.path.join(WEIGHTS, "nisqa.tar"), "--data_dir", str(tmp_path),
+                                 "--csv_file", "file.csv", "--csv_con", "con.csv", "--csv_deg", "deg", "--bs", "5", "--num_workers", "2"])
+    mapping = a.pop("mapping"); a.pop("plot")
+    m = nisqaModel(a)
+    df = m.predict()
+    capsys.readouterr()
+    m.evaluate(mapping=mapping, do_print=True, do_plot=False)
+    out = capsys.readouterr().out
+    assert "--> MOS:" in out and "--> LOUD:" in out and "Average over MOS and dimensions" in out
+    got = df[["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]].to_numpy()
+    want = np.stack(dfile["oracle"].to_numpy())
+    assert np.abs(got - want).max() <= SCORE_TOL
+    # the statistics of the engine's table == the statistics of the oracle's table (same labels) to the score tolerance
+    dref = dfile.drop(columns=["oracle"]).copy()
+    for j, k in enumerate(("mos", "noi", "dis", "col", "loud")):
+        dref[k + "_pred"] = want[:, j]
+    _, r_ref = EV.eval_results(dref, dcon=dcon, target_mos="mos", target_ci="mos_ci", pred="mos_pred", mapping="first_order")
+    for key in ("r_p_mean_file", "rmse_mean_file", "r_p_mean_con", "rmse_mean_con", "rmse_star_map_mean_con"):
+        assert abs(m.r[key] - r_ref[key]) <= 2e-3, (key, m.r[key], r_ref[key])
+    m.model.close()
+
+
 def test_reference_error_behaviour(tmp_path, built_lib):
     from nisqa_b200.NISQA_model import nisqaModel
     ck = os.path.join(WEIGHTS, "nisqa.tar")

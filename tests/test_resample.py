@@ -66,9 +66,12 @@ class _HostPool(object):                   # stands in for the pinned ring (torc
         return self.buf
 
 
-def test_loader_converts_to_ms_sr(tmp_path, built_lib):
+def test_loader_converts_to_ms_sr(tmp_path, built_lib, monkeypatch):
     """Dataset with ms_sr = 16000: files at 48 kHz (stereo, mono mix first), 8 kHz A-law and 16 kHz (untouched) come
-    out of the batch loader as float32 at 16 kHz, equal to the oracle's lb.load(path, sr=16000)."""
+    out of the batch loader as float32 at 16 kHz, equal to the oracle's lb.load(path, sr=16000).  (The host conversion
+    of the loader, NISQA_RESAMPLE=host; by default the clips travel at their own rates and are converted on the device,
+    tests/test_gpu_parity.py::test_device_resampler_is_bit_identical_to_the_host_resampler.)"""
+    monkeypatch.setenv("NISQA_RESAMPLE", "host")
     import pandas as pd
     import struct
     rng = np.random.default_rng(3)
