@@ -32,6 +32,24 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
+def shutdown(engine=None):
+    """Orderly end of a multi-rank run: barrier, close the engine (its NCCL communicator), destroy the process group.
+    A no-op for the parts that do not exist (single process, no engine)."""
+    rank, world, _ = env_world()
+    initialised = False
+    if world > 1:
+        import torch.distributed as dist
+        initialised = dist.is_initialized()
+        if initialised:
+            dist.barrier()
+    if engine is not None:
+        engine.close()
+    if initialised:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def shard_rows(weights, world):
     """Deterministic balanced partition of row indices over ranks.
 

@@ -59,4 +59,9 @@ if __name__ == "__main__":
     from nisqa_b200 import dist as nb_dist
     # the CLI process only feeds the GPU: keep it (and its pinned batch buffers) on the GPU's NUMA node
     nb_dist.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
-    nisqaModel(parse_args()).predict()
+    nisqa = nisqaModel(parse_args())
+    nisqa.predict()
+    # orderly exit under torchrun: every rank is past the score gather before any communicator goes away (the engine's
+    # NCCL communicator first, then torch.distributed's) - a rank that simply exits can leave its peers hanging in
+    # communicator teardown
+    nb_dist.shutdown(nisqa.model)

@@ -32,7 +32,7 @@ def _n_gpus():
         return 0
 
 
-def _run(cmd, timeout=900):
+def _run(cmd, timeout=150):       # (a hang must fail fast: GPU-box minutes are charged per GPU)
     env = dict(os.environ, PYTHONPATH=ROOT)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
     assert r.returncode == 0, (" ".join(cmd), r.stdout[-3000:], r.stderr[-3000:])
@@ -45,8 +45,9 @@ def test_predict_csv_sharded_equals_single_rank(tmp_path, built_lib):
     rng = np.random.default_rng(3)
     specs = []
     for i in range(64):                                  # mixed lengths and sample rates: uneven shards, ragged batches
+        # (short clips: the synthesiser runs on the host)
         sr = int(rng.choice([48000, 48000, 16000, 44100]))
-        specs.append((1200 + i, float(rng.uniform(1.0, 6.0)), sr))
+        specs.append((1200 + i, float(rng.uniform(0.6, 2.5)), sr))
     data = tmp_path / "data"
     data.mkdir()
     for seed, sec, sr in specs:
