@@ -59,13 +59,17 @@ class SpeechQualityDataset(object):
         self.ms_channel = ms_channel
         self.double_ended = bool(double_ended)
         self.filename_column_ref = filename_column_ref
+        self._paths = None
         self.dim = dim
 
     def __len__(self):
         return len(self.df)
 
     def file_path(self, index):
-        return os.path.join(self.data_dir, self.df[self.filename_column].iloc[index])
+        # (the column is read once: a pandas scalar lookup per file costs more than decoding a short clip)
+        if self._paths is None or len(self._paths) != len(self.df):
+            self._paths = [os.path.join(self.data_dir, f) for f in self.df[self.filename_column].tolist()]
+        return self._paths[index]
 
     def file_path_ref(self, index):
         """Reference signal of a double-ended row (lib:2132-2134)."""
