@@ -10,6 +10,7 @@
 //
 //   warps 0..7    epilogue: TMEM -> bias / ReLU -> staging -> max-pool -> fp16 hi / lo planes of pool2 (conv3's input)
 //   warps 8..15   producers: one thread per pooled cell (24 x 7 or 24 x 8; a warp owns three pooled rows), all 16 channels
+//                 (NISQA_C12_GROUPS = 2 splits the channels over two groups of eight warps: measured, no gain)
 //                 (conv1_cell.cuh, packed FFMA2).  Lanes run along the pooled columns: consecutive plane rows, so that
 //                 the 16-byte stores into the swizzled A image are bank-conflict free
 //   warp  16      loads conv2's weights (all nine taps stay resident: 18 KB) and stages every segment's 15 mel rows
@@ -45,9 +46,13 @@ struct C12Cfg {
   using C = typename std::conditional<MODE == 0, SpConv2A, SpConv2S>::type;
   static constexpr int PW = C::W;                       // pooled width of conv1's output = conv2's input width
   static constexpr int NCELL = 24 * PW;                 // producer threads with work
-  static constexpr int N_PROD_WARPS = 8;
+#ifndef NISQA_C12_GROUPS
+#define NISQA_C12_GROUPS 1      // producer warp groups: 2 = the 16 conv1 channels split over two groups of eight warps (measured: no gain, profiles/r02v_ab_kernels.txt)
+#endif
+  static constexpr int N_GROUPS = NISQA_C12_GROUPS;     // each group computes 16 / N_GROUPS channels of every cell
+  static constexpr int N_PROD_WARPS = 8 * N_GROUPS;
   static constexpr int CPW = 3 * PW;                    // cells per producer warp: three pooled rows
-  static_assert(CPW <= 32 && N_PROD_WARPS * CPW == NCELL, "a warp owns three pooled rows");
+  static_assert(CPW <= 32 && 8 * CPW == NCELL && (N_GROUPS == 1 || N_GROUPS == 2), "a warp owns three pooled rows");
   static constexpr int NT = (8 + N_PROD_WARPS + 1 + 2) * 32;
   static constexpr int W_PROD0 = 8, W_LOAD = 8 + N_PROD_WARPS, W_MMA0 = W_LOAD + 1;
   static constexpr int NA = 3;                          // A buffers (hi + lo tile each)
@@ -119,36 +124,39 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
 
   if (warp >= K::W_PROD0 && warp < K::W_LOAD) {
     // ===== producers: conv1 + pool1 of tile `it` into A buffer it % NA =====
-    const int cell = (warp - K::W_PROD0) * K::CPW + lane;
+    const int grp = (warp - K::W_PROD0) >> 3;                 // channel group: channels 8 grp .. 8 grp + 7 when N_GROUPS == 2
+    const int cell = ((warp - K::W_PROD0) & 7) * K::CPW + lane;
     const bool has_cell = lane < K::CPW;
     const int ph = cell / K::PW, pw = cell - ph * K::PW;      // lanes run along the pooled columns: consecutive plane rows
     const uint32_t row = (uint32_t)(HALO + (ph + 1) * P + (pw + 1));   // plane row q of the cell sits at tile row HALO + q
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it % NA, use = it / NA, ms = it % K::NM;
-      float res[16];
+      constexpr int NCQ = 4 / K::N_GROUPS;
+      float res[4 * NCQ];
       long long tw = C12_NOW();
-      mbar_wait(bar_mel_full + 8 * ms, (it / K::NM) & 1);     // the segment's 15 mel rows are in the ring
+      mbar_wait_relaxed(bar_mel_full + 8 * ms, (it / K::NM) & 1);     // the segment's 15 mel rows are in the ring
       if (tid == K::W_PROD0 * 32) C12_ADD(0, tw);
       tw = C12_NOW();
       const float* mslot = reinterpret_cast<const float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT);
       const float thr = mslot[kMels];                         // the clip's top_db floor, left in row 0's padding by the load warp
-      if (has_cell) conv1_cell<MODE, false, K::MEL_PITCH>(mslot, 0, thr, ws, ph, pw, res);
+      if (has_cell) conv1_cell<MODE, false, K::MEL_PITCH, NCQ>(mslot, 0, thr, ws, ph, pw, res, grp * NCQ);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mel_free + 8 * ms);      // (the patch sits in registers: the slot may be refilled)
       if (tid == K::W_PROD0 * 32) C12_ADD(1, tw);
       tw = C12_NOW();
-      mbar_wait(bar_a_free + 8 * buf, (use & 1) ^ 1);         // the MMAs of tile it - NA have read the buffer
+      mbar_wait_relaxed(bar_a_free + 8 * buf, (use & 1) ^ 1);         // the MMAs of tile it - NA have read the buffer
       if (tid == K::W_PROD0 * 32) C12_ADD(2, tw);
       tw = C12_NOW();
       if (has_cell) {
         unsigned char* a_hi = smem + buf * K::BUF_BYTES;
         unsigned char* a_lo = a_hi + C::A_BYTES;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c_ = 0; c_ < NCQ / 2; ++c_) {
+          const int c = K::N_GROUPS == 2 ? grp : c_;          // the 16-byte chunk (8 channels) of the plane row
           uint4 hi, lo;
-          split8(make_float4(res[8 * c], res[8 * c + 1], res[8 * c + 2], res[8 * c + 3]),
-                 make_float4(res[8 * c + 4], res[8 * c + 5], res[8 * c + 6], res[8 * c + 7]), hi, lo);
+          split8(make_float4(res[8 * c_], res[8 * c_ + 1], res[8 * c_ + 2], res[8 * c_ + 3]),
+                 make_float4(res[8 * c_ + 4], res[8 * c_ + 5], res[8 * c_ + 6], res[8 * c_ + 7]), hi, lo);
           uint32_t o = row * 32u + (uint32_t)c * 16u;
           o ^= (o >> 3) & 16u;                                // Swizzle<1,4,3> of the absolute (1024-aligned) tile address
           *reinterpret_cast<uint4*>(a_hi + o) = hi;
@@ -172,7 +180,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       const int f0 = __ldg(seg_frame0 + tile);
       if (lane == 0) {
         const float thr = __ldg(seg_thr + tile);               // (a global-load latency the producers must not see)
-        mbar_wait(bar_mel_free + 8 * ms, ((it / K::NM) & 1) ^ 1);
+        mbar_wait_relaxed(bar_mel_free + 8 * ms, ((it / K::NM) & 1) ^ 1);
         *reinterpret_cast<float*>(smem + K::OFF_MEL + ms * K::MEL_SLOT + kMels * 4) = thr;   // released by the arrive below
         mbar_expect_tx(bar_mel_full + 8 * ms, K::MEL_BYTES);
       }
@@ -225,7 +233,7 @@ conv12_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
       const int ab = it & 1, aph = (it >> 1) & 1;
       float* stg = reinterpret_cast<float*>(smem + K::OFF_STG + (it & 1) * K::STG_BYTES);
       long long tw = C12_NOW();
-      mbar_wait(bar_acc_full + 8 * ab, aph);
+      mbar_wait_relaxed(bar_acc_full + 8 * ab, aph);
       if (tid == 0) C12_ADD(7, tw);
       tw = C12_NOW();
       tc_fence_after();

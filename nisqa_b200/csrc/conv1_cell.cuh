@@ -14,9 +14,10 @@ namespace nisqa {
 
 // ws: [9][16] folded conv1 weights followed by the 16 biases (shared memory).  LDG: `mel` is global memory read through
 // the read-only path; false: a shared-memory copy of the segment's 15 mel rows (f0 = 0), rows PITCH floats apart.
-template <int MODE, bool LDG = true, int PITCH = kMels>
+// NCQ channel quads starting at quad cq0 (NCQ = 4, cq0 = 0: all 16 channels; the fused kernel splits them over two warp groups).
+template <int MODE, bool LDG = true, int PITCH = kMels, int NCQ = 4>
 __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0, float thr, const float* ws,
-                                           int ph, int pw, float (&res)[16]) {
+                                           int ph, int pw, float (&res)[4 * NCQ], int cq0 = 0) {
   constexpr int NWC = (MODE == 0) ? 3 : 2;       // window columns
   constexpr int PC = NWC + 2;                    // patch columns
   const int r0 = 2 * ph - 1;                     // first patch row (mel index)
@@ -37,7 +38,8 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
   // 16 channels as 8 packed pairs (FFMA2: the same fp32 FMA per element and tap order as the scalar form, half the
   // instructions - the producer warps of conv12 are issue bound)
 #pragma unroll
-  for (int cq = 0; cq < 4; ++cq) {
+  for (int cq_ = 0; cq_ < NCQ; ++cq_) {
+    const int cq = cq0 + cq_;
     f2 acc[2][NWC][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -70,14 +72,15 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
             m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
           }
         }
-      res[cq * 4 + 2 * h] = fmaxf(m0 + ws[144 + cq * 4 + 2 * h], 0.f);           // bias + ReLU commute with max
-      res[cq * 4 + 2 * h + 1] = fmaxf(m1 + ws[144 + cq * 4 + 2 * h + 1], 0.f);
+      res[cq_ * 4 + 2 * h] = fmaxf(m0 + ws[144 + cq * 4 + 2 * h], 0.f);           // bias + ReLU commute with max
+      res[cq_ * 4 + 2 * h + 1] = fmaxf(m1 + ws[144 + cq * 4 + 2 * h + 1], 0.f);
     }
   }
 }
 #else
 #pragma unroll
-  for (int cq = 0; cq < 4; ++cq) {
+  for (int cq_ = 0; cq_ < NCQ; ++cq_) {
+    const int cq = cq0 + cq_;
     float acc[2][NWC][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -110,7 +113,7 @@ __device__ __forceinline__ void conv1_cell(const float* __restrict__ mel, int f0
           const int col = c0 + 1 + j;            // conv output column of this window slot
           if (MODE == 0 || (col >= 0 && col < kSegLen)) m = fmaxf(m, acc[i][j][c]);
         }
-      res[cq * 4 + c] = fmaxf(m + ws[144 + cq * 4 + c], 0.f);   // bias + ReLU commute with max
+      res[cq_ * 4 + c] = fmaxf(m + ws[144 + cq * 4 + c], 0.f);   // bias + ReLU commute with max
     }
   }
 }

@@ -30,6 +30,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1u << 26)) __trap();
   } while (!done);
 }
+// The same wait for roles whose wake-up latency is not on the critical path (whole warps of producers / epilogue that poll
+// together): a failed poll is followed by a short sleep, so that waiting warps leave the issue slots of their scheduler to
+// the warps that have work (NISQA_MBAR_SLEEP ns; 0 = plain polling).
+#ifndef NISQA_MBAR_SLEEP
+#define NISQA_MBAR_SLEEP 0
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#if NISQA_MBAR_SLEEP > 0
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) {
+      __nanosleep(NISQA_MBAR_SLEEP);
+      if (++spins > (1u << 24)) __trap();
+    }
+  } while (!done);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
