@@ -53,11 +53,13 @@ enum nisqa_pool {
 
 /* double-ended model NISQA_DE (reference lib:272-424; train_nisqa_double_ended.yaml): time alignment of the reference
  * clip's features to the degraded clip's (Alignment, lib:1228-1285), how the alignment is applied, and the fusion of the
- * two feature streams (Fusion, lib:1380-1417).  The attention modules with learned weights (AttBahdanau, AttLuong) and
- * de_align 'none' are refused. */
-enum nisqa_de_align { NISQA_DE_ALIGN_DOT = 1, NISQA_DE_ALIGN_COSINE = 2, NISQA_DE_ALIGN_DISTANCE = 3 };
+ * two feature streams (Fusion, lib:1380-1417).  de_align 'none' is refused (it needs equally long signals). */
+enum nisqa_de_align { NISQA_DE_ALIGN_DOT = 1, NISQA_DE_ALIGN_COSINE = 2, NISQA_DE_ALIGN_DISTANCE = 3,
+                      NISQA_DE_ALIGN_LUONG = 4 /* AttLuong lib:1344-1357 */, NISQA_DE_ALIGN_BAHDANAU = 5 /* AttBahdanau lib:1325-1342 */ };
 enum nisqa_de_apply { NISQA_DE_APPLY_HARD = 0, NISQA_DE_APPLY_SOFT = 1 };
 enum nisqa_de_fuse  { NISQA_DE_FUSE_XY_MINUS = 0 /* 'x/y/-' */, NISQA_DE_FUSE_PLUS_MINUS = 1 /* '+/-' */, NISQA_DE_FUSE_XY = 2 /* 'x/y' */ };
+
+enum nisqa_cnn_kind { NISQA_CNN_CONV = 0, NISQA_CNN_SKIP = 1, NISQA_CNN_DFF = 2 };
 
 enum nisqa_sample_fmt { NISQA_FMT_S16 = 0, NISQA_FMT_F32 = 1 };
 
@@ -114,6 +116,9 @@ typedef struct nisqa_config {
   int32_t td2_layers;    /* td_2 = 'self_att' (d_model 64, one head, h 64): number of layers; 0 = td_2 'skip'.  NISQA_DE needs >= 1;
                           * NISQA / NISQA_DIM run it as a second stack behind the first (lib:114-141, 236-268) */
   int32_t td2_pos_enc;   /* td_2_sa_pos_enc */
+  /* framewise model in front of the self-attention stack (arch NISQA_ARCH_ADAPT_SA_ATTFF): */
+  int32_t cnn_kind;      /* enum nisqa_cnn_kind: 0 = the convolutional networks, 1 = SkipCNN (lib:504-534), 2 = DFF (lib:536-583) */
+  int32_t cnn_fc;        /* cnn_fc_out_h of SkipCNN (0 = no Linear: 720 features) / DFF (hidden width); a multiple of 64 */
 } nisqa_config;
 
 /* One state_dict entry, passed straight through: name as in the checkpoint

@@ -63,8 +63,11 @@ void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*
 struct ResampleClip { long long in_off, out_off, time_off; int n_in, n_out, n_fix, copy; double ratio; };
 void launch_resample(cudaStream_t, const void*, int, const ResampleClip*, int, int, double*, const double*, int, int, float*);
 bool resample_table(std::vector<double>*, int*);
-void launch_de_align(cudaStream_t, const float*, const ClipDesc*, int, const int*, int, int, int, int, float*, int, float*);
+struct DeAlignParams { const float* wT; const float* b; const float* wqT; const float* bq; const float* wyT; const float* by; const float* v; };
+void launch_de_align(cudaStream_t, const float*, const ClipDesc*, int, const int*, int, int, int, int, const DeAlignParams&, float*);
 void launch_de_finalize(cudaStream_t, const ClipDesc*, int, int, float*);
+void launch_seg_feats(cudaStream_t, const float*, const int*, const float*, const float*, int, float*);
+void launch_linear_tile(cudaStream_t, const float*, int, const float*, const float*, int, float*, int, int, int, int);
 void launch_td_in(cudaStream_t, const float*, const float*, int, const float*, const float*, const float*,
                   const float*, const float*, const float*, const int*, const ClipDesc*, float*, float*, int);
 struct PoolSimpleParams { const float* a1; const float* a1b; const float* w3; const float* b3; };
@@ -148,13 +151,13 @@ constexpr int kLanes = 3;
 constexpr int kStages = 6;     // staging slots / submissions in flight (uploads run ahead of the lanes)
 struct Lane {
   cudaStream_t stream = nullptr;
-  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, qkv2, logits, feats20, tdout, partial, fused, td2in;
+  DevBuf mel, segtab, act1, act2, act3, act4, act5, feats, xa, xb, qkv, qkv2, logits, feats20, tdout, partial, fused, td2in, ffa, ffb;
   DevBuf planes[7];        // planes[l]: fp16 hi | lo plane pair feeding conv layer l (2..6), conv_split.cu
   size_t plane_bytes[7] = {0, 0, 0, 0, 0, 0, 0};   // offset of the lo plane inside planes[l] (half of the allocation)
   void release() {
     for (auto& b : planes) b.release();
     DevBuf* all[] = {&mel, &segtab, &act1, &act2, &act3, &act4, &act5,
-                     &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout, &partial, &fused, &td2in};
+                     &feats, &xa, &xb, &qkv, &qkv2, &logits, &feats20, &tdout, &partial, &fused, &td2in, &ffa, &ffb};
     for (auto* b : all) b->release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -485,10 +488,57 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
   }
   e->woff.clear();
   const int cin[7] = {0, 1, 16, 32, 64, 64, 64}, cout[7] = {0, 16, 32, 64, 64, 64, 64};
-  for (int i = 1; i <= 6; ++i)
+  const bool conv_net = e->cfg.cnn_kind == NISQA_CNN_CONV;
+  if (!conv_net) {
+    // SkipCNN / DFF (lib:504-583): the BatchNorm2d(1) in front as a scalar affine map (applied by seg_feats_kernel, so
+    // that the Linear layers see what the reference's see), Linear layers k-major, DFF's BatchNorm1d folded into them
+    const bool dff = e->cfg.cnn_kind == NISQA_CNN_DFF;
+    const std::string p = "cnn.model.";
+    const std::string bn = dff ? "bn1." : "bn.";
+    const TensorView* g = P.get(p + bn + "weight", {1});
+    const TensorView* be = P.get(p + bn + "bias", {1});
+    const TensorView* mu = P.get(p + bn + "running_mean", {1});
+    const TensorView* var = P.get(p + bn + "running_var", {1});
+    if (!g || !be || !mu || !var) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    const double a = (double)g->d[0] / sqrt((double)var->d[0] + 1e-5);
+    size_t o = P.alloc("ff.bn", 2);
+    P.arena[o] = (float)a; P.arena[o + 1] = (float)((double)be->d[0] - (double)mu->d[0] * a);
+    const int H = e->cfg.cnn_fc;
+    auto pack_lin = [&](const std::string& wname, const std::string& bnname, int n_in, int n_in_pad, int n_out, const std::string& key) -> bool {
+      const TensorView* w = P.get(p + wname + ".weight", {n_out, n_in});
+      const TensorView* b = P.get(p + wname + ".bias", {n_out});
+      if (!w || !b) return false;
+      std::vector<double> sc(n_out, 1.0), sh(n_out, 0.0);
+      if (!bnname.empty()) {            // eval-mode BatchNorm1d (eps 1e-5) folded into the Linear in front of it
+        const TensorView* g2 = P.get(p + bnname + ".weight", {n_out});
+        const TensorView* b2 = P.get(p + bnname + ".bias", {n_out});
+        const TensorView* m2 = P.get(p + bnname + ".running_mean", {n_out});
+        const TensorView* v2 = P.get(p + bnname + ".running_var", {n_out});
+        if (!g2 || !b2 || !m2 || !v2) return false;
+        for (int j = 0; j < n_out; ++j) {
+          sc[j] = (double)g2->d[j] / sqrt((double)v2->d[j] + 1e-5);
+          sh[j] = (double)b2->d[j] - (double)m2->d[j] * sc[j];
+        }
+      }
+      const size_t ow = P.alloc(key + ".wT", (size_t)n_in_pad * n_out), ob = P.alloc(key + ".b", n_out);
+      for (int k = 0; k < n_in; ++k)
+        for (int j = 0; j < n_out; ++j) P.arena[ow + (size_t)k * n_out + j] = (float)((double)w->d[(size_t)j * n_in + k] * sc[j]);
+      for (int j = 0; j < n_out; ++j) P.arena[ob + j] = (float)((double)b->d[j] * sc[j] + sh[j]);
+      return true;
+    };
+    bool ok = true;
+    if (dff) {
+      ok = pack_lin("lin1", "bn2", 720, 768, H, "ff1") && pack_lin("lin2", "bn3", H, H, H, "ff2") &&
+           pack_lin("lin3", "bn4", H, H, H, "ff3") && pack_lin("lin4", "bn5", H, H, H, "ff4");
+    } else if (H > 0) {
+      ok = pack_lin("linear", "", 720, 768, H, "ff1");
+    }
+    if (!ok) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+  }
+  for (int i = 1; conv_net && i <= 6; ++i)
     if (!pack_conv(P, i, cin[i], cout[i])) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
   // conv2..conv6 for the tcgen05 path: [tap][ci/8][hi co | lo co][8] fp16 two-term split of w * 2^S
-  for (int i = 2; i <= 6; ++i) {
+  for (int i = 2; conv_net && i <= 6; ++i) {
     char k1[32], k2[32];
     snprintf(k1, sizeof k1, "conv%d.w", i); snprintf(k2, sizeof k2, "conv%d.wtc", i);
     const int ci_n = cin[i], co_n = cout[i], nch = ci_n / 8;
@@ -525,7 +575,7 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       const TensorView* ng = P.get(ck + "norm1.weight", {64});
       const TensorView* nb = P.get(ck + "norm1.bias", {64});
       if (!lw || !lb || !ng || !nb) return false;
-      size_t o = P.alloc("lin" + kp + ".wT", (size_t)in_dim * 64);
+      size_t o = P.alloc("lin" + kp + ".wT", (size_t)((in_dim + 63) / 64 * 64) * 64);      // (rows beyond in_dim stay zero)
       if (cnn_order) {
         // engine feature order k' = h*64 + c  <->  reference view(-1, 64*6) order c*6 + h (lib:706)
         for (int h = 0; h < 6; ++h)
@@ -587,7 +637,10 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       memcpy(&P.arena[o2], it->second.d, (size_t)it->second.numel * 4);
       return 0;
     };
-    if (!pack_sa_stack(td, "", 384, e->cfg.sa_layers, true)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    // framewise features feeding the first stack: 384 (AdaptCNN, engine order), 720 (SkipCNN without Linear: padded to 768
+    // with zero rows) or cnn_fc_out_h
+    const int feat_dim = conv_net ? 384 : (e->cfg.cnn_fc > 0 ? e->cfg.cnn_fc : 720);
+    if (!pack_sa_stack(td, "", feat_dim, e->cfg.sa_layers, conv_net)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
     if (e->cfg.double_ended || e->cfg.td2_layers > 0) {
       // time_dependency_2: behind the fusion of the double-ended model (input 192 / 128), or a second stack behind the
       // first one in NISQA / NISQA_DIM (lib:114-141, 236-268; input 64)
@@ -595,6 +648,26 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
       const int fdim = !e->cfg.double_ended ? 64 : (e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128);
       if (!pack_sa_stack(td2, "2", fdim, e->cfg.td2_layers, false)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
       if (e->cfg.td2_pos_enc) { int rc = pack_pos_enc(td2, "pe2"); if (rc) return rc; }
+      if (e->cfg.de_align == NISQA_DE_ALIGN_LUONG) {            // AttLuong: W = Linear(y_dim -> q_dim), lib:1348-1351
+        const TensorView* w = P.get("align.att.W.weight", {64, 64});
+        const TensorView* b = P.get("align.att.W.bias", {64});
+        if (!w || !b) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+        size_t o = P.alloc("de.wT", 4096); pack_linear_T(P, o, w, 64, 64);
+        o = P.alloc("de.b", 64); memcpy(&P.arena[o], b->d, 256);
+      }
+      if (e->cfg.de_align == NISQA_DE_ALIGN_BAHDANAU) {         // AttBahdanau: Wq, Wy (-> att_dim 128), v, lib:1329-1337
+        const TensorView* wq = P.get("align.att.Wq.weight", {128, 64});
+        const TensorView* bq = P.get("align.att.Wq.bias", {128});
+        const TensorView* wy = P.get("align.att.Wy.weight", {128, 64});
+        const TensorView* by = P.get("align.att.Wy.bias", {128});
+        const TensorView* v = P.get("align.att.v.weight", {1, 128});
+        if (!wq || !bq || !wy || !by || !v) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+        size_t o = P.alloc("de.wqT", 64 * 128); pack_linear_T(P, o, wq, 128, 64);
+        o = P.alloc("de.bq", 128); memcpy(&P.arena[o], bq->d, 512);
+        o = P.alloc("de.wyT", 64 * 128); pack_linear_T(P, o, wy, 128, 64);
+        o = P.alloc("de.by", 128); memcpy(&P.arena[o], by->d, 512);
+        o = P.alloc("de.v", 128); memcpy(&P.arena[o], v->d, 512);
+      }
     }
     const int nh = e->cfg.n_out;
     auto head_prefix = [&](int h) {
@@ -813,7 +886,9 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     CK(LN.segtab.reserve((size_t)n_seg * 12));
     const bool split = e->conv_split && e->conv_tc == 0x7c;
     e->last_split = split;
-    if (split) {
+    const bool conv_net = c.cnn_kind == NISQA_CNN_CONV;
+    if (!conv_net) {
+    } else if (split) {
       for (int l = (e->conv12 ? 3 : 2); l <= 6; ++l) {
         // the lo plane sits at a fixed offset of the ALLOCATION (not of this pass's n_seg): the zero rows /
         // columns of both planes must stay where they were when the buffer was cleared
@@ -843,7 +918,30 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
     auto plane_lo = [&](int l) { return LN.planes[l].as<char>() + LN.plane_bytes[l]; };
     const bool fused12 = split && e->conv12;
     e->last_conv12 = fused12;
-    if (fused12) {
+    const float* sa_in = LN.feats.as<float>();       // rows fed to the first self-attention stack
+    int sa_nk = 6;                                   // ... in 64-wide chunks
+    if (!conv_net) {
+      // SkipCNN / DFF (lib:504-583): BN + flatten (+ Linear layers), no convolution
+      Scope s(e, "framewise", 5);
+      const int H = c.cnn_fc;
+      CK(LN.ffa.reserve((size_t)n_seg * std::max(768, H) * 4));
+      launch_seg_feats(st, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "ff.bn"), n_seg, LN.ffa.as<float>());
+      sa_in = LN.ffa.as<float>(); sa_nk = 12;
+      if (H > 0) {
+        CK(LN.ffb.reserve((size_t)n_seg * H * 4));
+        const bool dff = c.cnn_kind == NISQA_CNN_DFF;
+        launch_linear_tile(st, LN.ffa.as<float>(), 768, W(e, "ff1.wT"), W(e, "ff1.b"), dff, LN.ffb.as<float>(), H, n_seg, 768, H);
+        sa_in = LN.ffb.as<float>(); sa_nk = H / 64;
+        if (dff) {
+          float* pp2[2] = {LN.ffa.as<float>(), LN.ffb.as<float>()};
+          const char* keys[3] = {"ff2", "ff3", "ff4"};
+          for (int l = 0; l < 3; ++l)       // ffb -> ffa -> ffb -> ffa
+            launch_linear_tile(st, pp2[(l + 1) & 1], H, W(e, std::string(keys[l]) + ".wT"), W(e, std::string(keys[l]) + ".b"), 1,
+                               pp2[l & 1], H, n_seg, H, H);
+          sa_in = LN.ffa.as<float>();
+        }
+      }
+    } else if (fused12) {
       Scope s(e, "conv12");
       launch_conv12(st, std_mode, LN.mel.as<float>(), seg_frame0, seg_thr, W(e, "conv1.w"), W(e, "conv1.b"),
                     W(e, "conv2.wtc"), W(e, "conv2.b"), e->tc_scale[2], plane_hi(3), plane_lo(3), n_seg);
@@ -853,7 +951,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
                    W(e, "conv1.b"), split ? nullptr : LN.act1.as<float>(), n_seg,
                    split ? plane_hi(2) : nullptr, split ? plane_lo(2) : nullptr);
     }
-    {
+    if (conv_net) {
       const float* cin_[7] = {nullptr, nullptr, LN.act1.as<float>(), LN.act2.as<float>(), LN.act3.as<float>(),
                               LN.act4.as<float>(), LN.act5.as<float>()};
       float* cout_[7] = {nullptr, nullptr, LN.act2.as<float>(), LN.act3.as<float>(), LN.act4.as<float>(),
@@ -924,7 +1022,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         return cur2;
       };
       const bool td2_single = !de && c.td2_layers > 0;      // NISQA / NISQA_DIM with td_2 = 'self_att'
-      cur = sa_stack("", LN.feats.as<float>(), 6, c.sa_layers, c.pos_enc != 0, !de && !td2_single, LN.tdout.as<float>());
+      cur = sa_stack("", sa_in, sa_nk, c.sa_layers, c.pos_enc != 0, !de && !td2_single, LN.tdout.as<float>());
       if (td2_single) {
         CK(LN.td2in.reserve((size_t)n_seg * 64 * 4));
         cur = sa_stack("2", cur, 1, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
@@ -935,9 +1033,14 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         CK(LN.fused.reserve((size_t)n_seg * 64 * nf * 4));
         CK(LN.td2in.reserve((size_t)n_seg * 64 * 4));
         CK(cudaMemsetAsync(LN.fused.p, 0, (size_t)n_seg * 64 * nf * 4, st));      // rows of the reference clips stay zero
+        DeAlignParams AP = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (c.de_align == NISQA_DE_ALIGN_LUONG) { AP.wT = W(e, "de.wT"); AP.b = W(e, "de.b"); }
+        if (c.de_align == NISQA_DE_ALIGN_BAHDANAU) {
+          AP.wqT = W(e, "de.wqT"); AP.bq = W(e, "de.bq"); AP.wyT = W(e, "de.wyT"); AP.by = W(e, "de.by"); AP.v = W(e, "de.v");
+        }
         { Scope s(e, "de_align");
           launch_de_align(st, cur, d_clips, n, d_qt64, n_qt64, c.de_align, c.de_align_apply == NISQA_DE_APPLY_SOFT, c.de_fuse,
-                          LN.fused.as<float>(), n_out, nullptr); }
+                          AP, LN.fused.as<float>()); }
         cur = sa_stack("2", LN.fused.as<float>(), nf, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
       }
       e->last_td_out = cur;
@@ -1115,13 +1218,17 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
       (cfg->arch == NISQA_ARCH_STD_LSTM_LASTBI && (cfg->pool == NISQA_POOL_ATT_FF || cfg->pool == NISQA_POOL_ATT)))
     return fail(e, NISQA_ERR_INVALID, "pooling module not available for this architecture");
   if (cfg->pos_enc && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) return fail(e, NISQA_ERR_INVALID, "pos_enc needs the self-attention architecture");
+  if (cfg->cnn_kind < NISQA_CNN_CONV || cfg->cnn_kind > NISQA_CNN_DFF || cfg->cnn_fc < 0 || cfg->cnn_fc % 64 != 0 || cfg->cnn_fc > 8192 ||
+      (cfg->cnn_kind == NISQA_CNN_DFF && cfg->cnn_fc == 0) || (cfg->cnn_kind == NISQA_CNN_CONV && cfg->cnn_fc != 0) ||
+      (cfg->cnn_kind != NISQA_CNN_CONV && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF))
+    return fail(e, NISQA_ERR_INVALID, "cnn_kind / cnn_fc: SkipCNN and DFF feed the self-attention architecture; cnn_fc_out_h a multiple of 64");
   if (cfg->td2_layers < 0 || cfg->td2_layers > 8 || (cfg->td2_layers > 0 && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF))
     return fail(e, NISQA_ERR_INVALID, "td_2 = 'self_att' needs the self-attention architecture (td2_layers 0..8)");
   if (cfg->double_ended) {
     if (cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF || cfg->n_out != 1)
       return fail(e, NISQA_ERR_INVALID, "NISQA_DE: AdaptCNN + self-attention, one output");
-    if (cfg->de_align < NISQA_DE_ALIGN_DOT || cfg->de_align > NISQA_DE_ALIGN_DISTANCE)
-      return fail(e, NISQA_ERR_INVALID, "de_align: dot, cosine or distance");
+    if (cfg->de_align < NISQA_DE_ALIGN_DOT || cfg->de_align > NISQA_DE_ALIGN_BAHDANAU)
+      return fail(e, NISQA_ERR_INVALID, "de_align: dot, cosine, distance, luong or bahd");
     if (cfg->de_align_apply != NISQA_DE_APPLY_HARD && cfg->de_align_apply != NISQA_DE_APPLY_SOFT)
       return fail(e, NISQA_ERR_INVALID, "de_align_apply");
     if (cfg->de_fuse < NISQA_DE_FUSE_XY_MINUS || cfg->de_fuse > NISQA_DE_FUSE_XY) return fail(e, NISQA_ERR_INVALID, "de_fuse");

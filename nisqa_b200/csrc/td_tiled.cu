@@ -523,12 +523,14 @@ td_sa_kernel(const float* __restrict__ x_in, const float* __restrict__ qkv, cons
 // clip's (Alignment, lib:1228-1285) and feature fusion (Fusion, lib:1380-1417), for 64 degraded steps of one pair.
 //   x = time_dependency output of the degraded clip (clip 2p), y = of the reference clip (clip 2p + 1)
 //   score[i][j] : dot  x_i . y_j (AttDot, lib:1287-1296) | cosine similarity (AttCosine, lib:1298-1308, eps 1e-8) |
-//                 -mean_d |x_id - y_jd| (AttDistance with its default norms, lib:1310-1323); keys j >= n_wins_y masked
+//                 -mean_d |x_id - y_jd| (AttDistance with its default norms, lib:1310-1323) | x_i . (W y_j + b) (AttLuong,
+//                 lib:1344-1357) | v . tanh(Wq x_i + bq + Wy y_j + by) (AttBahdanau, att_dim 128, lib:1325-1342; its
+//                 output bias shifts every score of a row alike and drops out of softmax / argmax); keys j >= n_wins_y masked
 //   hard        : y_al[i] = y[argmax_j softmax(score[i])] = y[first maximal score] (ApplyHardAttention, lib:1359-1368)
 //   soft        : y_al[i] = softmax_j(score[i]) . y (ApplySoftAttention, lib:1370-1378), online max / sum over key blocks
 //   fuse        : [x, y_al, x - y_al] | [x + y_al, x - y_al] | [x, y_al]  ->  fused[row][64 * nf]
 // Same 64 x 64 register tiling as td_sa_kernel; the y block serves as K (row-major, pitch 68) and as V.
-enum { DE_ALIGN_DOT = 1, DE_ALIGN_COSINE = 2, DE_ALIGN_DISTANCE = 3 };      // = enum nisqa_de_align (the learned / 'none' modules are refused)
+enum { DE_ALIGN_DOT = 1, DE_ALIGN_COSINE = 2, DE_ALIGN_DISTANCE = 3, DE_ALIGN_LUONG = 4, DE_ALIGN_BAHD = 5 };      // = enum nisqa_de_align
 enum { DE_FUSE_XY_MINUS = 0, DE_FUSE_PLUS_MINUS = 1, DE_FUSE_XY = 2 };
 
 // s[i][j] -= sum_k |A[4ty+i][k] - B[tx+16j][k]|
@@ -551,16 +553,22 @@ __device__ __forceinline__ void absdiff_nt(float (&s)[4][4], const float* __rest
 }
 
 constexpr int kDeSmemFloats = 2 * kTileF + 2 * kTileF + 2 * kT;      // Qs | Ps | Yb[2] | 1 / |y| of the two blocks
+constexpr int kBhLd = 132;                                            // pitch of the [64][128] projections (AttBahdanau)
+constexpr int kDeLuongFloats = 4096 + kTileF;                          // W^T | projected keys
+constexpr int kDeBahdFloats = 64 * 128 + 2 * 64 * kBhLd;               // Wy^T | Wq x + bq | Wy y + by
+// learned weights of AttLuong (wT [64][64] k-major, b [64]) / AttBahdanau (wqT, wyT [64][128] k-major, bq, by, v [128])
+struct DeAlignParams { const float* wT; const float* b; const float* wqT; const float* bq; const float* wyT; const float* by; const float* v; };
 
 __global__ void __launch_bounds__(kNT, 2)
 de_align_kernel(const float* __restrict__ x_td /*[n_seg][64]*/, const ClipDesc* __restrict__ clips, int n_clips,
-                const int* __restrict__ qtile_prefix /*64-row tiles*/, int align, int soft, int fuse,
+                const int* __restrict__ qtile_prefix /*64-row tiles*/, int align, int soft, int fuse, DeAlignParams A,
                 float* __restrict__ fused /*[n_seg][64 nf]*/) {
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                          // [64][68] degraded rows x
   float* Ps = sm + kTileF;                 // [64][68] softmax numerators (soft attention)
   float* Yb = Ps + kTileF;                 // [2][64][68] reference rows y
   float* Yn = Yb + 2 * kTileF;             // [2][64] 1 / max(|y_j|, eps)
+  float* Ex = Yn + 2 * kT;                 // AttLuong: W^T [64][64] | W y + b [64][68];  AttBahdanau: Wy^T [64][128] | XQ | YK [64][132]
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int c = upper_slot(qtile_prefix, n_clips, blockIdx.x);
   if (c & 1) return;                       // reference clips are keys only
@@ -576,8 +584,33 @@ de_align_kernel(const float* __restrict__ x_td /*[n_seg][64]*/, const ClipDesc* 
   tile_load_async(Qs, kLd, x_td + row0 * 64, 64, rows_valid, tid);
   tile_load_async(Yb, kLd, y_base, 64, min(kT, Sy), tid);
   cp_commit();
+  if (align == DE_ALIGN_LUONG) tile_load_async(Ex, 64, A.wT, 64, 64, tid);
+  if (align == DE_ALIGN_BAHD) { tile_load_async(Ex, 128, A.wyT, 128, 64, tid); tile_load_async(Ex + 64, 128, A.wyT + 64, 128, 64, tid); }
+  cp_commit();
   float o[4][4];
   zero_acc(o);
+  if (align == DE_ALIGN_BAHD) {
+    // XQ = Wq x + bq for the CTA's 64 degraded steps: two 64-column halves, Wq^T staged through Ps
+    float* XQ = Ex + 64 * 128;
+    cp_wait<0>();
+    __syncthreads();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      tile_load_async(Ps, 64, A.wqT + half * 64, 128, 64, tid);
+      cp_commit();
+      cp_wait<0>();
+      __syncthreads();
+      float acc[4][4];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(A.bq + half * 64) + tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+      gemm_nn(acc, Qs, Ps, 64, ty, tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(XQ + (4 * ty + i) * kBhLd + half * 64 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+    }
+  }
   {
     float m[4], l[4], rq[4];
     int best[4];
@@ -617,7 +650,52 @@ de_align_kernel(const float* __restrict__ x_td /*[n_seg][64]*/, const ClipDesc* 
       }
       float s[4][4];
       zero_acc(s);
-      if (align == DE_ALIGN_DISTANCE) {
+      if (align == DE_ALIGN_LUONG) {
+        // y' = W y + b for the block's keys, then x . y'
+        float* Yp = Ex + 4096;
+        float acc[4][4];
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(A.b) + tx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+        gemm_nn(acc, Y, Ex, 64, ty, tx);
+        store_rows_smem(Yp, acc, ty, tx);
+        __syncthreads();
+        gemm_nt(s, Qs, Yp, ty, tx);
+      } else if (align == DE_ALIGN_BAHD) {
+        const float* WyT = Ex;
+        const float* XQ = Ex + 64 * 128;
+        float* YK = Ex + 64 * 128 + 64 * kBhLd;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {                 // YK = Wy y + by for the block's keys
+          float acc[4][4];
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(A.by + half * 64) + tx);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+          gemm_nn(acc, Y, WyT + half * 64, 128, ty, tx);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(YK + (4 * ty + i) * kBhLd + half * 64 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int a = 0; a < 128; a += 4) {
+          const float4 vv = __ldg(reinterpret_cast<const float4*>(A.v + a));
+          float4 xq[4], yk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xq[i] = *reinterpret_cast<const float4*>(XQ + (4 * ty + i) * kBhLd + a);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yk[j] = *reinterpret_cast<const float4*>(YK + (tx + 16 * j) * kBhLd + a);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t = s[i][j];
+              t = fmaf(vv.x, tanhf(xq[i].x + yk[j].x), t); t = fmaf(vv.y, tanhf(xq[i].y + yk[j].y), t);
+              t = fmaf(vv.z, tanhf(xq[i].z + yk[j].z), t); t = fmaf(vv.w, tanhf(xq[i].w + yk[j].w), t);
+              s[i][j] = t;
+            }
+        }
+      } else if (align == DE_ALIGN_DISTANCE) {
         absdiff_nt(s, Qs, Y, ty, tx);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -710,6 +788,75 @@ __global__ void de_finalize_kernel(const ClipDesc* __restrict__ clips, int n_cli
   if (bad) for (int h = 0; h < n_out; ++h) scores[c * n_out + h] = __int_as_float(0x7fc00000);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Framewise models without convolutions (reference lib:504-583, user checkpoints): SkipCNN = BatchNorm2d(1) + flatten
+// (+ Linear), DFF = BatchNorm2d(1) + flatten + 4 x (Linear + BatchNorm1d + ReLU).
+//   seg_feats_kernel  : segment s -> row [768]: a * max(mel[frame0 + t][m], thr) + c at index m * 15 + t (x.view(-1, 720),
+//                       lib:531 / 572), columns 720..767 zero (the rows feed 64-wide k chunks)
+//   linear_tile_kernel: Y[n][N] = act(X[n][K] W^T + b), 64 x 64 output tiles, K in chunks of 64 (K, N multiples of 64),
+//                       the same register-tiled fp32 product as the time-dependency block
+__global__ void seg_feats_kernel(const float* __restrict__ mel, const int* __restrict__ seg_frame0,
+                                 const float* __restrict__ seg_thr, const float* __restrict__ bn /*a, c*/, int n_seg,
+                                 float* __restrict__ out /*[n_seg][768]*/) {
+  const int s = blockIdx.x;
+  if (s >= n_seg) return;
+  const float* src = mel + (size_t)__ldg(seg_frame0 + s) * kMels;
+  const float thr = __ldg(seg_thr + s), a = __ldg(bn), c = __ldg(bn + 1);
+  for (int j = threadIdx.x; j < 768; j += blockDim.x) {
+    float v = 0.f;
+    if (j < kMels * kSegLen) {
+      const int m = j / kSegLen, t = j - m * kSegLen;
+      v = fmaf(a, fmaxf(__ldg(src + t * kMels + m), thr), c);
+    }
+    out[(size_t)s * 768 + j] = v;
+  }
+}
+
+constexpr int kLinSmemFloats = 2 * kTileF + 2 * 4096;
+
+__global__ void __launch_bounds__(kNT, 2)
+linear_tile_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ WT /*[K][N]*/, const float* __restrict__ bias,
+                   int relu, float* __restrict__ Y, int ldy, int n_rows, int K, int N) {
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                       // [2][64][68]
+  float* Ws = sm + 2 * kTileF;          // [2][64][64]
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const long long row0 = (long long)blockIdx.x * kT;
+  const int n0 = blockIdx.y * kT;
+  const int rows_valid = (int)min((long long)kT, (long long)n_rows - row0);
+  const float* src = X + row0 * ldx;
+  const int nk = K / kT;
+  tile_load_async(As, kLd, src, ldx, rows_valid, tid);
+  tile_load_async(Ws, 64, WT + n0, N, 64, tid);
+  cp_commit();
+  float acc[4][4];
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0) + tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+  }
+#pragma unroll 1
+  for (int c = 0; c < nk; ++c) {
+    if (c + 1 < nk) {
+      tile_load_async(As + ((c + 1) & 1) * kTileF, kLd, src + (c + 1) * 64, ldx, rows_valid, tid);
+      tile_load_async(Ws + ((c + 1) & 1) * 4096, 64, WT + (size_t)(c + 1) * 64 * N + n0, N, 64, tid);
+    }
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    gemm_nn(acc, As + (c & 1) * kTileF, Ws + (c & 1) * 4096, 64, ty, tx);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * ty + i < rows_valid) {
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      *reinterpret_cast<float4*>(Y + (row0 + 4 * ty + i) * ldy + n0 + 4 * tx) = v;
+    }
+}
+
 // ------------------------------------------------------------------ host launchers
 void launch_td_in(cudaStream_t st, const float* feats, const float* WT, int nk, const float* b, const float* g, const float* be,
                   const float* qkvT, const float* qkvb, const float* pe, const int* seg_clip, const ClipDesc* clips,
@@ -721,12 +868,26 @@ void launch_td_in(cudaStream_t st, const float* feats, const float* WT, int nk, 
 }
 
 void launch_de_align(cudaStream_t st, const float* x_td, const ClipDesc* clips, int n_clips, const int* qtile64_prefix,
-                     int n_qtiles, int align, int soft, int fuse, float* fused, int n_out, float* scores_unused) {
-  (void)n_out; (void)scores_unused;
+                     int n_qtiles, int align, int soft, int fuse, const DeAlignParams& A, float* fused) {
   static unsigned long long cfg = 0;
-  const int smem = kDeSmemFloats * 4;
-  if (first_launch_on_device(cfg)) cudaFuncSetAttribute(de_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  de_align_kernel<<<n_qtiles, kNT, smem, st>>>(x_td, clips, n_clips, qtile64_prefix, align, soft, fuse, fused);
+  if (first_launch_on_device(cfg))
+    cudaFuncSetAttribute(de_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kDeSmemFloats + kDeBahdFloats) * 4);
+  const int smem = (kDeSmemFloats + (align == DE_ALIGN_LUONG ? kDeLuongFloats : align == DE_ALIGN_BAHD ? kDeBahdFloats : 0)) * 4;
+  de_align_kernel<<<n_qtiles, kNT, smem, st>>>(x_td, clips, n_clips, qtile64_prefix, align, soft, fuse, A, fused);
+}
+
+void launch_seg_feats(cudaStream_t st, const float* mel, const int* seg_frame0, const float* seg_thr, const float* bn, int n_seg,
+                      float* out) {
+  if (n_seg > 0) seg_feats_kernel<<<n_seg, 256, 0, st>>>(mel, seg_frame0, seg_thr, bn, n_seg, out);
+}
+
+void launch_linear_tile(cudaStream_t st, const float* X, int ldx, const float* WT, const float* bias, int relu, float* Y, int ldy,
+                        int n_rows, int K, int N) {
+  static unsigned long long cfg = 0;
+  const int smem = kLinSmemFloats * 4;
+  if (first_launch_on_device(cfg)) cudaFuncSetAttribute(linear_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const dim3 grid((n_rows + kT - 1) / kT, N / kT);
+  linear_tile_kernel<<<grid, kNT, smem, st>>>(X, ldx, WT, bias, relu, Y, ldy, n_rows, K, N);
 }
 
 void launch_de_finalize(cudaStream_t st, const ClipDesc* clips, int n_clips, int n_out, float* scores) {

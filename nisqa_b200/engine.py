@@ -20,7 +20,8 @@ FMT_S16, FMT_F32 = 0, 1
 CLIP_OK, CLIP_TOO_SHORT, CLIP_TOO_LONG = 0, 1, 2
 POOL_ATT_FF, POOL_ATT, POOL_AVG, POOL_MAX, POOL_LAST_STEP, POOL_LAST_STEP_BI = range(6)
 # NISQA_DE options (enum nisqa_de_align / nisqa_de_apply / nisqa_de_fuse)
-DE_ALIGN = {"dot": 1, "cosine": 2, "distance": 3}
+CNN_CONV, CNN_SKIP, CNN_DFF = 0, 1, 2
+DE_ALIGN = {"dot": 1, "cosine": 2, "distance": 3, "luong": 4, "bahd": 5}
 DE_APPLY = {"hard": 0, "soft": 1}
 DE_FUSE = {"x/y/-": 0, "+/-": 1, "x/y": 2}
 (STAGE_MEL_DB, STAGE_POOL1, STAGE_POOL2, STAGE_CONV3, STAGE_POOL3, STAGE_CONV5, STAGE_CNN_FEAT,
@@ -46,7 +47,8 @@ class NisqaConfig(C.Structure):
                 ("win_s", C.c_double), ("fmax", C.c_double), ("sa_layers", C.c_int32),
                 ("max_chunk_segments", C.c_int32), ("pool", C.c_int32), ("pos_enc", C.c_int32),
                 ("double_ended", C.c_int32), ("de_align", C.c_int32), ("de_align_apply", C.c_int32),
-                ("de_fuse", C.c_int32), ("td2_layers", C.c_int32), ("td2_pos_enc", C.c_int32)]
+                ("de_fuse", C.c_int32), ("td2_layers", C.c_int32), ("td2_pos_enc", C.c_int32),
+                ("cnn_kind", C.c_int32), ("cnn_fc", C.c_int32)]
 
 
 class NisqaTensor(C.Structure):
@@ -158,11 +160,22 @@ def config_from_args(args, max_chunk_segments=0):
             raise NotImplementedError("pool_att_h=%r is not implemented by the B200 engine (128 or None)" % args.get("pool_att_h"))
     if pool_mode is None:
         raise NotImplementedError("Pool option not available in the B200 engine: %r" % pool)
+    cnn_kind, cnn_fc = CNN_CONV, 0
     if (cnn, td) == ("adapt", "self_att") and pool_mode != POOL_LAST_STEP_BI:
         arch = ARCH_ADAPT_SA_ATTFF
         ok = (list(args["cnn_pool_1"]) == [24, 7] and list(args["cnn_pool_2"]) == [12, 5]
               and list(args["cnn_pool_3"]) == [6, 3] and args.get("cnn_fc_out_h") in (None, 0)
               and args["td_sa_d_model"] == 64 and args["td_sa_nhead"] == 1 and args["td_sa_h"] == 64)
+    elif cnn in (None, "skip", "dff") and td == "self_att" and pool_mode != POOL_LAST_STEP_BI:
+        # framewise models without convolutions (lib:504-583) in front of the self-attention stack
+        arch = ARCH_ADAPT_SA_ATTFF
+        cnn_kind = CNN_DFF if cnn == "dff" else CNN_SKIP
+        cnn_fc = int(args.get("cnn_fc_out_h") or 0)
+        if cnn_kind == CNN_DFF and cnn_fc == 0:
+            cnn_fc = 4096                                   # DFF's default hidden width (lib:544)
+        if cnn_fc % 64 != 0:
+            raise NotImplementedError("cnn_fc_out_h=%d: the B200 engine needs a multiple of 64" % cnn_fc)
+        ok = args["td_sa_d_model"] == 64 and args["td_sa_nhead"] == 1 and args["td_sa_h"] == 64
     elif (cnn, td) == ("standard", "lstm") and pool_mode in (POOL_LAST_STEP_BI, POOL_AVG, POOL_MAX, POOL_LAST_STEP):
         arch = ARCH_STD_LSTM_LASTBI
         ok = (args.get("cnn_fc_out_h") == 20 and args["td_lstm_h"] == 128
@@ -179,7 +192,7 @@ def config_from_args(args, max_chunk_segments=0):
         if arch != ARCH_ADAPT_SA_ATTFF:
             raise NotImplementedError("NISQA_DE is implemented for cnn_model='adapt', td='self_att'")
         if args.get("de_align") not in DE_ALIGN:
-            raise NotImplementedError("de_align=%r is not implemented by the B200 engine (dot, cosine, distance)" % (args.get("de_align"),))
+            raise NotImplementedError("de_align=%r is not implemented by the B200 engine (dot, cosine, distance, luong, bahd)" % (args.get("de_align"),))
         if args.get("de_align_apply") not in DE_APPLY or args.get("de_fuse") not in DE_FUSE:
             raise NotImplementedError("de_align_apply / de_fuse option not available: %r / %r" % (args.get("de_align_apply"), args.get("de_fuse")))
         if args.get("de_fuse_dim"):
@@ -192,7 +205,7 @@ def config_from_args(args, max_chunk_segments=0):
             and args.get("td_2_sa_h") == 64
     else:
         ok = ok and args.get("td_2") in (None, "skip")
-    ok = ok and (args["cnn_c_out_1"], args["cnn_c_out_2"], args["cnn_c_out_3"]) == (16, 32, 64)
+    ok = ok and (cnn_kind != CNN_CONV or (args["cnn_c_out_1"], args["cnn_c_out_2"], args["cnn_c_out_3"]) == (16, 32, 64))
     ok = ok and args["ms_n_fft"] == 4096 and args["ms_n_mels"] == 48 and args["ms_seg_length"] == 15
     if not ok:
         raise NotImplementedError("checkpoint hyper-parameters outside the shipped NISQA configurations")
@@ -211,6 +224,7 @@ def config_from_args(args, max_chunk_segments=0):
     cfg.max_chunk_segments = int(max_chunk_segments) or int(os.environ.get("NISQA_MAX_CHUNK", "0"))
     cfg.pool = pool_mode
     cfg.pos_enc = 1 if (arch == ARCH_ADAPT_SA_ATTFF and args.get("td_sa_pos_enc")) else 0
+    cfg.cnn_kind, cfg.cnn_fc = cnn_kind, cnn_fc
     if args.get("td_2") == "self_att":
         cfg.td2_layers = int(args["td_2_sa_num_layers"])
         cfg.td2_pos_enc = 1 if args.get("td_2_sa_pos_enc") else 0

@@ -133,6 +133,28 @@ def standard_cnn(sd, x, args, taps=None):
     return x
 
 
+def skip_cnn(sd, x):
+    """SkipCNN.forward (lib:529-533): BatchNorm2d(1) (eval) -> view(-1, 720) -> Linear or Identity."""
+    p = "cnn.model."
+    x = F.batch_norm(x, sd[p + "bn.running_mean"], sd[p + "bn.running_var"], sd[p + "bn.weight"], sd[p + "bn.bias"], training=False, eps=1e-5)
+    x = x.reshape(-1, x.shape[2] * x.shape[3])
+    if p + "linear.weight" in sd:
+        x = F.linear(x, sd[p + "linear.weight"], sd[p + "linear.bias"])
+    return x
+
+
+def dff(sd, x):
+    """DFF.forward (lib:569-583, eval: dropout is the identity): BN2d(1), then 4 x (Linear, BatchNorm1d, ReLU)."""
+    p = "cnn.model."
+    x = F.batch_norm(x, sd[p + "bn1.running_mean"], sd[p + "bn1.running_var"], sd[p + "bn1.weight"], sd[p + "bn1.bias"], training=False, eps=1e-5)
+    x = x.reshape(-1, x.shape[2] * x.shape[3])
+    for i in range(1, 5):
+        x = F.linear(x, sd[p + "lin%d.weight" % i], sd[p + "lin%d.bias" % i])
+        b = p + "bn%d." % (i + 1)
+        x = F.relu(F.batch_norm(x, sd[b + "running_mean"], sd[b + "running_var"], sd[b + "weight"], sd[b + "bias"], training=False, eps=1e-5))
+    return x
+
+
 # --------------------------------------------------------- time dependency (a11/a12/a16)
 def self_attention(sd, feats, taps=None, pos_enc=False):
     """lib:988-996 + lib:1025-1040 for ONE clip (so no key-padding mask is needed).
@@ -187,7 +209,7 @@ def bilstm(sd, feats):
 
 
 # ------------------------------------------------- double-ended model
-def de_align(args, x, y):
+def de_align(args, x, y, sd=None):
     """Alignment.forward (lib:1274-1285) for ONE pair: attention scores of every degraded step against the reference
     clip's own steps (no padding, so no mask), softmax over the reference steps, hard (argmax -> gather, lib:1359-1368)
     or soft (att @ y, lib:1370-1378) application.  x [Sx, d], y [Sy, d] -> y aligned to x [Sx, d]."""
@@ -198,6 +220,12 @@ def de_align(args, x, y):
         att = F.cosine_similarity(x[:, None, :], y[None, :, :], dim=2, eps=1e-8)
     elif method == "distance":                             # AttDistance lib:1310-1323 with dist_norm = weight_norm = 1
         att = -(x[None, :, :] - y[:, None, :]).abs().pow(1).mean(dim=2).pow(1).t()
+    elif method == "luong":                                # AttLuong lib:1344-1357: x . (W y + b)
+        att = x @ F.linear(y, sd["align.att.W.weight"], sd["align.att.W.bias"]).t()
+    elif method == "bahd":                                 # AttBahdanau lib:1325-1342: v . tanh(Wq x + Wy y) (+ bias)
+        h = torch.tanh(F.linear(x, sd["align.att.Wq.weight"], sd["align.att.Wq.bias"])[None, :, :]
+                       + F.linear(y, sd["align.att.Wy.weight"], sd["align.att.Wy.bias"])[:, None, :])
+        att = F.linear(h, sd["align.att.v.weight"], sd["align.att.v.bias"]).squeeze(2).t()
     else:
         raise NotImplementedError(method)
     att = torch.softmax(att, dim=1)
@@ -230,7 +258,7 @@ def forward_de_from_mel(args, sd, spec, spec_ref, taps=None):
             feats = adapt_cnn(sd, segments(sp, args), args)
             outs.append(self_attention(sd, feats, pos_enc=bool(args.get("td_sa_pos_enc"))))
         x, y = outs
-        y_al = de_align(args, x, y)
+        y_al = de_align(args, x, y, sd)
         if taps is not None: taps["de_x"], taps["de_y"], taps["de_y_aligned"] = x, y, y_al
         fused = de_fuse(args, x, y_al)
         sd2 = {k.replace("time_dependency_2.", "time_dependency."): v for k, v in sd.items() if k.startswith("time_dependency_2.")}
@@ -309,6 +337,10 @@ def forward_from_mel(args, sd, spec, taps=None):
             feats = adapt_cnn(sd, x, args, taps)
         elif args["cnn_model"] == "standard":
             feats = standard_cnn(sd, x, args, taps)
+        elif args["cnn_model"] in (None, "skip"):
+            feats = skip_cnn(sd, x)
+        elif args["cnn_model"] == "dff":
+            feats = dff(sd, x)
         else:
             raise NotImplementedError(args["cnn_model"])
         if taps is not None: taps["cnn_feat"] = feats

@@ -27,6 +27,10 @@ VARIANTS = {
                                  "td_2_sa_num_layers": 2, "td_2_sa_pos_enc": None, "td_2_sa_dropout": 0.1}),
     "mos_td2_sa_pos_enc": ("nisqa_mos_only.tar", {"td_2": "self_att", "td_2_sa_d_model": 64, "td_2_sa_nhead": 1, "td_2_sa_h": 64,
                                                   "td_2_sa_num_layers": 1, "td_2_sa_pos_enc": True, "td_2_sa_dropout": 0.1}),
+    # framewise models without convolutions (lib:504-583): seeded weights for the framewise module and the first Linear
+    "mos_skip": ("nisqa_mos_only.tar", {"cnn_model": "skip", "cnn_fc_out_h": None}),
+    "dim_skip_fc": ("nisqa.tar", {"cnn_model": "skip", "cnn_fc_out_h": 128}),
+    "mos_dff": ("nisqa_mos_only.tar", {"cnn_model": "dff", "cnn_fc_out_h": 256}),
 }
 # double-ended variants (NISQA_DE, reference lib:272-424): nisqa_mos_only.tar's CNN, first self-attention stack and
 # PoolAttFF head (identical shapes) + seeded weights for time_dependency_2 (input width 192 or 128)
@@ -36,6 +40,10 @@ DE_VARIANTS = {
     "de_distance_soft_xy": {"de_align": "distance", "de_align_apply": "soft", "de_fuse": "x/y", "td_2_sa_pos_enc": True,
                             "td_2_sa_num_layers": 1},
     "de_dot_hard": {"de_align": "dot", "de_align_apply": "hard", "de_fuse": "x/y"},
+    # the alignment modules with learned weights (seeded): AttLuong (lib:1344-1357), AttBahdanau (lib:1325-1342)
+    "de_luong_soft": {"de_align": "luong", "de_align_apply": "soft", "de_fuse": "x/y/-"},
+    "de_luong_hard": {"de_align": "luong", "de_align_apply": "hard", "de_fuse": "+/-"},
+    "de_bahd_soft": {"de_align": "bahd", "de_align_apply": "soft", "de_fuse": "x/y/-"},
 }
 # (degraded, reference) pairs: (seed, seconds, sample rate) each; the degraded signal of pair 0 / 1 is derived from its
 # reference (delay + noise + clipping: what a double-ended model is for), pair 2 has unrelated signals of other lengths
@@ -88,7 +96,17 @@ def de_checkpoint(name, base_args, base_sd):
     args.update(over)
     sd = {k: v for k, v in base_sd.items()}
     fdim = 192 if args["de_fuse"] == "x/y/-" else 128
-    td2_weights(sd, args, fdim, np.random.default_rng(sum(map(ord, name))))
+    rng = np.random.default_rng(sum(map(ord, name)))
+    td2_weights(sd, args, fdim, rng)
+
+    def put(key, shape, scale):
+        sd["align.att." + key] = torch.from_numpy((rng.standard_normal(shape) * scale).astype(np.float32))
+    if args["de_align"] == "luong":
+        put("W.weight", (64, 64), 0.125); put("W.bias", (64,), 0.05)
+    if args["de_align"] == "bahd":
+        put("Wq.weight", (128, 64), 0.125); put("Wq.bias", (128,), 0.05)
+        put("Wy.weight", (128, 64), 0.125); put("Wy.bias", (128,), 0.05)
+        put("v.weight", (1, 128), 0.3); put("v.bias", (1,), 0.05)
     return args, sd
 
 
@@ -132,4 +150,33 @@ def variant_checkpoint(name, base_args, base_sd):
         sd["time_dependency.model.pos_encoder.pe"] = positional_encoding()
     if args.get("td_2") == "self_att":
         td2_weights(sd, args, 64, np.random.default_rng(sum(map(ord, name))))
+    if args.get("cnn_model") in ("skip", "dff"):
+        rng = np.random.default_rng(sum(map(ord, name)) + 1)
+        sd = {k: v for k, v in sd.items() if not k.startswith("cnn.")}
+        t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+
+        def bn(prefix, n):      # running statistics in the range the data really has (mel dB / unit-scale activations)
+            sd[prefix + "weight"] = t(rng.uniform(0.8, 1.2, n)); sd[prefix + "bias"] = t(rng.normal(0, 0.1, n))
+            sd[prefix + "running_mean"] = t(rng.normal(0, 0.2, n)); sd[prefix + "running_var"] = t(rng.uniform(0.5, 1.5, n))
+            sd[prefix + "num_batches_tracked"] = torch.tensor(1)
+
+        def lin(prefix, n_out, n_in):
+            sd[prefix + "weight"] = t(rng.standard_normal((n_out, n_in)) / math.sqrt(n_in)); sd[prefix + "bias"] = t(rng.normal(0, 0.05, n_out))
+        h = args.get("cnn_fc_out_h")
+        if args["cnn_model"] == "skip":
+            bn("cnn.model.bn.", 1)
+            sd["cnn.model.bn.running_mean"] = t([-35.0]); sd["cnn.model.bn.running_var"] = t([400.0])
+            if h:
+                lin("cnn.model.linear.", h, 720)
+            fan = h or 720
+        else:
+            bn("cnn.model.bn1.", 1)
+            sd["cnn.model.bn1.running_mean"] = t([-35.0]); sd["cnn.model.bn1.running_var"] = t([400.0])
+            lin("cnn.model.lin1.", h, 720)
+            for i in (2, 3, 4):
+                lin("cnn.model.lin%d." % i, h, h)
+            for i in (2, 3, 4, 5):
+                bn("cnn.model.bn%d." % i, h)
+            fan = h
+        sd["time_dependency.model.linear.weight"] = t(rng.standard_normal((64, fan)) / math.sqrt(fan))
     return args, sd

@@ -68,8 +68,8 @@ def test_segment_counts_bit_exact_vs_oracle(built_lib, ckpt):
 
 def test_config_refuses_unknown_architectures():
     args, _ = O.load_checkpoint(os.path.join(WEIGHTS, "nisqa.tar"))
-    for k, v in (("pool", "last_step_bi"), ("pool_att_h", 64), ("td", "lstm"), ("cnn_model", "dff"), ("model", "NISQA_DE"),
-                 ("td_sa_nhead", 4)):
+    for k, v in (("pool", "last_step_bi"), ("pool_att_h", 64), ("td", "lstm"), ("cnn_model", "resnet"), ("model", "NISQA_DE"),
+                 ("td_sa_nhead", 4), ("cnn_fc_out_h", 100), ("td_2", "lstm"), ("cnn_c_out_1", 8)):
         bad = dict(args); bad[k] = v
         with pytest.raises(NotImplementedError):
             E.config_from_args(bad)
@@ -78,6 +78,17 @@ def test_config_refuses_unknown_architectures():
     # the other pooling modules and the positional encoding are implemented
     assert E.config_from_args(dict(args, pool="avg")).pool == E.POOL_AVG
     assert E.config_from_args(dict(args, pool="att", pool_att_h=None, td_sa_pos_enc=True)).pos_enc == 1
+    # ... and so are the framewise models without convolutions, td_2 and the double-ended model
+    c = E.config_from_args(dict(args, cnn_model="dff", cnn_fc_out_h=None))
+    assert (c.cnn_kind, c.cnn_fc) == (E.CNN_DFF, 4096)
+    assert E.config_from_args(dict(args, cnn_model="skip", cnn_fc_out_h=None)).cnn_kind == E.CNN_SKIP
+    de = dict(args, model="NISQA_DE", td_2="self_att", td_2_sa_d_model=64, td_2_sa_nhead=1, td_2_sa_h=64, td_2_sa_num_layers=2,
+              de_align="bahd", de_align_apply="soft", de_fuse="x/y/-", de_fuse_dim=None)
+    c = E.config_from_args(de)
+    assert (c.double_ended, c.de_align, c.td2_layers, c.n_out) == (1, 5, 2, 1)
+    for k, v in (("de_align", "none"), ("de_fuse_dim", 64), ("td_2", "skip")):
+        with pytest.raises(NotImplementedError):
+            E.config_from_args(dict(de, **{k: v}))
 
 
 def test_no_cpu_fallback(built_lib):
