@@ -303,11 +303,28 @@ struct PipeCfg {
                                                              : (C::OUT_SPLIT ? 2 : 1) * C::IMG_BYTES;
   static constexpr int BUF_RAW = (2 * C::A_BYTES > STG_BYTES) ? 2 * C::A_BYTES : STG_BYTES;
   static constexpr int BUF_BYTES = (BUF_RAW + 1023) & ~1023;
-  static constexpr bool RESIDENT = 2 * BUF_BYTES + 9 * C::B_STAGE <= 196 * 1024;      // all nine taps stay in shared memory
-  static constexpr int NSW = RESIDENT ? 9 : ((2 * BUF_BYTES + 4 * C::B_STAGE <= 216 * 1024) ? 4 : 3);
-  static constexpr int OFF_B = 2 * BUF_BYTES;
+#ifndef NISQA_PIPE_SEP
+#define NISQA_PIPE_SEP 0      // measured: 0 (shared buffers) 0.164 ms, 1 0.187 ms, 2 0.177 ms for conv3 (profiles/r02z_ab_kernels.txt)
+#endif
+  // EXPERIMENT (off): un-pooled layers whose output image is larger than the activation tile (conv3) with two dedicated
+  // activation buffers and separate staging, so that the next tile's activations are fetched as soon as the MMAs of tile
+  // it-2 have retired, not after its epilogue has staged and shipped its output (34 % of conv3's issue time waits for
+  // that).  Measured slower: with ONE staging buffer the 60 KB image's way out of the SM (~3 600 cycles) serialises with
+  // the next tile's staging; with two, the weights no longer fit and stream through the ring.
+  static constexpr int A_PAIR = (2 * C::A_BYTES + 1023) & ~1023;
+  static constexpr int STG_AL = (STG_BYTES + 1023) & ~1023;
+  // NISQA_PIPE_SEP: 1 = one staging buffer, weights resident; 2 = two staging buffers, weights through a 4-stage ring
+  static constexpr int NSTG = NISQA_PIPE_SEP == 2 ? 2 : 1;
+  static constexpr bool SEP_STAGE = NISQA_PIPE_SEP && C::POOL == SP_POOL_NONE && STG_BYTES > 2 * C::A_BYTES &&
+                                    2 * A_PAIR + NSTG * STG_AL + (NSTG == 2 ? 4 : 9) * C::B_STAGE <= 227 * 1024 - 2048;
+  static constexpr int A_STRIDE = SEP_STAGE ? A_PAIR : BUF_BYTES;       // bytes between the two activation buffers
+  static constexpr int OFF_STG = 2 * A_PAIR;                            // (SEP_STAGE) the staging buffer(s)
+  static constexpr int AB_BYTES = SEP_STAGE ? 2 * A_PAIR + NSTG * STG_AL : 2 * BUF_BYTES;
+  static constexpr bool RESIDENT = (SEP_STAGE && NSTG == 1) || (!SEP_STAGE && AB_BYTES + 9 * C::B_STAGE <= 196 * 1024);      // all nine taps stay in shared memory
+  static constexpr int NSW = RESIDENT ? 9 : ((AB_BYTES + 4 * C::B_STAGE <= 216 * 1024) ? 4 : 3);
+  static constexpr int OFF_B = AB_BYTES;
   static constexpr int OFF_BAR = OFF_B + NSW * C::B_STAGE;
-  static constexpr int N_BAR = 2 + 2 + 2 * NSW + 2 + 2 + 2;
+  static constexpr int N_BAR = 2 + 2 + 2 * NSW + 2 + 2 + 2 + 2;
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * N_BAR + 32 + 1024;
   static constexpr int COLS_TILE = 4 * C::COUT;                        // 2 M-tiles x [hi*hi+lo*hi | hi*lo]
   static constexpr int TMEM_ALLOC = 2 * COLS_TILE;                     // 512 (C_out 64) / 256 (C_out 32): powers of two
@@ -332,18 +349,21 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
   const uint32_t bar0 = sbase + Pc::OFF_BAR;
   const uint32_t bar_a_full = bar0, bar_a_free = bar0 + 16, bar_b_full = bar0 + 32, bar_b_empty = bar_b_full + 8 * NSW;
   const uint32_t bar_acc_full = bar_b_empty + 8 * NSW, bar_acc_free = bar_acc_full + 16, bar_stage_ready = bar_acc_free + 16;
+  const uint32_t bar_stg_free = bar_stage_ready + 16;              // (SEP_STAGE) the shipped image has left the staging buffer
+  constexpr bool SEP = Pc::SEP_STAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Pc::OFF_BAR + 8 * Pc::N_BAR + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), Pc::TMEM_ALLOC);
   if (tid == 256) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_free + 8 * i, 1);
+      mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_free + 8 * i, SEP ? 2 : 1);   // SEP: both MMA issuers commit
       mbar_init(bar_acc_full + 8 * i, 2);          // both MMA issuers commit
       mbar_init(bar_acc_free + 8 * i, 8);          // one arrival per epilogue warp
       mbar_init(bar_stage_ready + 8 * i, 8);       // un-pooled layers: the staged output image is complete
     }
     for (int i = 0; i < NSW; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 2); }
+    mbar_init(bar_stg_free, 1); mbar_init(bar_stg_free + 8, 1);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -359,10 +379,11 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
       constexpr uint32_t A_COPY = (uint32_t)C::AROWS * ROWB;
       auto store_tile = [&](int j) {
         const int b = j & 1;
-        mbar_wait(bar_stage_ready + 8 * b, (j >> 1) & 1);          // all eight epilogue warps have staged tile j
+        if constexpr (SEP && Pc::NSTG == 1) mbar_wait(bar_stage_ready, j & 1);      // one staging buffer: a completion per tile
+        else mbar_wait(bar_stage_ready + 8 * b, (j >> 1) & 1);     // all eight epilogue warps have staged tile j
         const int seg0 = (blockIdx.x + j * (int)gridDim.x) * G;
         const int nvalid = min(G, n_seg - seg0);
-        const uint32_t sb = sbase + b * Pc::BUF_BYTES;
+        const uint32_t sb = SEP ? sbase + Pc::OFF_STG + (Pc::NSTG == 2 ? b * Pc::STG_AL : 0) : sbase + b * Pc::BUF_BYTES;
         if constexpr (C::OUT_SPLIT) {
           const size_t img0 = (size_t)(kSplitLead + seg0 * BLK) * C::OROWB;
           const uint32_t bytes = (uint32_t)nvalid * C::OBLK * C::OROWB;
@@ -374,20 +395,23 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
         }
         bulk_commit();
         bulk_wait_read0();                                         // the stores have read the buffer
+        if constexpr (SEP) mbar_arrive(bar_stg_free + (Pc::NSTG == 2 ? 8 * b : 0));
       };
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1, ph = (it >> 1) & 1;
         const long long tw = PIPE_NOW();
-        if constexpr (C::POOL == SP_POOL_NONE) { if (it >= 2) store_tile(it - 2); }
+        if constexpr (SEP) mbar_wait(bar_a_free + 8 * buf, ph ^ 1);           // the MMAs of tile it-2 have read the buffer
+        else if constexpr (C::POOL == SP_POOL_NONE) { if (it >= 2) store_tile(it - 2); }
         else mbar_wait(bar_a_free + 8 * buf, ph ^ 1);              // the pooling epilogue of tile it-2 has left the buffer
         PIPE_ADD(9, tw);
         const int g0 = kSplitLead + tile * G * BLK - HALO;
         const uint32_t sh = (uint32_t)(g0 & 7);
-        const uint32_t a_hi = sbase + buf * Pc::BUF_BYTES, a_lo = a_hi + C::A_BYTES;
+        const uint32_t a_hi = sbase + buf * Pc::A_STRIDE, a_lo = a_hi + C::A_BYTES;
         mbar_expect_tx(bar_a_full + 8 * buf, 2 * A_COPY);
         bulk_g2s(a_hi + sh * ROWB, in_hi + (size_t)g0 * ROWB, A_COPY, bar_a_full + 8 * buf);
         bulk_g2s(a_lo + sh * ROWB, in_lo + (size_t)g0 * ROWB, A_COPY, bar_a_full + 8 * buf);
+        if constexpr (SEP) { if (it >= 2) store_tile(it - 2); }    // (its epilogue started when those MMAs retired)
       }
       if constexpr (C::POOL == SP_POOL_NONE)
         for (int j = (it >= 2 ? it - 2 : 0); j < it; ++j) store_tile(j);
@@ -425,7 +449,7 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
         tc_fence_after();
         const int g0 = kSplitLead + tile * G * BLK - HALO;
         const uint32_t sh = (uint32_t)(g0 & 7);
-        const uint32_t a_hi = sbase + buf * Pc::BUF_BYTES, a_lo = a_hi + C::A_BYTES;
+        const uint32_t a_hi = sbase + buf * Pc::A_STRIDE, a_lo = a_hi + C::A_BYTES;
         const uint32_t d = tmem + buf * Pc::COLS_TILE + mt * (2 * COUT);
         for (int t = 0; t < 9; ++t, ++cnt) {
           const int s = Pc::RESIDENT ? t : cnt % NSW;
@@ -447,6 +471,7 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
           }
           if (!Pc::RESIDENT) umma_commit(bar_b_empty + 8 * s);
         }
+        if constexpr (SEP) umma_commit(bar_a_free + 8 * buf);      // the activation buffer may be refilled
         umma_commit(bar_acc_full + 8 * buf);
       }
       if (mt == 0) { PIPE_ADD(4, t_all); PIPE_COUNT(15, it); }
@@ -458,11 +483,15 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1, ph = (it >> 1) & 1;
       const int seg0 = tile * G;
-      unsigned char* sbuf = smem + buf * Pc::BUF_BYTES;          // staging = the tile's own activation buffer
+      unsigned char* sbuf = SEP ? smem + Pc::OFF_STG + (Pc::NSTG == 2 ? buf * Pc::STG_AL : 0) : smem + buf * Pc::BUF_BYTES;   // staging = the tile's own activation buffer, or the one staging buffer
       float* stg = reinterpret_cast<float*>(sbuf);
       long long tw = PIPE_NOW();
       mbar_wait(bar_acc_full + 8 * buf, ph);                     // every MMA of the tile has retired
       if (tid == 0) PIPE_ADD(5, tw);
+      if constexpr (SEP) {                                       // the image of tile it-1 (it-2) has left the staging buffer
+        if constexpr (Pc::NSTG == 1) mbar_wait(bar_stg_free, (it & 1) ^ 1);
+        else mbar_wait(bar_stg_free + 8 * buf, ph ^ 1);
+      }
       tw = PIPE_NOW();
       tc_fence_after();
       {
@@ -526,7 +555,7 @@ conv_pipe_kernel(const unsigned char* __restrict__ in_hi, const unsigned char* _
       if constexpr (C::POOL == SP_POOL_NONE) {
         fence_proxy_async();                                       // staged image -> visible to the producer's bulk stores
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_stage_ready + 8 * buf);
+        if (lane == 0) mbar_arrive((SEP && Pc::NSTG == 1) ? bar_stage_ready : bar_stage_ready + 8 * buf);
         if (tid == 0) PIPE_ADD(6, tw);
       } else {
         if (tid == 0) PIPE_ADD(6, tw);

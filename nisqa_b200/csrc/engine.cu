@@ -147,7 +147,10 @@ struct Ticket {          // one asynchronous nisqa_submit_pcm call
 // submissions run on different streams: wave tails and the small low-occupancy kernels of one
 // pass are filled with CTAs of another (+8..12 % throughput measured, tools/two_engines.py), and
 // the upload of the next pass (copy stream) overlaps compute.
-constexpr int kLanes = 3;
+#ifndef NISQA_LANES
+#define NISQA_LANES 3
+#endif
+constexpr int kLanes = NISQA_LANES;
 constexpr int kStages = 6;     // staging slots / submissions in flight (uploads run ahead of the lanes)
 struct Lane {
   cudaStream_t stream = nullptr;

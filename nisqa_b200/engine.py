@@ -68,7 +68,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("NISQA_LIB") or LIB_PATH          # NISQA_LIB: a variant build for A/B measurements
     if not os.path.exists(p):
         raise EngineError(
             "libnisqa_b200.so is missing (%s): build it with `python -m nisqa_b200.build`; "
