@@ -404,7 +404,13 @@ constexpr int kSpanMax = 1536;                    // hop + win limit of this ker
 template <typename T> __host__ __device__ constexpr int pp_slot_bytes() {
   return ((kSpanMax + 16 / (int)sizeof(T)) * (int)sizeof(T) + 15) / 16 * 16;
 }
-template <typename T> constexpr int pp_smem_bytes() { return 2 * pp_slot_bytes<T>() + 4 * kScratchPerWarp * 8; }
+#ifndef NISQA_FE_CTAS
+#define NISQA_FE_CTAS 6        // PCM16 input: resident CTAs per SM the kernel is built for (6 = one sample slot, <= 80 registers)
+#endif
+// PCM16 with six CTAs per SM: ONE sample slot (the slot is only live during the input stage: the next pair's copy is issued
+// behind the barrier that follows the FFT, still a whole mel stage ahead of its use) - 37.4 KB of shared memory per CTA
+template <typename T> __host__ __device__ constexpr int pp_slots() { return (sizeof(T) == 2 && NISQA_FE_CTAS >= 6) ? 1 : 2; }
+template <typename T> constexpr int pp_smem_bytes() { return pp_slots<T>() * pp_slot_bytes<T>() + 4 * kScratchPerWarp * 8; }
 
 template <typename T>
 __device__ __forceinline__ void pp_issue_pair(const T* __restrict__ y, int a, int span, int n_samples,
@@ -424,13 +430,14 @@ __device__ __forceinline__ void pp_issue_pair(const T* __restrict__ y, int a, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kFeThreads, 5)
+__global__ void __launch_bounds__(kFeThreads, (sizeof(T) == 2 && NISQA_FE_CTAS >= 6) ? 6 : 5)
 frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips,
                    const FbTables* __restrict__ fbs, const float2* __restrict__ tw1,
                    const float4* __restrict__ tw2, float* __restrict__ mel, unsigned* __restrict__ clipmax,
                    int ppc /*frame pairs per CTA*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* scratch = reinterpret_cast<float2*>(smem_raw + 2 * pp_slot_bytes<T>());
+  constexpr int NSLOT = pp_slots<T>();
+  float2* scratch = reinterpret_cast<float2*>(smem_raw + NSLOT * pp_slot_bytes<T>());
   __shared__ int band_meta[2 * kMels + 1];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -450,11 +457,11 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
   const int r = warp;
   float wmax = -INFINITY;
   for (int p = p0; p < p1; ++p) {
-    const int s = (p - p0) & 1;
+    const int s = NSLOT == 2 ? (p - p0) & 1 : 0;
     const int a = cd.s0 + 2 * p * cd.hop;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                    // slot s complete and visible; planes of pair p-1 consumed
-    if (p + 1 < p1)
+    if (NSLOT == 2 && p + 1 < p1)
       pp_issue_pair<T>(y, a + 2 * cd.hop, span, cd.n_samples,
                        reinterpret_cast<T*>(smem_raw + (s ^ 1) * pp_slot_bytes<T>()), tid);
     const bool validB = 2 * p + 1 < cd.n_frames;
@@ -489,7 +496,9 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
         x[j0 + u] = pk(fmaf(sa[u], wt[u].x, -(sb[u] * wt[u].y)), fmaf(sa[u], wt[u].y, sb[u] * wt[u].x));
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
-    __syncthreads();                    // all four planes written
+    __syncthreads();                    // all four planes written (and every warp is past the input stage: the slot is free)
+    if (NSLOT == 1 && p + 1 < p1)
+      pp_issue_pair<T>(y, a + 2 * cd.hop, span, cd.n_samples, reinterpret_cast<T*>(smem_raw), tid);
     mag_stage(scratch, fb.n_mag, tid);
     __syncthreads();                    // magnitudes staged
     wmax = fmaxf(wmax, mel_bands_staged(scratch, band_meta, fb.weights, warp, lane, validB,
