@@ -58,7 +58,7 @@ struct LstmParams { const float* w_ih; const float* w_hh; const float* b; const 
 void launch_fc20(cudaStream_t, const float*, const float*, const float*, float*, int);
 void launch_lstm(cudaStream_t, const float*, const ClipDesc*, int, const LstmParams&, float*, float*, float, float*);
 void launch_lstm_batched(cudaStream_t, const float*, const ClipDesc*, const int*, int, const LstmParams&, float*, float*, float, float*);
-void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, float*);
+void launch_pool_final(cudaStream_t, const float*, const float*, const ClipDesc*, int, const PoolHeadParams&, int, int, float*);
 // td_tiled.cu
 struct ResampleClip { long long in_off, out_off, time_off; int n_in, n_out, n_fix, copy; double ratio; };
 void launch_resample(cudaStream_t, const void*, int, const ResampleClip*, int, int, double*, const double*, int, int, float*);
@@ -1048,7 +1048,7 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       }
       e->last_td_out = cur;
       { Scope s(e, "pool");
-        if (attff) launch_pool_final(st, cur, LN.logits.as<float>(), d_clips, n, H, n_out, scores);
+        if (attff) launch_pool_final(st, cur, LN.logits.as<float>(), d_clips, n, H, n_out, max_n_seg, scores);
         else {
           PoolSimpleParams Q = {W(e, "pool.a1"), W(e, "pool.a1b"), W(e, "pool.w3"), W(e, "pool.b3")};
           launch_pool_simple(st, cur, 64, d_clips, n, c.pool, Q, n_out, max_n_seg, scores);

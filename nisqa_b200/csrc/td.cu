@@ -9,6 +9,8 @@
 // inner loop is a warp-broadcast LDS.128 per 4 FMAs.  Clips are ragged: every kernel works
 // on the valid rows only, so no key-padding mask exists (masked keys in the reference
 // contribute exactly 0 after softmax).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nisqa {
@@ -106,16 +108,20 @@ struct PoolHeadParams {      // device pointers, heads concatenated
 };
 
 // softmax over the clip's time steps, weighted sum of x, Linear 64->1   (lib:1177-1181)
-// grid = n_clips, block = 64 * n_heads; thread (h, d)
+// grid = n_clips, block = 64 * n_heads; thread (h, d).  The softmax numerators are formed once per (head, step) into shared
+// memory; the weighted sum keeps ONE accumulator per thread in step order (the result does not depend on the unrolling) with
+// eight independent loads in flight.
 __global__ void pool_final_kernel(const float* __restrict__ x, const float* __restrict__ logits,
-                                  const ClipDesc* __restrict__ clips, PoolHeadParams P, int n_heads,
+                                  const ClipDesc* __restrict__ clips, PoolHeadParams P, int n_heads, int max_seg,
                                   float* __restrict__ scores) {
   __shared__ float red[5 * 64];
+  extern __shared__ float pnum[];                       // [n_heads][max_seg] softmax numerators
   const ClipDesc cd = clips[blockIdx.x];
   const int S = cd.n_seg;
   const int h = threadIdx.x >> 6, d = threadIdx.x & 63;
   if (S <= 0) { if (d == 0) scores[blockIdx.x * n_heads + h] = __int_as_float(0x7fc00000); return; }
   const float* lg = logits + (size_t)cd.seg_off * n_heads + h;
+  float* pn = pnum + (size_t)h * max_seg;
   float mx = -INFINITY;
   for (int t = d; t < S; t += 64) mx = fmaxf(mx, __ldg(lg + (size_t)t * n_heads));
   red[threadIdx.x] = mx;
@@ -124,7 +130,7 @@ __global__ void pool_final_kernel(const float* __restrict__ x, const float* __re
   mx = red[h * 64];
   __syncthreads();
   float sum = 0.f;
-  for (int t = d; t < S; t += 64) sum += expf(__ldg(lg + (size_t)t * n_heads) - mx);
+  for (int t = d; t < S; t += 64) { const float e = expf(__ldg(lg + (size_t)t * n_heads) - mx); pn[t] = e; sum += e; }
   red[threadIdx.x] = sum;
   __syncthreads();
   for (int o = 32; o > 0; o >>= 1) { if (d < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
@@ -132,7 +138,15 @@ __global__ void pool_final_kernel(const float* __restrict__ x, const float* __re
   __syncthreads();
   const float* xb = x + (size_t)cd.seg_off * 64 + d;
   float acc = 0.f;
-  for (int t = 0; t < S; ++t) acc = fmaf(expf(__ldg(lg + (size_t)t * n_heads) - mx), __ldg(xb + (size_t)t * 64), acc);
+  int t = 0;
+  for (; t + 8 <= S; t += 8) {
+    float xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = __ldg(xb + (size_t)(t + u) * 64);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(pn[t + u], xv[u], acc);
+  }
+  for (; t < S; ++t) acc = fmaf(pn[t], __ldg(xb + (size_t)t * 64), acc);
   acc = (acc / sum) * __ldg(P.w3 + h * 64 + d);
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -500,8 +514,10 @@ void launch_fc20(cudaStream_t st, const float* feats, const float* WT, const flo
   linear_rows_kernel<20, false><<<(n_rows + kRows - 1) / kRows, kRows, kRowSmem20, st>>>(feats, 768, WT, b, nullptr, nullptr, out, n_rows);
 }
 void launch_pool_final(cudaStream_t st, const float* x, const float* logits, const ClipDesc* clips, int n_clips,
-                       const PoolHeadParams& P, int n_heads, float* scores) {
-  pool_final_kernel<<<n_clips, 64 * n_heads, 0, st>>>(x, logits, clips, P, n_heads, scores);
+                       const PoolHeadParams& P, int n_heads, int max_seg, float* scores) {
+  const int smem = n_heads * std::max(max_seg, 1) * 4;          // <= 5 x 1300 x 4 bytes at ms_max_segments = 1300
+  if (smem > 40 * 1024) cudaFuncSetAttribute(pool_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pool_final_kernel<<<n_clips, 64 * n_heads, smem, st>>>(x, logits, clips, P, n_heads, std::max(max_seg, 1), scores);
 }
 void launch_lstm(cudaStream_t st, const float* feats20, const ClipDesc* clips, int n_clips,
                  const LstmParams& P, float* td_out, float* partial, float pool_bias, float* scores) {
