@@ -185,6 +185,86 @@ def test_two_rank_error_is_raised_on_every_rank(tmp_path):
     assert (tmp_path / "msg0").read_text() == (tmp_path / "msg1").read_text() == "Could not load file c5.wav"
 
 
+def test_double_ended_rows_pair_up_on_the_host(tmp_path):
+    """NISQA_DE host logic without a GPU (stub engine): a dataset row becomes the clip pair (degraded, reference) in that
+    order, ``ms_channel`` applies to the degraded file only (lib:2136-2154), the pair's score is row 2p of the engine's
+    output, and a too-short reference raises the reference's error naming the DEGRADED file (lib:2187-2192)."""
+    import pandas as pd
+    from nisqa_b200 import NISQA_lib as NL, engine as E, wav
+    rng = np.random.default_rng(5)
+    st = rng.integers(-3000, 3000, (4000, 2)).astype(np.int16)
+    wav.write_wav_pcm16(str(tmp_path / "d0.wav"), st, 16000)                       # stereo degraded file
+    wav.write_wav_pcm16(str(tmp_path / "r0.wav"), st, 16000)                       # stereo reference: always the mono mix
+    wav.write_wav_pcm16(str(tmp_path / "d1.wav"), rng.integers(-3000, 3000, 5000).astype(np.int16), 16000)
+    wav.write_wav_pcm16(str(tmp_path / "r1.wav"), rng.integers(-3000, 3000, 100).astype(np.int16), 16000)      # too short
+    df = pd.DataFrame({"deg": ["d0.wav", "d1.wav"], "ref": ["r0.wav", "r1.wav"]})
+    ds = NL.SpeechQualityDataset(df, data_dir=str(tmp_path), filename_column="deg", mos_column="predict_only",
+                                 ms_sr=None, ms_channel=1, double_ended=True, filename_column_ref="ref",
+                                 seg_length=15, ms_hop_length=0.01)
+    with pytest.raises(KeyError):
+        NL.SpeechQualityDataset(df, data_dir=str(tmp_path), filename_column="deg", mos_column="predict_only",
+                                double_ended=True, filename_column_ref=None)       # predict_file / predict_dir (lib:2133)
+
+    class StubEngine(object):
+        n_out = 1
+        seen = []
+
+        def submit_pcm(self, clips, srs):
+            self.seen.append([c.copy() for c in clips])
+            n = len(clips)
+            scores = np.full((n, 1), np.nan, np.float32)
+            status = np.zeros(n, np.int32)
+            for i, c in enumerate(clips):
+                if c.shape[0] < 15 * 160:
+                    status[i] = E.CLIP_TOO_SHORT
+            scores[0::2, 0] = [float(np.abs(c.astype(np.float64)).sum() % 97) for c in clips[0::2]]
+            return (None, scores, np.full(n, 3, np.int32), status)
+
+        def wait(self, handle):
+            return handle[1], handle[2], handle[3]
+
+        def drain(self):
+            pass
+
+    eng = StubEngine()
+    out = NL._predict_rows(eng, ds, np.array([0]), 4, 0)
+    deg, ref = eng.seen[0]
+    # channel pick on the degraded file (int16 -> float32 / 32768 because its partner in the call is float32)
+    assert deg.dtype == np.float32 and np.array_equal(deg, st[:, 1].astype(np.float32) / np.float32(32768.0))
+    mix = (st.astype(np.float32) / np.float32(32768.0)).mean(axis=1, dtype=np.float32)
+    assert ref.dtype == np.float32 and np.allclose(ref, mix, atol=1e-7)            # mono mix on the reference
+    assert out.shape == (1, 1) and np.isfinite(out[0, 0])
+    with pytest.raises(ValueError) as ei:
+        NL._predict_rows(eng, ds, np.array([0, 1]), 4, 0)
+    assert "Sample too short" in str(ei.value) and str(ei.value).endswith("d1.wav")
+
+
+def test_orderly_multi_rank_shutdown(tmp_path):
+    """dist.shutdown (what run_predict.py calls last): barrier, engine close, barrier, process group destroyed - on
+    two gloo ranks, and a no-op in a single process."""
+    from nisqa_b200 import dist as D
+    D.shutdown(None)                                             # single process: nothing to do
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch.distributed as dist\n"
+        "from nisqa_b200 import dist as D\n"
+        "rank, world, _ = D.init_process_group(backend='gloo')\n"
+        "class Eng:\n"
+        "    closed = False\n"
+        "    def close(self): self.closed = True\n"
+        "e = Eng(); D.shutdown(e)\n"
+        "assert e.closed and not dist.is_initialized()\n"
+        "open(os.path.join(%r, 'done%%d' %% rank), 'w').write('ok')\n" % (ROOT, str(tmp_path)))
+    port = 33500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "done0").exists() and (tmp_path / "done1").exists()
+
+
 @pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "f32", "f64", "u8", "ext16", "alaw", "ulaw_stereo"])
 def test_native_wav_reader_matches_oracle_loader(tmp_path, kind, built_lib):
     """csrc/wavio.cpp (nisqa_wav_probe / nisqa_wav_decode, host-only entry points of the C-ABI)."""
