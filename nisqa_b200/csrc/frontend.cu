@@ -22,6 +22,9 @@
 #ifndef NISQA_FE_PK_MAG
 #define NISQA_FE_PK_MAG 0      // magnitude stage with packed adds
 #endif
+#ifndef NISQA_FE_DIT
+#define NISQA_FE_DIT 0         // 32-point transforms as decimation in time with fused twiddle butterflies (6 FMAs instead of 8 FP instructions)
+#endif
 #ifndef NISQA_FE_MEL
 #define NISQA_FE_MEL 2         // 0: scalar band loop unrolled by 4, 1: rolled packed loop, 2: packed loop unrolled by 4
 #endif
@@ -94,6 +97,47 @@ __device__ __forceinline__ void fft32(f2 (&x)[32]) {
   }
 }
 
+// The same transform as decimation in TIME: input n sits at x[rev5(n)], X[k] ends up in x[k].  A butterfly with a
+// non-trivial twiddle is out1 = a + w b (4 FMAs), out2 = 2 a - out1 (2 FMAs) instead of add, subtract and a 4-instruction
+// complex product; 34 of the 80 butterflies of a 32-point transform have one.
+__device__ __forceinline__ void fft32_dit(f2 (&x)[32]) {
+#pragma unroll
+  for (int half = 1; half <= 16; half <<= 1) {
+#pragma unroll
+    for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const int k = j * (16 / half);                 // twiddle W_32^k = e^{-2 pi i j / (2 half)}
+        const float2 a = upk(x[base + j]), b = upk(x[base + j + half]);
+        if (k == 0) {
+          x[base + j] = pk(a.x + b.x, a.y + b.y);
+          x[base + j + half] = pk(a.x - b.x, a.y - b.y);
+        } else if (k == 8) {                            // w = -i: w b = (b.y, -b.x)
+          x[base + j] = pk(a.x + b.y, a.y - b.x);
+          x[base + j + half] = pk(a.x - b.y, a.y + b.x);
+        } else {
+          const float2 w = w32(k);
+          const float ox = fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x));
+          const float oy = fmaf(w.x, b.y, fmaf(w.y, b.x, a.y));
+          x[base + j] = pk(ox, oy);
+          x[base + j + half] = pk(fmaf(2.0f, a.x, -ox), fmaf(2.0f, a.y, -oy));
+        }
+      }
+    }
+  }
+}
+
+// slot of input / output index i in the register array handed to the 32-point transform
+__host__ __device__ constexpr int fe_in(int i) { return NISQA_FE_DIT ? rev5(i) : i; }
+__host__ __device__ constexpr int fe_out(int i) { return NISQA_FE_DIT ? i : rev5(i); }
+__device__ __forceinline__ void fe_fft32(f2 (&x)[32]) {
+#if NISQA_FE_DIT
+  fft32_dit(x);
+#else
+  fft32(x);
+#endif
+}
+
 __device__ __forceinline__ int reflect_index(int i, int n) {
   // numpy.pad(mode='reflect') index map, valid for any i (repeated reflection when the pad
   // is longer than the signal)
@@ -124,11 +168,12 @@ int frontend_smem_bytes(int Q) { return fe_region0_bytes(Q) + 4 * kScratchPerWar
 // both operand forms of the packed complex product in one 16-byte load.
 __device__ __forceinline__ void fft1024_plane(f2 (&x)[32], float2* tile_, int lane,
                                               const float4* __restrict__ tw2x) {
+  // x[fe_in(j)] = input n = lane + 32 j on entry
   f2* tile = reinterpret_cast<f2*>(tile_);
-  fft32(x);                                      // A_l[q] at x[rev5(q)]
+  fe_fft32(x);                                   // A_l[q] at x[fe_out(q)]
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    f2 v = x[rev5(q)];
+    f2 v = x[fe_out(q)];
     if (q != 0) {
 #if NISQA_FE_PK_FFT
       const float4 t = __ldg(tw2x + q * 32 + lane);                        // W_1024^(l q), coalesced
@@ -142,11 +187,11 @@ __device__ __forceinline__ void fft1024_plane(f2 (&x)[32], float2* tile_, int la
   }
   __syncwarp();
 #pragma unroll
-  for (int l = 0; l < 32; ++l) x[l] = tile[l * 33 + lane];
+  for (int l = 0; l < 32; ++l) x[fe_in(l)] = tile[l * 33 + lane];
   __syncwarp();
-  fft32(x);                                      // Z_r[lane + 32 p] at x[rev5(p)]
+  fe_fft32(x);                                   // Z_r[lane + 32 p] at x[fe_out(p)]
 #pragma unroll
-  for (int p = 0; p < 32; ++p) tile[lane + 32 * p] = x[rev5(p)];
+  for (int p = 0; p < 32; ++p) tile[lane + 32 * p] = x[fe_out(p)];
 }
 
 // Fused unpack of the two real spectra, |.|, sparse mel, dB for the 12 bands of this warp
@@ -378,7 +423,7 @@ frontend_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips, i
         }
       }
       if (r != 0) v = cmul(v, __ldg(tw1 + ((r - 1) * 32 + j) * 32 + lane));   // coalesced per-lane table
-      x[j] = pk(v);
+      x[fe_in(j)] = pk(v);
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
   }
@@ -493,7 +538,7 @@ frontend_pp_kernel(const T* __restrict__ pcm, const ClipDesc* __restrict__ clips
       }
 #pragma unroll
       for (int u = 0; u < CH; ++u)
-        x[j0 + u] = pk(fmaf(sa[u], wt[u].x, -(sb[u] * wt[u].y)), fmaf(sa[u], wt[u].y, sb[u] * wt[u].x));
+        x[fe_in(j0 + u)] = pk(fmaf(sa[u], wt[u].x, -(sb[u] * wt[u].y)), fmaf(sa[u], wt[u].y, sb[u] * wt[u].x));
     }
     fft1024_plane(x, scratch + r * kScratchPerWarp, lane, tw2);
     __syncthreads();                    // all four planes written (and every warp is past the input stage: the slot is free)
