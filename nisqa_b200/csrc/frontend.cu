@@ -23,7 +23,7 @@
 #define NISQA_FE_PK_MAG 0      // magnitude stage with packed adds
 #endif
 #ifndef NISQA_FE_DIT
-#define NISQA_FE_DIT 0         // 32-point transforms as decimation in time with fused twiddle butterflies (6 FMAs instead of 8 FP instructions)
+#define NISQA_FE_DIT 1         // 32-point transforms as decimation in time with fused twiddle butterflies (6 FMAs instead of 8 FP instructions)
 #endif
 #ifndef NISQA_FE_MEL
 #define NISQA_FE_MEL 2         // 0: scalar band loop unrolled by 4, 1: rolled packed loop, 2: packed loop unrolled by 4
