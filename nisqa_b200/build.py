@@ -29,8 +29,8 @@ def _digest():
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "nisqa_b200.h"))
     for f in files:
-        with open(f, "rb") as fh:
-            h.update(f.encode()); h.update(fh.read())
+        with open(f, "rb") as fh:       # (file NAME, not path: the digest must not depend on where the tree is checked out)
+            h.update(os.path.basename(f).encode()); h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
