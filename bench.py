@@ -265,6 +265,8 @@ def load_traffic_table():
     if have != want:
         return {}, "profiles/roofline_traffic.json was measured on other kernel sources (digest %s..., library %s...): traffic = null" % (
             str(have)[:12], want[:12])
+    if "td_sa_kernel" in tab and "sa_layer" not in tab:
+        tab["sa_layer"] = 2 * tab["td_sa_kernel"]          # the group "sa_layer" = the two encoder-layer launches of a step
     return tab, "profiles/roofline_traffic.json (%s), same kernel sources as this library" % tab.get("_note", "")
 
 
