@@ -261,7 +261,7 @@ def load_traffic_table():
         return {}, "no profiles/roofline_traffic.json"
     tab = json.load(open(tp))
     from nisqa_b200 import build as nb_build
-    have, want = tab.get("_source_digest"), nb_build._digest()
+    have, want = tab.get("_source_digest"), nb_build.kernel_digest()
     if have != want:
         return {}, "profiles/roofline_traffic.json was measured on other kernel sources (digest %s..., library %s...): traffic = null" % (
             str(have)[:12], want[:12])

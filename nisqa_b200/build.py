@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnisqa_b200.so")
 STAMP = os.path.join(HERE, ".libnisqa_b200.stamp")
-SOURCES = ["engine.cu", "frontend.cu", "cnn.cu", "conv_tc.cu", "conv_split.cu", "conv12.cu", "td.cu", "td_tiled.cu", "wavio.cpp", "resample.cpp", "resample_gpu.cu"]
+SOURCES = ["engine.cu", "frontend.cu", "cnn.cu", "conv_tc.cu", "conv_split.cu", "conv12.cu", "td.cu", "td_tiled.cu", "wavio.cpp", "flac.cpp", "resample.cpp", "resample_gpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared"]
 
@@ -31,6 +31,18 @@ def _digest():
     for f in files:
         with open(f, "rb") as fh:       # (file NAME, not path: the digest must not depend on where the tree is checked out)
             h.update(os.path.basename(f).encode()); h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def kernel_digest():
+    """Digest of the CUDA sources alone (*.cu, *.cuh + flags): what a measured per-kernel table (profiles/roofline_traffic.json)
+    is tied to - a change to the host-side readers does not invalidate it."""
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(CSRC, name), "rb") as fh:
+                h.update(name.encode()); h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

@@ -1,4 +1,4 @@
-// wavio.cpp - native RIFF/WAVE ingest (the caller side of the hot path).
+// wavio.cpp - native RIFF/WAVE (and FLAC, flac.cpp) ingest (the caller side of the hot path).
 // Replaces what lb.load(path, sr=None[, mono=False]) + the ms_channel pick do at reference
 // nisqa/NISQA_lib.py:2298-2306 (libsndfile conversion rules, float32 mean over channels).
 //
@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/nisqa_b200.h"
+#include "flac.h"
 
 namespace {
 
@@ -122,6 +123,16 @@ extern "C" {
 int nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t* sample_rate, int64_t* n_frames,
                     int32_t* channels, int32_t* kind_out) {
   if (!path) return NISQA_ERR_INVALID;
+  if (nisqa::flac_is(path)) {       // FLAC: integers of 8..32 bits, delivered like PCM of that width
+    nisqa::FlacInfo fi;
+    if (!nisqa::flac_probe(path, &fi) || fi.channels < 1 || fi.channels > 8) return NISQA_ERR_INVALID;
+    if (ms_channel >= 0 && fi.channels > 1 && ms_channel >= fi.channels) return NISQA_ERR_INVALID;
+    if (sample_rate) *sample_rate = fi.sample_rate;
+    if (n_frames) *n_frames = fi.n_frames;
+    if (channels) *channels = fi.channels;
+    if (kind_out) *kind_out = (fi.bits == 16 && (fi.channels == 1 || ms_channel >= 0)) ? NISQA_FMT_S16 : NISQA_FMT_F32;
+    return 0;
+  }
   FILE* f = fopen(path, "rb");
   if (!f) return NISQA_ERR_INVALID;
   WavInfo w;
@@ -140,8 +151,41 @@ int nisqa_wav_probe(const char* path, int32_t ms_channel, int32_t* sample_rate, 
 // probe reported S16; NISQA_FMT_F32 is always legal (PCM16 is then scaled by 1/32768).
 // ms_channel < 0: mono mix = float32 mean over the channels (librosa.to_mono); else that channel
 // (ignored for mono files, lib:2301).  Returns the number of frames written, or a negative status.
+// FLAC: decode to integers (flac.cpp), then libsndfile's rules - int16 as is, float = v * 2^-(bits-1), mono mix = float32
+// mean over the channels
+static int64_t flac_decode_into(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
+  nisqa::FlacInfo fi;
+  std::vector<int32_t> pcm;
+  if (!nisqa::flac_decode_all(path, &fi, &pcm) || fi.n_frames > cap_frames) return NISQA_ERR_INVALID;
+  const int ch = fi.channels;
+  if (ms_channel >= 0 && ch > 1 && ms_channel >= ch) return NISQA_ERR_INVALID;
+  const int pick = (ch > 1 && ms_channel >= 0) ? ms_channel : -1;
+  if (out_fmt == NISQA_FMT_S16) {
+    if (!(fi.bits == 16 && (ch == 1 || pick >= 0))) return NISQA_ERR_INVALID;
+    int16_t* o = static_cast<int16_t*>(dst);
+    for (int64_t i = 0; i < fi.n_frames; ++i) o[i] = (int16_t)pcm[(size_t)i * ch + (pick >= 0 ? pick : 0)];
+  } else if (out_fmt == NISQA_FMT_F32) {
+    float* o = static_cast<float*>(dst);
+    const float scale = 1.0f / (float)(1u << (fi.bits - 1));
+    for (int64_t i = 0; i < fi.n_frames; ++i) {
+      const int32_t* p = pcm.data() + (size_t)i * ch;
+      if (ch == 1) o[i] = (float)p[0] * scale;
+      else if (pick >= 0) o[i] = (float)p[pick] * scale;
+      else {
+        float s2 = 0.f;
+        for (int c = 0; c < ch; ++c) s2 += (float)p[c] * scale;
+        o[i] = s2 / (float)ch;
+      }
+    }
+  } else {
+    return NISQA_ERR_INVALID;
+  }
+  return fi.n_frames;
+}
+
 static int64_t wav_decode_impl(const char* path, int32_t ms_channel, int32_t out_fmt, void* dst, int64_t cap_frames) {
   if (!path || !dst) return NISQA_ERR_INVALID;
+  if (nisqa::flac_is(path)) return flac_decode_into(path, ms_channel, out_fmt, dst, cap_frames);
   FILE* f = fopen(path, "rb");
   if (!f) return NISQA_ERR_INVALID;
   WavInfo w;

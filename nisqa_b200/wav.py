@@ -1,4 +1,4 @@
-"""Host-side WAV ingest for the engine.
+"""Host-side WAV (and FLAC) ingest for the engine.
 
 Mirrors what ``lb.load(path, sr=None[, mono=False])`` + the channel pick does at reference
 ``nisqa/NISQA_lib.py:2298-2306`` (libsndfile float conversion; mono = float32 mean over
@@ -68,6 +68,8 @@ def read_wav(path, ms_channel=None):
     try:
         with open(path, "rb") as f:
             buf = f.read()
+        if buf[:4] == b"fLaC":                    # FLAC goes through the native reader (csrc/flac.cpp): no NumPy twin
+            return read_wav_native(path, ms_channel)
         (tag, ch, sr, bits), (s, e) = _parse(memoryview(buf))
         width = bits // 8
         n_frames = (e - s) // (width * ch)

@@ -594,6 +594,29 @@ def test_run_evaluate_end_to_end(tmp_path, built_lib, capsys):
     m.model.close()
 
 
+def test_flac_files_score_like_their_wav_twins(tmp_path, built_lib):
+    """a FLAC file (native reader csrc/flac.cpp; test encoder tests/flac_enc.py) goes through predict_csv
+    like a wav file and scores bit-identically to the wav holding the same samples (mono 16-bit stays int16 on the way to the
+    GPU; the 24-bit stereo file takes the float32 mono-mix path in both containers)."""
+    import flac_enc as FE
+    from nisqa_b200.NISQA_model import nisqaModel
+    a = synth.synth_speech_pcm16(801, 1.4, 48000)
+    wav.write_wav_pcm16(str(tmp_path / "a.wav"), a, 48000)
+    open(str(tmp_path / "a.flac"), "wb").write(FE.encode(a, 48000, 16))
+    st = np.stack([synth.synth_speech_pcm16(802, 1.1, 16000), synth.synth_speech_pcm16(803, 1.1, 16000)], axis=1)
+    wav.write_wav_pcm16(str(tmp_path / "s.wav"), st, 16000)
+    open(str(tmp_path / "s.flac"), "wb").write(FE.encode(st, 16000, 16, blocksize=1152, plan=lambda f, c: ("ms", "ls", "rs", "indep")[f % 4] if c is None else {"kind": "auto"}))
+    pd.DataFrame({"deg": ["a.wav", "a.flac", "s.wav", "s.flac"]}).to_csv(str(tmp_path / "f.csv"), index=False)
+    df = nisqaModel({"mode": "predict_csv", "pretrained_model": os.path.join(WEIGHTS, "nisqa.tar"), "data_dir": str(tmp_path),
+                     "csv_file": "f.csv", "csv_deg": "deg", "output_dir": None, "tr_bs_val": 4, "tr_num_workers": 2}).predict()
+    cols = ["mos_pred", "noi_pred", "dis_pred", "col_pred", "loud_pred"]
+    v = df[cols].to_numpy()
+    np.testing.assert_array_equal(v[0], v[1])
+    np.testing.assert_array_equal(v[2], v[3])
+    ref = _oracle_file("nisqa.tar", str(tmp_path / "a.wav"))
+    assert np.abs(v[1] - ref).max() <= SCORE_TOL
+
+
 def test_reference_error_behaviour(tmp_path, built_lib):
     from nisqa_b200.NISQA_model import nisqaModel
     ck = os.path.join(WEIGHTS, "nisqa.tar")

@@ -94,7 +94,7 @@ def main():
                         "bench.py 64 x 10 s clips (profiles/%s_ncu_full_one_step.csv)" % tag)
     sys.path.insert(0, ROOT)
     from nisqa_b200 import build as nb_build
-    traffic["_source_digest"] = nb_build._digest()      # bench.py refuses the table on any other kernel sources
+    traffic["_source_digest"] = nb_build.kernel_digest()      # bench.py refuses the table on any other kernel sources
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
     print("wrote", dst)
     for r in out[2:]:

@@ -5,7 +5,7 @@
 #   bash tools/sass_summary.sh > profiles/sass_summary.txt          (no GPU needed)
 cd "$(dirname "$0")/.."
 LIB=nisqa_b200/libnisqa_b200.so
-echo "# cuobjdump -sass $LIB ($(date -u +%Y-%m-%dT%H:%MZ)), source digest $(python -c 'from nisqa_b200 import build; print(build._digest()[:16])')"
+echo "# cuobjdump -sass $LIB ($(date -u +%Y-%m-%dT%H:%MZ)), source digest $(python -c 'from nisqa_b200 import build; print(build.kernel_digest()[:16])')"
 cuobjdump -sass $LIB | awk '
   /Function :/ { name=$3; order[++n]=name }
   /UTCHMMA/ {a[name]++} /LDTM/ {b[name]++} /UTCBAR/ {c[name]++} /UBLKCP/ {d[name]++} /SYNCS/ {e[name]++}
