@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "flac.h"
@@ -228,7 +229,8 @@ bool flac_decode_all(const char* path, FlacInfo* info, std::vector<int32_t>* out
   if (!pos) return false;
   const int ch = fi.channels;
   out->clear();
-  if (fi.n_frames > 0) out->reserve((size_t)fi.n_frames * ch);
+  // (a declared length is only a hint until the frames confirm it: a damaged header must not reserve gigabytes)
+  if (fi.n_frames > 0) out->reserve((size_t)std::min<int64_t>(fi.n_frames, (int64_t)d.size() * 64) * ch);
   std::vector<int64_t> sub[8];
   int64_t total = 0;
   while (pos + 6 <= d.size()) {
