@@ -1441,6 +1441,8 @@ int64_t nisqa_stage_dump(nisqa_engine* e, int stage, float* out, int64_t cap) {
   const int std_mode = e->cfg.arch == NISQA_ARCH_STD_LSTM_LASTBI;
   const int W1 = std_mode ? 8 : 7, W2 = std_mode ? 4 : 5, W3 = std_mode ? 2 : 3;
   const int64_t ns = e->last_n_seg;
+  if (e->cfg.cnn_kind != NISQA_CNN_CONV && stage >= NISQA_STAGE_POOL1 && stage <= NISQA_STAGE_CNN_FEAT)
+    return fail(e, NISQA_ERR_INVALID, "stage not available: this checkpoint has no convolutional framewise model");
   int64_t count = 0;
   const float* src = nullptr;
   int hw = 0, ch = 0;    // NHWC -> NCHW conversion when ch > 0

@@ -19,57 +19,72 @@
 namespace nisqa {
 namespace {
 
+// MSB-first bit reader over the file image: a 64-bit window refilled byte-wise, unary runs counted with clz
 struct BitReader {
   const uint8_t* p;
-  size_t n, pos = 0;       // pos in BITS
+  size_t n;
+  size_t byte = 0;          // next byte to load into the window
+  uint64_t win = 0;         // the unread bits, left-aligned
+  int have = 0;             // valid bits in `win`
   bool bad = false;
   BitReader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
-  uint32_t bits(int k) {    // k <= 32, MSB first
-    uint64_t v = 0;
-    for (int i = 0; i < k; ++i) {
-      const size_t byte = pos >> 3;
-      if (byte >= n) { bad = true; return 0; }
-      v = (v << 1) | ((p[byte] >> (7 - (pos & 7))) & 1u);
-      ++pos;
-    }
-    return (uint32_t)v;
+  void refill() {
+    while (have <= 56 && byte < n) { win |= (uint64_t)p[byte++] << (56 - have); have += 8; }
+  }
+  uint32_t bits(int k) {    // k <= 32
+    if (k == 0) return 0;
+    if (have < k) { refill(); if (have < k) { bad = true; have = 0; win = 0; return 0; } }
+    const uint32_t v = (uint32_t)(win >> (64 - k));
+    win <<= k; have -= k;
+    return v;
   }
   int64_t sbits(int k) {    // two's complement, k <= 33 (side channel of 32-bit streams)
     if (k == 0) return 0;
-    uint64_t v = 0;
-    int left = k;
-    while (left > 0) { const int t = left > 16 ? 16 : left; v = (v << t) | bits(t); left -= t; }
+    uint64_t v;
+    if (k > 32) { v = (uint64_t)bits(k - 32) << 32; v |= bits(32); }
+    else v = bits(k);
     const uint64_t sign = 1ull << (k - 1);
     return (int64_t)((v ^ sign) - sign);
   }
   uint32_t unary() {        // number of 0 bits before the next 1
     uint32_t q = 0;
     for (;;) {
-      const size_t byte = pos >> 3;
-      if (byte >= n) { bad = true; return 0; }
-      const uint32_t b = (p[byte] >> (7 - (pos & 7))) & 1u;
-      ++pos;
-      if (b) return q;
-      if (++q > (1u << 24)) { bad = true; return 0; }
+      if (have == 0) { refill(); if (have == 0) { bad = true; return 0; } }
+      if (win == 0) { q += (uint32_t)have; have = 0; if (q > (1u << 24)) { bad = true; return 0; } continue; }
+      const int z = __builtin_clzll(win);          // < have: a set bit lies inside the valid part
+      q += (uint32_t)z;
+      win <<= (z + 1); have -= z + 1;
+      return q;
     }
   }
-  void align() { pos = (pos + 7) & ~(size_t)7; }
+  size_t bit_pos() const { return byte * 8 - (size_t)have; }
+  void align() { const int drop = have & 7; win <<= drop; have -= drop; }
 };
 
-uint8_t crc8(const uint8_t* p, size_t n) {         // polynomial x^8 + x^2 + x + 1
-  uint8_t c = 0;
-  for (size_t i = 0; i < n; ++i) {
-    c ^= p[i];
-    for (int b = 0; b < 8; ++b) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1));
+struct CrcTables {
+  uint8_t t8[256];
+  uint16_t t16[256];
+  CrcTables() {
+    for (int i = 0; i < 256; ++i) {
+      uint8_t c = (uint8_t)i;                       // polynomial x^8 + x^2 + x + 1
+      for (int b = 0; b < 8; ++b) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1));
+      t8[i] = c;
+      uint16_t w = (uint16_t)(i << 8);              // polynomial x^16 + x^15 + x^2 + 1
+      for (int b = 0; b < 8; ++b) w = (uint16_t)((w & 0x8000) ? (w << 1) ^ 0x8005 : (w << 1));
+      t16[i] = w;
+    }
   }
+};
+const CrcTables kCrc;
+
+uint8_t crc8(const uint8_t* p, size_t n) {
+  uint8_t c = 0;
+  for (size_t i = 0; i < n; ++i) c = kCrc.t8[c ^ p[i]];
   return c;
 }
-uint16_t crc16(const uint8_t* p, size_t n) {       // polynomial x^16 + x^15 + x^2 + 1
+uint16_t crc16(const uint8_t* p, size_t n) {
   uint16_t c = 0;
-  for (size_t i = 0; i < n; ++i) {
-    c ^= (uint16_t)(p[i] << 8);
-    for (int b = 0; b < 8; ++b) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1));
-  }
+  for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ kCrc.t16[(c >> 8) ^ p[i]]);
   return c;
 }
 
@@ -257,7 +272,7 @@ bool flac_decode_all(const char* path, FlacInfo* info, std::vector<int32_t>* out
     else if (sr_code == 13 || sr_code == 14) br.bits(16);
     else if (sr_code == 15) return false;
     if (br.bad) return false;
-    const size_t hdr_bytes = br.pos >> 3;
+    const size_t hdr_bytes = br.bit_pos() >> 3;
     if (crc8(h, hdr_bytes) != (uint8_t)br.bits(8)) return false;
     static const int ss_table[8] = {0, 8, 12, -1, 16, 20, 24, 32};
     const int bps = ss_code == 0 ? fi.bits : ss_table[ss_code];
@@ -273,7 +288,7 @@ bool flac_decode_all(const char* path, FlacInfo* info, std::vector<int32_t>* out
       if (!read_subframe(br, bps + (side ? 1 : 0), blocksize, sub[c].data())) return false;
     }
     br.align();
-    const size_t body = br.pos >> 3;
+    const size_t body = br.bit_pos() >> 3;
     if (pos + body + 2 > d.size()) return false;
     if (crc16(h, body) != (uint16_t)((h[body] << 8) | h[body + 1])) return false;
     for (int i = 0; i < blocksize; ++i) {
