@@ -36,11 +36,11 @@ def _digest():
 
 
 def kernel_digest():
-    """Digest of the CUDA sources alone (*.cu, *.cuh + flags): what a measured per-kernel table (profiles/roofline_traffic.json)
+    """Digest of the kernel sources alone (*.cu, *.cuh except engine.cu, + flags): what a measured per-kernel table (profiles/roofline_traffic.json)
     is tied to - a change to the host-side readers does not invalidate it."""
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)):
-        if name.endswith((".cu", ".cuh")):
+        if name.endswith((".cu", ".cuh")) and name != "engine.cu":        # (engine.cu holds the host side: ABI, passes, packing)
             with open(os.path.join(CSRC, name), "rb") as fh:
                 h.update(name.encode()); h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
