@@ -112,13 +112,16 @@ typedef struct nisqa_config {
   int32_t double_ended;  /* 1: NISQA_DE */
   int32_t de_align;      /* enum nisqa_de_align */
   int32_t de_align_apply;/* enum nisqa_de_apply */
-  int32_t de_fuse;       /* enum nisqa_de_fuse (de_fuse_dim must be None) */
+  int32_t de_fuse;       /* enum nisqa_de_fuse */
   int32_t td2_layers;    /* td_2 = 'self_att' (d_model 64, one head, h 64): number of layers; 0 = td_2 'skip'.  NISQA_DE needs >= 1;
                           * NISQA / NISQA_DIM run it as a second stack behind the first (lib:114-141, 236-268) */
   int32_t td2_pos_enc;   /* td_2_sa_pos_enc */
   /* framewise model in front of the self-attention stack (arch NISQA_ARCH_ADAPT_SA_ATTFF): */
   int32_t cnn_kind;      /* enum nisqa_cnn_kind: 0 = the convolutional networks, 1 = SkipCNN (lib:504-534), 2 = DFF (lib:536-583) */
-  int32_t cnn_fc;        /* cnn_fc_out_h of SkipCNN (0 = no Linear: 720 features) / DFF (hidden width); a multiple of 64 */
+  int32_t cnn_fc;        /* cnn_fc_out_h: Linear behind the AdaptCNN (lib:682-684, 708-709), of SkipCNN (0 = none: 720 features),
+                          * hidden width of DFF; a multiple of 64 */
+  int32_t de_fuse_dim;   /* NISQA_DE: Linear(fused features -> de_fuse_dim) behind the fusion (lib:1399-1401, 1414-1415); 0 = none;
+                          * a multiple of 64 */
 } nisqa_config;
 
 /* One state_dict entry, passed straight through: name as in the checkpoint

@@ -642,13 +642,35 @@ int pack_weights(nisqa_engine* e, const nisqa_tensor* tensors, int n) {
     };
     // framewise features feeding the first stack: 384 (AdaptCNN, engine order), 720 (SkipCNN without Linear: padded to 768
     // with zero rows) or cnn_fc_out_h
-    const int feat_dim = conv_net ? 384 : (e->cfg.cnn_fc > 0 ? e->cfg.cnn_fc : 720);
-    if (!pack_sa_stack(td, "", feat_dim, e->cfg.sa_layers, conv_net)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+    const int feat_dim = e->cfg.cnn_fc > 0 ? e->cfg.cnn_fc : (conv_net ? 384 : 720);
+    if (conv_net && e->cfg.cnn_fc > 0) {
+      // AdaptCNN's optional Linear (lib:682-684, 708-709): k-major, rows in the engine's feature order h*64 + c
+      const int H = e->cfg.cnn_fc;
+      const TensorView* w = P.get("cnn.model.fc.weight", {H, 384});
+      const TensorView* b = P.get("cnn.model.fc.bias", {H});
+      if (!w || !b) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+      const size_t ow = P.alloc("ffc.wT", (size_t)384 * H), ob = P.alloc("ffc.b", H);
+      for (int h = 0; h < 6; ++h)
+        for (int c = 0; c < 64; ++c)
+          for (int j = 0; j < H; ++j) P.arena[ow + ((size_t)h * 64 + c) * H + j] = w->d[(size_t)j * 384 + c * 6 + h];
+      memcpy(&P.arena[ob], b->d, (size_t)H * 4);
+    }
+    if (!pack_sa_stack(td, "", feat_dim, e->cfg.sa_layers, conv_net && e->cfg.cnn_fc == 0)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
     if (e->cfg.double_ended || e->cfg.td2_layers > 0) {
       // time_dependency_2: behind the fusion of the double-ended model (input 192 / 128), or a second stack behind the
       // first one in NISQA / NISQA_DIM (lib:114-141, 236-268; input 64)
       const std::string td2 = "time_dependency_2.model.";
-      const int fdim = !e->cfg.double_ended ? 64 : (e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128);
+      int fdim = !e->cfg.double_ended ? 64 : (e->cfg.de_fuse == NISQA_DE_FUSE_XY_MINUS ? 192 : 128);
+      if (e->cfg.double_ended && e->cfg.de_fuse_dim > 0) {        // Fusion.lin_fusion (lib:1399-1401)
+        const int D = e->cfg.de_fuse_dim;
+        const TensorView* w = P.get("fuse.lin_fusion.weight", {D, fdim});
+        const TensorView* b = P.get("fuse.lin_fusion.bias", {D});
+        if (!w || !b) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
+        const size_t ow = P.alloc("defuse.wT", (size_t)fdim * D), ob = P.alloc("defuse.b", D);
+        pack_linear_T(P, ow, w, D, fdim);
+        memcpy(&P.arena[ob], b->d, (size_t)D * 4);
+        fdim = D;
+      }
       if (!pack_sa_stack(td2, "2", fdim, e->cfg.td2_layers, false)) return fail(e, NISQA_ERR_WEIGHTS, P.missing);
       if (e->cfg.td2_pos_enc) { int rc = pack_pos_enc(td2, "pe2"); if (rc) return rc; }
       if (e->cfg.de_align == NISQA_DE_ALIGN_LUONG) {            // AttLuong: W = Linear(y_dim -> q_dim), lib:1348-1351
@@ -976,6 +998,12 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
       }
     }
 
+    if (conv_net && c.cnn_fc > 0) {      // AdaptCNN's Linear behind conv6 (lib:708-709)
+      Scope s(e, "framewise");
+      CK(LN.ffb.reserve((size_t)n_seg * c.cnn_fc * 4));
+      launch_linear_tile(st, LN.feats.as<float>(), 384, W(e, "ffc.wT"), W(e, "ffc.b"), 0, LN.ffb.as<float>(), c.cnn_fc, n_seg, 384, c.cnn_fc);
+      sa_in = LN.ffb.as<float>(); sa_nk = c.cnn_fc / 64;
+    }
     if (!std_mode) {
       CK(LN.xa.reserve((size_t)n_seg * 64 * 4));
       CK(LN.xb.reserve((size_t)n_seg * 64 * 4));
@@ -1044,7 +1072,16 @@ int run_pass(nisqa_engine* e, const PassInput& in) {
         { Scope s(e, "de_align");
           launch_de_align(st, cur, d_clips, n, d_qt64, n_qt64, c.de_align, c.de_align_apply == NISQA_DE_APPLY_SOFT, c.de_fuse,
                           AP, LN.fused.as<float>()); }
-        cur = sa_stack("2", LN.fused.as<float>(), nf, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
+        const float* td2_rows = LN.fused.as<float>();
+        int td2_nk = nf;
+        if (c.de_fuse_dim > 0) {         // Fusion.lin_fusion (lib:1414-1415)
+          Scope s(e, "de_align");
+          CK(LN.ffa.reserve((size_t)n_seg * c.de_fuse_dim * 4));
+          launch_linear_tile(st, LN.fused.as<float>(), 64 * nf, W(e, "defuse.wT"), W(e, "defuse.b"), 0, LN.ffa.as<float>(), c.de_fuse_dim,
+                             n_seg, 64 * nf, c.de_fuse_dim);
+          td2_rows = LN.ffa.as<float>(); td2_nk = c.de_fuse_dim / 64;
+        }
+        cur = sa_stack("2", td2_rows, td2_nk, c.td2_layers, c.td2_pos_enc != 0, true, LN.td2in.as<float>());
       }
       e->last_td_out = cur;
       { Scope s(e, "pool");
@@ -1222,8 +1259,9 @@ int nisqa_create(nisqa_engine** out, int device, const nisqa_config* cfg) {
     return fail(e, NISQA_ERR_INVALID, "pooling module not available for this architecture");
   if (cfg->pos_enc && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) return fail(e, NISQA_ERR_INVALID, "pos_enc needs the self-attention architecture");
   if (cfg->cnn_kind < NISQA_CNN_CONV || cfg->cnn_kind > NISQA_CNN_DFF || cfg->cnn_fc < 0 || cfg->cnn_fc % 64 != 0 || cfg->cnn_fc > 8192 ||
-      (cfg->cnn_kind == NISQA_CNN_DFF && cfg->cnn_fc == 0) || (cfg->cnn_kind == NISQA_CNN_CONV && cfg->cnn_fc != 0) ||
-      (cfg->cnn_kind != NISQA_CNN_CONV && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF))
+      (cfg->cnn_kind == NISQA_CNN_DFF && cfg->cnn_fc == 0) || (cfg->cnn_fc != 0 && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) ||
+      (cfg->cnn_kind != NISQA_CNN_CONV && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF) ||
+      cfg->de_fuse_dim < 0 || cfg->de_fuse_dim % 64 != 0 || cfg->de_fuse_dim > 8192 || (cfg->de_fuse_dim != 0 && !cfg->double_ended))
     return fail(e, NISQA_ERR_INVALID, "cnn_kind / cnn_fc: SkipCNN and DFF feed the self-attention architecture; cnn_fc_out_h a multiple of 64");
   if (cfg->td2_layers < 0 || cfg->td2_layers > 8 || (cfg->td2_layers > 0 && cfg->arch != NISQA_ARCH_ADAPT_SA_ATTFF))
     return fail(e, NISQA_ERR_INVALID, "td_2 = 'self_att' needs the self-attention architecture (td2_layers 0..8)");

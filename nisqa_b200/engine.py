@@ -48,7 +48,7 @@ class NisqaConfig(C.Structure):
                 ("max_chunk_segments", C.c_int32), ("pool", C.c_int32), ("pos_enc", C.c_int32),
                 ("double_ended", C.c_int32), ("de_align", C.c_int32), ("de_align_apply", C.c_int32),
                 ("de_fuse", C.c_int32), ("td2_layers", C.c_int32), ("td2_pos_enc", C.c_int32),
-                ("cnn_kind", C.c_int32), ("cnn_fc", C.c_int32)]
+                ("cnn_kind", C.c_int32), ("cnn_fc", C.c_int32), ("de_fuse_dim", C.c_int32)]
 
 
 class NisqaTensor(C.Structure):
@@ -164,8 +164,11 @@ def config_from_args(args, max_chunk_segments=0):
     if (cnn, td) == ("adapt", "self_att") and pool_mode != POOL_LAST_STEP_BI:
         arch = ARCH_ADAPT_SA_ATTFF
         ok = (list(args["cnn_pool_1"]) == [24, 7] and list(args["cnn_pool_2"]) == [12, 5]
-              and list(args["cnn_pool_3"]) == [6, 3] and args.get("cnn_fc_out_h") in (None, 0)
+              and list(args["cnn_pool_3"]) == [6, 3]
               and args["td_sa_d_model"] == 64 and args["td_sa_nhead"] == 1 and args["td_sa_h"] == 64)
+        cnn_fc = int(args.get("cnn_fc_out_h") or 0)           # optional Linear behind conv6 (lib:682-684)
+        if cnn_fc % 64 != 0:
+            raise NotImplementedError("cnn_fc_out_h=%d: the B200 engine needs a multiple of 64" % cnn_fc)
     elif cnn in (None, "skip", "dff") and td == "self_att" and pool_mode != POOL_LAST_STEP_BI:
         # framewise models without convolutions (lib:504-583) in front of the self-attention stack
         arch = ARCH_ADAPT_SA_ATTFF
@@ -195,8 +198,8 @@ def config_from_args(args, max_chunk_segments=0):
             raise NotImplementedError("de_align=%r is not implemented by the B200 engine (dot, cosine, distance, luong, bahd)" % (args.get("de_align"),))
         if args.get("de_align_apply") not in DE_APPLY or args.get("de_fuse") not in DE_FUSE:
             raise NotImplementedError("de_align_apply / de_fuse option not available: %r / %r" % (args.get("de_align_apply"), args.get("de_fuse")))
-        if args.get("de_fuse_dim"):
-            raise NotImplementedError("de_fuse_dim is not implemented by the B200 engine")
+        if args.get("de_fuse_dim") and int(args["de_fuse_dim"]) % 64 != 0:
+            raise NotImplementedError("de_fuse_dim=%r: the B200 engine needs a multiple of 64" % (args.get("de_fuse_dim"),))
         ok = ok and args.get("td_2") == "self_att" and args.get("td_2_sa_d_model") == 64 and args.get("td_2_sa_nhead") == 1 \
             and args.get("td_2_sa_h") == 64
     elif args.get("td_2") == "self_att":
@@ -230,6 +233,7 @@ def config_from_args(args, max_chunk_segments=0):
         cfg.td2_pos_enc = 1 if args.get("td_2_sa_pos_enc") else 0
     if de:
         cfg.double_ended = 1
+        cfg.de_fuse_dim = int(args.get("de_fuse_dim") or 0)
         cfg.de_align, cfg.de_align_apply, cfg.de_fuse = DE_ALIGN[args["de_align"]], DE_APPLY[args["de_align_apply"]], DE_FUSE[args["de_fuse"]]
     return cfg
 

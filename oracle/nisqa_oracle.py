@@ -108,7 +108,10 @@ def adapt_cnn(sd, x, args, taps=None):
     x = _conv_bn_relu(sd, 5, x, (1, 1))
     if taps is not None: taps["conv5"] = x
     x = _conv_bn_relu(sd, 6, x, (1, 0))          # kernel (3, pool_3[1]) pad (1,0): W 3 -> 1
-    return x.reshape(-1, 64 * args["cnn_pool_3"][0])
+    x = x.reshape(-1, 64 * args["cnn_pool_3"][0])
+    if "cnn.model.fc.weight" in sd:              # cnn_fc_out_h (lib:682-684, 708-709)
+        x = F.linear(x, sd["cnn.model.fc.weight"], sd["cnn.model.fc.bias"])
+    return x
 
 
 def standard_cnn(sd, x, args, taps=None):
@@ -236,21 +239,25 @@ def de_align(args, x, y, sd=None):
     raise NotImplementedError(args["de_align_apply"])
 
 
-def de_fuse(args, x, y):
-    """Fusion.forward (lib:1402-1417); de_fuse_dim (the optional Linear) is not restated."""
+def de_fuse(args, x, y, sd=None):
+    """Fusion.forward (lib:1402-1417) with the optional Linear (de_fuse_dim, lib:1399-1401)."""
     mode = args["de_fuse"]
     if mode == "x/y/-":
-        return torch.cat((x, y, x - y), 1)
-    if mode == "+/-":
-        return torch.cat((x + y, x - y), 1)
-    if mode == "x/y":
-        return torch.cat((x, y), 1)
-    raise NotImplementedError(mode)
+        f = torch.cat((x, y, x - y), 1)
+    elif mode == "+/-":
+        f = torch.cat((x + y, x - y), 1)
+    elif mode == "x/y":
+        f = torch.cat((x, y), 1)
+    else:
+        raise NotImplementedError(mode)
+    if args.get("de_fuse_dim"):
+        f = F.linear(f, sd["fuse.lin_fusion.weight"], sd["fuse.lin_fusion.bias"])
+    return f
 
 
 def forward_de_from_mel(args, sd, spec, spec_ref, taps=None):
     """NISQA_DE.forward (lib:404-424) for one (degraded, reference) pair of mel dB spectrograms -> score [1]."""
-    if args["cnn_model"] != "adapt" or args["td"] != "self_att" or args.get("td_2") != "self_att" or args.get("de_fuse_dim"):
+    if args["cnn_model"] != "adapt" or args["td"] != "self_att" or args.get("td_2") != "self_att":
         raise NotImplementedError("oracle: NISQA_DE with AdaptCNN + self-attention + td_2 self-attention")
     with torch.no_grad():
         outs = []
@@ -260,7 +267,7 @@ def forward_de_from_mel(args, sd, spec, spec_ref, taps=None):
         x, y = outs
         y_al = de_align(args, x, y, sd)
         if taps is not None: taps["de_x"], taps["de_y"], taps["de_y_aligned"] = x, y, y_al
-        fused = de_fuse(args, x, y_al)
+        fused = de_fuse(args, x, y_al, sd)
         sd2 = {k.replace("time_dependency_2.", "time_dependency."): v for k, v in sd.items() if k.startswith("time_dependency_2.")}
         td2 = self_attention(sd2, fused, pos_enc=bool(args.get("td_2_sa_pos_enc")))
         if taps is not None: taps["td2_out"] = td2

@@ -31,6 +31,8 @@ VARIANTS = {
     "mos_skip": ("nisqa_mos_only.tar", {"cnn_model": "skip", "cnn_fc_out_h": None}),
     "dim_skip_fc": ("nisqa.tar", {"cnn_model": "skip", "cnn_fc_out_h": 128}),
     "mos_dff": ("nisqa_mos_only.tar", {"cnn_model": "dff", "cnn_fc_out_h": 256}),
+    # AdaptCNN with its optional Linear behind conv6 (lib:682-684): seeded fc and first Linear of the stack
+    "dim_adapt_fc": ("nisqa.tar", {"cnn_fc_out_h": 128}),
 }
 # double-ended variants (NISQA_DE, reference lib:272-424): nisqa_mos_only.tar's CNN, first self-attention stack and
 # PoolAttFF head (identical shapes) + seeded weights for time_dependency_2 (input width 192 or 128)
@@ -44,6 +46,8 @@ DE_VARIANTS = {
     "de_luong_soft": {"de_align": "luong", "de_align_apply": "soft", "de_fuse": "x/y/-"},
     "de_luong_hard": {"de_align": "luong", "de_align_apply": "hard", "de_fuse": "+/-"},
     "de_bahd_soft": {"de_align": "bahd", "de_align_apply": "soft", "de_fuse": "x/y/-"},
+    # Fusion with its optional Linear (de_fuse_dim, lib:1399-1401)
+    "de_cosine_soft_fuse_dim": {"de_align": "cosine", "de_align_apply": "soft", "de_fuse": "x/y/-", "de_fuse_dim": 64},
 }
 # (degraded, reference) pairs: (seed, seconds, sample rate) each; the degraded signal of pair 0 / 1 is derived from its
 # reference (delay + noise + clipping: what a double-ended model is for), pair 2 has unrelated signals of other lengths
@@ -97,6 +101,11 @@ def de_checkpoint(name, base_args, base_sd):
     sd = {k: v for k, v in base_sd.items()}
     fdim = 192 if args["de_fuse"] == "x/y/-" else 128
     rng = np.random.default_rng(sum(map(ord, name)))
+    if args.get("de_fuse_dim"):
+        d = args["de_fuse_dim"]
+        sd["fuse.lin_fusion.weight"] = torch.from_numpy((rng.standard_normal((d, fdim)) / math.sqrt(fdim)).astype(np.float32))
+        sd["fuse.lin_fusion.bias"] = torch.from_numpy(rng.normal(0, 0.05, d).astype(np.float32))
+        fdim = d
     td2_weights(sd, args, fdim, rng)
 
     def put(key, shape, scale):
@@ -150,6 +159,12 @@ def variant_checkpoint(name, base_args, base_sd):
         sd["time_dependency.model.pos_encoder.pe"] = positional_encoding()
     if args.get("td_2") == "self_att":
         td2_weights(sd, args, 64, np.random.default_rng(sum(map(ord, name))))
+    if args.get("cnn_model") == "adapt" and args.get("cnn_fc_out_h"):
+        rng = np.random.default_rng(sum(map(ord, name)) + 2)
+        h = args["cnn_fc_out_h"]
+        sd["cnn.model.fc.weight"] = torch.from_numpy((rng.standard_normal((h, 384)) / math.sqrt(384)).astype(np.float32))
+        sd["cnn.model.fc.bias"] = torch.from_numpy(rng.normal(0, 0.05, h).astype(np.float32))
+        sd["time_dependency.model.linear.weight"] = torch.from_numpy((rng.standard_normal((64, h)) / math.sqrt(h)).astype(np.float32))
     if args.get("cnn_model") in ("skip", "dff"):
         rng = np.random.default_rng(sum(map(ord, name)) + 1)
         sd = {k: v for k, v in sd.items() if not k.startswith("cnn.")}

@@ -86,7 +86,9 @@ def test_config_refuses_unknown_architectures():
               de_align="bahd", de_align_apply="soft", de_fuse="x/y/-", de_fuse_dim=None)
     c = E.config_from_args(de)
     assert (c.double_ended, c.de_align, c.td2_layers, c.n_out) == (1, 5, 2, 1)
-    for k, v in (("de_align", "none"), ("de_fuse_dim", 64), ("td_2", "skip")):
+    assert E.config_from_args(dict(de, de_fuse_dim=64)).de_fuse_dim == 64
+    assert E.config_from_args(dict(args, cnn_fc_out_h=128)).cnn_fc == 128         # AdaptCNN's optional Linear
+    for k, v in (("de_align", "none"), ("de_fuse_dim", 100), ("td_2", "skip")):
         with pytest.raises(NotImplementedError):
             E.config_from_args(dict(de, **{k: v}))
 
