@@ -205,7 +205,9 @@ def _predict_rows(engine, ds, rows, bs, num_workers):
     out = np.empty((len(rows), n_out), dtype=np.float32)
     bs = max(1, int(bs))
     batches = [rows[i:i + bs] for i in range(0, len(rows), bs)]
-    n_threads = max(1, int(num_workers) if num_workers else 1)     # native decode threads per batch
+    # native decode threads per batch; three batches are decoded concurrently (DEPTH), so more than half of the CPUs the
+    # process is granted per batch only oversubscribes them
+    n_threads = max(1, min(int(num_workers) if num_workers else 1, max(1, nb_dist.usable_cpus() // 2)))
 
     de = getattr(ds, "double_ended", False)
     per_row = 2 if de else 1          # a double-ended row is a (degraded, reference) pair of clips

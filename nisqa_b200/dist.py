@@ -32,6 +32,24 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
+def usable_cpus():
+    """CPUs this process may really use: the affinity mask cut down to the cgroup CPU quota (cgroup v2 ``cpu.max``).  The
+    GPU boxes show 128 logical CPUs but grant 16: decode threads beyond the grant only fight each other
+    (profiles/r02ac_bench_files.txt: 8 threads per batch 15 400 clips/s, 16 threads 10 500)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max" and int(quota) > 0:
+            n = max(1, min(n, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def shutdown(engine=None):
     """Orderly end of a multi-rank run: barrier, close the engine (its NCCL communicator), destroy the process group.
     A no-op for the parts that do not exist (single process, no engine)."""
